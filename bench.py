@@ -1,0 +1,357 @@
+"""bench.py — HEPT attention fwd+bwd throughput on synthetic tracking-60k-shaped events.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path over one event: ``HEPTAttention`` forward + backward w.r.t.
+q, k, v, w_rpe.weight and out_linear.* (BASELINE.json configs[1]: ~60k hits, block_size 100, 3 hash
+tables, 8 heads x 24 dims, coords_dim 6).  Prints ONE JSON line (rank 0).
+
+  value      hits/s, whole job, inputs already resident in HBM, CUDA-event timed, max over ranks
+  e2e        the same metric through the module call with HOST (pinned) inputs: H2D of q, k, v, coords,
+             combined_shifts and D2H of the output + parameter gradients inside the timed region
+  roofline   dominant kernel, algorithmic bytes per launch / its CUDA-event duration, vs the measured HBM peak
+  cpu_baseline  the oracle (a torch-CPU restatement of the reference, kind "port") timed on this box's cores
+
+``--impl reference`` times that CPU path alone with the same metric / config (rank 0 only).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "HEPT attention hits/sec fwd+bwd, tracking-60k shape; % of HBM roofline"
+UNIT = "hits/s"
+N_RAW = 60000
+FWD_BWD_BYTES_PER_HIT = 8336          # compulsory bytes at the module boundary, fp32 I/O
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def make_event(seed: int, n_raw: int = N_RAW):
+    """Synthetic tracking-shaped event, prepared with the product-side prepare_input -> CPU tensors."""
+    from hept_b200 import prepare, synthetic
+
+    cfg = dict(synthetic.TRACKING)
+    coords_raw, batch = synthetic.batched_cloud([n_raw], cfg["coords_dim"], seed)
+    params = synthetic.module_params(cfg, 0)
+    helper = {"block_size": cfg["block_size"], "regions": params["regions"], "num_heads": cfg["num_heads"]}
+    _, kw, _ = prepare.prepare_input(torch.zeros(n_raw, 1), coords_raw, batch, helper)
+    n = kw["coords"].shape[0]
+    q, k, v = synthetic.qkv(n, cfg, seed)
+    g = torch.randn(n, cfg["h_dim"], generator=torch.Generator().manual_seed(seed + 5))
+    return cfg, params, dict(query=q, key=k, value=v, coords=kw["coords"], combined_shifts=kw["combined_shifts"]), g
+
+
+# ------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz, self._stop = [], set(), None, threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nv = None
+
+    def _run(self):
+        nv = self._nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def __enter__(self):
+        if self._nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+
+    def summary(self):
+        s = sorted(self.samples)
+        med = s[len(s) // 2] if s else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# --------------------------------------------------------------------------------------- CPU baseline
+def cpu_port_rate(n_hits: int, steps: int, warmup: int):
+    """Oracle (torch-CPU restatement of the reference) fwd+bwd on ``n_hits``-hit events -> hits/s, seconds/step."""
+    from oracle import hept_oracle as O
+
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    cfg, params, inputs, g = make_event(1234, n_hits)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.forward_backward(inputs, params, cfg, g, torch.float32)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    dt = sum(times) / len(times)
+    return n_hits / dt, dt, threads
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port; the reference is Python and cannot travel)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # bounded sample: events small enough that warmup+steps finish in ~2 minutes (cost is linear in hits)
+    probe_rate, _, threads = cpu_port_rate(6000, 1, 1)
+    budget_s = 110.0
+    n = int(min(N_RAW, max(2000, probe_rate * budget_s / max(1, args.steps + args.warmup))) // 100 * 100)
+    rate, dt, threads = cpu_port_rate(n, args.steps, args.warmup)
+    line = {
+        "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "impl": "reference",
+        "config": {"workload": "tracking-60k fwd+bwd (HEPTAttention, H=8 D=24 C=6 T=3 B=100)",
+                   "sample": f"{n}-hit events, cost linear in hits"},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} fwd+bwd steps on {n}-hit synthetic tracking events, torch CPU eager fp32"},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch.distributed as dist
+
+    from hept_b200 import HEPTAttention, ops, sharding, _lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+    n_sets = 4                                  # rotate over 4 events: ~0.75 GB of inputs, far beyond the 126 MB L2
+    events = [make_event(100 * rank + i) for i in range(n_sets)]
+    cfg, params = events[0][0], events[0][1]
+    mod = HEPTAttention(cfg["h_dim"] + cfg["coords_dim"], **cfg)
+    mod.load_state_dict({k: params[k] for k in ("out_linear.weight", "out_linear.bias", "e2lsh.alpha")}, strict=True)
+    mod = mod.to(dev)
+    w_rpe = torch.nn.Linear(params["w_rpe.weight"].shape[1], params["w_rpe.weight"].shape[0])
+    w_rpe.load_state_dict({"weight": params["w_rpe.weight"], "bias": params["w_rpe.bias"]})
+    w_rpe = w_rpe.to(dev)
+    trainable = [w_rpe.weight, mod.out_linear.weight, mod.out_linear.bias]
+
+    host = [{k: v.pin_memory() for k, v in e[2].items()} for e in events]
+    gouts = [e[3].to(dev) for e in events]
+    resident = [{k: v.to(dev) for k, v in h.items()} for h in host]
+    for r in resident:
+        for k in ("query", "key", "value"):
+            r[k].requires_grad_(True)
+    n_hits = resident[0]["query"].shape[0]
+
+    def step(inp, g):
+        for p in trainable:
+            p.grad = None
+        for k in ("query", "key", "value"):
+            inp[k].grad = None
+        out = mod(inp["query"], inp["key"], inp["value"], w_rpe=w_rpe, coords=inp["coords"],
+                  combined_shifts=inp["combined_shifts"])
+        out.backward(g)
+        if world > 1:
+            sharding.allreduce_gradients(trainable)
+        return out
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ops.launch_count(reset=True)
+        e0.record()
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record()
+        torch.cuda.synchronize()
+        launches = ops.launch_count(reset=True)
+        if world > 1:
+            dist.barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches
+
+    # ---- device-resident throughput -----------------------------------------------------------------
+    with ClockSampler(local) as clocks:
+        ms, launches = timed(lambda i: step(resident[i % n_sets], gouts[i % n_sets]), args.steps, args.warmup)
+    value = world * args.steps * N_RAW / (ms * 1e-3)
+
+    # ---- end to end through the module with host buffers -------------------------------------------
+    staging = {k: torch.empty_like(v, device=dev) for k, v in host[0].items()}
+    out_host = torch.empty(n_hits, cfg["h_dim"]).pin_memory()
+    grad_host = [torch.empty_like(p, device="cpu").pin_memory() for p in trainable]
+    h2d = sum(v.numel() * v.element_size() for v in host[0].values())
+    d2h = out_host.numel() * 4 + sum(g.numel() * 4 for g in grad_host)
+
+    def e2e_step(i):
+        h = host[i % n_sets]
+        inp = {}
+        for k, v in h.items():
+            staging[k].copy_(v, non_blocking=True)
+            inp[k] = staging[k]
+        for k in ("query", "key", "value"):
+            inp[k] = inp[k].detach().requires_grad_(True)
+        out = step(inp, gouts[i % n_sets])
+        out_host.copy_(out.detach(), non_blocking=True)
+        for gh, p in zip(grad_host, trainable):
+            gh.copy_(p.grad, non_blocking=True)
+
+    e2e_steps = max(3, min(args.steps, 10))
+    ms_e2e, _ = timed(e2e_step, e2e_steps, 3)
+    e2e_value = world * e2e_steps * N_RAW / (ms_e2e * 1e-3)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "tracking-60k fwd+bwd (HEPTAttention, H=8 D=24 C=6 T=3 B=100), one 60000-hit event per step per GPU",
+                   "l2": f"inputs rotate over {n_sets} events (~190 MB each) so no step re-reads L2-resident inputs",
+                   "collective": "NCCL all-reduce of parameter gradients per step" if world > 1 else "none"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / e2e_steps},
+        "gpu_launches": launches,
+        "clocks": clocks.summary(),
+    }
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        line["path_roofline"] = {"bytes_per_hit": FWD_BWD_BYTES_PER_HIT,
+                                 "achieved_gbs": FWD_BWD_BYTES_PER_HIT * value / world / 1e9,
+                                 "frac": FWD_BWD_BYTES_PER_HIT * value / world / 1e9 / peak}
+        line["roofline"] = kernel_roofline(resident, gouts, cfg, mod, w_rpe, peak, peak_src, n_sets)
+        if world == 1:
+            rate, dt, threads = cpu_port_rate(N_RAW, 2, 1)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": "2 fwd+bwd steps (after 1 warm-up) on one 60000-hit event, torch CPU eager fp32"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def kernel_roofline(resident, gouts, cfg, mod, w_rpe, peak, peak_src, n_sets):
+    """Time each native stage alone with CUDA events (same inputs, rotating) and report the dominant kernel.
+
+    Algorithmic bytes per launch = that kernel's compulsory traffic (fp32 rows in, fp32 rows out, int32
+    permutations), per hit x 60 000 hits — DESIGN.md "Kernels" lists the per-hit figures."""
+    from hept_b200 import ops, _lib
+
+    lib = _lib.load()
+    H, D, C, T, B = cfg["num_heads"], cfg["h_dim"], cfg["coords_dim"], cfg["n_hashes"], cfg["block_size"]
+    n = resident[0]["query"].shape[0]
+    d = ops.Dims(N=n, H=H, D=D, C=C, T=T, B=B, raw_size=n)
+    K = cfg["num_w_per_dist"]
+    saved = []
+    for r in resident:
+        q, k, v = (r[x].detach() for x in ("query", "key", "value"))
+        out_pre, den, scale, pos = ops.attention_fwd(d, q, k, v, r["coords"], w_rpe.weight.detach(), K, mod.e2lsh.alpha,
+                                                     combined_shifts=r["combined_shifts"])
+        saved.append((q, k, v, r["coords"], scale, pos, out_pre, den, torch.randn_like(out_pre)))
+
+    def ev_time(fn, reps=8):
+        for i in range(3):
+            fn(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(reps):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps * 1e-3
+
+    qkv_b, perm_b, stage_b = 3 * H * D * 4, 2 * T * H * 4, T * H * 128
+    per_hit = {   # algorithmic bytes per hit of each tile kernel (reads + writes at its own boundary)
+        "block_attn_fwd": qkv_b + 4 * C + perm_b + stage_b,
+        "block_attn_bwd_dq": qkv_b + 4 * C + perm_b + 2 * H * D * 4 + 4 * H + stage_b,
+        "block_attn_bwd_dkv": qkv_b + 4 * C + perm_b + 2 * H * D * 4 + 4 * H + stage_b + T * H * D * 4,
+    }
+    times = {}
+    times["block_attn_fwd"] = ev_time(lambda i: ops.block_attention_fwd(d, *saved[i % n_sets][:6]))
+    for name, mask in (("block_attn_bwd_dq", 1), ("block_attn_bwd_dkv", 2)):
+        lib.hept_set_bwd_stage_mask(mask)
+        times[name] = ev_time(lambda i: ops.attention_bwd(d, *saved[i % n_sets]))
+    lib.hept_set_bwd_stage_mask(7)
+    top = max(times, key=times.get)
+    achieved = per_hit[top] * N_RAW / times[top] / 1e9
+    flops = {"block_attn_fwd": 2 * T * H * B * (D + C + D), "block_attn_bwd_dq": 2 * T * H * B * (2 * (D + C) + D),
+             "block_attn_bwd_dkv": 2 * T * H * B * (2 * (D + C) + 2 * D)}
+    return {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": None, "peak_source": peak_src, "bytes_per_launch": per_hit[top] * N_RAW,
+            "kernel_ms": {k: v * 1e3 for k, v in times.items()},
+            "fp32_tflops": {k: flops[k] * N_RAW / times[k] / 1e12 for k in times},
+            "note": "tile kernels are fp32-FMA bound, not HBM bound (SURVEY.md 7.3-3); fp32_tflops is against ~74 TF/s SIMT peak"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,91 @@
+// Error plumbing, launch accounting and the one-call forward (a3..a12) of the C ABI.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace hept {
+
+static thread_local char g_error[512] = "";
+static thread_local int g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches += n; }
+static int g_bwd_mask = 7;
+int bwd_stage_mask() { return g_bwd_mask; }
+
+struct FwdPlan {
+  size_t ext_bytes, span_bytes, proj_bytes, keys_bytes, sort_bytes, stage_bytes, total;
+};
+static FwdPlan plan_fwd(const hept_shape* s) {
+  FwdPlan p;
+  const size_t th = (size_t)s->T * s->H, thn = th * s->N;
+  p.ext_bytes = align_up(sizeof(uint32_t) * 2 * th, 256);
+  p.span_bytes = align_up(sizeof(float) * th, 256);
+  p.proj_bytes = align_up(sizeof(float) * 2 * thn, 256);
+  p.keys_bytes = align_up(sizeof(float) * 2 * thn, 256);
+  p.sort_bytes = align_up(hept_argsort_workspace_bytes((int32_t)(2 * th), s->N), 256);
+  p.stage_bytes = align_up(sizeof(float) * (size_t)s->H * s->N * s->T * kStageRow, 256);
+  // proj/keys/sort scratch is dead once the permutations exist; the staging rows reuse that space.
+  size_t front = p.proj_bytes + p.keys_bytes + p.sort_bytes;
+  p.total = p.ext_bytes + p.span_bytes + (front > p.stage_bytes ? front : p.stage_bytes);
+  return p;
+}
+
+}  // namespace hept
+
+using namespace hept;
+
+extern "C" int hept_abi_version(void) { return 1; }
+extern "C" const char* hept_last_error(void) { return g_error; }
+extern "C" int hept_launch_count(int reset) {
+  int n = g_launches;
+  if (reset) g_launches = 0;
+  return n;
+}
+
+extern "C" void hept_set_bwd_stage_mask(int mask) { g_bwd_mask = mask & 7; }
+
+extern "C" size_t hept_attention_fwd_workspace_bytes(const hept_shape* s) {
+  if (!s || s->N <= 0 || s->H <= 0 || s->T <= 0) return 0;
+  return plan_fwd(s).total;
+}
+
+extern "C" int hept_attention_fwd(const hept_shape* s, const float* q, const float* k, const float* v,
+                                  const float* coords, const float* w_rpe_weight, int32_t K, const float* alpha,
+                                  const int64_t* combined_shifts, const float* region_eta, const float* region_phi,
+                                  const float* regions_h, float* scale, int32_t* positions, float* out_pre,
+                                  float* den_sum, void* workspace, size_t workspace_bytes, void* stream) {
+  if (int rc = validate_shape(s)) return rc;
+  HEPT_REQUIRE(q && k && v && coords && w_rpe_weight && alpha && scale && positions && out_pre && den_sum && workspace,
+               HEPT_EINVAL, "attention_fwd: null pointer");
+  const bool packed = combined_shifts != nullptr;
+  const bool regions = region_eta && region_phi && regions_h;
+  HEPT_REQUIRE(packed != regions, HEPT_EINVAL,
+               "attention_fwd: pass either combined_shifts or (region_eta, region_phi, regions_h)");
+  HEPT_REQUIRE(hept_shape_supported(s->D, s->C, s->B), HEPT_EUNSUPPORTED,
+               "attention_fwd: (D=%d, C=%d, B=%d) not compiled in", s->D, s->C, s->B);
+  FwdPlan p = plan_fwd(s);
+  HEPT_REQUIRE(workspace_bytes >= p.total, HEPT_EWORKSPACE, "attention_fwd: workspace needs %zu bytes, got %zu", p.total,
+               workspace_bytes);
+  char* w = (char*)workspace;
+  void* ext = w;                       w += p.ext_bytes;
+  float* span = (float*)w;             w += p.span_bytes;
+  float* stage = (float*)w;            // aliases proj/keys/sort scratch (dead by then)
+  float* proj = (float*)w;             w += p.proj_bytes;
+  float* keys = (float*)w;             w += p.keys_bytes;
+  void* sort_ws = w;
+  int rc;
+  if ((rc = hept_coord_scale_fwd(w_rpe_weight, s->H, s->D, s->C - 1, K, scale, stream))) return rc;
+  if ((rc = hept_hash_project(s, q, k, coords, scale, alpha, proj, span, ext, p.ext_bytes, stream))) return rc;
+  if (packed) rc = hept_keys_from_packed_shifts(s, proj, span, combined_shifts, keys, stream);
+  else rc = hept_keys_from_region_indices(s, proj, span, region_eta, region_phi, regions_h, keys, stream);
+  if (rc) return rc;
+  if ((rc = hept_segmented_argsort(keys, 2 * s->T * s->H, s->N, positions, sort_ws, p.sort_bytes, stream))) return rc;
+  if ((rc = hept_block_attention_fwd(s, q, k, v, coords, scale, positions, stage, stream))) return rc;
+  return hept_or_combine(s, stage, out_pre, den_sum, stream);
+}

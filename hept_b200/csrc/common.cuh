@@ -1,0 +1,94 @@
+// Shared device/host helpers for the hept_b200 sm_100a library.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/hept_b200.h"
+
+namespace hept {
+
+// ---- host-side error plumbing -------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+int bwd_stage_mask();
+
+#define HEPT_REQUIRE(cond, code, ...)      \
+  do {                                     \
+    if (!(cond)) {                         \
+      ::hept::set_error(__VA_ARGS__);      \
+      return (code);                       \
+    }                                      \
+  } while (0)
+
+#define HEPT_CHECK_LAUNCH(name)                                                            \
+  do {                                                                                     \
+    cudaError_t e__ = cudaGetLastError();                                                  \
+    if (e__ != cudaSuccess) {                                                              \
+      ::hept::set_error("%s: launch failed: %s", (name), cudaGetErrorString(e__));         \
+      return HEPT_ECUDA;                                                                   \
+    }                                                                                      \
+    ::hept::count_launch();                                                                \
+  } while (0)
+
+inline int validate_shape(const hept_shape* s) {
+  HEPT_REQUIRE(s != nullptr, HEPT_EINVAL, "shape is null");
+  HEPT_REQUIRE(s->N > 0 && s->H > 0 && s->D > 0 && s->C > 1 && s->T > 0 && s->B > 0, HEPT_EINVAL,
+               "non-positive dimension (N=%d H=%d D=%d C=%d T=%d B=%d)", s->N, s->H, s->D, s->C, s->T, s->B);
+  HEPT_REQUIRE(s->N % s->B == 0, HEPT_EINVAL, "N=%d is not a multiple of block_size=%d", s->N, s->B);
+  HEPT_REQUIRE(s->raw_size >= 0 && s->raw_size <= s->N, HEPT_EINVAL, "raw_size=%d outside [0, N=%d]", s->raw_size,
+               s->N);
+  return HEPT_OK;
+}
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- device helpers --------------------------------------------------------------------------------
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+constexpr int kStageRow = 32;  // floats per staged (hit, head, table) row: 128 bytes
+
+// float -> uint32 whose unsigned order equals the float order (-0.0 canonicalised to +0.0 first).
+__device__ __forceinline__ uint32_t ordered_bits(float x) {
+  x = x + 0.0f;  // -0.0 + 0.0 == +0.0 under round-to-nearest
+  uint32_t b = __float_as_uint(x);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float from_ordered_bits(uint32_t u) {
+  uint32_t b = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+  return __uint_as_float(b);
+}
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float2 ldg2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+
+// 2^x, x <= 0.  ex2.approx.ftz: max relative error 2^-22; inputs below -126 flush to 0.
+__device__ __forceinline__ float exp2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Loads `COUNT` consecutive floats (COUNT % 4 == 0 -> float4 loads, else float2 / scalar) into dst.
+template <int COUNT>
+__device__ __forceinline__ void load_row(const float* __restrict__ src, float* dst) {
+  if constexpr (COUNT % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < COUNT / 4; ++i) {
+      float4 t = ldg4(src + 4 * i);
+      dst[4 * i + 0] = t.x; dst[4 * i + 1] = t.y; dst[4 * i + 2] = t.z; dst[4 * i + 3] = t.w;
+    }
+  } else if constexpr (COUNT % 2 == 0) {
+#pragma unroll
+    for (int i = 0; i < COUNT / 2; ++i) {
+      float2 t = ldg2(src + 2 * i);
+      dst[2 * i + 0] = t.x; dst[2 * i + 1] = t.y;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < COUNT; ++i) dst[i] = __ldg(src + i);
+  }
+}
+
+}  // namespace hept

@@ -1,0 +1,230 @@
+"""Stage-wise torch wrappers over the C ABI (include/hept_b200.h).
+
+torch is plumbing here: it owns device memory and the current CUDA stream; every function below
+validates its tensors, allocates outputs / workspace from torch's caching allocator and hands raw
+device pointers to libhept_sm100.so.  Nothing here computes on the host and nothing falls back.
+The stage-wise entry points exist so parity tests can inject the oracle's intermediates
+(SURVEY.md 8(b)).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+STAGE_ROW = 32  # floats per staged (hit, head, table) row
+
+
+@dataclass(frozen=True)
+class Dims:
+    N: int
+    H: int
+    D: int
+    C: int
+    T: int
+    B: int
+    raw_size: int
+
+    def struct(self) -> _lib.Shape:
+        return _lib.Shape(self.N, self.H, self.D, self.C, self.T, self.B, self.raw_size)
+
+    @property
+    def E(self) -> int:
+        return self.D + self.C
+
+
+def _stream(t: torch.Tensor) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _need(t: torch.Tensor, name: str, dtype, shape: Optional[Sequence[int]] = None) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} is on {t.device}: hept_b200 runs on CUDA (sm_100a) only, there is no CPU path")
+    if t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise ValueError(f"{name} must have shape {tuple(shape)}, got {tuple(t.shape)}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _workspace(nbytes: int, like: torch.Tensor) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=like.device)
+
+
+def supported(D: int, C_: int, B: int) -> bool:
+    return bool(_lib.load().hept_shape_supported(D, C_, B))
+
+
+def launch_count(reset: bool = False) -> int:
+    return int(_lib.load().hept_launch_count(1 if reset else 0))
+
+
+# ------------------------------------------------------------------------------------------ stages
+def coord_scale(w_rpe_weight: torch.Tensor, H: int, D: int, K: int) -> torch.Tensor:
+    lib = _lib.load()
+    w = _need(w_rpe_weight, "w_rpe.weight", torch.float32)
+    if w.dim() != 2 or w.shape[0] != H * D or w.shape[1] % K:
+        raise ValueError(f"w_rpe.weight must be (H*D={H * D}, R*K) with K={K}, got {tuple(w.shape)}")
+    R = w.shape[1] // K
+    scale = torch.empty(H, R + 1, dtype=torch.float32, device=w.device)
+    _lib.check(lib.hept_coord_scale_fwd(_ptr(w), H, D, R, K, _ptr(scale), _stream(w)), "hept_coord_scale_fwd")
+    return scale
+
+
+def coord_scale_backward(w_rpe_weight: torch.Tensor, scale: torch.Tensor, dscale: torch.Tensor, H: int, D: int,
+                         K: int) -> torch.Tensor:
+    lib = _lib.load()
+    w = _need(w_rpe_weight, "w_rpe.weight", torch.float32)
+    R = w.shape[1] // K
+    scale = _need(scale, "scale", torch.float32, (H, R + 1))
+    dscale = _need(dscale, "dscale", torch.float32, (H, R + 1))
+    dw = torch.empty_like(w)
+    _lib.check(lib.hept_coord_scale_bwd(_ptr(w), _ptr(scale), _ptr(dscale), H, D, R, K, _ptr(dw), _stream(w)),
+               "hept_coord_scale_bwd")
+    return dw
+
+
+def hash_project(d: Dims, q, k, coords, scale, alpha) -> Tuple[torch.Tensor, torch.Tensor]:
+    """-> proj (2, T, H, N), span (T, H)."""
+    lib = _lib.load()
+    q = _need(q, "query", torch.float32, (d.N, d.H * d.D))
+    k = _need(k, "key", torch.float32, (d.N, d.H * d.D))
+    coords = _need(coords, "coords", torch.float32, (d.N, d.C))
+    scale = _need(scale, "scale", torch.float32, (d.H, d.C))
+    alpha = _need(alpha, "e2lsh.alpha", torch.float32, (d.H, d.E, d.T))
+    proj = torch.empty(2, d.T, d.H, d.N, dtype=torch.float32, device=q.device)
+    span = torch.empty(d.T, d.H, dtype=torch.float32, device=q.device)
+    ws = _workspace(8 * d.T * d.H, q)
+    s = d.struct()
+    _lib.check(lib.hept_hash_project(C.byref(s), _ptr(q), _ptr(k), _ptr(coords), _ptr(scale), _ptr(alpha), _ptr(proj),
+                                     _ptr(span), _ptr(ws), ws.numel(), _stream(q)), "hept_hash_project")
+    return proj, span
+
+
+def keys_from_packed_shifts(d: Dims, proj, span, combined_shifts) -> torch.Tensor:
+    lib = _lib.load()
+    proj = _need(proj, "proj", torch.float32, (2, d.T, d.H, d.N))
+    span = _need(span, "span", torch.float32, (d.T, d.H))
+    sh = _need(combined_shifts, "combined_shifts", torch.int64, (d.T, d.H, d.N))
+    keys = torch.empty_like(proj)
+    s = d.struct()
+    _lib.check(lib.hept_keys_from_packed_shifts(C.byref(s), _ptr(proj), _ptr(span), _ptr(sh), _ptr(keys), _stream(proj)),
+               "hept_keys_from_packed_shifts")
+    return keys
+
+
+def keys_from_region_indices(d: Dims, proj, span, region_eta, region_phi, regions_h) -> torch.Tensor:
+    lib = _lib.load()
+    proj = _need(proj, "proj", torch.float32, (2, d.T, d.H, d.N))
+    span = _need(span, "span", torch.float32, (d.T, d.H))
+    eta = _need(region_eta, "region_indices[0]", torch.float32, (d.T * d.H, d.N))
+    phi = _need(region_phi, "region_indices[1]", torch.float32, (d.T * d.H, d.N))
+    rh = _need(regions_h, "regions_h", torch.float32, (2, d.T * d.H))
+    keys = torch.empty_like(proj)
+    s = d.struct()
+    _lib.check(lib.hept_keys_from_region_indices(C.byref(s), _ptr(proj), _ptr(span), _ptr(eta), _ptr(phi), _ptr(rh),
+                                                 _ptr(keys), _stream(proj)), "hept_keys_from_region_indices")
+    return keys
+
+
+def segmented_argsort(keys: torch.Tensor) -> torch.Tensor:
+    """Stable ascending argsort along the last dim of a float32 tensor -> int32 positions, same shape."""
+    lib = _lib.load()
+    keys = _need(keys, "keys", torch.float32)
+    n = keys.shape[-1]
+    segs = keys.numel() // n
+    pos = torch.empty(keys.shape, dtype=torch.int32, device=keys.device)
+    nbytes = lib.hept_argsort_workspace_bytes(segs, n)
+    ws = _workspace(nbytes, keys)
+    _lib.check(lib.hept_segmented_argsort(_ptr(keys), segs, n, _ptr(pos), _ptr(ws), ws.numel(), _stream(keys)),
+               "hept_segmented_argsort")
+    return pos
+
+
+def block_attention_fwd(d: Dims, q, k, v, coords, scale, positions) -> torch.Tensor:
+    """-> stage (H, N, T, 32): numerator [0:D) and normaliser [D] per (head, hit, table), original hit order."""
+    lib = _lib.load()
+    q = _need(q, "query", torch.float32, (d.N, d.H * d.D))
+    k = _need(k, "key", torch.float32, (d.N, d.H * d.D))
+    v = _need(v, "value", torch.float32, (d.N, d.H * d.D))
+    coords = _need(coords, "coords", torch.float32, (d.N, d.C))
+    scale = _need(scale, "scale", torch.float32, (d.H, d.C))
+    pos = _need(positions, "positions", torch.int32, (2, d.T, d.H, d.N))
+    stage = torch.empty(d.H, d.N, d.T, STAGE_ROW, dtype=torch.float32, device=q.device)
+    s = d.struct()
+    _lib.check(lib.hept_block_attention_fwd(C.byref(s), _ptr(q), _ptr(k), _ptr(v), _ptr(coords), _ptr(scale), _ptr(pos),
+                                            _ptr(stage), _stream(q)), "hept_block_attention_fwd")
+    return stage
+
+
+def or_combine(d: Dims, stage) -> Tuple[torch.Tensor, torch.Tensor]:
+    lib = _lib.load()
+    stage = _need(stage, "stage", torch.float32, (d.H, d.N, d.T, STAGE_ROW))
+    out_pre = torch.empty(d.N, d.H * d.D, dtype=torch.float32, device=stage.device)
+    den = torch.empty(d.N, d.H, dtype=torch.float32, device=stage.device)
+    s = d.struct()
+    _lib.check(lib.hept_or_combine(C.byref(s), _ptr(stage), _ptr(out_pre), _ptr(den), _stream(stage)), "hept_or_combine")
+    return out_pre, den
+
+
+# --------------------------------------------------------------------------------------- whole path
+def attention_fwd(d: Dims, q, k, v, coords, w_rpe_weight, K: int, alpha, combined_shifts=None, region_indices=None,
+                  regions_h=None):
+    """a3..a12 in one native call -> (out_pre (N,H*D), den_sum (N,H), scale (H,C), positions (2,T,H,N) int32)."""
+    lib = _lib.load()
+    q = _need(q, "query", torch.float32, (d.N, d.H * d.D))
+    k = _need(k, "key", torch.float32, (d.N, d.H * d.D))
+    v = _need(v, "value", torch.float32, (d.N, d.H * d.D))
+    coords = _need(coords, "coords", torch.float32, (d.N, d.C))
+    w = _need(w_rpe_weight, "w_rpe.weight", torch.float32, (d.H * d.D, (d.C - 1) * K))
+    alpha = _need(alpha, "e2lsh.alpha", torch.float32, (d.H, d.E, d.T))
+    sh = eta = phi = rh = None
+    if combined_shifts is not None:
+        sh = _need(combined_shifts, "combined_shifts", torch.int64, (d.T, d.H, d.N))
+    else:
+        eta = _need(region_indices[0], "region_indices[0]", torch.float32, (d.T * d.H, d.N))
+        phi = _need(region_indices[1], "region_indices[1]", torch.float32, (d.T * d.H, d.N))
+        rh = _need(regions_h, "regions_h", torch.float32, (2, d.T * d.H))
+    dev = q.device
+    scale = torch.empty(d.H, d.C, dtype=torch.float32, device=dev)
+    pos = torch.empty(2, d.T, d.H, d.N, dtype=torch.int32, device=dev)
+    out_pre = torch.empty(d.N, d.H * d.D, dtype=torch.float32, device=dev)
+    den = torch.empty(d.N, d.H, dtype=torch.float32, device=dev)
+    s = d.struct()
+    ws = _workspace(lib.hept_attention_fwd_workspace_bytes(C.byref(s)), q)
+    _lib.check(lib.hept_attention_fwd(C.byref(s), _ptr(q), _ptr(k), _ptr(v), _ptr(coords), _ptr(w), K, _ptr(alpha),
+                                      _ptr(sh), _ptr(eta), _ptr(phi), _ptr(rh), _ptr(scale), _ptr(pos), _ptr(out_pre),
+                                      _ptr(den), _ptr(ws), ws.numel(), _stream(q)), "hept_attention_fwd")
+    return out_pre, den, scale, pos
+
+
+def attention_bwd(d: Dims, q, k, v, coords, scale, positions, out_pre, den_sum, d_out_pre):
+    """-> dq, dk, dv (N, H*D), dscale (H, C)."""
+    lib = _lib.load()
+    q = _need(q, "query", torch.float32, (d.N, d.H * d.D))
+    k = _need(k, "key", torch.float32, (d.N, d.H * d.D))
+    v = _need(v, "value", torch.float32, (d.N, d.H * d.D))
+    coords = _need(coords, "coords", torch.float32, (d.N, d.C))
+    scale = _need(scale, "scale", torch.float32, (d.H, d.C))
+    pos = _need(positions, "positions", torch.int32, (2, d.T, d.H, d.N))
+    out_pre = _need(out_pre, "out_pre", torch.float32, (d.N, d.H * d.D))
+    den_sum = _need(den_sum, "den_sum", torch.float32, (d.N, d.H))
+    g = _need(d_out_pre, "d_out_pre", torch.float32, (d.N, d.H * d.D))
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)
+    dscale = torch.empty(d.H, d.C, dtype=torch.float32, device=q.device)
+    s = d.struct()
+    ws = _workspace(lib.hept_attention_bwd_workspace_bytes(C.byref(s)), q)
+    _lib.check(lib.hept_block_attention_bwd(C.byref(s), _ptr(q), _ptr(k), _ptr(v), _ptr(coords), _ptr(scale), _ptr(pos),
+                                            _ptr(out_pre), _ptr(den_sum), _ptr(g), _ptr(dq), _ptr(dk), _ptr(dv),
+                                            _ptr(dscale), _ptr(ws), ws.numel(), _stream(q)), "hept_block_attention_bwd")
+    return dq, dk, dv, dscale

@@ -1,0 +1,127 @@
+/* hept_b200 — C ABI of the sm_100a library behind the HEPT attention drop-in.
+ *
+ * The reference (Graph-COM/HEPT) is pure PyTorch: it has no FFI of its own.  The boundary it
+ * offers is the Python module `HEPTAttention.forward(query, key, value, **kwargs)`
+ * (example/hept.py:43-81, src/models/attention/hept.py:71-117).  These entry points are what a
+ * binding for that path calls; each one names the reference lines it replaces.  The host-side
+ * mirror of the module (same ctor / forward / state_dict) is hept_b200/attention.py, which binds
+ * this header through ctypes; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless named `*_host`; tensors are dense row-major;
+ *   - the library never allocates, frees or synchronises: the caller (torch) owns every buffer,
+ *     including `workspace`, and passes the CUDA stream to enqueue on (`stream` is a cudaStream_t
+ *     passed as void*);
+ *   - every function returns 0 on success or a negative HEPT_E* code; hept_last_error() returns
+ *     a thread-local message for the last failure;
+ *   - symbols: N hits (multiple of B), H heads, D dims/head, C coords_dim, E = D + C,
+ *     T n_hashes, B block_size, R = C - 1, K num_w_per_dist.
+ *
+ * Supported compile-time shapes (D, C, B): (24,6,100) tracking, (24,4,100) pileup, (8,6,10) test.
+ * Anything else returns HEPT_EUNSUPPORTED (no slow fallback, no CPU path).
+ */
+#ifndef HEPT_B200_H
+#define HEPT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HEPT_OK 0
+#define HEPT_EINVAL (-1)       /* bad argument (null pointer, N % B != 0, ...) */
+#define HEPT_EUNSUPPORTED (-2) /* (D, C, B) combination not compiled in */
+#define HEPT_ECUDA (-3)        /* a CUDA launch failed; see hept_last_error() */
+#define HEPT_EWORKSPACE (-4)   /* workspace too small */
+
+/* Problem shape shared by all calls. raw_size: rows >= raw_size are the zero/+inf padding of the
+ * src/ flavour (src/models/attention/hept.py:89-96); pass raw_size == N for the example/ flavour. */
+typedef struct hept_shape {
+  int32_t N, H, D, C, T, B;
+  int32_t raw_size;
+} hept_shape;
+
+int hept_abi_version(void);
+const char* hept_last_error(void);
+/* 1 if kernels for (D, C, B) are compiled in. */
+int hept_shape_supported(int32_t D, int32_t C, int32_t B);
+
+/* ---- a3  prep_qk coordinate scale (example/hept.py:21-25) -------------------------------------
+ * scale[h,c] = sqrt(2 * qw[h, max(c-1,0)]),  qw[h,r] = sum_k exp(min(sum_d w[h*D+d, r*K+k], 50)).
+ * w_rpe_weight (H*D, R*K) -> scale (H, C=R+1). */
+int hept_coord_scale_fwd(const float* w_rpe_weight, int32_t H, int32_t D, int32_t R, int32_t K,
+                         float* scale, void* stream);
+/* gradient of the above: dscale (H, C) -> dw (H*D, R*K) (autograd of example/hept.py:22-25). */
+int hept_coord_scale_bwd(const float* w_rpe_weight, const float* scale, const float* dscale, int32_t H,
+                         int32_t D, int32_t R, int32_t K, float* dw, void* stream);
+
+/* ---- a4+a5  E2LSH.forward x2 + lsh_mapping (example/hept_utils.py:45-47, 64-71) ---------------
+ * q,k (N, H*D); coords (N, C); scale (H, C); alpha (H, E, T).
+ * proj (2, T, H, N): [0] = queries, [1] = keys.  span (T, H) = max - min over both. */
+int hept_hash_project(const hept_shape* s, const float* q, const float* k, const float* coords,
+                      const float* scale, const float* alpha, float* proj, float* span,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- a6  AND-construction, example/ flavour (example/hept.py:63-65) ---------------------------
+ * keys[s,t,h,n] = proj[s,t,h,n] + float(combined_shifts[t,h,n]) * span[t,h]   (convert, mul, add). */
+int hept_keys_from_packed_shifts(const hept_shape* s, const float* proj, const float* span,
+                                 const int64_t* combined_shifts, float* keys, void* stream);
+/* ---- a6' AND-construction, src/ flavour (src/models/attention/hept.py:46-56, 93-101) ----------
+ * region_eta/phi (T*H, N) float, regions_h (2, T*H); rows >= raw_size get +inf. */
+int hept_keys_from_region_indices(const hept_shape* s, const float* proj, const float* span,
+                                  const float* region_eta, const float* region_phi,
+                                  const float* regions_h, float* keys, void* stream);
+
+/* ---- a7  argsort x2 (example/hept.py:67-68), tie-break = stable ascending ---------------------
+ * keys (num_segments, n) float32 -> positions (num_segments, n) int32, one stable LSD radix sort
+ * per segment.  -0.0 sorts equal to +0.0; NaN sorts last. */
+size_t hept_argsort_workspace_bytes(int32_t num_segments, int32_t n);
+int hept_segmented_argsort(const float* keys, int32_t num_segments, int32_t n, int32_t* positions,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- a8+a9+a10+a11  sort_to_buckets, qkv_res, unsort_from_buckets ------------------------------
+ * (example/hept_utils.py:74-97, example/hept.py:7-18,70-78).  positions (2, T, H, N) int32.
+ * Output `stage` (H, N, T, 32): per hit/head/table one 128-byte row holding the numerator
+ * so[0..D) and, at [D], the normaliser denom = rowsum + 1e-20, already back in ORIGINAL hit order. */
+int hept_block_attention_fwd(const hept_shape* s, const float* q, const float* k, const float* v,
+                             const float* coords, const float* scale, const int32_t* positions,
+                             float* stage, void* stream);
+
+/* ---- a12  OR-combine (example/hept.py:79) -----------------------------------------------------
+ * out_pre (N, H*D) = sum_t numer / sum_t denom ; den_sum (N, H) kept for backward. */
+int hept_or_combine(const hept_shape* s, const float* stage, float* out_pre, float* den_sum, void* stream);
+
+/* ---- a18  backward of a8..a12 and of the coordinate scale's use in a3 --------------------------
+ * d_out_pre (N, H*D) is the gradient arriving from out_linear.  Writes dq, dk, dv (N, H*D) and
+ * dscale (H, C).  Deterministic (no floating-point atomics). */
+size_t hept_attention_bwd_workspace_bytes(const hept_shape* s);
+int hept_block_attention_bwd(const hept_shape* s, const float* q, const float* k, const float* v,
+                             const float* coords, const float* scale, const int32_t* positions,
+                             const float* out_pre, const float* den_sum, const float* d_out_pre,
+                             float* dq, float* dk, float* dv, float* dscale, void* workspace,
+                             size_t workspace_bytes, void* stream);
+
+/* ---- whole forward of a3..a12 in one call (fewer host round trips) ----------------------------
+ * Exactly one of combined_shifts / (region_eta, region_phi, regions_h) is non-null.
+ * Outputs: scale (H,C), positions (2,T,H,N), out_pre (N,H*D), den_sum (N,H). */
+size_t hept_attention_fwd_workspace_bytes(const hept_shape* s);
+int hept_attention_fwd(const hept_shape* s, const float* q, const float* k, const float* v,
+                       const float* coords, const float* w_rpe_weight, int32_t K, const float* alpha,
+                       const int64_t* combined_shifts, const float* region_eta, const float* region_phi,
+                       const float* regions_h, float* scale, int32_t* positions, float* out_pre,
+                       float* den_sum, void* workspace, size_t workspace_bytes, void* stream);
+
+/* kernel launches this library enqueued from the calling thread since the counter was last reset
+ * (bench.py's gpu_launches); reset != 0 zeroes the counter after reading it. */
+int hept_launch_count(int reset);
+
+/* profiling aid for bench.py / ncu: choose which kernels hept_block_attention_bwd launches
+ * (bit 0: dq tile kernel, bit 1: dk/dv tile kernel, bit 2: table reduction); default 7 = all. */
+void hept_set_bwd_stage_mask(int mask);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HEPT_B200_H */
