@@ -52,7 +52,7 @@ __global__ void __launch_bounds__((TileLayout<D, C, B, G, 1>::THREADS), MINB)
   const int n = __ldg(qpos + (size_t)blk * B + i);
   float a[1][E], s_init, gd[D], gy = 0.f;
   {
-    const int n0 = __ldg(kpos + (size_t)blk * B);
+    const int n0 = __ldg(kpos + (size_t)blk * B + (B - 1));  // centre = last key of the block
     float ctr[E];
     load_hat_row<D, C>(k, coords, sc, n0, h, H, n0 < raw_size, ctr);
     load_resident_row<L>(q, coords, sc, ctr, n, h, H, raw_size, a[0], s_init);
@@ -98,7 +98,17 @@ __global__ void __launch_bounds__((TileLayout<D, C, B, G, 1>::THREADS), MINB)
     }
   }
 
-  // dq^_i = sum_j dS_ij k'_j - (sum_j dS_ij) q'_i ; q' = a / log2e
+  // dq^_i = sum_j dS_ij k'_j - (sum_j dS_ij) q'_i.  q' is re-read exactly (a * ln2 would carry two extra
+  // roundings into a difference of large terms, and d scale sums those differences over all hits).
+  float qx[E];
+  {
+    const int n0 = __ldg(kpos + (size_t)blk * B + (B - 1));
+    float ctr[E];
+    load_hat_row<D, C>(k, coords, sc, n0, h, H, n0 < raw_size, ctr);
+    load_hat_row<D, C>(q, coords, sc, n, h, H, n < raw_size, qx);
+#pragma unroll
+    for (int e = 0; e < E; ++e) qx[e] -= ctr[e];
+  }
   float4* dst = reinterpret_cast<float4*>(stage_dq + (((size_t)h * N + n) * T + t) * kStageRow);
 #pragma unroll
   for (int c = 0; c < L::ROW_CHUNKS; ++c) {
@@ -106,7 +116,7 @@ __global__ void __launch_bounds__((TileLayout<D, C, B, G, 1>::THREADS), MINB)
 #pragma unroll
     for (int x = 0; x < 4; ++x) {
       const int e = 4 * c + x;
-      o4[x] = e < E ? fmaf(-sds * kLn2, a[0][e < E ? e : 0], acc[e < E ? e : 0]) : 0.f;
+      o4[x] = e < E ? fmaf(-sds, qx[e < E ? e : 0], acc[e < E ? e : 0]) : 0.f;
     }
     dst[c] = make_float4(o4[0], o4[1], o4[2], o4[3]);
   }
@@ -144,7 +154,7 @@ __global__ void __launch_bounds__((TileLayout<D, C, B, G, 1>::THREADS), MINB)
     const int g = rr / B, blk = blk0 + g;
     if (blk >= nb) continue;
     const int n = __ldg(qpos + (size_t)blk * B + (rr - g * B));
-    const int n0 = __ldg(kpos + (size_t)blk * B);
+    const int n0 = __ldg(kpos + (size_t)blk * B + (B - 1));  // centre = last key of the block
     float qr[E], ctr[E];
     load_hat_row<D, C>(q, coords, sc, n, h, H, n < raw_size, qr);
     load_hat_row<D, C>(k, coords, sc, n0, h, H, n0 < raw_size, ctr);
@@ -179,7 +189,7 @@ __global__ void __launch_bounds__((TileLayout<D, C, B, G, 1>::THREADS), MINB)
   const bool real = n < raw_size;
   float a[1][E], s_init, vj[D];
   {
-    const int n0 = __ldg(kpos + (size_t)blk * B);
+    const int n0 = __ldg(kpos + (size_t)blk * B + (B - 1));  // centre = last key of the block
     float ctr[E];
     load_hat_row<D, C>(k, coords, sc, n0, h, H, n0 < raw_size, ctr);
     load_resident_row<L>(k, coords, sc, ctr, n, h, H, raw_size, a[0], s_init);
@@ -229,7 +239,16 @@ __global__ void __launch_bounds__((TileLayout<D, C, B, G, 1>::THREADS), MINB)
     }
   }
 
-  // dk^_j = sum_i dS_ij q'_i - (sum_i dS_ij) k'_j ; k' = a / log2e
+  // dk^_j = sum_i dS_ij q'_i - (sum_i dS_ij) k'_j, with k' re-read exactly (see the dq kernel)
+  float kx[E];
+  {
+    const int n0 = __ldg(kpos + (size_t)blk * B + (B - 1));
+    float ctr[E];
+    load_hat_row<D, C>(k, coords, sc, n0, h, H, n0 < raw_size, ctr);
+    load_hat_row<D, C>(k, coords, sc, n, h, H, real, kx);
+#pragma unroll
+    for (int e = 0; e < E; ++e) kx[e] -= ctr[e];
+  }
   const size_t srow = ((size_t)h * N + n) * T + t;
   float4* dstk = reinterpret_cast<float4*>(stage_dk + srow * kStageRow);
 #pragma unroll
@@ -238,7 +257,7 @@ __global__ void __launch_bounds__((TileLayout<D, C, B, G, 1>::THREADS), MINB)
 #pragma unroll
     for (int x = 0; x < 4; ++x) {
       const int e = 4 * c + x;
-      o4[x] = e < E ? fmaf(-sds * kLn2, a[0][e < E ? e : 0], dk[e < E ? e : 0]) : 0.f;
+      o4[x] = e < E ? fmaf(-sds, kx[e < E ? e : 0], dk[e < E ? e : 0]) : 0.f;
     }
     dstk[c] = make_float4(o4[0], o4[1], o4[2], o4[3]);
   }

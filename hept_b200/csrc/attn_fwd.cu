@@ -44,7 +44,7 @@ __global__ void __launch_bounds__((TileLayout<D, C, B, G, R>::THREADS), MINB)
   float a[R][E], s_init[R], o[R][D], l[R];
   int nrow[R];
   {
-    const int n0 = __ldg(kpos + (size_t)blk * B);
+    const int n0 = __ldg(kpos + (size_t)blk * B + (B - 1));  // centre = last key of the block
     float ctr[E];
     load_hat_row<D, C>(k, coords, sc, n0, h, H, n0 < raw_size, ctr);
 #pragma unroll

@@ -112,7 +112,7 @@ __device__ __forceinline__ void gather_key_rows(const float* __restrict__ k, con
     const int g = rr / B, blk = blk0 + g;
     if (blk >= nb) continue;
     const int n = __ldg(kpos + (size_t)blk * B + (rr - g * B));
-    const int n0 = __ldg(kpos + (size_t)blk * B);
+    const int n0 = __ldg(kpos + (size_t)blk * B + (B - 1));  // centre = last key of the block
     float kr[E], ctr[E];
     load_hat_row<D, C>(k, coords, sc, n, h, H, n < raw_size, kr);
     load_hat_row<D, C>(k, coords, sc, n0, h, H, n0 < raw_size, ctr);
