@@ -16,7 +16,7 @@
 namespace hept {
 
 // ---------------------------------------------------------------------------------------------------
-// dq: resident query row i (a = q' log2e, gd, gy); streamed k'_j (+nk2), v_j.
+// dq: resident query row i (a = q', gd, gy); streamed k'_j (+nk), v_j.
 // ---------------------------------------------------------------------------------------------------
 template <int D, int C, int B, int G, int MINB>
 __global__ void __launch_bounds__((TileLayout<D, C, B, G, 1>::THREADS), MINB)
@@ -36,12 +36,10 @@ __global__ void __launch_bounds__((TileLayout<D, C, B, G, 1>::THREADS), MINB)
   const int blk0 = blockIdx.x * G;
   const int32_t* qpos = positions + (size_t)th * N;
   const int32_t* kpos = positions + ((size_t)T * H + th) * N;
+  const float* scale_h = scale + h * C;
   const int tid = threadIdx.x;
 
-  float sc[C];
-#pragma unroll
-  for (int c = 0; c < C; ++c) sc[c] = __ldg(scale + h * C + c);
-  gather_key_rows<L>(k, v, coords, sc, kpos, blk0, nb, h, H, raw_size, ks, vs);
+  gather_streamed_rows<L, false>(k, k, v, nullptr, nullptr, coords, scale_h, kpos, kpos, blk0, nb, h, H, raw_size, ks, vs);
   __syncthreads();
 
   if (tid >= L::LANES) return;
@@ -50,44 +48,27 @@ __global__ void __launch_bounds__((TileLayout<D, C, B, G, 1>::THREADS), MINB)
   if (blk >= nb) return;
 
   const int n = __ldg(qpos + (size_t)blk * B + i);
-  float a[1][E], s_init, gd[D], gy = 0.f;
-  {
-    const int n0 = __ldg(kpos + (size_t)blk * B + (B - 1));  // centre = last key of the block
-    float ctr[E];
-    load_hat_row<D, C>(k, coords, sc, n0, h, H, n0 < raw_size, ctr);
-    load_resident_row<L>(q, coords, sc, ctr, n, h, H, raw_size, a[0], s_init);
-    const float inv_den = 1.f / __ldg(den_sum + (size_t)n * H + h);
-    float y[D];
-    load_row<D>(d_out_pre + ((size_t)n * H + h) * D, gd);
-    load_row<D>(out_pre + ((size_t)n * H + h) * D, y);
-#pragma unroll
-    for (int d = 0; d < D; ++d) {
-      gd[d] *= inv_den;
-      gy = fmaf(gd[d], y[d], gy);
-    }
-  }
+  float a[1][E], nq, gd[D], gy;
+  load_resident_row<L>(q, k, coords, scale_h, n, __ldg(kpos + (size_t)blk * B + (B - 1)), h, H, raw_size, a[0], nq);
+  load_resident_grad<L>(d_out_pre, out_pre, den_sum, n, h, H, gd, gy);
   float acc[E], sds = 0.f;
 #pragma unroll
   for (int e = 0; e < E; ++e) acc[e] = 0.f;
 
-  const int row0 = g * B;
-#pragma unroll 2
-  for (int j = 0; j < B; ++j) {
-    float s[1] = {s_init}, nk2 = 0.f, unused = 0.f;
+  const float4* krow = ks + (size_t)g * B * L::ROW_CHUNKS;
+  const float4* vrow = vs + (size_t)g * B * L::VCH;
+#pragma unroll 1
+  for (int j = 0; j < B; ++j, krow += L::ROW_CHUNKS, vrow += L::VCH) {
+    float s[1], nk = 0.f, unused = 0.f;
     float4 keep[L::USED_CHUNKS];
-    dot_rows<L>(ks, row0 + j, a, s, nk2, unused, keep);
-    const float s2 = s[0] + nk2;
-    const float p = exp2_fast(fminf(s2, 0.f));
+    dot_rows<L>(krow, a, s, nk, unused, keep);
+    const float s2 = (s[0] + nq) + nk;  // canonical order (dot + nq) + nk, see tile.cuh
+    const float p = exp2_fast(fminf(s2 * kLog2e, 0.f));
     float dp0 = -gy, dp1 = 0.f;
 #pragma unroll
-    for (int c = 0; c < L::VCH; ++c) {
-      const float4 vv = vs[(row0 + j) * L::VCH + c];
-      dp0 = fmaf(gd[4 * c + 0], vv.x, dp0);
-      dp1 = fmaf(gd[4 * c + 1], vv.y, dp1);
-      dp0 = fmaf(gd[4 * c + 2], vv.z, dp0);
-      dp1 = fmaf(gd[4 * c + 3], vv.w, dp1);
-    }
-    const float ds = s2 <= 0.f ? p * (dp0 + dp1) : 0.f;
+    for (int c = 0; c < L::VCH; ++c)
+      dp_step(make_float4(gd[4 * c], gd[4 * c + 1], gd[4 * c + 2], gd[4 * c + 3]), vrow[c], dp0, dp1);
+    const float ds = s2 <= 0.f ? p * (dp0 + dp1) : 0.f;  // clamp(max=0) passes gradient where S <= 0
     sds += ds;
 #pragma unroll
     for (int c = 0; c < L::USED_CHUNKS; ++c) {
@@ -98,17 +79,7 @@ __global__ void __launch_bounds__((TileLayout<D, C, B, G, 1>::THREADS), MINB)
     }
   }
 
-  // dq^_i = sum_j dS_ij k'_j - (sum_j dS_ij) q'_i.  q' is re-read exactly (a * ln2 would carry two extra
-  // roundings into a difference of large terms, and d scale sums those differences over all hits).
-  float qx[E];
-  {
-    const int n0 = __ldg(kpos + (size_t)blk * B + (B - 1));
-    float ctr[E];
-    load_hat_row<D, C>(k, coords, sc, n0, h, H, n0 < raw_size, ctr);
-    load_hat_row<D, C>(q, coords, sc, n, h, H, n < raw_size, qx);
-#pragma unroll
-    for (int e = 0; e < E; ++e) qx[e] -= ctr[e];
-  }
+  // dq^_i = sum_j dS_ij k'_j - (sum_j dS_ij) q'_i   (a[0] holds q' exactly)
   float4* dst = reinterpret_cast<float4*>(stage_dq + (((size_t)h * N + n) * T + t) * kStageRow);
 #pragma unroll
   for (int c = 0; c < L::ROW_CHUNKS; ++c) {
@@ -116,16 +87,16 @@ __global__ void __launch_bounds__((TileLayout<D, C, B, G, 1>::THREADS), MINB)
 #pragma unroll
     for (int x = 0; x < 4; ++x) {
       const int e = 4 * c + x;
-      o4[x] = e < E ? fmaf(-sds, qx[e < E ? e : 0], acc[e < E ? e : 0]) : 0.f;
+      o4[x] = e < E ? fmaf(-sds, a[0][e < E ? e : 0], acc[e < E ? e : 0]) : 0.f;
     }
     dst[c] = make_float4(o4[0], o4[1], o4[2], o4[3]);
   }
 }
 
 // ---------------------------------------------------------------------------------------------------
-// dkv: resident key row j (a = k' log2e, v_j); streamed q'_i (+nq2, gy_i) and gd_i.
+// dkv: resident key row j (a = k', v_j); streamed q'_i (+nq, gy_i) and gd_i.
 // ---------------------------------------------------------------------------------------------------
-template <int D, int C, int B, int G, int MINB, bool KEEP>
+template <int D, int C, int B, int G, int MINB>
 __global__ void __launch_bounds__((TileLayout<D, C, B, G, 1>::THREADS), MINB)
     block_attn_bwd_dkv_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
                               const float* __restrict__ coords, const float* __restrict__ scale,
@@ -135,7 +106,7 @@ __global__ void __launch_bounds__((TileLayout<D, C, B, G, 1>::THREADS), MINB)
   using L = TileLayout<D, C, B, G, 1>;
   constexpr int E = L::E;
   extern __shared__ float4 smem[];
-  float4* qs = smem;                           // [G*B] q' rows: q'[0..E), nq2, gy
+  float4* qs = smem;                           // [G*B][8]   q' rows: q'[0..E), nq, gy
   float4* gs = smem + G * B * L::ROW_CHUNKS;   // [G*B][D/4] gd rows
 
   const int th = blockIdx.y, t = th / H, h = th % H;
@@ -143,41 +114,11 @@ __global__ void __launch_bounds__((TileLayout<D, C, B, G, 1>::THREADS), MINB)
   const int blk0 = blockIdx.x * G;
   const int32_t* qpos = positions + (size_t)th * N;
   const int32_t* kpos = positions + ((size_t)T * H + th) * N;
+  const float* scale_h = scale + h * C;
   const int tid = threadIdx.x;
 
-  float sc[C];
-#pragma unroll
-  for (int c = 0; c < C; ++c) sc[c] = __ldg(scale + h * C + c);
-
-  // gather the query side: one thread per query row
-  for (int rr = tid; rr < G * B; rr += L::THREADS) {
-    const int g = rr / B, blk = blk0 + g;
-    if (blk >= nb) continue;
-    const int n = __ldg(qpos + (size_t)blk * B + (rr - g * B));
-    const int n0 = __ldg(kpos + (size_t)blk * B + (B - 1));  // centre = last key of the block
-    float qr[E], ctr[E];
-    load_hat_row<D, C>(q, coords, sc, n, h, H, n < raw_size, qr);
-    load_hat_row<D, C>(k, coords, sc, n0, h, H, n0 < raw_size, ctr);
-    float sq = 0.f;
-#pragma unroll
-    for (int e = 0; e < E; ++e) {
-      qr[e] -= ctr[e];
-      sq = fmaf(qr[e], qr[e], sq);
-    }
-    const float inv_den = 1.f / __ldg(den_sum + (size_t)n * H + h);
-    float gdr[D], y[D], gy = 0.f;
-    load_row<D>(d_out_pre + ((size_t)n * H + h) * D, gdr);
-    load_row<D>(out_pre + ((size_t)n * H + h) * D, y);
-#pragma unroll
-    for (int d = 0; d < D; ++d) {
-      gdr[d] *= inv_den;
-      gy = fmaf(gdr[d], y[d], gy);
-    }
-    store_hat_row<L>(qs, rr, qr, -0.5f * kLog2e * sq, gy);
-#pragma unroll
-    for (int c = 0; c < L::VCH; ++c)
-      gs[rr * L::VCH + c] = make_float4(gdr[4 * c], gdr[4 * c + 1], gdr[4 * c + 2], gdr[4 * c + 3]);
-  }
+  gather_streamed_rows<L, true>(q, k, d_out_pre, out_pre, den_sum, coords, scale_h, qpos, kpos, blk0, nb, h, H,
+                                raw_size, qs, gs);
   __syncthreads();
 
   if (tid >= L::LANES) return;
@@ -186,18 +127,12 @@ __global__ void __launch_bounds__((TileLayout<D, C, B, G, 1>::THREADS), MINB)
   if (blk >= nb) return;
 
   const int n = __ldg(kpos + (size_t)blk * B + j);
-  const bool real = n < raw_size;
-  float a[1][E], s_init, vj[D];
-  {
-    const int n0 = __ldg(kpos + (size_t)blk * B + (B - 1));  // centre = last key of the block
-    float ctr[E];
-    load_hat_row<D, C>(k, coords, sc, n0, h, H, n0 < raw_size, ctr);
-    load_resident_row<L>(k, coords, sc, ctr, n, h, H, raw_size, a[0], s_init);
-    if (real) load_row<D>(v + ((size_t)n * H + h) * D, vj);
-    else {
+  float a[1][E], nk, vj[D];
+  load_resident_row<L>(k, k, coords, scale_h, n, __ldg(kpos + (size_t)blk * B + (B - 1)), h, H, raw_size, a[0], nk);
+  if (n < raw_size) load_row<D>(v + ((size_t)n * H + h) * D, vj);
+  else {
 #pragma unroll
-      for (int d = 0; d < D; ++d) vj[d] = 0.f;
-    }
+    for (int d = 0; d < D; ++d) vj[d] = 0.f;
   }
   float dk[E], dv[D], sds = 0.f;
 #pragma unroll
@@ -205,22 +140,20 @@ __global__ void __launch_bounds__((TileLayout<D, C, B, G, 1>::THREADS), MINB)
 #pragma unroll
   for (int d = 0; d < D; ++d) dv[d] = 0.f;
 
-  const int row0 = g * B;
+  const float4* qrow = qs + (size_t)g * B * L::ROW_CHUNKS;
+  const float4* grow = gs + (size_t)g * B * L::VCH;
 #pragma unroll 1
-  for (int i = 0; i < B; ++i) {
-    float s[1] = {s_init}, nq2 = 0.f, gy = 0.f;
+  for (int i = 0; i < B; ++i, qrow += L::ROW_CHUNKS, grow += L::VCH) {
+    float s[1], nq = 0.f, gy = 0.f;
     float4 keep[L::USED_CHUNKS];
-    dot_rows<L>(qs, row0 + i, a, s, nq2, gy, keep);
-    const float s2 = s[0] + nq2;
-    const float p = exp2_fast(fminf(s2, 0.f));
+    dot_rows<L>(qrow, a, s, nq, gy, keep);
+    const float s2 = (s[0] + nq) + nk;  // canonical order (dot + nq) + nk: bit-identical to the dq pass
+    const float p = exp2_fast(fminf(s2 * kLog2e, 0.f));
     float dp0 = -gy, dp1 = 0.f;
 #pragma unroll
     for (int c = 0; c < L::VCH; ++c) {
-      const float4 gg = gs[(row0 + i) * L::VCH + c];
-      dp0 = fmaf(gg.x, vj[4 * c + 0], dp0);
-      dp1 = fmaf(gg.y, vj[4 * c + 1], dp1);
-      dp0 = fmaf(gg.z, vj[4 * c + 2], dp0);
-      dp1 = fmaf(gg.w, vj[4 * c + 3], dp1);
+      const float4 gg = grow[c];
+      dp_step(gg, make_float4(vj[4 * c], vj[4 * c + 1], vj[4 * c + 2], vj[4 * c + 3]), dp0, dp1);
       dv[4 * c + 0] = fmaf(p, gg.x, dv[4 * c + 0]);
       dv[4 * c + 1] = fmaf(p, gg.y, dv[4 * c + 1]);
       dv[4 * c + 2] = fmaf(p, gg.z, dv[4 * c + 2]);
@@ -228,27 +161,16 @@ __global__ void __launch_bounds__((TileLayout<D, C, B, G, 1>::THREADS), MINB)
     }
     const float ds = s2 <= 0.f ? p * (dp0 + dp1) : 0.f;
     sds += ds;
-    // the q' chunks are re-read (broadcast LDS) rather than kept: 32 fewer live registers
 #pragma unroll
     for (int c = 0; c < L::USED_CHUNKS; ++c) {
-      const float4 qq = KEEP ? keep[c] : qs[L::hat_off(row0 + i, c)];
-      const float tq[4] = {qq.x, qq.y, qq.z, qq.w};
+      const float tq[4] = {keep[c].x, keep[c].y, keep[c].z, keep[c].w};
 #pragma unroll
       for (int x = 0; x < 4; ++x)
         if (4 * c + x < E) dk[4 * c + x] = fmaf(ds, tq[x], dk[4 * c + x]);
     }
   }
 
-  // dk^_j = sum_i dS_ij q'_i - (sum_i dS_ij) k'_j, with k' re-read exactly (see the dq kernel)
-  float kx[E];
-  {
-    const int n0 = __ldg(kpos + (size_t)blk * B + (B - 1));
-    float ctr[E];
-    load_hat_row<D, C>(k, coords, sc, n0, h, H, n0 < raw_size, ctr);
-    load_hat_row<D, C>(k, coords, sc, n, h, H, real, kx);
-#pragma unroll
-    for (int e = 0; e < E; ++e) kx[e] -= ctr[e];
-  }
+  // dk^_j = sum_i dS_ij q'_i - (sum_i dS_ij) k'_j   (a[0] holds k' exactly)
   const size_t srow = ((size_t)h * N + n) * T + t;
   float4* dstk = reinterpret_cast<float4*>(stage_dk + srow * kStageRow);
 #pragma unroll
@@ -257,7 +179,7 @@ __global__ void __launch_bounds__((TileLayout<D, C, B, G, 1>::THREADS), MINB)
 #pragma unroll
     for (int x = 0; x < 4; ++x) {
       const int e = 4 * c + x;
-      o4[x] = e < E ? fmaf(-sds, kx[e < E ? e : 0], dk[e < E ? e : 0]) : 0.f;
+      o4[x] = e < E ? fmaf(-sds, a[0][e < E ? e : 0], dk[e < E ? e : 0]) : 0.f;
     }
     dstk[c] = make_float4(o4[0], o4[1], o4[2], o4[3]);
   }
@@ -372,7 +294,7 @@ static int launch_bwd(const hept_shape* s, const float* q, const float* k, const
   using LQ = TileLayout<D, C, B, GQ, 1>;
   using LK = TileLayout<D, C, B, GK, 1>;
   auto kq = block_attn_bwd_dq_kernel<D, C, B, GQ, MINQ>;
-  auto kk = block_attn_bwd_dkv_kernel<D, C, B, GK, MINK, false>;
+  auto kk = block_attn_bwd_dkv_kernel<D, C, B, GK, MINK>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e1 = cudaFuncSetAttribute(kq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LQ::SMEM_BYTES);

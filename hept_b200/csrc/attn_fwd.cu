@@ -17,7 +17,7 @@ __global__ void __launch_bounds__((TileLayout<D, C, B, G, R>::THREADS), MINB)
   using L = TileLayout<D, C, B, G, R>;
   constexpr int E = L::E;
   extern __shared__ float4 smem[];
-  float4* ks = smem;                             // [G*B] k' rows: k'[0..E), nk2
+  float4* ks = smem;                             // [G*B][8]   k' rows: k'[0..E), nk
   float4* vs = smem + G * B * L::ROW_CHUNKS;     // [G*B][D/4] value rows
 
   const int th = blockIdx.y, t = th / H, h = th % H;
@@ -25,14 +25,10 @@ __global__ void __launch_bounds__((TileLayout<D, C, B, G, R>::THREADS), MINB)
   const int blk0 = blockIdx.x * G;
   const int32_t* qpos = positions + (size_t)th * N;
   const int32_t* kpos = positions + ((size_t)T * H + th) * N;
+  const float* scale_h = scale + h * C;
   const int tid = threadIdx.x;
 
-  float sc[C];
-#pragma unroll
-  for (int c = 0; c < C; ++c) sc[c] = __ldg(scale + h * C + c);
-
-  // ---- gather: one thread per key row ------------------------------------------------------------
-  gather_key_rows<L>(k, v, coords, sc, kpos, blk0, nb, h, H, raw_size, ks, vs);
+  gather_streamed_rows<L, false>(k, k, v, nullptr, nullptr, coords, scale_h, kpos, kpos, blk0, nb, h, H, raw_size, ks, vs);
   __syncthreads();
 
   // ---- each lane owns R query rows of one block ----------------------------------------------------
@@ -41,40 +37,38 @@ __global__ void __launch_bounds__((TileLayout<D, C, B, G, R>::THREADS), MINB)
   const int blk = blk0 + g;
   if (blk >= nb) return;
 
-  float a[R][E], s_init[R], o[R][D], l[R];
+  float a[R][E], nq[R], o[R][D], l[R];
   int nrow[R];
   {
-    const int n0 = __ldg(kpos + (size_t)blk * B + (B - 1));  // centre = last key of the block
-    float ctr[E];
-    load_hat_row<D, C>(k, coords, sc, n0, h, H, n0 < raw_size, ctr);
+    const int n0 = __ldg(kpos + (size_t)blk * B + (B - 1));
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const int i = pp + r * L::LPB;
       nrow[r] = i < B ? __ldg(qpos + (size_t)blk * B + i) : -1;
-      load_resident_row<L>(q, coords, sc, ctr, nrow[r], h, H, raw_size, a[r], s_init[r]);
+      load_resident_row<L>(q, k, coords, scale_h, nrow[r], n0, h, H, raw_size, a[r], nq[r]);
       l[r] = 0.f;
 #pragma unroll
       for (int d = 0; d < D; ++d) o[r][d] = 0.f;
     }
   }
 
-  const int row0 = g * B;
-#pragma unroll 2
-  for (int j = 0; j < B; ++j) {
-    float s[R], nk2 = 0.f, unused = 0.f;
+  const float4* krow = ks + (size_t)g * B * L::ROW_CHUNKS;
+  const float4* vrow = vs + (size_t)g * B * L::VCH;
+#pragma unroll 1
+  for (int j = 0; j < B; ++j, krow += L::ROW_CHUNKS, vrow += L::VCH) {
+    float s[R], nk = 0.f, unused = 0.f;
     float4 keep[L::USED_CHUNKS];
-#pragma unroll
-    for (int r = 0; r < R; ++r) s[r] = s_init[r];
-    dot_rows<L>(ks, row0 + j, a, s, nk2, unused, keep);
+    dot_rows<L>(krow, a, s, nk, unused, keep);
     float p[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      p[r] = exp2_fast(fminf(s[r] + nk2, 0.f));  // exp(min(S, 0)), example/hept.py:12
+      const float tt = (s[r] + nq[r]) + nk;        // canonical order, see tile.cuh
+      p[r] = exp2_fast(fminf(tt * kLog2e, 0.f));  // exp(min(S, 0)), example/hept.py:12
       l[r] += p[r];
     }
 #pragma unroll
     for (int c = 0; c < L::VCH; ++c) {
-      const float4 vv = vs[(row0 + j) * L::VCH + c];
+      const float4 vv = vrow[c];
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         o[r][4 * c + 0] = fmaf(p[r], vv.x, o[r][4 * c + 0]);

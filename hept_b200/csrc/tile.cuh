@@ -4,13 +4,24 @@
 // "Streamed" rows of a block (keys in the forward / dq pass, queries in the dkv pass) are gathered
 // through the sort permutation into shared memory once; every lane owns R "resident" rows of one
 // block in registers and walks the block's streamed rows.  Lanes of a warp that belong to the same
-// block read the same shared-memory address (broadcast), so one LDS.128 wavefront feeds 32 lanes x 4
-// values; that is what keeps the fp32 FMA pipe, not the LSU, the limiter.
+// block read the same shared-memory address (broadcast), so one LDS.128 feeds 32 lanes x 4 values;
+// that is what keeps the fp32 FMA pipe, not the LSU, the limiter.
 //
-// Numerics: scores are evaluated on rows re-centred on the block's first key, q' = q_hat - c,
-// k' = k_hat - c (S depends only on q_hat - k_hat), which removes the catastrophic cancellation of
-// q.k - |q|^2/2 - |k|^2/2 at trained-weight magnitudes.  exp is evaluated as
-// ex2(S * log2 e) with log2 e folded into the resident rows.
+// Gather: eight lanes per row, one 16-byte chunk each — the 96-byte q/k/v row of a hit is read by six
+// adjacent lanes (coalesced) and a warp writes 512 contiguous bytes of shared memory (conflict-free
+// without swizzling, so readers address rows with immediates).
+//
+// Numerics: scores are evaluated on rows re-centred on the block's last key, q' = q_hat - c,
+// k' = k_hat - c (S depends only on q_hat - k_hat), which tames the cancellation of
+// q.k - |q|^2/2 - |k|^2/2 when blocks are spatially tight (trained weights).
+//
+// Canonical arithmetic: all three tile kernels evaluate  t = (dot(q', k') + nq) + nk,
+// P = ex2(min(t * log2 e, 0)),  dP = chain(gd . v) - gy  with the SAME operation order, and every
+// row-wise reduction (|x'|^2, gd . y) is "4-element FMA chain per 16-byte chunk, then a fixed
+// pairwise tree over the 8 chunks" whether it is computed by one lane or by eight.  The forward
+// pass and the two backward passes therefore see bit-identical P and dS.  That matters: d scale is a
+// sum over all hits of coords * (dq^ + dk^) that cancels by ~|q^|^2 / |q^ - k^|^2, and any mismatch
+// between the dS used for dq^ and the dS used for dk^ is amplified by that factor.
 #pragma once
 
 #include "common.cuh"
@@ -23,61 +34,171 @@ struct TileLayout {
   static constexpr int E = D + C;
   static_assert(D % 4 == 0, "dims per head must be a multiple of 4 (float4 rows)");
   static_assert(E + 2 <= 32, "hash_dim + 2 side slots must fit one 32-float row");
-  // 32-float (128-byte) rows: E values, then two side slots (E, E+1).  Eight 16-byte chunks per row,
-  // stored with chunk ^= (row & 7) so that eight consecutive rows written by eight lanes hit eight
-  // different bank groups (conflict-free STS.128); readers use the same XOR (uniform per row).
-  static constexpr int ROW_CHUNKS = 8;
+  static constexpr int ROW_CHUNKS = 8;                 // 32-float (128-byte) rows: E values, side slots E, E+1
   static constexpr int USED_CHUNKS = (E + 2 + 3) / 4;  // chunks that carry data
   static constexpr int VCH = D / 4;                    // chunks of a value / gradient row
+  static_assert(VCH <= 8, "value rows are gathered by the same 8 lanes");
   static constexpr int LPB = (B + R - 1) / R;          // lanes per block
   static constexpr int LANES = G * LPB;
   static constexpr int THREADS = (LANES + 31) / 32 * 32;
   static constexpr size_t SMEM_BYTES = (size_t)G * B * (ROW_CHUNKS + VCH) * sizeof(float4);
-  __device__ static __forceinline__ int hat_off(int row, int chunk) { return row * ROW_CHUNKS + (chunk ^ (row & 7)); }
 };
 
-// q_hat / k_hat row of hit n, head h: [x[n,h,:] | scale[h,:] * coords[n,:]]; zero for src/ padding rows.
+// fixed pairwise tree over eight partial sums: ((p0+p1)+(p2+p3)) + ((p4+p5)+(p6+p7))
+__device__ __forceinline__ float tree8(const float* p) {
+  return ((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]));
+}
+// the same tree evaluated across the 8 lanes of a row group (xor butterfly: every lane gets the total)
+__device__ __forceinline__ float tree8_lanes(float p) {
+  p += __shfl_xor_sync(0xffffffffu, p, 1);
+  p += __shfl_xor_sync(0xffffffffu, p, 2);
+  p += __shfl_xor_sync(0xffffffffu, p, 4);
+  return p;
+}
+
+// chunk `chunk` of the hat row of hit n, head h: x[n,h,e] for e < D, scale[h,e-D] * coords[n,e-D] up to E, else 0
 template <int D, int C>
-__device__ __forceinline__ void load_hat_row(const float* __restrict__ x, const float* __restrict__ coords,
-                                             const float* sc, int n, int h, int H, bool real, float* out) {
-  if (real) {
-    load_row<D>(x + ((size_t)n * H + h) * D, out);
-    float cc[C];
-    load_row<C>(coords + (size_t)n * C, cc);
+__device__ __forceinline__ float4 load_hat_chunk(const float* __restrict__ x, const float* __restrict__ coords,
+                                                 const float* __restrict__ scale_h, int n, int h, int H, int chunk,
+                                                 bool real) {
+  if (!real) return make_float4(0.f, 0.f, 0.f, 0.f);
+  if (4 * chunk + 3 < D) return ldg4(x + ((size_t)n * H + h) * D + 4 * chunk);
+  float t[4];
 #pragma unroll
-    for (int c = 0; c < C; ++c) out[D + c] = __fmul_rn(sc[c], cc[c]);
-  } else {
-#pragma unroll
-    for (int e = 0; e < D + C; ++e) out[e] = 0.f;
+  for (int u = 0; u < 4; ++u) {
+    const int e = 4 * chunk + u;
+    if (e < D) t[u] = __ldg(x + ((size_t)n * H + h) * D + e);
+    else if (e < D + C) t[u] = __fmul_rn(__ldg(scale_h + (e - D)), __ldg(coords + (size_t)n * C + (e - D)));
+    else t[u] = 0.f;
   }
+  return make_float4(t[0], t[1], t[2], t[3]);
 }
 
-// Store a 32-float row (values[0..E) then side0, side1, zero padding) into swizzled shared memory.
-template <class L>
-__device__ __forceinline__ void store_hat_row(float4* base, int row, const float* vals, float side0, float side1) {
+// sum of squares of the (at most 4) real elements of a chunk, FMA chain from 0 in element order
+template <int E>
+__device__ __forceinline__ float chunk_sq(float4 d, int chunk) {
+  const float t[4] = {d.x, d.y, d.z, d.w};
+  float s = 0.f;
 #pragma unroll
-  for (int c = 0; c < L::USED_CHUNKS; ++c) {
-    float t[4];
-#pragma unroll
-    for (int x = 0; x < 4; ++x) {
-      const int e = 4 * c + x;
-      t[x] = e < L::E ? vals[e] : (e == L::E ? side0 : (e == L::E + 1 ? side1 : 0.f));
+  for (int u = 0; u < 4; ++u)
+    if (4 * chunk + u < E) s = fmaf(t[u], t[u], s);
+  return s;
+}
+
+// Gather the streamed side of the G blocks a CTA owns, eight lanes per row.
+//   hat rows  -> `hs` [G*B][8] float4: x' = x_hat - centre in [0,E), side0 = -|x'|^2/2 at slot E, side1 at E+1
+//   aux rows  -> `as` [G*B][VCH] float4: value rows (GRAD == false) or gd = g / den rows (GRAD == true, in which
+//               case side1 = gy = gd . y; otherwise side1 = 0)
+// `spos` are the sorted positions of the streamed side, `kpos` those of the keys (the centre is the block's last key).
+template <class L, bool GRAD>
+__device__ __forceinline__ void gather_streamed_rows(const float* __restrict__ x, const float* __restrict__ kx,
+                                                     const float* __restrict__ aux, const float* __restrict__ y,
+                                                     const float* __restrict__ den, const float* __restrict__ coords,
+                                                     const float* __restrict__ scale_h, const int32_t* __restrict__ spos,
+                                                     const int32_t* __restrict__ kpos, int blk0, int nb, int h, int H,
+                                                     int raw_size, float4* hs, float4* as) {
+  constexpr int D = L::D, C = L::C, B = L::B, E = L::E;
+  constexpr int ROWS_PER_PASS = L::THREADS / 8;
+  const int sub = threadIdx.x >> 3, c = threadIdx.x & 7;
+  for (int base = 0; base < L::G * B; base += ROWS_PER_PASS) {
+    const int rr = base + sub;
+    const int g = rr / B, blk = blk0 + g;
+    const bool valid = rr < L::G * B && blk < nb;
+    int n = 0, n0 = 0;
+    if (valid) {
+      n = __ldg(spos + (size_t)blk * B + (rr - g * B));
+      n0 = __ldg(kpos + (size_t)blk * B + (B - 1));
     }
-    base[L::hat_off(row, c)] = make_float4(t[0], t[1], t[2], t[3]);
+    const bool real = valid && n < raw_size;
+    float4 d = load_hat_chunk<D, C>(x, coords, scale_h, n, h, H, c, real);
+    const float4 ctr = load_hat_chunk<D, C>(kx, coords, scale_h, n0, h, H, c, valid && n0 < raw_size);
+    d.x -= ctr.x; d.y -= ctr.y; d.z -= ctr.z; d.w -= ctr.w;
+    const float half_sq = -0.5f * tree8_lanes(chunk_sq<E>(d, c));
+    float side1 = 0.f;
+    float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (GRAD) {
+      float part = 0.f;
+      if (c < L::VCH && valid) {
+        const float inv_den = 1.f / __ldg(den + (size_t)n * H + h);
+        const float4 gg = ldg4(aux + ((size_t)n * H + h) * D + 4 * c);
+        const float4 yy = ldg4(y + ((size_t)n * H + h) * D + 4 * c);
+        av = make_float4(gg.x * inv_den, gg.y * inv_den, gg.z * inv_den, gg.w * inv_den);
+        part = fmaf(av.w, yy.w, fmaf(av.z, yy.z, fmaf(av.y, yy.y, fmaf(av.x, yy.x, 0.f))));
+      }
+      side1 = tree8_lanes(part);
+    } else if (c < L::VCH && real) {
+      av = ldg4(aux + ((size_t)n * H + h) * D + 4 * c);
+    }
+    if (valid) {
+      float t[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = 4 * c + u;
+        if (e == E) t[u] = half_sq;
+        else if (e == E + 1) t[u] = side1;
+        else if (e > E + 1) t[u] = 0.f;
+      }
+      if (c < L::USED_CHUNKS) hs[rr * L::ROW_CHUNKS + c] = make_float4(t[0], t[1], t[2], t[3]);
+      if (c < L::VCH) as[rr * L::VCH + c] = av;
+    }
   }
 }
 
-// dot of a resident row with a streamed row; also hands back the two side slots of the streamed row.
-// Two partial sums (even / odd chunks) halve the dependent-FMA chain.
+// Resident row of a lane: x' = x_hat[n] - centre (E values) and -|x'|^2/2, canonical reduction order.
 template <class L>
-__device__ __forceinline__ void dot_rows(const float4* __restrict__ base, int row, const float (&a)[L::R][L::E],
-                                         float (&s)[L::R], float& side0, float& side1, float4 (&keep)[L::USED_CHUNKS]) {
+__device__ __forceinline__ void load_resident_row(const float* __restrict__ x, const float* __restrict__ kx,
+                                                  const float* __restrict__ coords, const float* __restrict__ scale_h,
+                                                  int n, int n0, int h, int H, int raw_size, float* a, float& half_sq) {
+  float part[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    part[c] = 0.f;
+    if (c < L::USED_CHUNKS && 4 * c < L::E) {
+      float4 d = load_hat_chunk<L::D, L::C>(x, coords, scale_h, n < 0 ? 0 : n, h, H, c, n >= 0 && n < raw_size);
+      const float4 ctr = load_hat_chunk<L::D, L::C>(kx, coords, scale_h, n0, h, H, c, n0 < raw_size);
+      d.x -= ctr.x; d.y -= ctr.y; d.z -= ctr.z; d.w -= ctr.w;
+      part[c] = chunk_sq<L::E>(d, c);
+      const float t[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (4 * c + u < L::E) a[4 * c + u] = t[u];
+    }
+  }
+  half_sq = -0.5f * tree8(part);
+}
+
+// gd = g / den (D values) and gy = gd . y of hit n, canonical reduction order.
+template <class L>
+__device__ __forceinline__ void load_resident_grad(const float* __restrict__ g, const float* __restrict__ y,
+                                                   const float* __restrict__ den, int n, int h, int H, float* gd,
+                                                   float& gy) {
+  const float inv_den = 1.f / __ldg(den + (size_t)n * H + h);
+  float part[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    part[c] = 0.f;
+    if (c < L::VCH) {
+      const float4 gg = ldg4(g + ((size_t)n * H + h) * L::D + 4 * c);
+      const float4 yy = ldg4(y + ((size_t)n * H + h) * L::D + 4 * c);
+      gd[4 * c + 0] = gg.x * inv_den; gd[4 * c + 1] = gg.y * inv_den;
+      gd[4 * c + 2] = gg.z * inv_den; gd[4 * c + 3] = gg.w * inv_den;
+      part[c] = fmaf(gd[4 * c + 3], yy.w, fmaf(gd[4 * c + 2], yy.z, fmaf(gd[4 * c + 1], yy.y, fmaf(gd[4 * c], yy.x, 0.f))));
+    }
+  }
+  gy = tree8(part);
+}
+
+// dot of R resident rows with one streamed row; also hands back the two side slots of the streamed row.
+// Two partial sums (even / odd chunks, both from 0) halve the dependent-FMA chain.
+template <class L>
+__device__ __forceinline__ void dot_rows(const float4* __restrict__ row, const float (&a)[L::R][L::E], float (&s)[L::R],
+                                         float& side0, float& side1, float4 (&keep)[L::USED_CHUNKS]) {
   float s1[L::R];
 #pragma unroll
-  for (int r = 0; r < L::R; ++r) s1[r] = 0.f;
+  for (int r = 0; r < L::R; ++r) { s[r] = 0.f; s1[r] = 0.f; }
 #pragma unroll
   for (int c = 0; c < L::USED_CHUNKS; ++c) {
-    const float4 kk = base[L::hat_off(row, c)];
+    const float4 kk = row[c];
     keep[c] = kk;
     const float t[4] = {kk.x, kk.y, kk.z, kk.w};
 #pragma unroll
@@ -100,51 +221,13 @@ __device__ __forceinline__ void dot_rows(const float4* __restrict__ base, int ro
   for (int r = 0; r < L::R; ++r) s[r] += s1[r];
 }
 
-// Gather the key side of the G blocks a CTA owns: k' rows (+ nk2 = -|k'|^2/2 * log2 e in side slot 0)
-// into `ks`, value rows into `vs`.  One thread per row; rows of blocks past the end are left untouched.
-template <class L>
-__device__ __forceinline__ void gather_key_rows(const float* __restrict__ k, const float* __restrict__ v,
-                                                const float* __restrict__ coords, const float* sc,
-                                                const int32_t* __restrict__ kpos, int blk0, int nb, int h, int H,
-                                                int raw_size, float4* ks, float4* vs) {
-  constexpr int D = L::D, C = L::C, B = L::B, E = L::E;
-  for (int rr = threadIdx.x; rr < L::G * B; rr += L::THREADS) {
-    const int g = rr / B, blk = blk0 + g;
-    if (blk >= nb) continue;
-    const int n = __ldg(kpos + (size_t)blk * B + (rr - g * B));
-    const int n0 = __ldg(kpos + (size_t)blk * B + (B - 1));  // centre = last key of the block
-    float kr[E], ctr[E];
-    load_hat_row<D, C>(k, coords, sc, n, h, H, n < raw_size, kr);
-    load_hat_row<D, C>(k, coords, sc, n0, h, H, n0 < raw_size, ctr);
-    float sq = 0.f;
-#pragma unroll
-    for (int e = 0; e < E; ++e) {
-      kr[e] -= ctr[e];
-      sq = fmaf(kr[e], kr[e], sq);
-    }
-    store_hat_row<L>(ks, rr, kr, -0.5f * kLog2e * sq, 0.f);
-    const bool real = n < raw_size;
-#pragma unroll
-    for (int c = 0; c < L::VCH; ++c)
-      vs[rr * L::VCH + c] = real ? ldg4(v + ((size_t)n * H + h) * D + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-}
-
-// Resident row of a lane: centred, log2(e)-scaled copy of x_hat[n] and its -|x'|^2/2 * log2 e.
-template <class L>
-__device__ __forceinline__ void load_resident_row(const float* __restrict__ x, const float* __restrict__ coords,
-                                                  const float* sc, const float* ctr, int n, int h, int H,
-                                                  int raw_size, float* a, float& half_sq) {
-  float xr[L::E];
-  load_hat_row<L::D, L::C>(x, coords, sc, n < 0 ? 0 : n, h, H, n >= 0 && n < raw_size, xr);
-  float sq = 0.f;
-#pragma unroll
-  for (int e = 0; e < L::E; ++e) {
-    const float d = xr[e] - ctr[e];
-    sq = fmaf(d, d, sq);
-    a[e] = d * kLog2e;
-  }
-  half_sq = -0.5f * kLog2e * sq;
+// dP = (gd . v) - gy with a fixed order: two interleaved FMA chains, the first seeded with -gy.
+// (gd, v) may come from registers or shared memory in either role: fmaf is commutative in its factors.
+__device__ __forceinline__ void dp_step(float4 gg, float4 vv, float& dp0, float& dp1) {
+  dp0 = fmaf(gg.x, vv.x, dp0);
+  dp1 = fmaf(gg.y, vv.y, dp1);
+  dp0 = fmaf(gg.z, vv.z, dp0);
+  dp1 = fmaf(gg.w, vv.w, dp1);
 }
 
 }  // namespace hept
