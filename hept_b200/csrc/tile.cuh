@@ -99,47 +99,72 @@ __device__ __forceinline__ void gather_streamed_rows(const float* __restrict__ x
                                                      int raw_size, float4* hs, float4* as) {
   constexpr int D = L::D, C = L::C, B = L::B, E = L::E;
   constexpr int ROWS_PER_PASS = L::THREADS / 8;
+  constexpr int PASSES = (L::G * B + ROWS_PER_PASS - 1) / ROWS_PER_PASS;
+  constexpr int BATCH = 4;  // rows in flight per lane: the gather is latency-bound, not bandwidth-bound
   const int sub = threadIdx.x >> 3, c = threadIdx.x & 7;
-  for (int base = 0; base < L::G * B; base += ROWS_PER_PASS) {
-    const int rr = base + sub;
+  // all permutation indices first (one round trip), then the row data BATCH passes at a time
+  int nidx[PASSES], n0idx[PASSES];
+#pragma unroll
+  for (int ps = 0; ps < PASSES; ++ps) {
+    const int rr = ps * ROWS_PER_PASS + sub;
     const int g = rr / B, blk = blk0 + g;
     const bool valid = rr < L::G * B && blk < nb;
-    int n = 0, n0 = 0;
-    if (valid) {
-      n = __ldg(spos + (size_t)blk * B + (rr - g * B));
-      n0 = __ldg(kpos + (size_t)blk * B + (B - 1));
-    }
-    const bool real = valid && n < raw_size;
-    float4 d = load_hat_chunk<D, C>(x, coords, scale_h, n, h, H, c, real);
-    const float4 ctr = load_hat_chunk<D, C>(kx, coords, scale_h, n0, h, H, c, valid && n0 < raw_size);
-    d.x -= ctr.x; d.y -= ctr.y; d.z -= ctr.z; d.w -= ctr.w;
-    const float half_sq = -0.5f * tree8_lanes(chunk_sq<E>(d, c));
-    float side1 = 0.f;
-    float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (GRAD) {
-      float part = 0.f;
-      if (c < L::VCH && valid) {
-        const float inv_den = 1.f / __ldg(den + (size_t)n * H + h);
-        const float4 gg = ldg4(aux + ((size_t)n * H + h) * D + 4 * c);
-        const float4 yy = ldg4(y + ((size_t)n * H + h) * D + 4 * c);
-        av = make_float4(gg.x * inv_den, gg.y * inv_den, gg.z * inv_den, gg.w * inv_den);
-        part = fmaf(av.w, yy.w, fmaf(av.z, yy.z, fmaf(av.y, yy.y, fmaf(av.x, yy.x, 0.f))));
-      }
-      side1 = tree8_lanes(part);
-    } else if (c < L::VCH && real) {
-      av = ldg4(aux + ((size_t)n * H + h) * D + 4 * c);
-    }
-    if (valid) {
-      float t[4] = {d.x, d.y, d.z, d.w};
+    nidx[ps] = valid ? __ldg(spos + (size_t)blk * B + (rr - g * B)) : -1;
+    n0idx[ps] = valid ? __ldg(kpos + (size_t)blk * B + (B - 1)) : 0;
+  }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int e = 4 * c + u;
-        if (e == E) t[u] = half_sq;
-        else if (e == E + 1) t[u] = side1;
-        else if (e > E + 1) t[u] = 0.f;
+  for (int p0 = 0; p0 < PASSES; p0 += BATCH) {
+    float4 d[BATCH], ctr[BATCH], av[BATCH], yy[BATCH];
+    float inv_den[BATCH];
+#pragma unroll
+    for (int u = 0; u < BATCH; ++u) {
+      const int ps = p0 + u;
+      if (ps >= PASSES) continue;
+      const int n = nidx[ps], n0 = n0idx[ps];
+      const bool valid = n >= 0, real = valid && n < raw_size;
+      d[u] = load_hat_chunk<D, C>(x, coords, scale_h, valid ? n : 0, h, H, c, real);
+      ctr[u] = load_hat_chunk<D, C>(kx, coords, scale_h, n0, h, H, c, valid && n0 < raw_size);
+      av[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      yy[u] = av[u];
+      inv_den[u] = 0.f;
+      if (GRAD) {
+        if (c < L::VCH && valid) {
+          inv_den[u] = 1.f / __ldg(den + (size_t)n * H + h);
+          av[u] = ldg4(aux + ((size_t)n * H + h) * D + 4 * c);
+          yy[u] = ldg4(y + ((size_t)n * H + h) * D + 4 * c);
+        }
+      } else if (c < L::VCH && real) {
+        av[u] = ldg4(aux + ((size_t)n * H + h) * D + 4 * c);
       }
-      if (c < L::USED_CHUNKS) hs[rr * L::ROW_CHUNKS + c] = make_float4(t[0], t[1], t[2], t[3]);
-      if (c < L::VCH) as[rr * L::VCH + c] = av;
+    }
+#pragma unroll
+    for (int u = 0; u < BATCH; ++u) {
+      const int ps = p0 + u;
+      if (ps >= PASSES) continue;
+      const int rr = ps * ROWS_PER_PASS + sub;
+      const bool valid = nidx[ps] >= 0;
+      float4 dd = d[u];
+      dd.x -= ctr[u].x; dd.y -= ctr[u].y; dd.z -= ctr[u].z; dd.w -= ctr[u].w;
+      const float half_sq = -0.5f * tree8_lanes(chunk_sq<E>(dd, c));
+      float side1 = 0.f;
+      float4 a4 = av[u];
+      if (GRAD) {
+        a4 = make_float4(a4.x * inv_den[u], a4.y * inv_den[u], a4.z * inv_den[u], a4.w * inv_den[u]);
+        const float part = fmaf(a4.w, yy[u].w, fmaf(a4.z, yy[u].z, fmaf(a4.y, yy[u].y, fmaf(a4.x, yy[u].x, 0.f))));
+        side1 = tree8_lanes(part);
+      }
+      if (valid) {
+        float t[4] = {dd.x, dd.y, dd.z, dd.w};
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          const int e = 4 * c + w;
+          if (e == E) t[w] = half_sq;
+          else if (e == E + 1) t[w] = side1;
+          else if (e > E + 1) t[w] = 0.f;
+        }
+        if (c < L::USED_CHUNKS) hs[rr * L::ROW_CHUNKS + c] = make_float4(t[0], t[1], t[2], t[3]);
+        if (c < L::VCH) as[rr * L::VCH + c] = a4;
+      }
     }
   }
 }

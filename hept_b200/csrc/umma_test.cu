@@ -1,0 +1,106 @@
+// Self-test of the tcgen05 building blocks (umma.cuh) on exactly representable data: an SS MMA with both
+// operands K-major (S = A B^T, 128 x 112 x 32) followed by a TS MMA whose A operand is read back from
+// TMEM and whose B operand is MN-major (O = S V, 128 x 32 x 112).  Used by tests/test_gpu_umma.py.
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace hept {
+
+constexpr int kTM = 128, kTN = 112, kTK = 32, kTV = 32;
+
+__global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ Bm,
+                                                               const float* __restrict__ V, float* __restrict__ S_out,
+                                                               float* __restrict__ O_out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;                       // 128 rows x 128 B
+  uint8_t* sB = sA + kTM * 128;             // 112 rows x 128 B
+  uint8_t* sV = sB + kTN * 128;             // 112 rows x 128 B   (row = k, 32 floats along n)
+  __shared__ uint64_t mbar;
+  __shared__ uint32_t tmem_base_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+
+  for (int idx = tid; idx < kTM * 8; idx += 128) {
+    const int r = idx >> 3, c = idx & 7;
+    *reinterpret_cast<float4*>(sA + umma::sw128_offset(r, c)) = *reinterpret_cast<const float4*>(A + r * kTK + 4 * c);
+  }
+  for (int idx = tid; idx < kTN * 8; idx += 128) {
+    const int r = idx >> 3, c = idx & 7;
+    *reinterpret_cast<float4*>(sB + umma::sw128_offset(r, c)) = *reinterpret_cast<const float4*>(Bm + r * kTK + 4 * c);
+    *reinterpret_cast<float4*>(sV + umma::sw128b32_offset(r, c)) = *reinterpret_cast<const float4*>(V + r * kTV + 4 * c);
+  }
+  if (tid == 0) umma::mbar_init(&mbar, 1);
+  if (warp == 0) umma::tmem_alloc<256>(&tmem_base_slot);
+  umma::fence_async_smem();
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem = tmem_base_slot;
+  const uint32_t tS = tmem, tO = tmem + 128;
+
+  if (tid == 0) {
+    constexpr uint32_t idesc = umma::idesc_tf32(kTM, kTN, false, false);
+#pragma unroll
+    for (int k = 0; k < kTK / 8; ++k) {
+      const uint64_t da = umma::smem_desc_sw128(umma::smem_u32(sA) + 32 * k, 1024, 16);
+      const uint64_t db = umma::smem_desc_sw128(umma::smem_u32(sB) + 32 * k, 1024, 16);
+      umma::mma_ss(tS, da, db, idesc, k > 0);
+    }
+    umma::commit(&mbar);
+  }
+  umma::mbar_wait(&mbar, 0);
+  umma::fence_after_sync();
+
+  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+#pragma unroll 1
+  for (int c0 = 0; c0 < kTN; c0 += 16) {
+    float v[16];
+    umma::tmem_ld16(tS + lane_base + c0, v);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) S_out[tid * kTN + c0 + i] = v[i];
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+
+  if (tid == 0) {
+    constexpr uint32_t idesc = umma::idesc_tf32(kTM, kTV, false, true);
+#pragma unroll 1
+    for (int k = 0; k < kTN / 8; ++k) {
+      const uint64_t db = umma::smem_desc(umma::smem_u32(sV) + 1024 * k, 512, 1024, umma::kLayoutSw128Base32);
+      umma::mma_ts(tO, tS + 8 * k, db, idesc, k > 0);
+    }
+    umma::commit(&mbar);
+  }
+  umma::mbar_wait(&mbar, 1);
+  umma::fence_after_sync();
+#pragma unroll 1
+  for (int c0 = 0; c0 < kTV; c0 += 16) {
+    float v[16];
+    umma::tmem_ld16(tO + lane_base + c0, v);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) O_out[tid * kTV + c0 + i] = v[i];
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc<256>(tmem);
+}
+
+}  // namespace hept
+
+using namespace hept;
+
+extern "C" int hept_debug_umma_selftest(const float* A, const float* Bm, const float* V, float* S_out, float* O_out,
+                                        void* stream) {
+  HEPT_REQUIRE(A && Bm && V && S_out && O_out, HEPT_EINVAL, "umma_selftest: null pointer");
+  const size_t smem = (size_t)(kTM + 2 * kTN) * 128 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "umma_selftest: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  umma_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, Bm, V, S_out, O_out);
+  HEPT_CHECK_LAUNCH("umma_selftest");
+  return HEPT_OK;
+}

@@ -121,6 +121,12 @@ int hept_launch_count(int reset);
  * (bit 0: dq tile kernel, bit 1: dk/dv tile kernel, bit 2: table reduction); default 7 = all. */
 void hept_set_bwd_stage_mask(int mask);
 
+/* self-test of the tcgen05 / TMEM building blocks (hept_b200/csrc/umma.cuh): S = A B^T with A (128,32),
+ * Bm (112,32) both K-major, then O = S V with S read back from TMEM and V (112,32) MN-major.
+ * Outputs S_out (128,112), O_out (128,32).  Used by tests/test_gpu_umma.py only. */
+int hept_debug_umma_selftest(const float* A, const float* Bm, const float* V, float* S_out, float* O_out,
+                             void* stream);
+
 #ifdef __cplusplus
 }
 #endif
