@@ -171,6 +171,9 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     torch.backends.cuda.matmul.allow_tf32 = False
+    if args.engine is not None:
+        _lib.load().hept_set_engine(1 if args.engine == "tcgen05" else 0)
+    engine_name = "tcgen05" if _lib.load().hept_get_engine() else "simt"
 
     n_sets = 4                                  # rotate over 4 events: ~0.75 GB of inputs, far beyond the 126 MB L2
     events = [make_event(100 * rank + i) for i in range(n_sets)]
@@ -262,7 +265,8 @@ def run_ours(args):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "tracking-60k fwd+bwd (HEPTAttention, H=8 D=24 C=6 T=3 B=100), one 60000-hit event per step per GPU",
                    "l2": f"inputs rotate over {n_sets} events (~190 MB each) so no step re-reads L2-resident inputs",
-                   "collective": "NCCL all-reduce of parameter gradients per step" if world > 1 else "none"},
+                   "collective": "NCCL all-reduce of parameter gradients per step" if world > 1 else "none",
+                   "tile_engine": engine_name},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / e2e_steps},
         "gpu_launches": launches,
@@ -345,6 +349,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--engine", default=None, choices=["simt", "tcgen05"], help="tile engine (default: library default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

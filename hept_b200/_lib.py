@@ -45,6 +45,8 @@ SIGNATURES = {
     "hept_attention_fwd": (C.c_int, [_SP, _p, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "hept_launch_count": (C.c_int, [C.c_int]),
     "hept_set_bwd_stage_mask": (None, [C.c_int]),
+    "hept_set_engine": (None, [C.c_int]),
+    "hept_get_engine": (C.c_int, []),
     "hept_debug_umma_selftest": (C.c_int, [_p, _p, _p, _p, _p, _p]),
 }
 

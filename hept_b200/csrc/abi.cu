@@ -17,6 +17,8 @@ void set_error(const char* fmt, ...) {
 void count_launch(int n) { g_launches += n; }
 static int g_bwd_mask = 7;
 int bwd_stage_mask() { return g_bwd_mask; }
+static int g_engine = 0;
+int engine() { return g_engine; }
 
 struct FwdPlan {
   size_t ext_bytes, span_bytes, proj_bytes, keys_bytes, sort_bytes, stage_bytes, total;
@@ -49,6 +51,8 @@ extern "C" int hept_launch_count(int reset) {
 }
 
 extern "C" void hept_set_bwd_stage_mask(int mask) { g_bwd_mask = mask & 7; }
+extern "C" void hept_set_engine(int engine) { g_engine = engine ? 1 : 0; }
+extern "C" int hept_get_engine(void) { return g_engine; }
 
 extern "C" size_t hept_attention_fwd_workspace_bytes(const hept_shape* s) {
   if (!s || s->N <= 0 || s->H <= 0 || s->T <= 0) return 0;

@@ -134,6 +134,9 @@ static int launch_fwd(const hept_shape* s, const float* q, const float* k, const
   return HEPT_OK;
 }
 
+int block_attention_fwd_tc(const hept_shape* s, const float* q, const float* k, const float* v, const float* coords,
+                           const float* scale, const int32_t* positions, float* stage, cudaStream_t st);
+
 }  // namespace hept
 
 using namespace hept;
@@ -149,6 +152,7 @@ extern "C" int hept_block_attention_fwd(const hept_shape* s, const float* q, con
   HEPT_REQUIRE(q && k && v && coords && scale && positions && stage, HEPT_EINVAL, "block_attention_fwd: null pointer");
   HEPT_REQUIRE((long long)s->T * s->H <= 65535, HEPT_EINVAL, "block_attention_fwd: T*H too large");
   cudaStream_t st = (cudaStream_t)stream;
+  if (engine() == 1) return block_attention_fwd_tc(s, q, k, v, coords, scale, positions, stage, st);
   if (s->D == 24 && s->C == 6 && s->B == 100) return launch_fwd<24, 6, 100, 5, 2, 2>(s, q, k, v, coords, scale, positions, stage, st);
   if (s->D == 24 && s->C == 4 && s->B == 100) return launch_fwd<24, 4, 100, 5, 2, 2>(s, q, k, v, coords, scale, positions, stage, st);
   if (s->D == 8 && s->C == 6 && s->B == 10) return launch_fwd<8, 6, 10, 4, 2, 1>(s, q, k, v, coords, scale, positions, stage, st);

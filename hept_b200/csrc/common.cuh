@@ -13,6 +13,7 @@ namespace hept {
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 int bwd_stage_mask();
+int engine();  // 0 = fp32 SIMT tiles, 1 = tcgen05 tiles
 
 #define HEPT_REQUIRE(cond, code, ...)      \
   do {                                     \

@@ -121,6 +121,11 @@ int hept_launch_count(int reset);
  * (bit 0: dq tile kernel, bit 1: dk/dv tile kernel, bit 2: table reduction); default 7 = all. */
 void hept_set_bwd_stage_mask(int mask);
 
+/* tile engine for a8-a11: 0 = fp32 CUDA-core tiles (attn_fwd.cu), 1 = tcgen05 tensor-core tiles with
+ * 3xTF32 operand splitting (attn_fwd_tc.cu).  Process-wide; both engines meet the same parity tolerance. */
+void hept_set_engine(int engine);
+int hept_get_engine(void);
+
 /* self-test of the tcgen05 / TMEM building blocks (hept_b200/csrc/umma.cuh): S = A B^T with A (128,32),
  * Bm (112,32) both K-major, then O = S V with S read back from TMEM and V (112,32) MN-major.
  * Outputs S_out (128,112), O_out (128,32).  Used by tests/test_gpu_umma.py only. */
