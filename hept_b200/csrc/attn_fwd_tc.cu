@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(kTcThreads, 2)
   const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
   const uint32_t sbase = umma::smem_u32(smem);
   uint32_t phase = 0;
+  const float4 mult = chunk_multiplier<D, C>(scale_h, c);
 
 #pragma unroll 1
   for (int it = 0; it < TILES; ++it) {
@@ -85,26 +86,28 @@ __global__ void __launch_bounds__(kTcThreads, 2)
     for (int ps = 0; ps < KP; ++ps) { const int j = ps * 32 + sub; nk_idx[ps] = j < B ? __ldg(kpos + (size_t)blk * B + j) : -1; }
 #pragma unroll
     for (int ps = 0; ps < QP; ++ps) { const int i = ps * 32 + sub; nq_idx[ps] = i < B ? __ldg(qpos + (size_t)blk * B + i) : -1; }
-    const float4 ctr = load_hat_chunk<D, C>(k, coords, scale_h, n0, h, H, c, n0 < raw_size);
+    const float4 ctr_raw = load_raw_chunk<D, C>(k, coords, n0, h, H, c, n0 < raw_size);
     float4 dk[KP], vk[KP], dq[QP];
 #pragma unroll
     for (int ps = 0; ps < KP; ++ps) {
       const int n = nk_idx[ps];
       const bool real = n >= 0 && n < raw_size;
-      dk[ps] = load_hat_chunk<D, C>(k, coords, scale_h, n < 0 ? 0 : n, h, H, c, real);
+      dk[ps] = load_raw_chunk<D, C>(k, coords, n < 0 ? 0 : n, h, H, c, real);
       vk[ps] = (c < D / 4 && real) ? ldg4(v + ((size_t)n * H + h) * D + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
     for (int ps = 0; ps < QP; ++ps) {
       const int n = nq_idx[ps];
-      dq[ps] = load_hat_chunk<D, C>(q, coords, scale_h, n < 0 ? 0 : n, h, H, c, n >= 0 && n < raw_size);
+      dq[ps] = load_raw_chunk<D, C>(q, coords, n < 0 ? 0 : n, h, H, c, n >= 0 && n < raw_size);
     }
+    // (no arithmetic above this line: every load of the tile is in flight before the first use)
+    const float4 ctr = apply_multiplier(ctr_raw, mult);
     // keys + values -> Kh, Kl, Vh, Vl
 #pragma unroll
     for (int ps = 0; ps < KP; ++ps) {
       const int j = ps * 32 + sub;
       const bool in = nk_idx[ps] >= 0;
-      float4 d = dk[ps];
+      float4 d = apply_multiplier(dk[ps], mult);
       if (in) { d.x -= ctr.x; d.y -= ctr.y; d.z -= ctr.z; d.w -= ctr.w; }
       const float sq = tree8_lanes(chunk_sq<E>(d, c));          // all lanes take part in the shuffle
       const float nk2 = in ? kLog2e * (-0.5f * sq) : -1e30f;    // padded keys: P = ex2(-1e30) = 0
@@ -139,7 +142,7 @@ __global__ void __launch_bounds__(kTcThreads, 2)
     for (int ps = 0; ps < QP; ++ps) {
       const int i = ps * 32 + sub;
       const bool in = nq_idx[ps] >= 0;
-      float4 d = dq[ps];
+      float4 d = apply_multiplier(dq[ps], mult);
       if (in) { d.x -= ctr.x; d.y -= ctr.y; d.z -= ctr.z; d.w -= ctr.w; }
       const float nq2 = kLog2e * (-0.5f * tree8_lanes(chunk_sq<E>(d, c)));
       if (c == 0) s_nq[i] = nq2;

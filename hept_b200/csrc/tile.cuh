@@ -56,11 +56,12 @@ __device__ __forceinline__ float tree8_lanes(float p) {
   return p;
 }
 
-// chunk `chunk` of the hat row of hit n, head h: x[n,h,e] for e < D, scale[h,e-D] * coords[n,e-D] up to E, else 0
+// Raw 16-byte chunk `chunk` of the hat row of hit n, head h, BEFORE the coordinate scale is applied:
+// x[n,h,e] for e < D, coords[n,e-D] for D <= e < E, else 0.  Loads only — no arithmetic — so that a gather can
+// put many of these in flight before the first use (the chunk index is a lane-dependent branch).
 template <int D, int C>
-__device__ __forceinline__ float4 load_hat_chunk(const float* __restrict__ x, const float* __restrict__ coords,
-                                                 const float* __restrict__ scale_h, int n, int h, int H, int chunk,
-                                                 bool real) {
+__device__ __forceinline__ float4 load_raw_chunk(const float* __restrict__ x, const float* __restrict__ coords, int n,
+                                                 int h, int H, int chunk, bool real) {
   if (!real) return make_float4(0.f, 0.f, 0.f, 0.f);
   if (4 * chunk + 3 < D) return ldg4(x + ((size_t)n * H + h) * D + 4 * chunk);
   float t[4];
@@ -68,10 +69,32 @@ __device__ __forceinline__ float4 load_hat_chunk(const float* __restrict__ x, co
   for (int u = 0; u < 4; ++u) {
     const int e = 4 * chunk + u;
     if (e < D) t[u] = __ldg(x + ((size_t)n * H + h) * D + e);
-    else if (e < D + C) t[u] = __fmul_rn(__ldg(scale_h + (e - D)), __ldg(coords + (size_t)n * C + (e - D)));
+    else if (e < D + C) t[u] = __ldg(coords + (size_t)n * C + (e - D));
     else t[u] = 0.f;
   }
   return make_float4(t[0], t[1], t[2], t[3]);
+}
+// per-chunk multipliers: 1 for feature columns, scale[h, e-D] for coordinate columns, 0 for padding
+template <int D, int C>
+__device__ __forceinline__ float4 chunk_multiplier(const float* __restrict__ scale_h, int chunk) {
+  float t[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int e = 4 * chunk + u;
+    t[u] = e < D ? 1.f : (e < D + C ? __ldg(scale_h + (e - D)) : 0.f);
+  }
+  return make_float4(t[0], t[1], t[2], t[3]);
+}
+// scale * coords with one rounding (x * 1.0f is exact for the feature columns), like the reference's fp32 product
+__device__ __forceinline__ float4 apply_multiplier(float4 raw, float4 m) {
+  return make_float4(__fmul_rn(m.x, raw.x), __fmul_rn(m.y, raw.y), __fmul_rn(m.z, raw.z), __fmul_rn(m.w, raw.w));
+}
+// chunk `chunk` of the hat row of hit n, head h: x[n,h,e] for e < D, scale[h,e-D] * coords[n,e-D] up to E, else 0
+template <int D, int C>
+__device__ __forceinline__ float4 load_hat_chunk(const float* __restrict__ x, const float* __restrict__ coords,
+                                                 const float* __restrict__ scale_h, int n, int h, int H, int chunk,
+                                                 bool real) {
+  return apply_multiplier(load_raw_chunk<D, C>(x, coords, n, h, H, chunk, real), chunk_multiplier<D, C>(scale_h, chunk));
 }
 
 // sum of squares of the (at most 4) real elements of a chunk, FMA chain from 0 in element order
@@ -102,6 +125,7 @@ __device__ __forceinline__ void gather_streamed_rows(const float* __restrict__ x
   constexpr int PASSES = (L::G * B + ROWS_PER_PASS - 1) / ROWS_PER_PASS;
   constexpr int BATCH = 4;  // rows in flight per lane: the gather is latency-bound, not bandwidth-bound
   const int sub = threadIdx.x >> 3, c = threadIdx.x & 7;
+  const float4 mult = chunk_multiplier<D, C>(scale_h, c);
   // all permutation indices first (one round trip), then the row data BATCH passes at a time
   int nidx[PASSES], n0idx[PASSES];
 #pragma unroll
@@ -122,8 +146,8 @@ __device__ __forceinline__ void gather_streamed_rows(const float* __restrict__ x
       if (ps >= PASSES) continue;
       const int n = nidx[ps], n0 = n0idx[ps];
       const bool valid = n >= 0, real = valid && n < raw_size;
-      d[u] = load_hat_chunk<D, C>(x, coords, scale_h, valid ? n : 0, h, H, c, real);
-      ctr[u] = load_hat_chunk<D, C>(kx, coords, scale_h, n0, h, H, c, valid && n0 < raw_size);
+      d[u] = load_raw_chunk<D, C>(x, coords, valid ? n : 0, h, H, c, real);
+      ctr[u] = load_raw_chunk<D, C>(kx, coords, n0, h, H, c, valid && n0 < raw_size);
       av[u] = make_float4(0.f, 0.f, 0.f, 0.f);
       yy[u] = av[u];
       inv_den[u] = 0.f;
@@ -143,8 +167,9 @@ __device__ __forceinline__ void gather_streamed_rows(const float* __restrict__ x
       if (ps >= PASSES) continue;
       const int rr = ps * ROWS_PER_PASS + sub;
       const bool valid = nidx[ps] >= 0;
-      float4 dd = d[u];
-      dd.x -= ctr[u].x; dd.y -= ctr[u].y; dd.z -= ctr[u].z; dd.w -= ctr[u].w;
+      float4 dd = apply_multiplier(d[u], mult);
+      const float4 cc = apply_multiplier(ctr[u], mult);
+      dd.x -= cc.x; dd.y -= cc.y; dd.z -= cc.z; dd.w -= cc.w;
       const float half_sq = -0.5f * tree8_lanes(chunk_sq<E>(dd, c));
       float side1 = 0.f;
       float4 a4 = av[u];
