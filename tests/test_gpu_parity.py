@@ -388,3 +388,106 @@ def test_full_size_backward_invariants_tracking60k():
     tot = (dq + dk).double().view(n, d.H, d.D).sum(0).abs().max()
     mass = (dq.double().abs() + dk.double().abs()).view(n, d.H, d.D).sum(0).max()
     assert float(tot) <= 1e-4 * float(mass)
+
+
+# ------------------------------------------------------- BASELINE.json configs[2..3] and the prepare step on device
+def test_prepare_input_on_device_matches_cpu():
+    from hept_b200 import prepare, synthetic
+
+    cfg = dict(synthetic.TRACKING)
+    sizes = [2100, 1500, 1130, 900, 300, 70, 130, 57]
+    coords, batch = synthetic.batched_cloud(sizes, cfg["coords_dim"], 9)
+    params = synthetic.module_params(cfg, 9)
+    helper = {"block_size": 100, "regions": params["regions"], "num_heads": 8}
+    x = torch.arange(coords.shape[0], dtype=torch.float32)[:, None]
+    xc, kc, rc = prepare.prepare_input(x, coords, batch, helper)
+    helper_d = dict(helper, regions=params["regions"].to(dev()))
+    xd, kd, rd = prepare.prepare_input(x.to(dev()), coords.to(dev()), batch.to(dev()), helper_d)
+    assert torch.equal(rd.cpu(), rc) and torch.equal(xd.cpu(), xc)
+    assert torch.equal(kd["combined_shifts"].cpu(), kc["combined_shifts"]) and torch.equal(kd["coords"].cpu(), kc["coords"])
+
+
+def test_batched_imbalanced_events_against_oracle():
+    """configs[3]: eight events of very different sizes (two shorter than a block) through prepare_input and the
+    module, forward + backward, against the float64 oracle (sizes scaled by 1/10 so the oracle runs in seconds)."""
+    from hept_b200 import HEPTAttention, ops, prepare, synthetic
+
+    cfg = dict(synthetic.TRACKING)
+    sizes = [2100, 1500, 1130, 900, 300, 70, 130, 57]
+    coords, batch = synthetic.batched_cloud(sizes, cfg["coords_dim"], 21)
+    params = synthetic.module_params(cfg, 21)
+    helper = {"block_size": 100, "regions": params["regions"], "num_heads": 8}
+    _, kw, real = prepare.prepare_input(torch.zeros(coords.shape[0], 1), coords, batch, helper)
+    n = kw["coords"].shape[0]
+    q, k, v = synthetic.qkv(n, cfg, 21)
+    g = torch.randn(n, cfg["h_dim"], generator=torch.Generator().manual_seed(2))
+    inputs = {"query": q, "key": k, "value": v, "coords": kw["coords"], "combined_shifts": kw["combined_shifts"]}
+    mod = HEPTAttention(30, **cfg)
+    mod.load_state_dict({kk: params[kk] for kk in ("out_linear.weight", "out_linear.bias", "e2lsh.alpha")}, strict=True)
+    mod = mod.to(dev())
+    w_rpe = torch.nn.Linear(50, 192)
+    w_rpe.load_state_dict({"weight": params["w_rpe.weight"], "bias": params["w_rpe.bias"]})
+    w_rpe = w_rpe.to(dev())
+    di = to_dev(inputs)
+    qd, kd, vd = (di[x].clone().requires_grad_(True) for x in ("query", "key", "value"))
+    out = mod(qd, kd, vd, w_rpe=w_rpe, coords=di["coords"], combined_shifts=di["combined_shifts"])
+    out.backward(g.to(dev()))
+    d = dims_of(cfg, n)
+    _, _, _, pos = ops.attention_fwd(d, qd.detach(), kd.detach(), vd.detach(), di["coords"], w_rpe.weight.detach(),
+                                     cfg["num_w_per_dist"], mod.e2lsh.alpha, combined_shifts=di["combined_shifts"])
+    positions = (pos[0].cpu().long(), pos[1].cpu().long())
+    r32 = O.forward_backward(inputs, params, cfg, g, torch.float32, positions)
+    r64 = O.forward_backward(inputs, params, cfg, g, torch.float64, positions)
+    mine = {"out": out.detach().cpu(), "dq": qd.grad.cpu(), "dk": kd.grad.cpu(), "dv": vd.grad.cpu(),
+            "dw_rpe": w_rpe.weight.grad.cpu()}
+    for key, val in mine.items():
+        e_o, e_r, ok = _err_budget(val, r32[key], r64[key], OUT_FLOOR if key == "out" else GRAD_FLOOR)
+        REPORT[rkey(f"imbalanced_{key}")] = [e_o, e_r]
+        assert ok, (key, e_o, e_r)
+    # the batch index sits in the top bits of every key: in sorted order events never interleave
+    ev_of_row = torch.repeat_interleave(torch.arange(len(sizes)), ((torch.tensor(sizes) + 99) // 100) * 100)
+    codes = kw["combined_shifts"][0, 0]
+    top = codes >> int(torch.log2(codes[real].max().float()).floor().item() - 2)   # coarse: monotone in the batch index
+    assert bool((top.gather(0, positions[0][0, 0])[1:] >= top.gather(0, positions[0][0, 0])[:-1]).all())
+    assert ev_of_row.shape[0] == n
+
+
+def test_pileup_shape_forward_inference():
+    """configs[2]: pileup shape (coords_dim 4, num_regions 140), 10 000 hits, forward only, through the src/ flavour
+    (zero / +inf padding with raw_size) — against the float64 oracle."""
+    from hept_b200 import HEPTAttention, ops, prepare, synthetic
+
+    cfg = dict(synthetic.PILEUP)
+    n_raw = 9950
+    coords_raw = synthetic.point_cloud(n_raw, 4, 31)
+    params = synthetic.module_params(cfg, 31)
+    x = torch.zeros(n_raw, 3)
+    _, kw = prepare.prepare_input_single(x, coords_raw, {"block_size": 100, "regions": params["regions"]})
+    n = kw["coords"].shape[0]
+    assert n == 10000 and kw["raw_size"] == n_raw
+    q, k, v = synthetic.qkv(n, cfg, 31)
+    inputs = {"query": q, "key": k, "value": v, "coords": kw["coords"], "raw_size": n_raw, "regions_h": kw["regions_h"],
+              "region_indices": kw["region_indices"]}
+    mod = HEPTAttention(28, **cfg)
+    mod.load_state_dict({kk: params[kk] for kk in ("out_linear.weight", "out_linear.bias", "e2lsh.alpha")}, strict=True)
+    mod = mod.to(dev()).eval()
+    w_rpe = torch.nn.Linear(30, 192)
+    w_rpe.load_state_dict({"weight": params["w_rpe.weight"], "bias": params["w_rpe.bias"]})
+    di = to_dev(inputs)
+    v_before = di["value"].clone()
+    with torch.no_grad():
+        out = mod(di["query"], di["key"], di["value"], w_rpe=w_rpe.to(dev()), coords=di["coords"], raw_size=n_raw,
+                  regions_h=di["regions_h"], region_indices=di["region_indices"])
+    assert torch.equal(di["value"], v_before)            # caller's tensor untouched (documented deviation)
+    d = dims_of(cfg, n, n_raw)
+    _, _, _, pos = ops.attention_fwd(d, di["query"], di["key"], di["value"], di["coords"], w_rpe.weight.to(dev()),
+                                     cfg["num_w_per_dist"], mod.e2lsh.alpha, region_indices=di["region_indices"],
+                                     regions_h=di["regions_h"])
+    positions = (pos[0].cpu().long(), pos[1].cpu().long())
+    assert bool((positions[0][..., -(n - n_raw):] >= n_raw).all())     # padding rows sort last (+inf keys)
+    t32 = oracle_trace(cfg, inputs, params, torch.float32, positions)
+    t64 = oracle_trace(cfg, inputs, params, torch.float64, positions)
+    lin = lambda tr, dt: torch.nn.functional.linear(tr["out_pre"], params["out_linear.weight"].to(dt), params["out_linear.bias"].to(dt))
+    e_o, e_r, ok = _err_budget(out.cpu()[:n_raw], lin(t32, torch.float32)[:n_raw], lin(t64, torch.float64)[:n_raw], OUT_FLOOR)
+    REPORT[rkey("pileup10k_out")] = [e_o, e_r]
+    assert ok, (e_o, e_r)
