@@ -173,7 +173,9 @@ def run_ours(args):
     torch.backends.cuda.matmul.allow_tf32 = False
     if args.engine is not None:
         _lib.load().hept_set_engine(1 if args.engine == "tcgen05" else 0)
-    engine_name = "tcgen05" if _lib.load().hept_get_engine() else "simt"
+    if args.bwd is not None:
+        _lib.load().hept_set_bwd_variant(args.bwd)
+    engine_name = ("tcgen05" if _lib.load().hept_get_engine() else "simt") + f"+bwd{_lib.load().hept_get_bwd_variant()}"
 
     n_sets = 4                                  # rotate over 4 events: ~0.75 GB of inputs, far beyond the 126 MB L2
     events = [make_event(100 * rank + i) for i in range(n_sets)]
@@ -367,6 +369,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--bwd", default=None, type=int, choices=[1, 2], help="backward tile variant (default: library default)")
     ap.add_argument("--engine", default=None, choices=["simt", "tcgen05"], help="tile engine (default: library default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

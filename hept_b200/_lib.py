@@ -47,6 +47,8 @@ SIGNATURES = {
     "hept_set_bwd_stage_mask": (None, [C.c_int]),
     "hept_set_engine": (None, [C.c_int]),
     "hept_get_engine": (C.c_int, []),
+    "hept_set_bwd_variant": (None, [C.c_int]),
+    "hept_get_bwd_variant": (C.c_int, []),
     "hept_debug_umma_selftest": (C.c_int, [_p, _p, _p, _p, _p, _p]),
 }
 

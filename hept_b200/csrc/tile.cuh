@@ -37,12 +37,32 @@ struct TileLayout {
   static constexpr int ROW_CHUNKS = 8;                 // 32-float (128-byte) rows: E values, side slots E, E+1
   static constexpr int USED_CHUNKS = (E + 2 + 3) / 4;  // chunks that carry data
   static constexpr int VCH = D / 4;                    // chunks of a value / gradient row
-  static_assert(VCH <= 8, "value rows are gathered by the same 8 lanes");
+  static_assert(VCH <= 8 && VCH % 2 == 0, "value rows are gathered by the same 8 lanes and split in two halves");
   static constexpr int LPB = (B + R - 1) / R;          // lanes per block
   static constexpr int LANES = G * LPB;
   static constexpr int THREADS = (LANES + 31) / 32 * 32;
   static constexpr size_t SMEM_BYTES = (size_t)G * B * (ROW_CHUNKS + VCH) * sizeof(float4);
 };
+
+// Canonical row reduction of the D-wide rows (gd . y): the row's VCH chunk partials are summed in order inside each
+// half of the row, then the two halves are added — the order a lane pair that splits the row in halves produces.
+template <int VCH>
+__device__ __forceinline__ float halves_sum(const float* p) {
+  constexpr int VH = VCH / 2;
+  float a = p[0], b = p[VH];
+#pragma unroll
+  for (int c = 1; c < VH; ++c) { a += p[c]; b += p[VH + c]; }
+  return a + b;
+}
+// the same reduction across the 8 lanes of a gather row group (lane c holds the partial of chunk c)
+template <int VCH>
+__device__ __forceinline__ float halves_sum_lanes(float part) {
+  float v[VCH];
+  const int base = (threadIdx.x & 31) & ~7;
+#pragma unroll
+  for (int c = 0; c < VCH; ++c) v[c] = __shfl_sync(0xffffffffu, part, base + c);
+  return halves_sum<VCH>(v);
+}
 
 // fixed pairwise tree over eight partial sums: ((p0+p1)+(p2+p3)) + ((p4+p5)+(p6+p7))
 __device__ __forceinline__ float tree8(const float* p) {
@@ -176,7 +196,7 @@ __device__ __forceinline__ void gather_streamed_rows(const float* __restrict__ x
       if (GRAD) {
         a4 = make_float4(a4.x * inv_den[u], a4.y * inv_den[u], a4.z * inv_den[u], a4.w * inv_den[u]);
         const float part = fmaf(a4.w, yy[u].w, fmaf(a4.z, yy[u].z, fmaf(a4.y, yy[u].y, fmaf(a4.x, yy[u].x, 0.f))));
-        side1 = tree8_lanes(part);
+        side1 = halves_sum_lanes<L::VCH>(part);
       }
       if (valid) {
         float t[4] = {dd.x, dd.y, dd.z, dd.w};
@@ -235,7 +255,7 @@ __device__ __forceinline__ void load_resident_grad(const float* __restrict__ g, 
       part[c] = fmaf(gd[4 * c + 3], yy.w, fmaf(gd[4 * c + 2], yy.z, fmaf(gd[4 * c + 1], yy.y, fmaf(gd[4 * c], yy.x, 0.f))));
     }
   }
-  gy = tree8(part);
+  gy = halves_sum<L::VCH>(part);
 }
 
 // dot of R resident rows with one streamed row; also hands back the two side slots of the streamed row.

@@ -126,6 +126,10 @@ void hept_set_bwd_stage_mask(int mask);
 void hept_set_engine(int engine);
 int hept_get_engine(void);
 
+/* backward tile kernels: 1 = one lane per row (attn_bwd.cu), 2 = lane pairs + packed FFMA2 (attn_bwd2.cu). */
+void hept_set_bwd_variant(int variant);
+int hept_get_bwd_variant(void);
+
 /* self-test of the tcgen05 / TMEM building blocks (hept_b200/csrc/umma.cuh): S = A B^T with A (128,32),
  * Bm (112,32) both K-major, then O = S V with S read back from TMEM and V (112,32) MN-major.
  * Outputs S_out (128,112), O_out (128,32).  Used by tests/test_gpu_umma.py only. */

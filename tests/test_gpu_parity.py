@@ -52,8 +52,10 @@ def engine(request):
 
     lib = _lib.load()
     lib.hept_set_engine(1 if request.param == "tcgen05" else 0)
+    lib.hept_set_bwd_variant(2 if request.param == "tcgen05" else 1)   # covers both generations of backward tiles
     yield request.param
-    lib.hept_set_engine(0)
+    lib.hept_set_engine(1)
+    lib.hept_set_bwd_variant(1)
 
 
 def dev():

@@ -14,6 +14,7 @@ from hept_b200 import ops
 
 from hept_b200 import _lib
 _lib.load().hept_set_engine(1 if os.environ.get("HEPT_ENGINE", "simt") == "tcgen05" else 0)
+_lib.load().hept_set_bwd_variant(int(os.environ.get("HEPT_BWD", "1")))
 n_raw = int(sys.argv[1]) if len(sys.argv) > 1 else 60000
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 cfg, params, inp, g = bench.make_event(7, n_raw)
