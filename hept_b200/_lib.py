@@ -37,7 +37,8 @@ SIGNATURES = {
     "hept_keys_from_region_indices": (C.c_int, [_SP, _p, _p, _p, _p, _p, _p, _p]),
     "hept_argsort_workspace_bytes": (_sz, [_i32, _i32]),
     "hept_segmented_argsort": (C.c_int, [_p, _i32, _i32, _p, _p, _sz, _p]),
-    "hept_block_attention_fwd": (C.c_int, [_SP, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "hept_hat_coords": (C.c_int, [_SP, _p, _p, _p, _p]),
+    "hept_block_attention_fwd": (C.c_int, [_SP, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "hept_or_combine": (C.c_int, [_SP, _p, _p, _p, _p]),
     "hept_attention_bwd_workspace_bytes": (_sz, [_SP]),
     "hept_block_attention_bwd": (C.c_int, [_SP] + [_p] * 14 + [_sz, _p]),

@@ -23,20 +23,21 @@ static int g_bwd_variant = 1;
 int bwd_variant() { return g_bwd_variant; }
 
 struct FwdPlan {
-  size_t ext_bytes, span_bytes, proj_bytes, keys_bytes, sort_bytes, stage_bytes, total;
+  size_t ext_bytes, span_bytes, hat_bytes, proj_bytes, keys_bytes, sort_bytes, stage_bytes, total;
 };
 static FwdPlan plan_fwd(const hept_shape* s) {
   FwdPlan p;
   const size_t th = (size_t)s->T * s->H, thn = th * s->N;
   p.ext_bytes = align_up(sizeof(uint32_t) * 2 * th, 256);
   p.span_bytes = align_up(sizeof(float) * th, 256);
+  p.hat_bytes = align_up(sizeof(float) * (size_t)s->N * s->H * 8, 256);
   p.proj_bytes = align_up(sizeof(float) * 2 * thn, 256);
   p.keys_bytes = align_up(sizeof(float) * 2 * thn, 256);
   p.sort_bytes = align_up(hept_argsort_workspace_bytes((int32_t)(2 * th), s->N), 256);
   p.stage_bytes = align_up(sizeof(float) * (size_t)s->H * s->N * s->T * kStageRow, 256);
   // proj/keys/sort scratch is dead once the permutations exist; the staging rows reuse that space.
   size_t front = p.proj_bytes + p.keys_bytes + p.sort_bytes;
-  p.total = p.ext_bytes + p.span_bytes + (front > p.stage_bytes ? front : p.stage_bytes);
+  p.total = p.ext_bytes + p.span_bytes + p.hat_bytes + (front > p.stage_bytes ? front : p.stage_bytes);
   return p;
 }
 
@@ -83,6 +84,7 @@ extern "C" int hept_attention_fwd(const hept_shape* s, const float* q, const flo
   char* w = (char*)workspace;
   void* ext = w;                       w += p.ext_bytes;
   float* span = (float*)w;             w += p.span_bytes;
+  float* hat = (float*)w;              w += p.hat_bytes;
   float* stage = (float*)w;            // aliases proj/keys/sort scratch (dead by then)
   float* proj = (float*)w;             w += p.proj_bytes;
   float* keys = (float*)w;             w += p.keys_bytes;
@@ -94,6 +96,7 @@ extern "C" int hept_attention_fwd(const hept_shape* s, const float* q, const flo
   else rc = hept_keys_from_region_indices(s, proj, span, region_eta, region_phi, regions_h, keys, stream);
   if (rc) return rc;
   if ((rc = hept_segmented_argsort(keys, 2 * s->T * s->H, s->N, positions, sort_ws, p.sort_bytes, stream))) return rc;
-  if ((rc = hept_block_attention_fwd(s, q, k, v, coords, scale, positions, stage, stream))) return rc;
+  if ((rc = hept_hat_coords(s, coords, scale, hat, stream))) return rc;
+  if ((rc = hept_block_attention_fwd(s, q, k, v, coords, scale, hat, positions, stage, stream))) return rc;
   return hept_or_combine(s, stage, out_pre, den_sum, stream);
 }

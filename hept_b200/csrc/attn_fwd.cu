@@ -134,8 +134,8 @@ static int launch_fwd(const hept_shape* s, const float* q, const float* k, const
   return HEPT_OK;
 }
 
-int block_attention_fwd_tc(const hept_shape* s, const float* q, const float* k, const float* v, const float* coords,
-                           const float* scale, const int32_t* positions, float* stage, cudaStream_t st);
+int block_attention_fwd_tc(const hept_shape* s, const float* q, const float* k, const float* v, const float* hat_coords,
+                           const int32_t* positions, float* stage, cudaStream_t st);
 
 }  // namespace hept
 
@@ -146,13 +146,16 @@ extern "C" int hept_shape_supported(int32_t D, int32_t C, int32_t B) {
 }
 
 extern "C" int hept_block_attention_fwd(const hept_shape* s, const float* q, const float* k, const float* v,
-                                        const float* coords, const float* scale, const int32_t* positions,
-                                        float* stage, void* stream) {
+                                        const float* coords, const float* scale, const float* hat_coords,
+                                        const int32_t* positions, float* stage, void* stream) {
   if (int rc = validate_shape(s)) return rc;
   HEPT_REQUIRE(q && k && v && coords && scale && positions && stage, HEPT_EINVAL, "block_attention_fwd: null pointer");
   HEPT_REQUIRE((long long)s->T * s->H <= 65535, HEPT_EINVAL, "block_attention_fwd: T*H too large");
   cudaStream_t st = (cudaStream_t)stream;
-  if (engine() == 1) return block_attention_fwd_tc(s, q, k, v, coords, scale, positions, stage, st);
+  if (engine() == 1) {
+    HEPT_REQUIRE(hat_coords, HEPT_EINVAL, "block_attention_fwd: the tcgen05 engine needs hat_coords (hept_hat_coords)");
+    return block_attention_fwd_tc(s, q, k, v, hat_coords, positions, stage, st);
+  }
   if (s->D == 24 && s->C == 6 && s->B == 100) return launch_fwd<24, 6, 100, 5, 2, 2>(s, q, k, v, coords, scale, positions, stage, st);
   if (s->D == 24 && s->C == 4 && s->B == 100) return launch_fwd<24, 4, 100, 5, 2, 2>(s, q, k, v, coords, scale, positions, stage, st);
   if (s->D == 8 && s->C == 6 && s->B == 10) return launch_fwd<8, 6, 10, 4, 2, 1>(s, q, k, v, coords, scale, positions, stage, st);

@@ -38,9 +38,8 @@ constexpr int kTcThreads = 256;   // warps 0-3 and 4-7 both map onto TMEM lanes 
 template <int D, int C, int B, int TILES>
 __global__ void __launch_bounds__(kTcThreads, 2)
     block_attn_fwd_tc_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
-                             const float* __restrict__ coords, const float* __restrict__ scale,
-                             const int32_t* __restrict__ positions, int N, int H, int T, int raw_size,
-                             float* __restrict__ stage) {
+                             const float* __restrict__ hatc, const int32_t* __restrict__ positions, int N, int H, int T,
+                             int raw_size, float* __restrict__ stage) {
   constexpr int E = D + C;
   static_assert(E + 2 <= 32 && D % 4 == 0 && D <= kTcVN && B <= kTcN && B <= kTcM, "tile shape");
   using SM = TcFwdSmem<D, C, B>;
@@ -55,7 +54,6 @@ __global__ void __launch_bounds__(kTcThreads, 2)
   const int nb = N / B;
   const int32_t* qpos = positions + (size_t)th * N;
   const int32_t* kpos = positions + ((size_t)T * H + th) * N;
-  const float* scale_h = scale + h * C;
   const int tid = threadIdx.x, warp = tid >> 5;
   const int sub = tid >> 3, c = tid & 7;                 // gather role: 8 lanes per row, 32 rows per pass
   const int row = (warp & 3) * 32 + (tid & 31);          // epilogue role: TMEM lane = query row
@@ -71,94 +69,115 @@ __global__ void __launch_bounds__(kTcThreads, 2)
   const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
   const uint32_t sbase = umma::smem_u32(smem);
   uint32_t phase = 0;
-  const float4 mult = chunk_multiplier<D, C>(scale_h, c);
+
+  // chunk c of a hat row: feature columns come from q / k, the coordinate columns from hat_coords (already scaled)
+  constexpr int XCH = D / 4;
+  auto hat_chunk = [&](const float* __restrict__ x, int n) -> float4 {
+    const float* src = c < XCH ? x + ((size_t)n * H + h) * D + 4 * c : hatc + ((size_t)n * H + h) * 8 + 4 * (c - XCH);
+    return (c < XCH + 2 && n < raw_size) ? ldg4(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+
+  // rows that never hold data are written once: query rows [B,128) zero, key rows [B,112) zero with nk = -1e30
+  // (P = ex2(-1e30) = 0), value rows [B,112) zero
+  for (int rr = B + sub; rr < kTcM; rr += kTcThreads / 8) {
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(smem + SM::OFF_AH + umma::sw128_offset(rr, c)) = z;
+    *reinterpret_cast<float4*>(smem + SM::OFF_AL + umma::sw128_offset(rr, c)) = z;
+    if (rr < kTcN) {
+      *reinterpret_cast<float4*>(smem + SM::OFF_KH + umma::sw128_offset(rr, c)) =
+          c == 7 ? make_float4(0.f, 0.f, umma::tf32_hi(-1e30f), 0.f) : z;
+      *reinterpret_cast<float4*>(smem + SM::OFF_KL + umma::sw128_offset(rr, c)) = z;
+      *reinterpret_cast<float4*>(smem + SM::OFF_VH + umma::sw128b32_offset(rr, c)) = z;
+      *reinterpret_cast<float4*>(smem + SM::OFF_VL + umma::sw128b32_offset(rr, c)) = z;
+    }
+    if (c == 0) s_nq[rr] = 0.f;
+  }
 
 #pragma unroll 1
   for (int it = 0; it < TILES; ++it) {
     const int blk = blockIdx.x * TILES + it;
     if (blk >= nb) break;
 
-    // ---- gather: all indices, then all rows (the loads of a tile are in flight together) ----------------
-    constexpr int KP = (kTcN + 31) / 32, QP = kTcM / 32;
-    int nk_idx[KP], nq_idx[QP];
+    // ---- gather: all indices, then all rows (every load of the tile is in flight before the first use) ------
+    constexpr int PASSES = (B + 31) / 32;                 // 32 rows per pass; the last pass is partial
+    int nk_idx[PASSES], nq_idx[PASSES];
     const int n0 = __ldg(kpos + (size_t)blk * B + (B - 1));
 #pragma unroll
-    for (int ps = 0; ps < KP; ++ps) { const int j = ps * 32 + sub; nk_idx[ps] = j < B ? __ldg(kpos + (size_t)blk * B + j) : -1; }
+    for (int ps = 0; ps < PASSES; ++ps) {
+      const int r = ps * 32 + sub;
+      nk_idx[ps] = r < B ? __ldg(kpos + (size_t)blk * B + r) : -1;
+      nq_idx[ps] = r < B ? __ldg(qpos + (size_t)blk * B + r) : -1;
+    }
+    const float4 ctr = hat_chunk(k, n0);
+    float4 dk[PASSES], vk[PASSES], dq[PASSES];
 #pragma unroll
-    for (int ps = 0; ps < QP; ++ps) { const int i = ps * 32 + sub; nq_idx[ps] = i < B ? __ldg(qpos + (size_t)blk * B + i) : -1; }
-    const float4 ctr_raw = load_raw_chunk<D, C>(k, coords, n0, h, H, c, n0 < raw_size);
-    float4 dk[KP], vk[KP], dq[QP];
-#pragma unroll
-    for (int ps = 0; ps < KP; ++ps) {
-      const int n = nk_idx[ps];
-      const bool real = n >= 0 && n < raw_size;
-      dk[ps] = load_raw_chunk<D, C>(k, coords, n < 0 ? 0 : n, h, H, c, real);
-      vk[ps] = (c < D / 4 && real) ? ldg4(v + ((size_t)n * H + h) * D + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int ps = 0; ps < PASSES; ++ps) {
+      const int nkk = nk_idx[ps], nqq = nq_idx[ps];
+      dk[ps] = nkk >= 0 ? hat_chunk(k, nkk) : make_float4(0.f, 0.f, 0.f, 0.f);
+      dq[ps] = nqq >= 0 ? hat_chunk(q, nqq) : make_float4(0.f, 0.f, 0.f, 0.f);
+      vk[ps] = (nkk >= 0 && c < XCH && nkk < raw_size) ? ldg4(v + ((size_t)nkk * H + h) * D + 4 * c)
+                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
-    for (int ps = 0; ps < QP; ++ps) {
-      const int n = nq_idx[ps];
-      dq[ps] = load_raw_chunk<D, C>(q, coords, n < 0 ? 0 : n, h, H, c, n >= 0 && n < raw_size);
-    }
-    // (no arithmetic above this line: every load of the tile is in flight before the first use)
-    const float4 ctr = apply_multiplier(ctr_raw, mult);
-    // keys + values -> Kh, Kl, Vh, Vl
+    for (int ps = 0; ps < PASSES; ++ps) {
+      const int r = ps * 32 + sub;
+      // the last pass covers rows [32*(PASSES-1), B): warps whose 4 rows are all past B skip it
+      if (ps == PASSES - 1 && (ps * 32 + (warp << 2)) >= B) continue;
+      const bool in = r < B;
+      // ---- key + value row r -> Kh, Kl, Vh, Vl
+      {
+        float4 d = dk[ps];
+        d.x -= ctr.x; d.y -= ctr.y; d.z -= ctr.z; d.w -= ctr.w;
+        const float sq = tree8_lanes(chunk_sq<E>(d, c));
+        const float nk2 = kLog2e * (-0.5f * sq);
+        float hi[4], lo[4];
+        const float dv[4] = {d.x, d.y, d.z, d.w};
 #pragma unroll
-    for (int ps = 0; ps < KP; ++ps) {
-      const int j = ps * 32 + sub;
-      const bool in = nk_idx[ps] >= 0;
-      float4 d = apply_multiplier(dk[ps], mult);
-      if (in) { d.x -= ctr.x; d.y -= ctr.y; d.z -= ctr.z; d.w -= ctr.w; }
-      const float sq = tree8_lanes(chunk_sq<E>(d, c));          // all lanes take part in the shuffle
-      const float nk2 = in ? kLog2e * (-0.5f * sq) : -1e30f;    // padded keys: P = ex2(-1e30) = 0
-      float hi[4], lo[4];
-      const float dv[4] = {d.x, d.y, d.z, d.w};
+        for (int u = 0; u < 4; ++u) {
+          const float x = (4 * c + u < E) ? dv[u] : 0.f;
+          hi[u] = umma::tf32_hi(x);
+          lo[u] = x - hi[u];
+        }
+        if (c == 7) {  // K slots 30, 31 carry the key-side norm, split three ways: nk2 = h0 + h1 + l0
+          const float h0 = umma::tf32_hi(nk2);
+          const float r1 = nk2 - h0;
+          const float h1 = umma::tf32_hi(r1);
+          hi[2] = h0; hi[3] = h1;
+          lo[2] = r1 - h1; lo[3] = 0.f;
+        }
+        if (in) {
+          const uint32_t off = umma::sw128_offset(r, c);
+          *reinterpret_cast<float4*>(smem + SM::OFF_KH + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<float4*>(smem + SM::OFF_KL + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+          const float4 vv = vk[ps];
+          const float vh[4] = {umma::tf32_hi(vv.x), umma::tf32_hi(vv.y), umma::tf32_hi(vv.z), umma::tf32_hi(vv.w)};
+          const uint32_t voff = umma::sw128b32_offset(r, c);
+          *reinterpret_cast<float4*>(smem + SM::OFF_VH + voff) = make_float4(vh[0], vh[1], vh[2], vh[3]);
+          *reinterpret_cast<float4*>(smem + SM::OFF_VL + voff) = make_float4(vv.x - vh[0], vv.y - vh[1], vv.z - vh[2], vv.w - vh[3]);
+        }
+      }
+      // ---- query row r -> Ah, Al, nq2
+      {
+        float4 d = dq[ps];
+        d.x -= ctr.x; d.y -= ctr.y; d.z -= ctr.z; d.w -= ctr.w;
+        const float nq2 = kLog2e * (-0.5f * tree8_lanes(chunk_sq<E>(d, c)));
+        float hi[4], lo[4];
+        const float dv[4] = {d.x, d.y, d.z, d.w};
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const float x = (4 * c + u < E) ? dv[u] : 0.f;
-        hi[u] = umma::tf32_hi(x);
-        lo[u] = x - hi[u];
+        for (int u = 0; u < 4; ++u) {
+          const int e = 4 * c + u;
+          const float x = e < E ? dv[u] * kLog2e : 0.f;
+          hi[u] = umma::tf32_hi(x);
+          lo[u] = x - hi[u];
+          if (e == 30 || e == 31) { hi[u] = 1.f; lo[u] = 0.f; }
+        }
+        if (in) {
+          if (c == 0) s_nq[r] = nq2;
+          const uint32_t off = umma::sw128_offset(r, c);
+          *reinterpret_cast<float4*>(smem + SM::OFF_AH + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<float4*>(smem + SM::OFF_AL + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        }
       }
-      if (c == 7) {  // K slots 30, 31 carry the key-side norm, split three ways: nk2 = h0 + h1 + l0
-        const float h0 = umma::tf32_hi(nk2);
-        const float r1 = in ? nk2 - h0 : 0.f;
-        const float h1 = umma::tf32_hi(r1);
-        hi[2] = h0; hi[3] = h1;
-        lo[2] = r1 - h1; lo[3] = 0.f;
-      }
-      if (j < kTcN) {
-        const uint32_t off = umma::sw128_offset(j, c);
-        *reinterpret_cast<float4*>(smem + SM::OFF_KH + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<float4*>(smem + SM::OFF_KL + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-        const float4 vv = vk[ps];
-        const float vh[4] = {umma::tf32_hi(vv.x), umma::tf32_hi(vv.y), umma::tf32_hi(vv.z), umma::tf32_hi(vv.w)};
-        const uint32_t voff = umma::sw128b32_offset(j, c);
-        *reinterpret_cast<float4*>(smem + SM::OFF_VH + voff) = make_float4(vh[0], vh[1], vh[2], vh[3]);
-        *reinterpret_cast<float4*>(smem + SM::OFF_VL + voff) = make_float4(vv.x - vh[0], vv.y - vh[1], vv.z - vh[2], vv.w - vh[3]);
-      }
-    }
-    // queries -> Ah, Al, nq2
-#pragma unroll
-    for (int ps = 0; ps < QP; ++ps) {
-      const int i = ps * 32 + sub;
-      const bool in = nq_idx[ps] >= 0;
-      float4 d = apply_multiplier(dq[ps], mult);
-      if (in) { d.x -= ctr.x; d.y -= ctr.y; d.z -= ctr.z; d.w -= ctr.w; }
-      const float nq2 = kLog2e * (-0.5f * tree8_lanes(chunk_sq<E>(d, c)));
-      if (c == 0) s_nq[i] = nq2;
-      float hi[4], lo[4];
-      const float dv[4] = {d.x, d.y, d.z, d.w};
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int e = 4 * c + u;
-        const float x = (e < E && in) ? dv[u] * kLog2e : 0.f;
-        hi[u] = umma::tf32_hi(x);
-        lo[u] = x - hi[u];
-        if ((e == 30 || e == 31) && in) { hi[u] = 1.f; lo[u] = 0.f; }
-      }
-      const uint32_t off = umma::sw128_offset(i, c);
-      *reinterpret_cast<float4*>(smem + SM::OFF_AH + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-      *reinterpret_cast<float4*>(smem + SM::OFF_AL + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
     }
     umma::fence_async_smem();
     umma::fence_before_sync();
@@ -273,8 +292,8 @@ __global__ void __launch_bounds__(kTcThreads, 2)
 }
 
 template <int D, int C, int B, int TILES>
-static int launch_fwd_tc(const hept_shape* s, const float* q, const float* k, const float* v, const float* coords,
-                         const float* scale, const int32_t* positions, float* stage, cudaStream_t st) {
+static int launch_fwd_tc(const hept_shape* s, const float* q, const float* k, const float* v, const float* hatc,
+                         const int32_t* positions, float* stage, cudaStream_t st) {
   using SM = TcFwdSmem<D, C, B>;
   auto kern = block_attn_fwd_tc_kernel<D, C, B, TILES>;
   const size_t smem = SM::TOTAL + 1024;
@@ -287,16 +306,16 @@ static int launch_fwd_tc(const hept_shape* s, const float* q, const float* k, co
   }
   const int nb = s->N / s->B;
   dim3 grid((nb + TILES - 1) / TILES, s->T * s->H);
-  kern<<<grid, kTcThreads, smem, st>>>(q, k, v, coords, scale, positions, s->N, s->H, s->T, s->raw_size, stage);
+  kern<<<grid, kTcThreads, smem, st>>>(q, k, v, hatc, positions, s->N, s->H, s->T, s->raw_size, stage);
   HEPT_CHECK_LAUNCH("block_attn_fwd_tc");
   return HEPT_OK;
 }
 
-int block_attention_fwd_tc(const hept_shape* s, const float* q, const float* k, const float* v, const float* coords,
-                           const float* scale, const int32_t* positions, float* stage, cudaStream_t st) {
-  if (s->D == 24 && s->C == 6 && s->B == 100) return launch_fwd_tc<24, 6, 100, 4>(s, q, k, v, coords, scale, positions, stage, st);
-  if (s->D == 24 && s->C == 4 && s->B == 100) return launch_fwd_tc<24, 4, 100, 4>(s, q, k, v, coords, scale, positions, stage, st);
-  if (s->D == 8 && s->C == 6 && s->B == 10) return launch_fwd_tc<8, 6, 10, 4>(s, q, k, v, coords, scale, positions, stage, st);
+int block_attention_fwd_tc(const hept_shape* s, const float* q, const float* k, const float* v, const float* hatc,
+                           const int32_t* positions, float* stage, cudaStream_t st) {
+  if (s->D == 24 && s->C == 6 && s->B == 100) return launch_fwd_tc<24, 6, 100, 4>(s, q, k, v, hatc, positions, stage, st);
+  if (s->D == 24 && s->C == 4 && s->B == 100) return launch_fwd_tc<24, 4, 100, 4>(s, q, k, v, hatc, positions, stage, st);
+  if (s->D == 8 && s->C == 6 && s->B == 10) return launch_fwd_tc<8, 6, 10, 4>(s, q, k, v, hatc, positions, stage, st);
   set_error("block_attention_fwd (tensor-core engine): (D=%d, C=%d, B=%d) not compiled in", s->D, s->C, s->B);
   return HEPT_EUNSUPPORTED;
 }

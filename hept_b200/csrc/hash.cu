@@ -118,6 +118,19 @@ __global__ void __launch_bounds__(256) hash_project_kernel(const float* __restri
   }
 }
 
+// hat_coords[n,h,0:8] = scale[h,c] * coords[n,c] (c < C), zero padded: the coordinate part of q_hat / k_hat, which is
+// the same for every table and for the query and the key side, materialised once so the tile gathers read two
+// 16-byte chunks instead of C scalars and C multiplies per row.
+__global__ void hat_coords_kernel(const float* __restrict__ coords, const float* __restrict__ scale, int N, int H, int C,
+                                  int raw_size, float* __restrict__ hat) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // (n, h, c8)
+  if (i >= (size_t)N * H * 8) return;
+  const int c = (int)(i & 7);
+  const int h = (int)((i >> 3) % H);
+  const size_t n = (i >> 3) / H;
+  hat[i] = (c < C && (int)n < raw_size) ? __fmul_rn(scale[h * C + c], coords[n * C + c]) : 0.f;
+}
+
 __global__ void finish_span_kernel(const uint32_t* __restrict__ ext, int th, float* __restrict__ span) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < th) span[i] = __fsub_rn(from_ordered_bits(ext[2 * i + 1]), from_ordered_bits(ext[2 * i + 0]));
@@ -210,6 +223,17 @@ extern "C" int hept_hash_project(const hept_shape* s, const float* q, const floa
   if (rc) return rc;
   finish_span_kernel<<<(th + 127) / 128, 128, 0, st>>>(ext, th, span);
   HEPT_CHECK_LAUNCH("finish_span");
+  return HEPT_OK;
+}
+
+extern "C" int hept_hat_coords(const hept_shape* s, const float* coords, const float* scale, float* hat_coords,
+                               void* stream) {
+  if (int rc = validate_shape(s)) return rc;
+  HEPT_REQUIRE(coords && scale && hat_coords && s->C <= 8, HEPT_EINVAL, "hat_coords: bad argument");
+  const size_t total = (size_t)s->N * s->H * 8;
+  hat_coords_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(coords, scale, s->N, s->H, s->C,
+                                                                                     s->raw_size, hat_coords);
+  HEPT_CHECK_LAUNCH("hat_coords");
   return HEPT_OK;
 }
 

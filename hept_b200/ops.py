@@ -151,6 +151,17 @@ def segmented_argsort(keys: torch.Tensor) -> torch.Tensor:
     return pos
 
 
+def hat_coords(d: Dims, coords, scale) -> torch.Tensor:
+    """-> (N, H, 8): scale[h,c] * coords[n,c], zero padded (the coordinate part of q_hat / k_hat)."""
+    lib = _lib.load()
+    coords = _need(coords, "coords", torch.float32, (d.N, d.C))
+    scale = _need(scale, "scale", torch.float32, (d.H, d.C))
+    hat = torch.empty(d.N, d.H, 8, dtype=torch.float32, device=coords.device)
+    s = d.struct()
+    _lib.check(lib.hept_hat_coords(C.byref(s), _ptr(coords), _ptr(scale), _ptr(hat), _stream(coords)), "hept_hat_coords")
+    return hat
+
+
 def block_attention_fwd(d: Dims, q, k, v, coords, scale, positions) -> torch.Tensor:
     """-> stage (H, N, T, 32): numerator [0:D) and normaliser [D] per (head, hit, table), original hit order."""
     lib = _lib.load()
@@ -161,9 +172,10 @@ def block_attention_fwd(d: Dims, q, k, v, coords, scale, positions) -> torch.Ten
     scale = _need(scale, "scale", torch.float32, (d.H, d.C))
     pos = _need(positions, "positions", torch.int32, (2, d.T, d.H, d.N))
     stage = torch.empty(d.H, d.N, d.T, STAGE_ROW, dtype=torch.float32, device=q.device)
+    hat = hat_coords(d, coords, scale)
     s = d.struct()
-    _lib.check(lib.hept_block_attention_fwd(C.byref(s), _ptr(q), _ptr(k), _ptr(v), _ptr(coords), _ptr(scale), _ptr(pos),
-                                            _ptr(stage), _stream(q)), "hept_block_attention_fwd")
+    _lib.check(lib.hept_block_attention_fwd(C.byref(s), _ptr(q), _ptr(k), _ptr(v), _ptr(coords), _ptr(scale), _ptr(hat),
+                                            _ptr(pos), _ptr(stage), _stream(q)), "hept_block_attention_fwd")
     return stage
 
 

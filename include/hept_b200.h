@@ -64,6 +64,10 @@ int hept_hash_project(const hept_shape* s, const float* q, const float* k, const
                       const float* scale, const float* alpha, float* proj, float* span,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- a3, coordinate half of prep_qk (example/hept.py:25): hat_coords (N, H, 8) = scale[h,c] * coords[n,c], zero
+ * padded (rows >= raw_size zero).  Shared by every table and by the query / key side of the tile kernels. */
+int hept_hat_coords(const hept_shape* s, const float* coords, const float* scale, float* hat_coords, void* stream);
+
 /* ---- a6  AND-construction, example/ flavour (example/hept.py:63-65) ---------------------------
  * keys[s,t,h,n] = proj[s,t,h,n] + float(combined_shifts[t,h,n]) * span[t,h]   (convert, mul, add). */
 int hept_keys_from_packed_shifts(const hept_shape* s, const float* proj, const float* span,
@@ -83,11 +87,12 @@ int hept_segmented_argsort(const float* keys, int32_t num_segments, int32_t n, i
 
 /* ---- a8+a9+a10+a11  sort_to_buckets, qkv_res, unsort_from_buckets ------------------------------
  * (example/hept_utils.py:74-97, example/hept.py:7-18,70-78).  positions (2, T, H, N) int32.
+ * hat_coords (N, H, 8) from hept_hat_coords (required by the tcgen05 engine, may be null for the fp32 engine).
  * Output `stage` (H, N, T, 32): per hit/head/table one 128-byte row holding the numerator
  * so[0..D) and, at [D], the normaliser denom = rowsum + 1e-20, already back in ORIGINAL hit order. */
 int hept_block_attention_fwd(const hept_shape* s, const float* q, const float* k, const float* v,
-                             const float* coords, const float* scale, const int32_t* positions,
-                             float* stage, void* stream);
+                             const float* coords, const float* scale, const float* hat_coords,
+                             const int32_t* positions, float* stage, void* stream);
 
 /* ---- a12  OR-combine (example/hept.py:79) -----------------------------------------------------
  * out_pre (N, H*D) = sum_t numer / sum_t denom ; den_sum (N, H) kept for backward. */

@@ -46,7 +46,7 @@ def test_library_rejects_bad_arguments_without_touching_a_gpu():
     lib = _lib.load()
     bad = _lib.Shape(6050, 8, 24, 6, 3, 100, 6050)        # N not a multiple of block_size
     one = ctypes.c_void_p(8)                              # non-null dummy pointers: validation fails first
-    rc = lib.hept_block_attention_fwd(ctypes.byref(bad), one, one, one, one, one, one, one, None)
+    rc = lib.hept_block_attention_fwd(ctypes.byref(bad), one, one, one, one, one, one, one, one, None)
     assert rc == _lib.HEPT_EINVAL and b"multiple of block_size" in lib.hept_last_error()
     rc = lib.hept_segmented_argsort(None, 4, 100, one, one, 0, None)
     assert rc == _lib.HEPT_EINVAL
@@ -54,7 +54,7 @@ def test_library_rejects_bad_arguments_without_touching_a_gpu():
     rc = lib.hept_block_attention_bwd(ctypes.byref(ok), *([one] * 14), 16, None)
     assert rc == _lib.HEPT_EWORKSPACE
     odd = _lib.Shape(6000, 8, 16, 6, 3, 100, 6000)        # D=16 not compiled in: no slow fallback
-    rc = lib.hept_block_attention_fwd(ctypes.byref(odd), one, one, one, one, one, one, one, None)
+    rc = lib.hept_block_attention_fwd(ctypes.byref(odd), one, one, one, one, one, one, one, one, None)
     assert rc == _lib.HEPT_EUNSUPPORTED
     with pytest.raises(ValueError):
         _lib.check(_lib.HEPT_EINVAL, "x")
