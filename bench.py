@@ -354,10 +354,22 @@ def kernel_roofline(resident, gouts, cfg, mod, w_rpe, peak, peak_src, n_sets):
     lib.hept_set_bwd_stage_mask(7)
     top = max(times, key=times.get)
     achieved = per_hit[top] * N_RAW / times[top] / 1e9
+    # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (tools/ncu_summary.py)
+    traffic, tsrc = None, None
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        variant = lib.hept_get_bwd_variant()
+        names = {"block_attn_fwd": "block_attn_fwd_tc_kernel" if lib.hept_get_engine() else "block_attn_fwd_kernel",
+                 "block_attn_bwd_dq": "block_attn_bwd_dq_kernel" if variant == 1 else "block_attn_bwd_pair_kernel",
+                 "block_attn_bwd_dkv": "block_attn_bwd_dkv_kernel" if variant == 1 else "block_attn_bwd_pair_kernel"}
+        if names[top] in tj:
+            traffic, tsrc = tj[names[top]]["dram_bytes_per_launch"], "profiles/r1_traffic.json (" + tj[names[top]]["source"] + ")"
     flops = {"block_attn_fwd": 2 * T * H * B * (D + C + D), "block_attn_bwd_dq": 2 * T * H * B * (2 * (D + C) + D),
              "block_attn_bwd_dkv": 2 * T * H * B * (2 * (D + C) + 2 * D)}
     return {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": None, "peak_source": peak_src, "bytes_per_launch": per_hit[top] * N_RAW,
+            "traffic": traffic, "traffic_source": tsrc, "peak_source": peak_src, "bytes_per_launch": per_hit[top] * N_RAW,
             "kernel_ms": {k: v * 1e3 for k, v in times.items()},
             "fp32_tflops": {k: flops[k] * N_RAW / times[k] / 1e12 for k in times},
             "note": "tile kernels are fp32-FMA bound, not HBM bound (SURVEY.md 7.3-3); fp32_tflops is against ~74 TF/s SIMT peak"}
