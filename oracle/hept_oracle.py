@@ -148,7 +148,7 @@ def block_kernel_attention(sq: Tensor, sk: Tensor, sv: Tensor) -> Tuple[Tensor, 
 def inverse_permutation(perm: Tensor) -> Tensor:
     n = perm.shape[-1]
     inv = torch.empty_like(perm)
-    src = torch.arange(n, dtype=perm.dtype).expand_as(perm)
+    src = torch.arange(n, dtype=perm.dtype, device=perm.device).expand_as(perm)
     inv.scatter_(-1, perm, src)
     return inv
 
@@ -208,7 +208,7 @@ def attention_core(
 
     src_flavour = raw_size is not None
     if src_flavour:
-        keep = (torch.arange(n) < raw_size).to(q_hat.dtype)[None, :, None]
+        keep = (torch.arange(n, device=q_hat.device) < raw_size).to(q_hat.dtype)[None, :, None]
         q_hat, k_hat, v = q_hat * keep, k_hat * keep, v * keep
         # multiplying by 0 would turn an inf coordinate into nan; the reference
         # zeroes the padded coords before the call (src/.../transformer.py:57).
