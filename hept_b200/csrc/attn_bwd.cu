@@ -31,7 +31,7 @@ __global__ void __launch_bounds__((TileLayout<D, C, B, G, 1>::THREADS), MINB)
   float4* ks = smem;
   float4* vs = smem + G * B * L::ROW_CHUNKS;
 
-  const int th = blockIdx.y, t = th / H, h = th % H;
+  const int h = blockIdx.y / T, t = blockIdx.y % T, th = t * H + h;  // tables of one head run back to back: its q/k/v slices stay in L2
   const int nb = N / B;
   const int blk0 = blockIdx.x * G;
   const int32_t* qpos = positions + (size_t)th * N;
@@ -109,7 +109,7 @@ __global__ void __launch_bounds__((TileLayout<D, C, B, G, 1>::THREADS), MINB)
   float4* qs = smem;                           // [G*B][8]   q' rows: q'[0..E), nq, gy
   float4* gs = smem + G * B * L::ROW_CHUNKS;   // [G*B][D/4] gd rows
 
-  const int th = blockIdx.y, t = th / H, h = th % H;
+  const int h = blockIdx.y / T, t = blockIdx.y % T, th = t * H + h;  // tables of one head run back to back: its q/k/v slices stay in L2
   const int nb = N / B;
   const int blk0 = blockIdx.x * G;
   const int32_t* qpos = positions + (size_t)th * N;

@@ -34,7 +34,7 @@ __global__ void __launch_bounds__((PairLayout<D, C, B, G, R>::THREADS), MINB)
   float4* hs = smem;                                   // [G*B][8]   streamed hat rows
   float4* as = smem + G * B * P::ROW_CHUNKS;           // [G*B][D/4] streamed aux rows (v or gd)
 
-  const int th = blockIdx.y, t = th / H, h = th % H;
+  const int h = blockIdx.y / T, t = blockIdx.y % T, th = t * H + h;  // tables of one head run back to back: its q/k/v slices stay in L2
   const int nb = N / B;
   const int blk0 = blockIdx.x * G;
   const int32_t* qpos = positions + (size_t)th * N;

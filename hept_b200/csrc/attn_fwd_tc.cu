@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(kTcThreads, 2)
   __shared__ uint32_t tmem_slot;
   __shared__ float s_l[kTcM];               // row sums of the upper column half
 
-  const int th = blockIdx.y, t = th / H, h = th % H;
+  const int h = blockIdx.y / T, t = blockIdx.y % T, th = t * H + h;  // tables of one head run back to back: its q/k/v slices stay in L2
   const int nb = N / B;
   const int32_t* qpos = positions + (size_t)th * N;
   const int32_t* kpos = positions + ((size_t)T * H + th) * N;

@@ -86,9 +86,74 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* __re
   if (warp == 0) umma::tmem_dealloc<256>(tmem);
 }
 
+// Is the tf32 MMA bitwise symmetric under an exchange of its operands?  S = X Y^T and S' = Y X^T on the same
+// 112 x 32 fp32 matrices (rows 112..127 of the M side are zero), each accumulated over the same four K = 8 steps.
+__global__ void __launch_bounds__(128, 1) umma_symmetry_kernel(const float* __restrict__ X, const float* __restrict__ Y,
+                                                               float* __restrict__ S_xy, float* __restrict__ S_yx) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sX = smem;                       // 128 rows x 128 B (rows >= 112 zero)
+  uint8_t* sY = sX + kTM * 128;             // 128 rows x 128 B
+  __shared__ uint64_t mbar;
+  __shared__ uint32_t tmem_base_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int idx = tid; idx < kTM * 8; idx += 128) {
+    const int r = idx >> 3, c = idx & 7;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(sX + umma::sw128_offset(r, c)) = r < kTN ? *reinterpret_cast<const float4*>(X + r * kTK + 4 * c) : z;
+    *reinterpret_cast<float4*>(sY + umma::sw128_offset(r, c)) = r < kTN ? *reinterpret_cast<const float4*>(Y + r * kTK + 4 * c) : z;
+  }
+  if (tid == 0) umma::mbar_init(&mbar, 1);
+  if (warp == 0) umma::tmem_alloc<256>(&tmem_base_slot);
+  umma::fence_async_smem();
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem = tmem_base_slot;
+  if (tid == 0) {
+    constexpr uint32_t idesc = umma::idesc_tf32(kTM, kTN, false, false);
+#pragma unroll
+    for (int k = 0; k < kTK / 8; ++k) {
+      const uint64_t dx = umma::smem_desc_sw128(umma::smem_u32(sX) + 32 * k, 1024, 16);
+      const uint64_t dy = umma::smem_desc_sw128(umma::smem_u32(sY) + 32 * k, 1024, 16);
+      umma::mma_ss(tmem, dx, dy, idesc, k > 0);          // S_xy[i][j] = x_i . y_j
+      umma::mma_ss(tmem + 128, dy, dx, idesc, k > 0);    // S_yx[j][i] = y_j . x_i
+    }
+    umma::commit(&mbar);
+  }
+  umma::mbar_wait(&mbar, 0);
+  umma::fence_after_sync();
+  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+#pragma unroll 1
+  for (int c0 = 0; c0 < kTN; c0 += 16) {
+    float a[16], b[16];
+    umma::tmem_ld16(tmem + lane_base + c0, a);
+    umma::tmem_ld16(tmem + 128 + lane_base + c0, b);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { S_xy[tid * kTN + c0 + i] = a[i]; S_yx[tid * kTN + c0 + i] = b[i]; }
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc<256>(tmem);
+}
+
 }  // namespace hept
 
 using namespace hept;
+
+extern "C" int hept_debug_umma_symmetry(const float* X, const float* Y, float* S_xy, float* S_yx, void* stream) {
+  HEPT_REQUIRE(X && Y && S_xy && S_yx, HEPT_EINVAL, "umma_symmetry: null pointer");
+  const size_t smem = (size_t)2 * kTM * 128 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(umma_symmetry_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "umma_symmetry: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  umma_symmetry_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(X, Y, S_xy, S_yx);
+  HEPT_CHECK_LAUNCH("umma_symmetry");
+  return HEPT_OK;
+}
 
 extern "C" int hept_debug_umma_selftest(const float* A, const float* Bm, const float* V, float* S_out, float* O_out,
                                         void* stream) {

@@ -141,6 +141,10 @@ int hept_get_bwd_variant(void);
 int hept_debug_umma_selftest(const float* A, const float* Bm, const float* V, float* S_out, float* O_out,
                              void* stream);
 
+/* S_xy = X Y^T and S_yx = Y X^T (X, Y (112,32) fp32; outputs (128,112), rows >= 112 zero) on the tensor core: probes
+ * whether the tf32 MMA is bitwise symmetric under an exchange of its operands (tests/test_gpu_umma.py). */
+int hept_debug_umma_symmetry(const float* X, const float* Y, float* S_xy, float* S_yx, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

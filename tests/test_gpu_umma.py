@@ -28,3 +28,32 @@ def test_umma_selftest_exact_on_small_integers():
     O_ref = S_ref @ V.double()
     assert torch.equal(S.cpu().double(), S_ref), (S.cpu()[:2, :8], S_ref[:2, :8])
     assert torch.equal(O.cpu().double(), O_ref), (O.cpu()[:2, :8], O_ref[:2, :8])
+
+
+def test_tf32_mma_is_symmetric_under_operand_exchange():
+    """x_i . y_j from MMA(X, Y) and from MMA(Y, X) on random fp32 data: bit-identical?  (Decides whether a tensor-core
+    backward can recompute S and S^T in two kernels and still see the same dS; recorded, not required.)"""
+    import json
+    import os
+
+    from hept_b200 import _lib
+
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(1)
+    X = (torch.randn(112, 32, generator=g) * 3).to(dev)
+    Y = (torch.randn(112, 32, generator=g) * 3).to(dev)
+    A = torch.empty(128, 112, device=dev)
+    B = torch.empty(128, 112, device=dev)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    _lib.check(lib.hept_debug_umma_symmetry(p(X), p(Y), p(A), p(B), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)),
+               "hept_debug_umma_symmetry")
+    torch.cuda.synchronize()
+    s_xy, s_yx = A[:112].cpu(), B[:112].cpu().T
+    ref = X.cpu().double() @ Y.cpu().double().T
+    same = bool(torch.equal(s_xy, s_yx))
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/umma_symmetry.json", "w") as f:
+        json.dump({"bitwise_symmetric": same, "max_abs_diff": float((s_xy - s_yx).abs().max()),
+                   "tf32_rel_err": float((s_xy.double() - ref).norm() / ref.norm())}, f)
+    assert float((s_xy.double() - ref).norm() / ref.norm()) < 2e-3      # plain tf32 product: ~2^-11 relative
