@@ -3,10 +3,11 @@
 // scatter.  All segments are processed by the same launches (grid = tiles x segments), so the 2*T*H
 // independent sorts of one attention call fill the machine together.
 //
-// Stability: inside a tile, keys are ranked warp by warp, 32 at a time in index order, with
-// __match_any_sync giving each lane its rank among equal digits; tiles and warps are combined by
-// exclusive prefix sums in index order.  Equal keys therefore keep ascending original index, the
-// tie-break the oracle pins (torch.argsort(stable=True)).
+// Stability: inside a tile, keys are ranked warp by warp, 32 at a time in index order, with a ballot-built
+// mask of the lanes holding the same digit giving each lane its rank among equals; tiles and warps are
+// combined by exclusive prefix sums in index order.  Equal keys therefore keep ascending original index,
+// the tie-break the oracle pins (torch.argsort(stable=True)).  The tile is reordered in shared memory
+// first so that the global writes of a digit run are contiguous.
 #include "common.cuh"
 
 namespace hept {
@@ -17,6 +18,21 @@ constexpr int kSortThreads = 256;
 constexpr int kSortWarps = kSortThreads / 32;
 constexpr int kItemsPerThread = 16;
 constexpr int kTile = kSortThreads * kItemsPerThread;  // 4096 keys per CTA
+
+// lanes of the warp whose (valid, 8-bit digit) equals mine, from nine ballots.  __match_any_sync gives the same mask
+// but its cost grows with the number of distinct values in the warp (measured: the low-byte passes, where all 32
+// digits differ, ran 2x slower than the exponent-byte pass); ballots cost the same whatever the data.
+__device__ __forceinline__ uint32_t same_digit_lanes(uint32_t digit, bool ok) {
+  uint32_t m = __ballot_sync(0xffffffffu, ok);
+  m = ok ? m : ~m;
+#pragma unroll
+  for (int b = 0; b < kRadixBits; ++b) {
+    const bool bit = (digit >> b) & 1u;
+    const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+    m &= bit ? bal : ~bal;
+  }
+  return m;
+}
 
 __device__ __forceinline__ uint32_t load_key(const void* keys, size_t i, bool as_float) {
   return as_float ? ordered_bits(reinterpret_cast<const float*>(keys)[i])
@@ -44,59 +60,78 @@ __global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const void* __
 
 // keys_in/idx_in -> keys_out/idx_out.  idx_in == nullptr means the identity (first pass);
 // keys_out == nullptr means the keys are no longer needed (last pass).
-__global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const void* __restrict__ keys_in, bool as_float,
+__global__ void __launch_bounds__(kSortThreads, 3) radix_scatter_kernel(const void* __restrict__ keys_in, bool as_float,
                                                                       const int32_t* __restrict__ idx_in, int n,
                                                                       int tiles, int shift,
                                                                       const uint32_t* __restrict__ tile_hist,
                                                                       uint32_t* __restrict__ keys_out,
                                                                       int32_t* __restrict__ idx_out) {
-  __shared__ uint32_t warp_off[kSortWarps][kRadix];
+  __shared__ uint32_t warp_off[kSortWarps][kRadix];   // per-warp digit counts, then tile-local start offsets
   __shared__ uint32_t scan_tmp[kRadix];
+  __shared__ uint32_t local_start[kRadix];            // first tile-local slot of each digit
+  __shared__ uint32_t global_base[kRadix];            // where this tile's run of each digit starts in the segment
+  __shared__ uint32_t s_key[kTile];                   // the tile, reordered by digit (stable)
+  __shared__ int32_t s_idx[kTile];
   const int tile = blockIdx.x, seg = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t base = (size_t)seg * n;
 
-  // (1) where does digit `tid` of this tile start in the segment?
-  uint32_t before = 0, total = 0;
-  {
-    const uint32_t* th = tile_hist + (size_t)seg * tiles * kRadix + tid;
-    for (int t = 0; t < tiles; ++t) {
-      uint32_t c = th[(size_t)t * kRadix];
-      total += c;
-      if (t < tile) before += c;
-    }
-  }
-  // exclusive scan of `total` over the 256 digits (Hillis-Steele in shared memory)
-  scan_tmp[tid] = total;
-  __syncthreads();
-  for (int off = 1; off < kRadix; off <<= 1) {
-    uint32_t v = tid >= off ? scan_tmp[tid - off] : 0u;
-    __syncthreads();
-    scan_tmp[tid] += v;
-    __syncthreads();
-  }
-  const uint32_t digit_start = scan_tmp[tid] - total + before;
-#pragma unroll
-  for (int w = 0; w < kSortWarps; ++w) warp_off[w][tid] = 0;
-  __syncthreads();
-
-  // (2) per-warp digit counts; each warp owns a contiguous run of 512 keys, kept in registers
-  uint32_t key[kItemsPerThread];
+  // (0) every global load of the CTA is issued before anything depends on one: keys, incoming indices, histograms
+  uint32_t key[kItemsPerThread], peers[kItemsPerThread];
   const int wstart = tile * kTile + warp * (32 * kItemsPerThread);
 #pragma unroll
   for (int it = 0; it < kItemsPerThread; ++it) {
-    int i = wstart + it * 32 + lane;
-    bool ok = i < n;
-    key[it] = ok ? load_key(keys_in, base + i, as_float) : 0u;
-    uint32_t dg = ok ? ((key[it] >> shift) & (kRadix - 1)) : 0xffffu;
-    uint32_t peers = __match_any_sync(0xffffffffu, dg);
-    if (ok && lane == __ffs(peers) - 1) warp_off[warp][dg] += __popc(peers);
+    const int i = wstart + it * 32 + lane;
+    key[it] = i < n ? load_key(keys_in, base + i, as_float) : 0u;
+  }
+  // (1) where does digit `tid` of this tile start in the segment?
+  uint32_t before = 0, total = 0, mine = 0;
+  {
+    const uint32_t* th = tile_hist + (size_t)seg * tiles * kRadix + tid;
+#pragma unroll 8
+    for (int t = 0; t < tiles; ++t) {
+      const uint32_t c = th[(size_t)t * kRadix];
+      total += c;
+      before += t < tile ? c : 0u;
+      mine = t == tile ? c : mine;
+    }
+  }
+  // exclusive scans over the 256 digits (segment-wide totals, this tile's own counts): shuffle scan inside each
+  // warp, then the 8 warp totals
+  uint32_t inc_t = total, inc_m = mine;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const uint32_t a = __shfl_up_sync(0xffffffffu, inc_t, off), c = __shfl_up_sync(0xffffffffu, inc_m, off);
+    if (lane >= off) { inc_t += a; inc_m += c; }
+  }
+  if (lane == 31) { scan_tmp[warp] = inc_t; scan_tmp[kSortWarps + warp] = inc_m; }
+#pragma unroll
+  for (int w = 0; w < kSortWarps; ++w) warp_off[w][tid] = 0;
+  __syncthreads();
+  uint32_t pre_t = 0, pre_m = 0;
+#pragma unroll
+  for (int w = 0; w < kSortWarps; ++w) {
+    pre_t += w < warp ? scan_tmp[w] : 0u;
+    pre_m += w < warp ? scan_tmp[kSortWarps + w] : 0u;
+  }
+  global_base[tid] = pre_t + inc_t - total + before;
+  const uint32_t my_local = pre_m + inc_m - mine;
+  local_start[tid] = my_local;
+
+  // (2) per-warp digit counts; each warp owns a contiguous run of 512 keys, kept in registers
+#pragma unroll
+  for (int it = 0; it < kItemsPerThread; ++it) {
+    const int i = wstart + it * 32 + lane;
+    const bool ok = i < n;
+    const uint32_t dg = (key[it] >> shift) & (kRadix - 1);
+    peers[it] = same_digit_lanes(dg, ok);
+    if (ok && lane == __ffs(peers[it]) - 1) warp_off[warp][dg] += __popc(peers[it]);
     __syncwarp();
   }
   __syncthreads();
-  // (3) exclusive prefix over warps, seeded with the digit's start
+  // (3) exclusive prefix over warps, seeded with the digit's tile-local start
   {
-    uint32_t run = digit_start;
+    uint32_t run = my_local;
 #pragma unroll
     for (int w = 0; w < kSortWarps; ++w) {
       uint32_t c = warp_off[w][tid];
@@ -105,23 +140,32 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const void*
     }
   }
   __syncthreads();
-  // (4) rank and scatter in the same order
+  // (4) rank in the same order and park every key at its tile-local slot
 #pragma unroll
   for (int it = 0; it < kItemsPerThread; ++it) {
     int i = wstart + it * 32 + lane;
     bool ok = i < n;
-    uint32_t dg = ok ? ((key[it] >> shift) & (kRadix - 1)) : 0xffffu;
-    uint32_t peers = __match_any_sync(0xffffffffu, dg);
-    uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+    uint32_t dg = (key[it] >> shift) & (kRadix - 1);
+    uint32_t rank = __popc(peers[it] & ((1u << lane) - 1u));
     uint32_t pos = 0;
     if (ok) pos = warp_off[warp][dg] + rank;
     __syncwarp();
-    if (ok && lane == __ffs(peers) - 1) warp_off[warp][dg] += __popc(peers);
+    if (ok && lane == __ffs(peers[it]) - 1) warp_off[warp][dg] += __popc(peers[it]);
     __syncwarp();
     if (ok) {
-      if (keys_out) keys_out[base + pos] = key[it];
-      idx_out[base + pos] = idx_in ? idx_in[base + i] : i;
+      s_key[pos] = key[it];
+      s_idx[pos] = idx_in ? idx_in[base + i] : i;
     }
+  }
+  __syncthreads();
+  // (5) write the tile out slot by slot: consecutive threads hit consecutive addresses inside each digit run
+  const int count = min(kTile, n - tile * kTile);
+  for (int e = tid; e < count; e += kSortThreads) {
+    const uint32_t kk = s_key[e];
+    const uint32_t dg = (kk >> shift) & (kRadix - 1);
+    const uint32_t pos = global_base[dg] + ((uint32_t)e - local_start[dg]);
+    if (keys_out) keys_out[base + pos] = kk;
+    idx_out[base + pos] = s_idx[e];
   }
 }
 
