@@ -54,6 +54,10 @@ __global__ void init_extrema_kernel(uint32_t* __restrict__ ext, int th) {
   }
 }
 
+// One CTA = 32 consecutive hits x all heads.  The q and k rows of those hits are 32 x H*D contiguous floats each: they
+// are copied into shared memory with fully coalesced 16-byte loads (every sector fetched is used, adjacent lanes read
+// adjacent addresses), then one thread per (hit, head) reads its own D-float slices back (row stride padded by 4 floats:
+// the 32 lanes of a warp — 32 hits of one head — hit distinct bank groups) and runs the sequential FMA chains.
 template <int D, int C>
 __global__ void __launch_bounds__(256) hash_project_kernel(const float* __restrict__ q, const float* __restrict__ k,
                                                            const float* __restrict__ coords,
@@ -62,33 +66,48 @@ __global__ void __launch_bounds__(256) hash_project_kernel(const float* __restri
                                                            int raw_size, float* __restrict__ proj,
                                                            uint32_t* __restrict__ ext) {
   constexpr int E = D + C;
-  extern __shared__ float s_alpha[];  // (H, E, T) then scale (H, C)
-  float* s_scale = s_alpha + H * E * T;
+  extern __shared__ float s_dyn[];
+  const int HD = H * D, stride = HD + 4;
+  float* s_alpha = s_dyn;                         // (H, E, T)
+  float* s_scale = s_alpha + H * E * T;           // (H, C)
+  float* s_q = s_scale + ((H * C + 3) & ~3);      // 32 rows x stride
+  float* s_k = s_q + 32 * stride;
   for (int i = threadIdx.x; i < H * E * T; i += blockDim.x) s_alpha[i] = alpha[i];
   for (int i = threadIdx.x; i < H * C; i += blockDim.x) s_scale[i] = scale[i];
+  const int n0 = blockIdx.x * 32;
+  const int rows = min(32, N - n0);
+  const int vec_per_row = HD / 4;
+  for (int i = threadIdx.x; i < rows * vec_per_row; i += blockDim.x) {
+    const int r = i / vec_per_row, c4 = i - r * vec_per_row;
+    const size_t g = ((size_t)(n0 + r) * HD) / 4 + c4;
+    *reinterpret_cast<float4*>(s_q + r * stride + 4 * c4) = __ldg(reinterpret_cast<const float4*>(q) + g);
+    *reinterpret_cast<float4*>(s_k + r * stride + 4 * c4) = __ldg(reinterpret_cast<const float4*>(k) + g);
+  }
   __syncthreads();
 
   const int lane = threadIdx.x & 31;
   const int warps = blockDim.x >> 5;
-  const int n = blockIdx.x * 32 + lane;
+  const int n = n0 + lane;
   const bool live = n < N;
   const bool real = live && n < raw_size;
+  float cc[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) cc[c] = 0.f;
+  if (real) load_row<C>(coords + (size_t)n * C, cc);
   for (int h = threadIdx.x >> 5; h < H; h += warps) {
     float qa[E], ka[E];
-    if (real) {
-      load_row<D>(q + ((size_t)n * H + h) * D, qa);
-      load_row<D>(k + ((size_t)n * H + h) * D, ka);
-      float cc[C];
-      load_row<C>(coords + (size_t)n * C, cc);
 #pragma unroll
-      for (int c = 0; c < C; ++c) {
-        float v = __fmul_rn(s_scale[h * C + c], cc[c]);
-        qa[D + c] = v;
-        ka[D + c] = v;
-      }
-    } else {
+    for (int c4 = 0; c4 < D / 4; ++c4) {
+      const float4 a = real ? *reinterpret_cast<const float4*>(s_q + lane * stride + h * D + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 b = real ? *reinterpret_cast<const float4*>(s_k + lane * stride + h * D + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      qa[4 * c4] = a.x; qa[4 * c4 + 1] = a.y; qa[4 * c4 + 2] = a.z; qa[4 * c4 + 3] = a.w;
+      ka[4 * c4] = b.x; ka[4 * c4 + 1] = b.y; ka[4 * c4 + 2] = b.z; ka[4 * c4 + 3] = b.w;
+    }
 #pragma unroll
-      for (int e = 0; e < E; ++e) { qa[e] = 0.f; ka[e] = 0.f; }
+    for (int c = 0; c < C; ++c) {
+      const float v = real ? __fmul_rn(s_scale[h * C + c], cc[c]) : 0.f;
+      qa[D + c] = v;
+      ka[D + c] = v;
     }
     for (int t = 0; t < T; ++t) {
       float pq = 0.f, pk = 0.f;
@@ -171,7 +190,15 @@ template <int D, int C>
 static int launch_project(const hept_shape* s, const float* q, const float* k, const float* coords, const float* scale,
                           const float* alpha, float* proj, uint32_t* ext, cudaStream_t st) {
   const int E = D + C;
-  size_t smem = sizeof(float) * (size_t)(s->H * E * s->T + s->H * C);
+  const size_t smem = sizeof(float) * ((size_t)s->H * E * s->T + (((size_t)s->H * C + 3) & ~(size_t)3) +
+                                       2 * 32 * ((size_t)s->H * D + 4));
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(hash_project_kernel<D, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "hash_project: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  HEPT_REQUIRE(smem <= 100 * 1024, HEPT_EUNSUPPORTED, "hash_project: H*D=%d too wide for the staging buffer", s->H * D);
   dim3 grid((s->N + 31) / 32);
   hash_project_kernel<D, C><<<grid, 256, smem, st>>>(q, k, coords, scale, alpha, s->N, s->H, s->T, s->raw_size, proj, ext);
   HEPT_CHECK_LAUNCH("hash_project");
