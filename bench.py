@@ -381,7 +381,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--bwd", default=None, type=int, choices=[1, 2], help="backward tile variant (default: library default)")
+    ap.add_argument("--bwd", default=None, type=int, choices=[1, 2, 3], help="backward tile variant (default: library default)")
     ap.add_argument("--engine", default=None, choices=["simt", "tcgen05"], help="tile engine (default: library default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

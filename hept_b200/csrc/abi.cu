@@ -19,7 +19,7 @@ static int g_bwd_mask = 7;
 int bwd_stage_mask() { return g_bwd_mask; }
 static int g_engine = 1;  // tcgen05 tiles by default (faster, same tolerance contract); 0 = fp32 CUDA-core tiles
 int engine() { return g_engine; }
-static int g_bwd_variant = 1;
+static int g_bwd_variant = 3;  // tcgen05 backward tiles by default; 1 = fp32 CUDA-core tiles, 2 = lane-pair FFMA2 tiles
 int bwd_variant() { return g_bwd_variant; }
 
 struct FwdPlan {
@@ -56,7 +56,7 @@ extern "C" int hept_launch_count(int reset) {
 extern "C" void hept_set_bwd_stage_mask(int mask) { g_bwd_mask = mask & 7; }
 extern "C" void hept_set_engine(int engine) { g_engine = engine ? 1 : 0; }
 extern "C" int hept_get_engine(void) { return g_engine; }
-extern "C" void hept_set_bwd_variant(int variant) { g_bwd_variant = variant == 2 ? 2 : 1; }
+extern "C" void hept_set_bwd_variant(int variant) { g_bwd_variant = (variant == 2 || variant == 3) ? variant : 1; }
 extern "C" int hept_get_bwd_variant(void) { return g_bwd_variant; }
 
 extern "C" size_t hept_attention_fwd_workspace_bytes(const hept_shape* s) {

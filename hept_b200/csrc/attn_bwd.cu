@@ -272,6 +272,16 @@ __global__ void __launch_bounds__(256) dscale_finish_kernel(const float* __restr
   if (threadIdx.x == 0) dscale[col] = red[0];
 }
 
+int block_attention_bwd_tiles2(const hept_shape* s, const float* q, const float* k, const float* v, const float* coords,
+                               const float* scale, const int32_t* positions, const float* out_pre, const float* den_sum,
+                               const float* d_out_pre, float* stage_dq, float* stage_dk, float* stage_dv, int mask,
+                               cudaStream_t st);
+int block_attention_bwd_tc(const hept_shape* s, const float* q, const float* k, const float* v, const float* coords,
+                           const float* scale, const int32_t* positions, const float* out_pre, const float* den_sum,
+                           const float* d_out_pre, float* dq, float* dk, float* dv, float* dscale, char* ws,
+                           cudaStream_t st);
+size_t bwd_tc_workspace_bytes(const hept_shape* s);
+
 struct BwdPlan {
   size_t dq_bytes, dv_bytes, partial_bytes, total;
   int nblk;
@@ -309,6 +319,11 @@ static int launch_bwd(const hept_shape* s, const float* q, const float* k, const
   float* partial = (float*)(ws + 2 * p.dq_bytes + p.dv_bytes);
   const int nb = s->N / s->B;
   const int mask = bwd_stage_mask();  // profiling aid: all stages unless hept_set_bwd_stage_mask() says otherwise
+  if (bwd_variant() == 2) {
+    if (int rc = block_attention_bwd_tiles2(s, q, k, v, coords, scale, positions, out_pre, den_sum, d_out_pre, stage_dq,
+                                            stage_dk, stage_dv, mask, st))
+      return rc;
+  } else {
   if (mask & 1) {
     kq<<<dim3((nb + GQ - 1) / GQ, s->T * s->H), LQ::THREADS, LQ::SMEM_BYTES, st>>>(
         q, k, v, coords, scale, positions, out_pre, den_sum, d_out_pre, s->N, s->H, s->T, s->raw_size, stage_dq);
@@ -318,6 +333,7 @@ static int launch_bwd(const hept_shape* s, const float* q, const float* k, const
     kk<<<dim3((nb + GK - 1) / GK, s->T * s->H), LK::THREADS, LK::SMEM_BYTES, st>>>(
         q, k, v, coords, scale, positions, out_pre, den_sum, d_out_pre, s->N, s->H, s->T, s->raw_size, stage_dk, stage_dv);
     HEPT_CHECK_LAUNCH("block_attn_bwd_dkv");
+  }
   }
   if (!(mask & 4)) return HEPT_OK;
   bwd_reduce_kernel<D, C><<<p.nblk, 256, 0, st>>>(stage_dq, stage_dk, stage_dv, coords, s->N, s->H, s->T, s->raw_size,
@@ -334,7 +350,8 @@ using namespace hept;
 
 extern "C" size_t hept_attention_bwd_workspace_bytes(const hept_shape* s) {
   if (!s || s->N <= 0) return 0;
-  return plan_bwd(s).total;
+  const size_t a = plan_bwd(s).total, b = bwd_tc_workspace_bytes(s);
+  return a > b ? a : b;   // whichever backward engine is selected later fits
 }
 
 extern "C" int hept_block_attention_bwd(const hept_shape* s, const float* q, const float* k, const float* v,
@@ -346,10 +363,12 @@ extern "C" int hept_block_attention_bwd(const hept_shape* s, const float* q, con
   HEPT_REQUIRE(q && k && v && coords && scale && positions && out_pre && den_sum && d_out_pre && dq && dk && dv &&
                    dscale && workspace,
                HEPT_EINVAL, "block_attention_bwd: null pointer");
-  HEPT_REQUIRE(workspace_bytes >= plan_bwd(s).total, HEPT_EWORKSPACE, "block_attention_bwd: workspace needs %zu bytes",
-               plan_bwd(s).total);
+  HEPT_REQUIRE(workspace_bytes >= hept_attention_bwd_workspace_bytes(s), HEPT_EWORKSPACE,
+               "block_attention_bwd: workspace needs %zu bytes", hept_attention_bwd_workspace_bytes(s));
   cudaStream_t st = (cudaStream_t)stream;
   char* ws = (char*)workspace;
+  if (bwd_variant() == 3)
+    return block_attention_bwd_tc(s, q, k, v, coords, scale, positions, out_pre, den_sum, d_out_pre, dq, dk, dv, dscale, ws, st);
   if (s->D == 24 && s->C == 6 && s->B == 100)
     return launch_bwd<24, 6, 100, 5, 1, 3, 1>(s, q, k, v, coords, scale, positions, out_pre, den_sum, d_out_pre, dq, dk, dv, dscale, ws, st);
   if (s->D == 24 && s->C == 4 && s->B == 100)

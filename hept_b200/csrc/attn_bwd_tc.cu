@@ -1,0 +1,776 @@
+// a18 on the 5th-generation tensor cores: backward of the block-local attention tiles (autograd of
+// example/hept.py:7-18,70-79) with every contraction of a tile issued as tcgen05.mma (kind::tf32, M = 128,
+// 3xTF32 operand splits, accumulators in TMEM).  One persistent, warp-specialised CTA per SM walks the tiles; a tile
+// is one block of B <= 104 sorted hits of one (table, head) and is processed from BOTH sides, because the tensor
+// core wants the reduced-over index on the TMEM columns:
+//
+//   query side (TMEM lane = query i)                     key side (TMEM lane = key j)
+//   S   = Q^ K^^T            SS, N = NP                   S^T  = K^ Q^^T            SS (operands exchanged)
+//   dP  = G' V'^T            SS                           dP^T = V' G'^T            SS
+//   dS  = [x<=0] P dP  -> TMEM (hi, lo), rs_i = sum_j     P^T -> TMEM (hi, lo), dS^T kept in registers, cs_j = sum_i
+//   dQ  = dS K^              TS, B = K^ MN-major          dV   = P^T G'             TS, B = G' MN-major
+//   dq^_i = dQ_i - rs_i q'_i                              dK   = dS^T Q^            TS (after dS^T replaced P^T)
+//                                                         dk^_j = dK_j - cs_j k'_j
+// with x = log2e (q'.k' - |k'|^2/2) - log2e |q'|^2/2 (the key norm rides in two spare K slots of the contraction,
+// split three ways so it is exact), P = ex2(min(x, 0)), G'_i = [g_i / den_i, -(g_i . y_i) / den_i], V'_j = [v_j, 1]
+// (so dP = gd . v - gy comes out of one contraction).  The tf32 MMA is bitwise symmetric under an exchange of its
+// operands (tests/test_gpu_umma.py) and both sides apply the same fmaf, so they see bit-identical P and dS.
+//
+// Warp roles (640 threads = 5 warpgroups, register budgets rebalanced with setmaxnreg):
+//   warps 0-7   epilogue: TMEM lane = (warp & 3) * 32 + lane, columns split in two parts (warp >> 2)
+//   warps 8-15  producer: gather rows through the sort permutation (q^, k^ into registers, v and G' with cp.async into
+//               a staging buffer, all issued one tile ahead), centre, split, write the K-major operand tiles as soon
+//               as the previous tile's score MMAs have consumed theirs, copy them to the MN-major tiles once the
+//               previous tile's last MMA is done
+//   warp 16     one thread issues every tcgen05.mma (warps 17-19 only give their registers away); the next tile's score MMAs are issued as soon as their TMEM
+//               columns are free, so the tensor pipe runs under the epilogue of the current tile
+// Hand-offs are mbarriers (tcgen05.commit on the MMA side, one arrive per warp on the others); each completes once
+// per tile, so the wait parity is the tile counter's low bit.
+//
+// d scale[h,c] = sum_n coords[n,c] (dq^ + dk^)[n,h,D+c] cancels by ~|x|^2 / |x_i - x_j|^2 when summed over hits in
+// detector coordinates.  Per tile sum_i dq^_i + sum_j dk^_j = 0, so the same sum may be taken with the tile's
+// CENTRED rows, sum_i q'_ic dq^_ic + sum_j k'_jc dk^_jc = scale_c * (the tile's share of d scale_c): no large
+// terms, nothing to cancel.  Per-tile partials are reduced in a fixed order (deterministic).
+#include "tile.cuh"
+#include "umma.cuh"
+
+namespace hept {
+
+constexpr int kBtEpiThreads = 256, kBtProdThreads = 256;
+constexpr int kBtThreads = kBtEpiThreads + kBtProdThreads + 128;
+// Launch budget 65536 / 640 -> 96 registers per thread = 61440 per CTA; setmaxnreg moves registers inside that pool:
+// 256 x 128 (epilogue) + 256 x 88 (producer) + 128 x 40 (MMA warpgroup) = 60416.
+constexpr int kBtRegsEpi = 128, kBtRegsProd = 88, kBtRegsMma = 40;
+static_assert(kBtEpiThreads * kBtRegsEpi + kBtProdThreads * kBtRegsProd + 128 * kBtRegsMma <= kBtThreads * 96, "register pool");
+constexpr int kBtParts = kBtEpiThreads / 128;   // epilogue warps w and w+4 share TMEM lane quarter w & 3
+
+constexpr int pow2_cols(int need) { return need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512; }
+
+template <int D, int C, int B>
+struct TcBwd {
+  static constexpr int E = D + C;
+  static constexpr int NP = (B + 15) / 16 * 16;   // N of the score MMAs (multiple of 16 at M = 128)
+  static constexpr int KC = (B + 7) / 8 * 8;      // contraction length of the TS MMAs
+  static constexpr int KSTEPS = KC / 8;
+  static constexpr int SK = (E + 2 + 7) / 8;      // k-steps of Q^ K^^T (two side slots at E, E + 1)
+  static constexpr int GK = (D + 1 + 7) / 8;      // k-steps of G' V'^T
+  static constexpr int VCH = D / 4;
+  static constexpr int SLOT_CH = E / 4, SLOT_U = E % 4;   // chunk / element of side slot E
+  // Operand tiles hold KC rows of 128 B.  The MMAs read M = 128 (A) or NP (B) rows: what lies past row KC belongs to
+  // the next tile and only reaches TMEM lanes / columns >= KC, which nothing reads.
+  static constexpr int TILE = KC * 128;
+  static constexpr int QH = 0, QL = 1, KH = 2, KL = 3, GH = 4, GL = 5, VH = 6, VL = 7;   // K-major tiles
+  static constexpr int MKH = 0, MKL = 1, MGH = 2, MGL = 3, MQH = 4, MQL = 5;             // MN-major tiles
+  static constexpr int RPP = kBtProdThreads / 8;   // producer: rows per pass (8 lanes per row)
+  static constexpr int PASSES = (B + RPP - 1) / RPP;
+  static constexpr int OFF_MN = 8 * TILE;
+  static constexpr int OFF_STG_V = OFF_MN + 6 * TILE;
+  static constexpr int OFF_STG_G = OFF_STG_V + PASSES * kBtProdThreads * 16;
+  static constexpr int OFF_AUX = OFF_STG_G + PASSES * kBtProdThreads * 16;
+  // aux words: nq2[2][128], qidx[3][128], kidx[3][128], rs[2][128], cs[2][128], dsc[8][8]
+  static constexpr int AUX_BYTES = (12 * 128 + 64) * 4;
+  static constexpr int TOTAL = OFF_AUX + AUX_BYTES;
+  static constexpr int TMEM_NEED = 4 * NP + 64;
+  static constexpr int TMEM_COLS = pow2_cols(TMEM_NEED);
+  static_assert(E % 2 == 0 && E + 2 <= 32 && D + 1 <= 32 && D % 4 == 0, "row shapes");
+  static_assert(B <= 128 && NP <= 128 && TMEM_NEED <= 512, "tile shape");
+  static_assert(7 * TILE + 128 * 128 <= TOTAL, "the M = 128 overrun of the last K-major tile stays inside the allocation");
+  static_assert(TOTAL + 1024 <= 227 * 1024, "shared memory");
+};
+
+enum BtBar { KFULL, MFULL, MFREE, QREADY, KREADY, DSRDY, DQDONE, PTRDY, DVDONE, DSTRDY, DKDONE, BT_NBAR };
+
+// hi = x rounded to tf32 (round half away, like cvt.rna; x finite), lo = x - hi (exact)
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+  lo = x - hi;
+}
+__device__ __forceinline__ void split4(const float4 x, float4& hi, float4& lo) {
+  split_tf32(x.x, hi.x, lo.x); split_tf32(x.y, hi.y, lo.y); split_tf32(x.z, hi.z, lo.z); split_tf32(x.w, hi.w, lo.w);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// G' rows (N, H, 32): [g / den (D), -(g . y) / den, 0 ...] — the gradient arriving at numerator and normaliser of
+// every table (d so_t = g / den, d denom_t = -(g . y) / den, attn_bwd.cu).  Eight lanes per row.
+// ---------------------------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256) grad_rows_kernel(const float* __restrict__ g, const float* __restrict__ y,
+                                                        const float* __restrict__ den, size_t rows,
+                                                        float* __restrict__ out) {
+  constexpr int VCH = D / 4;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t r = idx >> 3;
+  const int c = (int)(idx & 7);
+  const bool live = r < rows;
+  float4 gd = make_float4(0.f, 0.f, 0.f, 0.f);
+  float part = 0.f;
+  if (live && c < VCH) {
+    const float inv = 1.f / __ldg(den + r);
+    const float4 gg = ldg4(g + r * D + 4 * c), yy = ldg4(y + r * D + 4 * c);
+    gd = make_float4(gg.x * inv, gg.y * inv, gg.z * inv, gg.w * inv);
+    part = fmaf(gd.w, yy.w, fmaf(gd.z, yy.z, fmaf(gd.y, yy.y, gd.x * yy.x)));
+  }
+  const float gy = tree8_lanes(part);
+  if (c == VCH) gd.x = -gy;
+  if (live) *reinterpret_cast<float4*>(out + r * 32 + 4 * c) = gd;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// the tile kernel
+// ---------------------------------------------------------------------------------------------------------------
+template <int D, int C, int B>
+__global__ void __launch_bounds__(kBtThreads, 1)
+    block_attn_bwd_tc_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+                             const float* __restrict__ hatc, const float* __restrict__ grows,
+                             const int32_t* __restrict__ positions, int N, int H, int T, int raw_size, int total_tiles,
+                             float* __restrict__ stage_dq, float* __restrict__ stage_dk, float* __restrict__ stage_dv,
+                             float* __restrict__ ds_partial) {
+  using CF = TcBwd<D, C, B>;
+  constexpr int E = CF::E, NP = CF::NP, KSTEPS = CF::KSTEPS, VCH = CF::VCH, PASSES = CF::PASSES;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = umma::align1024(smem_raw);
+  uint8_t* mn = smem + CF::OFF_MN;
+  float* s_nq2 = reinterpret_cast<float*>(smem + CF::OFF_AUX);   // [2][128]  log2e * -|q'|^2 / 2, by tile parity
+  int* s_qidx = reinterpret_cast<int*>(s_nq2 + 256);             // [3][128]  original hit index of query row r, tile % 3
+  int* s_kidx = s_qidx + 384;                                    // [3][128]
+  float* s_rs = reinterpret_cast<float*>(s_kidx + 384);          // [2][128]  row sums of dS per column part
+  float* s_cs = s_rs + 256;                                      // [2][128]  column sums
+  float* s_dsc = s_cs + 256;                                     // [8][8]    d scale partials per epilogue warp
+  __shared__ uint64_t mbar[BT_NBAR];
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nb = N / B;
+  constexpr int EW = kBtEpiThreads / 32, PW = kBtProdThreads / 32;
+
+  if (tid == 0) {
+    umma::mbar_init(&mbar[KFULL], PW);
+    umma::mbar_init(&mbar[MFULL], PW);
+    umma::mbar_init(&mbar[MFREE], 1 + EW);
+    umma::mbar_init(&mbar[QREADY], 1);
+    umma::mbar_init(&mbar[KREADY], 1);
+    umma::mbar_init(&mbar[DSRDY], EW);
+    umma::mbar_init(&mbar[DQDONE], 1);
+    umma::mbar_init(&mbar[PTRDY], EW);
+    umma::mbar_init(&mbar[DVDONE], 1);
+    umma::mbar_init(&mbar[DSTRDY], EW);
+    umma::mbar_init(&mbar[DKDONE], 1);
+  }
+  if (warp == EW + PW) umma::tmem_alloc<CF::TMEM_COLS>(&tmem_slot);
+  if (warp >= EW && warp < EW + PW) {
+    // rows that never hold data are written once: zero operands, key norm -1e30 (P = ex2(-1e30) = 0)
+    const int ptid = tid - kBtEpiThreads, sub = ptid >> 3, c = ptid & 7;
+    for (int rr = B + sub; rr < CF::KC; rr += kBtProdThreads / 8) {
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 kz = z;
+      if (c == CF::SLOT_CH) umma::elem<CF::SLOT_U>(kz) = umma::tf32_hi(-1e30f);
+#pragma unroll
+      for (int tl = 0; tl < 8; ++tl)
+        *reinterpret_cast<float4*>(smem + tl * CF::TILE + umma::sw128_offset(rr, c)) = tl == CF::KH ? kz : z;
+#pragma unroll
+      for (int tl = 0; tl < 6; ++tl)
+        *reinterpret_cast<float4*>(mn + tl * CF::TILE + umma::sw128b32_offset(rr, c)) = tl == CF::MKH ? kz : z;
+    }
+    for (int rr = B + ptid; rr < 128; rr += kBtProdThreads) {
+      s_nq2[rr] = -1e30f; s_nq2[128 + rr] = -1e30f;
+#pragma unroll
+      for (int u = 0; u < 3; ++u) { s_qidx[u * 128 + rr] = -1; s_kidx[u * 128 + rr] = -1; }
+    }
+  }
+  umma::fence_async_smem();
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t tS = tmem, tDP = tmem + NP, tST = tmem + 2 * NP, tDPT = tmem + 3 * NP, tO0 = tmem + 4 * NP,
+                 tO1 = tmem + 4 * NP + 32;
+  const uint32_t sbase = umma::smem_u32(smem), mbase = sbase + CF::OFF_MN;
+
+  // tiles are ordered (head, table, block): the CTAs of a wave work on one head's rows, which stay in L2
+  auto decode = [&](int tile, int& h, int& t, int& blk) {
+    const int hl = tile / nb;
+    blk = tile - hl * nb;
+    h = hl / T;
+    t = hl - h * T;
+  };
+
+  if (warp < EW) {
+    // =========================================== epilogue warps =================================================
+    umma::setmaxnreg_inc<kBtRegsEpi>();
+    const int row = (warp & 3) * 32 + lane;                // TMEM lane
+    const int srow = row < CF::KC ? row : 0;               // lanes past the tile read row 0 of the operand tiles (unused)
+    const int part = warp >> 2;                            // column part of that lane
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    constexpr int MAXCH = (KSTEPS + kBtParts - 1) / kBtParts;   // 8-column chunks per thread
+    // warp-level arrive: every lane's TMEM stores are complete and fenced before lane 0 signals
+    auto arrive_tmem = [&](BtBar b) {
+      umma::tmem_wait_st();
+      umma::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) umma::mbar_arrive(&mbar[b]);
+    };
+    int it = 0;
+#pragma unroll 1
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const uint32_t ph = it & 1;
+      int h, t, blk;
+      decode(tile, h, t, blk);
+      const float* nq2s = s_nq2 + ph * 128;
+      const int* qidx = s_qidx + (it % 3) * 128;
+      const int* kidx = s_kidx + (it % 3) * 128;
+
+      // ---- query side: dS -> TMEM (hi over S, lo over dP), row sums ---------------------------------------------
+      umma::mbar_wait(&mbar[QREADY], ph);
+      umma::fence_after_sync();
+      {
+        const float nq2 = nq2s[row];
+        float rs = 0.f;
+#pragma unroll
+        for (int ci = 0; ci < MAXCH; ++ci) {
+          const int ch = part + ci * kBtParts;
+          if (ch < KSTEPS) {
+            uint32_t ra[8], rb[8];
+            umma::tmem_ld8_nowait(tS + lane_base + 8 * ch, ra);
+            umma::tmem_ld8_nowait(tDP + lane_base + 8 * ch, rb);
+            umma::tmem_wait_ld(ra, rb);
+            float dh[8], dl[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const float x = fmaf(__uint_as_float(ra[u]), kLog2e, nq2);
+              const float p = exp2_fast(fminf(x, 0.f));
+              const float ds = x <= 0.f ? p * __uint_as_float(rb[u]) : 0.f;   // clamp(max=0) passes gradient where S <= 0
+              rs += ds;
+              split_tf32(ds, dh[u], dl[u]);
+            }
+            umma::tmem_st8(tS + lane_base + 8 * ch, dh);
+            umma::tmem_st8(tDP + lane_base + 8 * ch, dl);
+          }
+        }
+        s_rs[part * 128 + row] = rs;
+      }
+      arrive_tmem(DSRDY);
+
+      // ---- key side: P^T -> TMEM (hi over S^T, lo over dP^T), dS^T kept in registers, column sums ---------------
+      float dsr[MAXCH * 8];
+      umma::mbar_wait(&mbar[KREADY], ph);
+      umma::fence_after_sync();
+      {
+        float cs = 0.f;
+#pragma unroll
+        for (int ci = 0; ci < MAXCH; ++ci) {
+          const int ch = part + ci * kBtParts;
+          if (ch < KSTEPS) {
+            uint32_t ra[8], rb[8];
+            umma::tmem_ld8_nowait(tST + lane_base + 8 * ch, ra);
+            umma::tmem_ld8_nowait(tDPT + lane_base + 8 * ch, rb);
+            const float4 n0v = *reinterpret_cast<const float4*>(nq2s + 8 * ch), n1v = *reinterpret_cast<const float4*>(nq2s + 8 * ch + 4);
+            const float nq2[8] = {n0v.x, n0v.y, n0v.z, n0v.w, n1v.x, n1v.y, n1v.z, n1v.w};
+            umma::tmem_wait_ld(ra, rb);
+            float phv[8], plv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const float x = fmaf(__uint_as_float(ra[u]), kLog2e, nq2[u]);   // the same fmaf as the query side
+              const float p = exp2_fast(fminf(x, 0.f));
+              const float ds = x <= 0.f ? p * __uint_as_float(rb[u]) : 0.f;
+              cs += ds;
+              dsr[ci * 8 + u] = ds;
+              split_tf32(p, phv[u], plv[u]);
+            }
+            umma::tmem_st8(tST + lane_base + 8 * ch, phv);
+            umma::tmem_st8(tDPT + lane_base + 8 * ch, plv);
+          }
+        }
+        s_cs[part * 128 + row] = cs;
+      }
+      arrive_tmem(PTRDY);
+      umma::bar_sync(1, kBtEpiThreads);                  // s_rs / s_cs of both column parts are visible
+
+      float dsc[C];   // this thread's share of sum_i q'_ic dq^_ic + sum_j k'_jc dk^_jc
+#pragma unroll
+      for (int cc = 0; cc < C; ++cc) dsc[cc] = 0.f;
+      // x'_e (e in this thread's 16 columns) of row `row` of an MN-major (hi, lo) tile pair: hi + lo is exact
+      auto centred_row = [&](int th_, int tl_, float (&xr)[16]) {
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          const uint32_t off = umma::sw128b32_offset(srow, 4 * part + cc);
+          const float4 a = *reinterpret_cast<const float4*>(mn + th_ * CF::TILE + off);
+          const float4 b = *reinterpret_cast<const float4*>(mn + tl_ * CF::TILE + off);
+          xr[4 * cc] = a.x + b.x; xr[4 * cc + 1] = a.y + b.y; xr[4 * cc + 2] = a.z + b.z; xr[4 * cc + 3] = a.w + b.w;
+        }
+      };
+      // out_e = acc_e - sum * x'_e; rows of D floats per (head, hit, table); coordinate columns feed d scale
+      auto finish_rows = [&](const float (&acc)[16], const float (&xr)[16], float sum, int n, float* __restrict__ stage) {
+        float o[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) o[u] = fmaf(-sum, xr[u], acc[u]);
+        if (n >= 0) {
+          float4* dst = reinterpret_cast<float4*>(stage + (((size_t)h * N + n) * T + t) * D);
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc)
+            if (4 * (4 * part + cc) < D) dst[4 * part + cc] = make_float4(o[4 * cc], o[4 * cc + 1], o[4 * cc + 2], o[4 * cc + 3]);
+#pragma unroll
+          for (int cc = 0; cc < C; ++cc)     // coordinate column D + cc lives in part (D + cc) / 16 (part is warp-uniform)
+            if (part == (D + cc) / 16) dsc[cc] = fmaf(xr[(D + cc) % 16], o[(D + cc) % 16], dsc[cc]);
+        }
+      };
+
+      // ---- dq^ rows ---------------------------------------------------------------------------------------------
+      umma::mbar_wait(&mbar[DQDONE], ph);
+      umma::fence_after_sync();
+      {
+        float acc[16], xr[16];
+        umma::tmem_ld16(tO0 + lane_base + 16 * part, acc);
+        centred_row(CF::MQH, CF::MQL, xr);
+        finish_rows(acc, xr, s_rs[row] + s_rs[128 + row], row < B ? qidx[row] : -1, stage_dq);
+      }
+
+      // ---- dS^T replaces P^T once dV has consumed it ------------------------------------------------------------
+      umma::mbar_wait(&mbar[DVDONE], ph);
+      umma::fence_after_sync();
+#pragma unroll
+      for (int ci = 0; ci < MAXCH; ++ci) {
+        const int ch = part + ci * kBtParts;
+        if (ch < KSTEPS) {
+          float dh[8], dl[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) split_tf32(dsr[ci * 8 + u], dh[u], dl[u]);
+          umma::tmem_st8(tST + lane_base + 8 * ch, dh);
+          umma::tmem_st8(tDPT + lane_base + 8 * ch, dl);
+        }
+      }
+      arrive_tmem(DSTRDY);                               // also: this warp has read dQ out of tO0
+
+      // ---- dv rows ----------------------------------------------------------------------------------------------
+      {
+        float acc[16];
+        umma::tmem_ld16(tO1 + lane_base + 16 * part, acc);
+        const int n = row < B ? kidx[row] : -1;
+        if (n >= 0) {
+          float4* dst = reinterpret_cast<float4*>(stage_dv + (((size_t)h * N + n) * T + t) * D);
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc)
+            if (4 * (4 * part + cc) < D) dst[4 * part + cc] = make_float4(acc[4 * cc], acc[4 * cc + 1], acc[4 * cc + 2], acc[4 * cc + 3]);
+        }
+      }
+
+      // ---- dk^ rows ---------------------------------------------------------------------------------------------
+      umma::mbar_wait(&mbar[DKDONE], ph);
+      umma::fence_after_sync();
+      {
+        float acc[16], xr[16];
+        umma::tmem_ld16(tO0 + lane_base + 16 * part, acc);
+        centred_row(CF::MKH, CF::MKL, xr);
+        finish_rows(acc, xr, s_cs[row] + s_cs[128 + row], row < B ? kidx[row] : -1, stage_dk);
+      }
+      umma::fence_before_sync();                         // the TMEM loads above precede the next tile's MMAs into tO0 / tO1
+      __syncwarp();
+      if (lane == 0) umma::mbar_arrive(&mbar[MFREE]);    // this warp is done with the MN-major tiles
+
+      // ---- d scale partials of this tile: fixed-order warp tree, then warps in order ------------------------------
+#pragma unroll
+      for (int cc = 0; cc < C; ++cc) {
+        float x = dsc[cc];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0) s_dsc[warp * 8 + cc] = x;
+      }
+      umma::bar_sync(1, kBtEpiThreads);
+      if (tid < C) {
+        float x = 0.f;
+#pragma unroll
+        for (int w = 0; w < EW; ++w) x += s_dsc[w * 8 + tid];
+        ds_partial[(size_t)tile * 8 + tid] = x;
+      }
+    }
+  } else if (warp < EW + PW) {
+    // =========================================== producer warps =================================================
+    umma::setmaxnreg_dec<kBtRegsProd>();
+    const int ptid = tid - kBtEpiThreads, sub = ptid >> 3, c = ptid & 7;   // 8 lanes per row, RPP rows per pass
+    constexpr int RPP = CF::RPP;
+    float4* stg_v = reinterpret_cast<float4*>(smem + CF::OFF_STG_V);
+    float4* stg_g = reinterpret_cast<float4*>(smem + CF::OFF_STG_G);
+    int nk_idx[PASSES], nq_idx[PASSES], n0 = 0;
+    float4 xq[PASSES], xk[PASSES], ctr;
+
+    auto load_indices = [&](int tile) {
+      int h, t, blk;
+      decode(tile, h, t, blk);
+      const int th = t * H + h;
+      const int32_t* qpos = positions + (size_t)th * N + (size_t)blk * B;
+      const int32_t* kpos = positions + ((size_t)T * H + th) * N + (size_t)blk * B;
+      n0 = __ldg(kpos + (B - 1));
+#pragma unroll
+      for (int ps = 0; ps < PASSES; ++ps) {
+        const int r = ps * RPP + sub;
+        nk_idx[ps] = r < B ? __ldg(kpos + r) : -1;
+        nq_idx[ps] = r < B ? __ldg(qpos + r) : -1;
+      }
+    };
+    // issue every row load of a tile: q^ / k^ chunks into registers, v / G' chunks into the staging buffer
+    auto issue_rows = [&](int tile, int it) {
+      int h, t, blk;
+      decode(tile, h, t, blk);
+      auto hat_chunk = [&](const float* __restrict__ x, int n) -> float4 {
+        const float* src = c < VCH ? x + ((size_t)n * H + h) * D + 4 * c : hatc + ((size_t)n * H + h) * 8 + 4 * (c - VCH);
+        return (c < VCH + 2 && n >= 0 && n < raw_size) ? ldg4(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+      };
+      ctr = hat_chunk(k, n0);
+#pragma unroll
+      for (int ps = 0; ps < PASSES; ++ps) {
+        const int nkk = nk_idx[ps], nqq = nq_idx[ps];
+        xk[ps] = hat_chunk(k, nkk);
+        xq[ps] = hat_chunk(q, nqq);
+        const bool vok = nkk >= 0 && c < VCH && nkk < raw_size;
+        umma::cp_async16(stg_v + ps * kBtProdThreads + ptid, vok ? v + ((size_t)nkk * H + h) * D + 4 * c : v, vok ? 16 : 0);
+        umma::cp_async16(stg_g + ps * kBtProdThreads + ptid, nqq >= 0 ? grows + ((size_t)nqq * H + h) * 32 + 4 * c : grows,
+                         nqq >= 0 ? 16 : 0);
+        const int r = ps * RPP + sub;
+        if (c == 0 && r < B) { s_qidx[(it % 3) * 128 + r] = nqq; s_kidx[(it % 3) * 128 + r] = nkk; }
+      }
+    };
+
+    int tile = blockIdx.x;
+    if (tile < total_tiles) {
+      load_indices(tile);
+      issue_rows(tile, 0);
+      if (tile + (int)gridDim.x < total_tiles) load_indices(tile + gridDim.x);
+    }
+    int it = 0;
+#pragma unroll 1
+    for (; tile < total_tiles; tile += gridDim.x, ++it) {
+      const uint32_t ph = it & 1;
+      // ---- K-major operand tiles: free once the previous tile's score MMAs (both sides) are done ------------------
+      if (it > 0) umma::mbar_wait(&mbar[KREADY], ph ^ 1);
+      umma::cp_async_wait_all();
+      float* nq2s = s_nq2 + ph * 128;
+#pragma unroll
+      for (int ps = 0; ps < PASSES; ++ps) {
+        const int r = ps * RPP + sub;
+        if (ps == PASSES - 1 && (ps * RPP + ((warp - EW) << 2)) >= B) continue;   // warps whose 4 rows are all past B
+        const bool in = r < B;
+        const uint32_t okm = umma::sw128_offset(r, c);
+        float4 hi, lo;
+        {  // key row: k' = k^ - centre; side slots carry nk = -|k'|^2 / 2 split three ways (exact)
+          float4 d = xk[ps];
+          d.x -= ctr.x; d.y -= ctr.y; d.z -= ctr.z; d.w -= ctr.w;
+          const float nk = -0.5f * tree8_lanes(chunk_sq<E>(d, c));
+          split4(d, hi, lo);
+          if (c == CF::SLOT_CH) {
+            const float h0 = umma::tf32_hi(nk), r1 = nk - h0, h1 = umma::tf32_hi(r1);
+            umma::elem<CF::SLOT_U>(hi) = h0; umma::elem<CF::SLOT_U + 1>(hi) = h1;
+            umma::elem<CF::SLOT_U>(lo) = r1 - h1; umma::elem<CF::SLOT_U + 1>(lo) = 0.f;
+          }
+          if (in) {
+            *reinterpret_cast<float4*>(smem + CF::KH * CF::TILE + okm) = hi;
+            *reinterpret_cast<float4*>(smem + CF::KL * CF::TILE + okm) = lo;
+          }
+        }
+        {  // query row: q' = q^ - centre; side slots carry 1
+          float4 d = xq[ps];
+          d.x -= ctr.x; d.y -= ctr.y; d.z -= ctr.z; d.w -= ctr.w;
+          const float nq2 = kLog2e * (-0.5f * tree8_lanes(chunk_sq<E>(d, c)));
+          split4(d, hi, lo);
+          if (c == CF::SLOT_CH) {
+            umma::elem<CF::SLOT_U>(hi) = 1.f; umma::elem<CF::SLOT_U + 1>(hi) = 1.f;
+            umma::elem<CF::SLOT_U>(lo) = 0.f; umma::elem<CF::SLOT_U + 1>(lo) = 0.f;
+          }
+          if (in) {
+            *reinterpret_cast<float4*>(smem + CF::QH * CF::TILE + okm) = hi;
+            *reinterpret_cast<float4*>(smem + CF::QL * CF::TILE + okm) = lo;
+            if (c == 0) nq2s[r] = nq2;
+          }
+        }
+        {  // value row with a 1 in slot D
+          float4 d = stg_v[ps * kBtProdThreads + ptid];
+          if (c == VCH) d.x = 1.f;
+          split4(d, hi, lo);
+          if (in) {
+            *reinterpret_cast<float4*>(smem + CF::VH * CF::TILE + okm) = hi;
+            *reinterpret_cast<float4*>(smem + CF::VL * CF::TILE + okm) = lo;
+          }
+        }
+        {  // gradient row (gd, -gy)
+          split4(stg_g[ps * kBtProdThreads + ptid], hi, lo);
+          if (in) {
+            *reinterpret_cast<float4*>(smem + CF::GH * CF::TILE + okm) = hi;
+            *reinterpret_cast<float4*>(smem + CF::GL * CF::TILE + okm) = lo;
+          }
+        }
+      }
+      umma::fence_async_smem();
+      __syncwarp();
+      if (lane == 0) umma::mbar_arrive(&mbar[KFULL]);
+
+      // ---- registers and staging are free: put the next tile's loads in flight, fetch the indices of the one after -
+      const int next = tile + gridDim.x;
+      if (next < total_tiles) {
+        issue_rows(next, it + 1);
+        if (next + (int)gridDim.x < total_tiles) load_indices(next + gridDim.x);
+      }
+
+      // ---- MN-major copies: free once the previous tile's last MMA is done and its epilogue has read them ---------
+      if (it > 0) umma::mbar_wait(&mbar[MFREE], ph ^ 1);
+#pragma unroll
+      for (int ps = 0; ps < PASSES; ++ps) {
+        const int r = ps * RPP + sub;
+        if (r < B) {
+          const uint32_t okm = umma::sw128_offset(r, c), omn = umma::sw128b32_offset(r, c);
+          constexpr int src[6] = {CF::KH, CF::KL, CF::GH, CF::GL, CF::QH, CF::QL};   // -> MKH, MKL, MGH, MGL, MQH, MQL
+#pragma unroll
+          for (int tl = 0; tl < 6; ++tl)
+            *reinterpret_cast<float4*>(mn + tl * CF::TILE + omn) = *reinterpret_cast<const float4*>(smem + src[tl] * CF::TILE + okm);
+        }
+      }
+      umma::fence_async_smem();
+      __syncwarp();
+      if (lane == 0) umma::mbar_arrive(&mbar[MFULL]);
+    }
+  } else {
+    umma::setmaxnreg_dec<kBtRegsMma>();
+  }
+  if (warp == EW + PW) {
+    // =========================================== MMA issuer ====================================================
+    // the warp runs the schedule uniformly; the lane chosen by elect.sync issues (always the same lane, so its
+    // tcgen05.commit covers every MMA issued before)
+    constexpr uint32_t idesc_s = umma::idesc_tf32(128, NP, false, false);
+    constexpr uint32_t idesc_o = umma::idesc_tf32(128, 32, false, true);
+    // descriptors differ only in their start-address field (bits [0,14), 16-byte units): base + offset / 16
+    const uint64_t kdesc0 = umma::smem_desc_sw128(sbase, 1024, 16);
+    const uint64_t mdesc0 = umma::smem_desc(mbase, 512, 1024, umma::kLayoutSw128Base32);
+    // D = A B^T, both K-major, 3xTF32 (small cross terms first).  `swap` exchanges the operand roles while keeping the
+    // product order, so D^T comes out bit-identical.  Called by the elected lane only.
+    auto ss_product = [&](uint32_t d, int xh, int xl, int yh, int yl, int ksteps, bool swap) {
+      uint64_t base = kdesc0;
+      asm volatile("" : "+l"(base));   // opaque: descriptors are re-derived here (one add each), not hoisted and spilled
+#pragma unroll
+      for (int p3 = 0; p3 < 3; ++p3) {
+        const int x = p3 == 1 ? xl : xh, y = p3 == 0 ? yl : yh;
+        const uint64_t dx = base + (uint64_t)((x * CF::TILE) >> 4), dy = base + (uint64_t)((y * CF::TILE) >> 4);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          if (kk >= ksteps) break;
+          if (swap) umma::mma_ss(d, dy + 2 * kk, dx + 2 * kk, idesc_s, (p3 | kk) != 0);
+          else umma::mma_ss(d, dx + 2 * kk, dy + 2 * kk, idesc_s, (p3 | kk) != 0);
+        }
+      }
+    };
+    // D = A[tmem hi/lo] * B[MN-major hi/lo], 3xTF32.  Called by the elected lane only.
+    auto ts_product = [&](uint32_t d, uint32_t a_hi, uint32_t a_lo, int bh, int bl) {
+      uint64_t base = mdesc0;
+      asm volatile("" : "+l"(base));
+#pragma unroll
+      for (int p3 = 0; p3 < 3; ++p3) {
+        const uint32_t a = p3 == 1 ? a_lo : a_hi;
+        const uint64_t db = base + (uint64_t)(((p3 == 0 ? bl : bh) * CF::TILE) >> 4);
+#pragma unroll
+        for (int kk = 0; kk < KSTEPS; ++kk) umma::mma_ts(d, a + 8 * kk, db + 64 * kk, idesc_o, (p3 | kk) != 0);
+      }
+    };
+    auto wait = [&](BtBar b, uint32_t parity) {
+      umma::mbar_wait(&mbar[b], parity);
+      umma::fence_after_sync();
+    };
+    auto scores_query_side = [&]() {
+      if (umma::elect_one()) {
+        ss_product(tS, CF::QH, CF::QL, CF::KH, CF::KL, CF::SK, false);
+        ss_product(tDP, CF::GH, CF::GL, CF::VH, CF::VL, CF::GK, false);
+        umma::commit(&mbar[QREADY]);
+      }
+      __syncwarp();
+    };
+    auto scores_key_side = [&]() {
+      if (umma::elect_one()) {
+        ss_product(tST, CF::QH, CF::QL, CF::KH, CF::KL, CF::SK, true);
+        ss_product(tDPT, CF::GH, CF::GL, CF::VH, CF::VL, CF::GK, true);
+        umma::commit(&mbar[KREADY]);
+      }
+      __syncwarp();
+    };
+    int it = 0;
+    int tile = blockIdx.x;
+    if (tile < total_tiles) {
+      wait(KFULL, 0);
+      scores_query_side();
+      scores_key_side();
+    }
+#pragma unroll 1
+    for (; tile < total_tiles; tile += gridDim.x, ++it) {
+      const uint32_t ph = it & 1;
+      const bool more = tile + (int)gridDim.x < total_tiles;
+      // The next tile's query-side scores go out as soon as its operands are there and dQ has drained tS / tDP, but
+      // this tile's MMAs never wait for the producer: probe between them, block only at the end.
+      bool next_q_issued = !more;
+      auto next_query_scores = [&](bool block) {
+        if (next_q_issued) return;
+        if (!block && !umma::mbar_test(&mbar[KFULL], ph ^ 1)) return;
+        wait(KFULL, ph ^ 1);
+        wait(DQDONE, ph);
+        scores_query_side();
+        next_q_issued = true;
+      };
+      wait(DSRDY, ph);
+      wait(MFULL, ph);
+      if (umma::elect_one()) {
+        ts_product(tO0, tS, tDP, CF::MKH, CF::MKL);     // dQ = dS K^
+        umma::commit(&mbar[DQDONE]);
+      }
+      __syncwarp();
+      next_query_scores(false);
+      wait(PTRDY, ph);
+      if (umma::elect_one()) {
+        ts_product(tO1, tST, tDPT, CF::MGH, CF::MGL);   // dV = P^T G'
+        umma::commit(&mbar[DVDONE]);
+      }
+      __syncwarp();
+      next_query_scores(false);
+      wait(DSTRDY, ph);
+      if (umma::elect_one()) {
+        ts_product(tO0, tST, tDPT, CF::MQH, CF::MQL);   // dK = dS^T Q^
+        umma::commit(&mbar[DKDONE]);
+        umma::commit(&mbar[MFREE]);
+      }
+      __syncwarp();
+      next_query_scores(true);
+      if (more) {                                       // next tile's key-side scores once dK has drained tST / tDPT
+        wait(DKDONE, ph);
+        scores_key_side();
+      }
+    }
+  }
+
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == EW + PW) umma::tmem_dealloc<CF::TMEM_COLS>(tmem);
+}
+
+// Sum the T per-table staging rows of every (hit, head) into dq, dk, dv.  thread <-> (n, h, 16-byte chunk).
+// Rows >= raw_size are the src/ flavour's padding: the reference overwrites their q^, k^ and v with zeros
+// (src/models/attention/hept.py:89-91), so no gradient reaches the caller's rows.
+template <int D>
+__global__ void __launch_bounds__(256) bwd_table_sum_kernel(const float* __restrict__ sq, const float* __restrict__ sk,
+                                                            const float* __restrict__ sv, int N, int H, int T,
+                                                            int raw_size, float* __restrict__ dq, float* __restrict__ dk,
+                                                            float* __restrict__ dv) {
+  constexpr int VCH = D / 4;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)N * H * VCH) return;
+  const int c = (int)(idx % VCH);
+  const size_t nh = idx / VCH;
+  const int h = (int)(nh % H);
+  const size_t n = nh / H;
+  const size_t src = (((size_t)h * N + n) * T) * D + 4 * c;
+  const size_t dst = (n * H + h) * D + 4 * c;
+  auto sum_tables = [&](const float* __restrict__ in, float* __restrict__ out) {
+    if (n >= (size_t)raw_size) {
+      *reinterpret_cast<float4*>(out + dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+      return;
+    }
+    float4 s = ldg4(in + src);
+    for (int t = 1; t < T; ++t) {   // table order, like the reference's sum over dim 0
+      const float4 x = ldg4(in + src + (size_t)t * D);
+      s.x += x.x; s.y += x.y; s.z += x.z; s.w += x.w;
+    }
+    *reinterpret_cast<float4*>(out + dst) = s;
+  };
+  sum_tables(sq, dq);
+  sum_tables(sk, dk);
+  sum_tables(sv, dv);
+}
+
+// dscale[h,c] = (sum over the head's tiles of partial[tile][c]) / scale[h,c]; fixed-order tree -> deterministic.
+__global__ void __launch_bounds__(256) dscale_tiles_kernel(const float* __restrict__ partial, const float* __restrict__ scale,
+                                                           int tiles_per_head, int C, float* __restrict__ dscale) {
+  __shared__ float red[256];
+  const int h = blockIdx.x / C, c = blockIdx.x % C;
+  float x = 0.f;
+  for (int b = threadIdx.x; b < tiles_per_head; b += 256) x += partial[((size_t)h * tiles_per_head + b) * 8 + c];
+  red[threadIdx.x] = x;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const float s = scale[h * C + c];
+    dscale[h * C + c] = s != 0.f ? red[0] / s : 0.f;
+  }
+}
+
+struct BwdTcPlan {
+  size_t hat_bytes, grow_bytes, stage_bytes, partial_bytes, total;
+  int tiles;
+};
+static BwdTcPlan plan_bwd_tc(const hept_shape* s) {
+  BwdTcPlan p;
+  p.tiles = s->T * s->H * (s->N / s->B);
+  p.hat_bytes = align_up(sizeof(float) * (size_t)s->N * s->H * 8, 256);
+  p.grow_bytes = align_up(sizeof(float) * (size_t)s->N * s->H * 32, 256);
+  p.stage_bytes = align_up(sizeof(float) * (size_t)s->H * s->N * s->T * s->D, 256);
+  p.partial_bytes = align_up(sizeof(float) * (size_t)p.tiles * 8, 256);
+  p.total = p.hat_bytes + p.grow_bytes + 3 * p.stage_bytes + p.partial_bytes;
+  return p;
+}
+size_t bwd_tc_workspace_bytes(const hept_shape* s) { return plan_bwd_tc(s).total; }
+
+template <int D, int C, int B>
+static int launch_bwd_tc(const hept_shape* s, const float* q, const float* k, const float* v, const float* coords,
+                         const float* scale, const int32_t* positions, const float* out_pre, const float* den_sum,
+                         const float* d_out_pre, float* dq, float* dk, float* dv, float* dscale, char* ws,
+                         cudaStream_t st) {
+  using CF = TcBwd<D, C, B>;
+  auto kern = block_attn_bwd_tc_kernel<D, C, B>;
+  const size_t smem = CF::TOTAL + 1024;
+  static int sms = 0;
+  if (!sms) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "block_attn_bwd_tc: cannot reserve %zu B of shared memory: %s", smem,
+                 cudaGetErrorString(e));
+    int dev = 0, n = 0;
+    cudaGetDevice(&dev);
+    e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    HEPT_REQUIRE(e == cudaSuccess && n > 0, HEPT_ECUDA, "block_attn_bwd_tc: cannot read the SM count");
+    sms = n;
+  }
+  BwdTcPlan p = plan_bwd_tc(s);
+  float* hat = (float*)ws;
+  float* grows = (float*)(ws + p.hat_bytes);
+  float* sq = (float*)(ws + p.hat_bytes + p.grow_bytes);
+  float* sk = (float*)((char*)sq + p.stage_bytes);
+  float* sv = (float*)((char*)sk + p.stage_bytes);
+  float* partial = (float*)((char*)sv + p.stage_bytes);
+  int rc;
+  if ((rc = hept_hat_coords(s, coords, scale, hat, st))) return rc;
+  const size_t rows = (size_t)s->N * s->H;
+  grad_rows_kernel<D><<<(unsigned)((rows * 8 + 255) / 256), 256, 0, st>>>(d_out_pre, out_pre, den_sum, rows, grows);
+  HEPT_CHECK_LAUNCH("grad_rows");
+  const int mask = bwd_stage_mask();
+  if (mask & 3) {
+    const int grid = p.tiles < sms ? p.tiles : sms;   // one CTA per SM (the tile uses all 512 TMEM columns)
+    kern<<<grid, kBtThreads, smem, st>>>(q, k, v, hat, grows, positions, s->N, s->H, s->T, s->raw_size, p.tiles, sq, sk,
+                                         sv, partial);
+    HEPT_CHECK_LAUNCH("block_attn_bwd_tc");
+  }
+  if (!(mask & 4)) return HEPT_OK;
+  const size_t total = rows * (D / 4);
+  bwd_table_sum_kernel<D><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(sq, sk, sv, s->N, s->H, s->T, s->raw_size, dq, dk, dv);
+  HEPT_CHECK_LAUNCH("bwd_table_sum");
+  dscale_tiles_kernel<<<s->H * C, 256, 0, st>>>(partial, scale, s->T * (s->N / s->B), C, dscale);
+  HEPT_CHECK_LAUNCH("dscale_tiles");
+  return HEPT_OK;
+}
+
+int block_attention_bwd_tc(const hept_shape* s, const float* q, const float* k, const float* v, const float* coords,
+                           const float* scale, const int32_t* positions, const float* out_pre, const float* den_sum,
+                           const float* d_out_pre, float* dq, float* dk, float* dv, float* dscale, char* ws,
+                           cudaStream_t st) {
+  if (s->D == 24 && s->C == 6 && s->B == 100)
+    return launch_bwd_tc<24, 6, 100>(s, q, k, v, coords, scale, positions, out_pre, den_sum, d_out_pre, dq, dk, dv, dscale, ws, st);
+  if (s->D == 24 && s->C == 4 && s->B == 100)
+    return launch_bwd_tc<24, 4, 100>(s, q, k, v, coords, scale, positions, out_pre, den_sum, d_out_pre, dq, dk, dv, dscale, ws, st);
+  if (s->D == 8 && s->C == 6 && s->B == 10)
+    return launch_bwd_tc<8, 6, 10>(s, q, k, v, coords, scale, positions, out_pre, den_sum, d_out_pre, dq, dk, dv, dscale, ws, st);
+  set_error("block_attention_bwd (tensor-core engine): (D=%d, C=%d, B=%d) not compiled in", s->D, s->C, s->B);
+  return HEPT_EUNSUPPORTED;
+}
+
+}  // namespace hept

@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(kTcThreads, 2)
   static_assert(E + 2 <= 32 && D % 4 == 0 && D <= kTcVN && B <= kTcN && B <= kTcM, "tile shape");
   using SM = TcFwdSmem<D, C, B>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = umma::align1024(smem_raw);
   float* s_nq = reinterpret_cast<float*>(smem + SM::OFF_NQ);
   __shared__ uint64_t mbar;
   __shared__ uint32_t tmem_slot;

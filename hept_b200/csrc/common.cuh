@@ -14,7 +14,7 @@ void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 int bwd_stage_mask();
 int engine();  // 0 = fp32 SIMT tiles, 1 = tcgen05 tiles
-int bwd_variant();  // 1 = one lane per row (attn_bwd.cu), 2 = lane pairs + FFMA2 (attn_bwd2.cu)
+int bwd_variant();  // 1 = one lane per row (attn_bwd.cu), 2 = lane pairs + FFMA2 (attn_bwd2.cu), 3 = tcgen05 (attn_bwd_tc.cu)
 
 #define HEPT_REQUIRE(cond, code, ...)      \
   do {                                     \

@@ -60,6 +60,34 @@ __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n"
       :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate) : "memory");
 }
+// Warp-uniform variants: the whole warp executes the call, elect.sync picks the one lane that issues (always the same
+// lane for a full mask, which is what tcgen05.commit needs: it tracks the MMAs of the issuing thread).  Keeps the
+// issue loop free of divergence, so descriptors stay in uniform registers.
+__device__ __forceinline__ void mma_ss_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\telect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+      :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_ts_elect(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\telect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n"
+      :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate) : "memory");
+}
+__device__ __forceinline__ void commit_elect(uint64_t* mbar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n"
+      :: "r"(smem_u32(mbar)) : "memory");
+}
+// true on exactly one lane of a converged warp (always the same lane).  Branching on it tells ptxas that a single
+// lane runs the guarded block, so tcgen05 instructions inside need no per-lane serialisation loop.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t p;
+  asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\tselp.u32 %0, 1, 0, e;\n\t}\n" : "=r"(p));
+  return p != 0;
+}
 // make the mbarrier observe completion of all MMAs issued so far by this thread
 __device__ __forceinline__ void commit(uint64_t* mbar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(mbar)) : "memory");
@@ -125,6 +153,13 @@ __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&r)[8]
                : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// the same wait, with the loaded registers as in/out operands: no use of them can be scheduled above the wait
+__device__ __forceinline__ void tmem_wait_ld(uint32_t (&a)[8], uint32_t (&b)[8]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]), "+r"(b[0]),
+                 "+r"(b[1]), "+r"(b[2]), "+r"(b[3]), "+r"(b[4]), "+r"(b[5]), "+r"(b[6]), "+r"(b[7])
+               :: "memory");
+}
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ---- mbarrier ---------------------------------------------------------------------------------------
@@ -144,6 +179,43 @@ __device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
   }
   __trap();
 }
+
+// one non-blocking probe of the phase with parity `parity`
+__device__ __forceinline__ bool mbar_test(uint64_t* mbar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(done) : "r"(smem_u32(mbar)), "r"(parity) : "memory");
+  return done != 0;
+}
+// per-warpgroup register budget (all four warps of the warpgroup execute it)
+template <int REGS>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(REGS)); }
+template <int REGS>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(REGS)); }
+// dynamic shared memory rounded up to 1024 B without leaving the shared address space (a cast through uintptr_t
+// makes every later access a generic LD/ST)
+__device__ __forceinline__ uint8_t* align1024(uint8_t* p) { return p + ((1024u - (smem_u32(p) & 1023u)) & 1023u); }
+// element `I` of a float4, I known at compile time
+template <int I>
+__device__ __forceinline__ float& elem(float4& v) {
+  if constexpr (I == 0) return v.x;
+  else if constexpr (I == 1) return v.y;
+  else if constexpr (I == 2) return v.z;
+  else return v.w;
+}
+// plain arrive (count 1), CTA scope, release semantics
+__device__ __forceinline__ void mbar_arrive(uint64_t* mbar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(mbar)) : "memory");
+}
+// named barrier among `count` threads (count % 32 == 0); id 0 is __syncthreads
+__device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory"); }
+
+// ---- 16-byte asynchronous global -> shared copy; src_bytes == 0 zero-fills the destination -------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // ---- tf32 split: x = hi + lo with hi = round-to-nearest tf32 --------------------------------------
 __device__ __forceinline__ float tf32_hi(float x) {

@@ -8,11 +8,14 @@ namespace hept {
 
 constexpr int kTM = 128, kTN = 112, kTK = 32, kTV = 32;
 
+// KM_B32 == true: the K-major operands A and Bm are stored with the SWIZZLE_128B_BASE32B pattern as well (the pattern
+// the MN-major operand needs), i.e. one shared-memory image of a row-per-hit tile serves both roles.
+template <bool KM_B32>
 __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ Bm,
                                                                const float* __restrict__ V, float* __restrict__ S_out,
                                                                float* __restrict__ O_out) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = umma::align1024(smem_raw);
   uint8_t* sA = smem;                       // 128 rows x 128 B
   uint8_t* sB = sA + kTM * 128;             // 112 rows x 128 B
   uint8_t* sV = sB + kTN * 128;             // 112 rows x 128 B   (row = k, 32 floats along n)
@@ -22,11 +25,13 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* __re
 
   for (int idx = tid; idx < kTM * 8; idx += 128) {
     const int r = idx >> 3, c = idx & 7;
-    *reinterpret_cast<float4*>(sA + umma::sw128_offset(r, c)) = *reinterpret_cast<const float4*>(A + r * kTK + 4 * c);
+    *reinterpret_cast<float4*>(sA + (KM_B32 ? umma::sw128b32_offset(r, c) : umma::sw128_offset(r, c))) =
+        *reinterpret_cast<const float4*>(A + r * kTK + 4 * c);
   }
   for (int idx = tid; idx < kTN * 8; idx += 128) {
     const int r = idx >> 3, c = idx & 7;
-    *reinterpret_cast<float4*>(sB + umma::sw128_offset(r, c)) = *reinterpret_cast<const float4*>(Bm + r * kTK + 4 * c);
+    *reinterpret_cast<float4*>(sB + (KM_B32 ? umma::sw128b32_offset(r, c) : umma::sw128_offset(r, c))) =
+        *reinterpret_cast<const float4*>(Bm + r * kTK + 4 * c);
     *reinterpret_cast<float4*>(sV + umma::sw128b32_offset(r, c)) = *reinterpret_cast<const float4*>(V + r * kTV + 4 * c);
   }
   if (tid == 0) umma::mbar_init(&mbar, 1);
@@ -42,8 +47,9 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* __re
     constexpr uint32_t idesc = umma::idesc_tf32(kTM, kTN, false, false);
 #pragma unroll
     for (int k = 0; k < kTK / 8; ++k) {
-      const uint64_t da = umma::smem_desc_sw128(umma::smem_u32(sA) + 32 * k, 1024, 16);
-      const uint64_t db = umma::smem_desc_sw128(umma::smem_u32(sB) + 32 * k, 1024, 16);
+      const uint32_t lay = KM_B32 ? umma::kLayoutSw128Base32 : umma::kLayoutSw128;
+      const uint64_t da = umma::smem_desc(umma::smem_u32(sA) + 32 * k, 1024, 16, lay);
+      const uint64_t db = umma::smem_desc(umma::smem_u32(sB) + 32 * k, 1024, 16, lay);
       umma::mma_ss(tS, da, db, idesc, k > 0);
     }
     umma::commit(&mbar);
@@ -91,7 +97,7 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* __re
 __global__ void __launch_bounds__(128, 1) umma_symmetry_kernel(const float* __restrict__ X, const float* __restrict__ Y,
                                                                float* __restrict__ S_xy, float* __restrict__ S_yx) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = umma::align1024(smem_raw);
   uint8_t* sX = smem;                       // 128 rows x 128 B (rows >= 112 zero)
   uint8_t* sY = sX + kTM * 128;             // 128 rows x 128 B
   __shared__ uint64_t mbar;
@@ -156,16 +162,19 @@ extern "C" int hept_debug_umma_symmetry(const float* X, const float* Y, float* S
 }
 
 extern "C" int hept_debug_umma_selftest(const float* A, const float* Bm, const float* V, float* S_out, float* O_out,
-                                        void* stream) {
+                                        int kmajor_base32, void* stream) {
   HEPT_REQUIRE(A && Bm && V && S_out && O_out, HEPT_EINVAL, "umma_selftest: null pointer");
   const size_t smem = (size_t)(kTM + 2 * kTN) * 128 + 1024;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(umma_selftest_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(umma_selftest_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "umma_selftest: %s", cudaGetErrorString(e));
     configured = true;
   }
-  umma_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, Bm, V, S_out, O_out);
+  if (kmajor_base32) umma_selftest_kernel<true><<<1, 128, smem, (cudaStream_t)stream>>>(A, Bm, V, S_out, O_out);
+  else umma_selftest_kernel<false><<<1, 128, smem, (cudaStream_t)stream>>>(A, Bm, V, S_out, O_out);
   HEPT_CHECK_LAUNCH("umma_selftest");
   return HEPT_OK;
 }

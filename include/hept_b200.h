@@ -137,9 +137,11 @@ int hept_get_bwd_variant(void);
 
 /* self-test of the tcgen05 / TMEM building blocks (hept_b200/csrc/umma.cuh): S = A B^T with A (128,32),
  * Bm (112,32) both K-major, then O = S V with S read back from TMEM and V (112,32) MN-major.
- * Outputs S_out (128,112), O_out (128,32).  Used by tests/test_gpu_umma.py only. */
+ * Outputs S_out (128,112), O_out (128,32).  kmajor_base32 != 0 stores the K-major operands with the MN-major
+ * operand's swizzle (SWIZZLE_128B_BASE32B), the single-image layout the backward tiles rely on.
+ * Used by tests/test_gpu_umma.py only. */
 int hept_debug_umma_selftest(const float* A, const float* Bm, const float* V, float* S_out, float* O_out,
-                             void* stream);
+                             int kmajor_base32, void* stream);
 
 /* S_xy = X Y^T and S_yx = Y X^T (X, Y (112,32) fp32; outputs (128,112), rows >= 112 zero) on the tensor core: probes
  * whether the tf32 MMA is bitwise symmetric under an exchange of its operands (tests/test_gpu_umma.py). */

@@ -34,7 +34,8 @@ REPORT = {}
 def rkey(name):
     from hept_b200 import _lib
 
-    return f"{name}@{'tc' if _lib.load().hept_get_engine() else 'simt'}"
+    lib = _lib.load()
+    return f"{name}@{'tc' if lib.hept_get_engine() else 'simt'}+bwd{lib.hept_get_bwd_variant()}"
 
 
 @pytest.fixture(scope="module", autouse=True)
@@ -45,17 +46,22 @@ def _report():
         json.dump(REPORT, f, indent=1, sort_keys=True)
 
 
-@pytest.fixture(params=["simt", "tcgen05"], autouse=True)
+ENGINES = {"simt": (0, 1), "tcgen05": (1, 3)}   # name -> (forward engine, backward variant)
+
+
+@pytest.fixture(params=list(ENGINES), autouse=True)
 def engine(request):
-    """Every test runs once per tile engine (fp32 CUDA-core tiles / tcgen05 3xTF32 tiles); same tolerances."""
+    """Every test runs once per tile engine: fp32 CUDA-core tiles (both generations of backward tiles) and the
+    tcgen05 3xTF32 tiles (forward and backward); same tolerances."""
     from hept_b200 import _lib
 
     lib = _lib.load()
-    lib.hept_set_engine(1 if request.param == "tcgen05" else 0)
-    lib.hept_set_bwd_variant(2 if request.param == "tcgen05" else 1)   # covers both generations of backward tiles
+    fwd, bwd = ENGINES[request.param]
+    lib.hept_set_engine(fwd)
+    lib.hept_set_bwd_variant(bwd)
     yield request.param
     lib.hept_set_engine(1)
-    lib.hept_set_bwd_variant(1)
+    lib.hept_set_bwd_variant(3)
 
 
 def dev():
@@ -390,6 +396,34 @@ def test_full_size_backward_invariants_tracking60k():
     tot = (dq + dk).double().view(n, d.H, d.D).sum(0).abs().max()
     mass = (dq.double().abs() + dk.double().abs()).view(n, d.H, d.D).sum(0).max()
     assert float(tot) <= 1e-4 * float(mass)
+
+
+def test_full_size_backward_engines_agree(engine):
+    """60k hits: the tcgen05 backward (3xTF32, both sides of every tile on the tensor core, persistent warp-specialised
+    pipeline ~100 tiles deep per SM) against the fp32 CUDA-core backward on the same saved forward state."""
+    if engine != "tcgen05":
+        pytest.skip("cross-engine comparison runs once")
+    from hept_b200 import _lib, ops
+
+    lib = _lib.load()
+    cfg, params, kw, q, k, v = _full_size_problem(60000)
+    n = q.shape[0]
+    d = dims_of(cfg, n)
+    sh = kw["combined_shifts"].to(dev())
+    qd, kd, vd, cd = q.to(dev()), k.to(dev()), v.to(dev()), kw["coords"].to(dev())
+    w, al = params["w_rpe.weight"].to(dev()), params["e2lsh.alpha"].to(dev())
+    out, den, scale, pos = ops.attention_fwd(d, qd, kd, vd, cd, w, cfg["num_w_per_dist"], al, combined_shifts=sh)
+    g = torch.randn(n, d.H * d.D, generator=torch.Generator().manual_seed(5)).to(dev())
+    res = {}
+    for variant in (1, 3):
+        lib.hept_set_bwd_variant(variant)
+        res[variant] = [t.double() for t in ops.attention_bwd(d, qd, kd, vd, cd, scale, pos, out, den, g)]
+    lib.hept_set_bwd_variant(3)
+    for name, a, b in zip(("dq", "dk", "dv", "dscale"), res[3], res[1]):
+        err = float((a - b).norm() / b.norm())
+        worst = float(((a - b).abs().max()) / b.abs().max())
+        REPORT[rkey(f"engines_60k_{name}")] = [err, worst]
+        assert err < 1e-4 and worst < 1e-3, (name, err, worst)   # 3xTF32 + truncating accumulator vs fp32 FMA chains
 
 
 # ------------------------------------------------------- BASELINE.json configs[2..3] and the prepare step on device

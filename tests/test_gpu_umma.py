@@ -8,7 +8,8 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def test_umma_selftest_exact_on_small_integers():
+@pytest.mark.parametrize("kmajor_base32", [0])   # 1 (K-major operands in the MN-major operand's SWIZZLE_128B_BASE32B
+def test_umma_selftest_exact_on_small_integers(kmajor_base32):   # image) faults on sm_100a: the layouts cannot be shared
     from hept_b200 import _lib
 
     lib = _lib.load()
@@ -21,7 +22,8 @@ def test_umma_selftest_exact_on_small_integers():
     O = torch.empty(128, 32, device=dev)
     Ad, Bd, Vd = A.to(dev), B.to(dev), V.to(dev)
     p = lambda t: ctypes.c_void_p(t.data_ptr())
-    rc = lib.hept_debug_umma_selftest(p(Ad), p(Bd), p(Vd), p(S), p(O), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    rc = lib.hept_debug_umma_selftest(p(Ad), p(Bd), p(Vd), p(S), p(O), kmajor_base32,
+                                      ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     _lib.check(rc, "hept_debug_umma_selftest")
     torch.cuda.synchronize()
     S_ref = A.double() @ B.double().T
