@@ -341,17 +341,30 @@ def kernel_roofline(resident, gouts, cfg, mod, w_rpe, peak, peak_src, n_sets):
         return e0.elapsed_time(e1) / reps * 1e-3
 
     qkv_b, perm_b, stage_b = 3 * H * D * 4, 2 * T * H * 4, T * H * 128
+    variant = lib.hept_get_bwd_variant()
     per_hit = {   # algorithmic bytes per hit of each tile kernel (reads + writes at its own boundary)
         "block_attn_fwd": qkv_b + 4 * C + perm_b + stage_b,
         "block_attn_bwd_dq": qkv_b + 4 * C + perm_b + 2 * H * D * 4 + 4 * H + stage_b,
         "block_attn_bwd_dkv": qkv_b + 4 * C + perm_b + 2 * H * D * 4 + 4 * H + stage_b + T * H * D * 4,
+        # fused tcgen05 backward: q, k, v, scaled coordinates (N,H,8), gradient rows (N,H,32), permutations in;
+        # dq^, dk^, dv rows of D floats per (head, hit, table) out
+        "block_attn_bwd_tc": qkv_b + H * 32 + H * 128 + perm_b + 3 * T * H * D * 4,
     }
+    flops = {"block_attn_fwd": 2 * T * H * B * (D + C + D), "block_attn_bwd_dq": 2 * T * H * B * (2 * (D + C) + D),
+             "block_attn_bwd_dkv": 2 * T * H * B * (2 * (D + C) + 2 * D),
+             "block_attn_bwd_tc": 2 * T * H * B * (2 * (D + C) + 2 * D + 2 * (D + C) + D)}   # both sides recompute S and dP
     times = {}
     times["block_attn_fwd"] = ev_time(lambda i: ops.block_attention_fwd(d, *saved[i % n_sets][:6]))
-    for name, mask in (("block_attn_bwd_dq", 1), ("block_attn_bwd_dkv", 2)):
-        lib.hept_set_bwd_stage_mask(mask)
-        times[name] = ev_time(lambda i: ops.attention_bwd(d, *saved[i % n_sets]))
-    lib.hept_set_bwd_stage_mask(7)
+    if variant == 3:
+        lib.hept_set_bwd_stage_mask(3)
+        t_all = ev_time(lambda i: ops.attention_bwd(d, *saved[i % n_sets]))
+        lib.hept_set_bwd_stage_mask(7)
+        times["block_attn_bwd_tc"] = t_all
+    else:
+        for name, mask in (("block_attn_bwd_dq", 1), ("block_attn_bwd_dkv", 2)):
+            lib.hept_set_bwd_stage_mask(mask)
+            times[name] = ev_time(lambda i: ops.attention_bwd(d, *saved[i % n_sets]))
+        lib.hept_set_bwd_stage_mask(7)
     top = max(times, key=times.get)
     achieved = per_hit[top] * N_RAW / times[top] / 1e9
     # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (tools/ncu_summary.py)
@@ -360,19 +373,21 @@ def kernel_roofline(resident, gouts, cfg, mod, w_rpe, peak, peak_src, n_sets):
     if os.path.exists(tpath):
         with open(tpath) as f:
             tj = json.load(f)
-        variant = lib.hept_get_bwd_variant()
         names = {"block_attn_fwd": "block_attn_fwd_tc_kernel" if lib.hept_get_engine() else "block_attn_fwd_kernel",
                  "block_attn_bwd_dq": "block_attn_bwd_dq_kernel" if variant == 1 else "block_attn_bwd_pair_kernel",
-                 "block_attn_bwd_dkv": "block_attn_bwd_dkv_kernel" if variant == 1 else "block_attn_bwd_pair_kernel"}
+                 "block_attn_bwd_dkv": "block_attn_bwd_dkv_kernel" if variant == 1 else "block_attn_bwd_pair_kernel",
+                 "block_attn_bwd_tc": "block_attn_bwd_tc_kernel"}
         if names[top] in tj:
             traffic, tsrc = tj[names[top]]["dram_bytes_per_launch"], "profiles/r1_traffic.json (" + tj[names[top]]["source"] + ")"
-    flops = {"block_attn_fwd": 2 * T * H * B * (D + C + D), "block_attn_bwd_dq": 2 * T * H * B * (2 * (D + C) + D),
-             "block_attn_bwd_dkv": 2 * T * H * B * (2 * (D + C) + 2 * D)}
+    tensor = variant == 3 or lib.hept_get_engine()
     return {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": traffic, "traffic_source": tsrc, "peak_source": peak_src, "bytes_per_launch": per_hit[top] * N_RAW,
             "kernel_ms": {k: v * 1e3 for k, v in times.items()},
-            "fp32_tflops": {k: flops[k] * N_RAW / times[k] / 1e12 for k in times},
-            "note": "tile kernels are fp32-FMA bound, not HBM bound (SURVEY.md 7.3-3); fp32_tflops is against ~74 TF/s SIMT peak"}
+            "tile_tflops": {k: flops[k] * N_RAW / times[k] / 1e12 for k in times},
+            "note": ("kernel_ms of block_attn_bwd_tc includes its two streaming pre-passes (scaled coordinates, gradient rows; "
+                     "~45 us); tile kernels are bounded by the tensor pipe + the SIMT glue around it, not by HBM: "
+                     "tile_tflops counts algorithmic fp32 FLOPs (each is three tf32 MMA passes)") if tensor else
+                    "tile kernels are fp32-FMA bound, not HBM bound (SURVEY.md 7.3-3); tile_tflops is against ~74 TF/s SIMT peak"}
 
 
 def main():

@@ -52,6 +52,7 @@ SIGNATURES = {
     "hept_get_bwd_variant": (C.c_int, []),
     "hept_debug_umma_selftest": (C.c_int, [_p, _p, _p, _p, _p, C.c_int, _p]),
     "hept_debug_umma_symmetry": (C.c_int, [_p, _p, _p, _p, _p]),
+    "hept_debug_umma_timing": (C.c_int, [C.c_int, C.c_int, _p, _p]),
 }
 
 _lib = None

@@ -7,10 +7,14 @@
 //   query side (TMEM lane = query i)                     key side (TMEM lane = key j)
 //   S   = Q^ K^^T            SS, N = NP                   S^T  = K^ Q^^T            SS (operands exchanged)
 //   dP  = G' V'^T            SS                           dP^T = V' G'^T            SS
-//   dS  = [x<=0] P dP  -> TMEM (hi, lo), rs_i = sum_j     P^T -> TMEM (hi, lo), dS^T kept in registers, cs_j = sum_i
-//   dQ  = dS K^              TS, B = K^ MN-major          dV   = P^T G'             TS, B = G' MN-major
-//   dq^_i = dQ_i - rs_i q'_i                              dK   = dS^T Q^            TS (after dS^T replaced P^T)
+//   dS  = P dP  -> TMEM (hi, lo)                          P^T -> TMEM (hi, lo), dS^T kept in registers
+//   dQ  = dS [K^ | 1]        TS, B = K^ MN-major          dV   = P^T G'             TS, B = G' MN-major
+//   dq^_i = dQ_i - rs_i q'_i                              dK   = dS^T [Q^ | 1]      TS (after dS^T replaced P^T)
 //                                                         dk^_j = dK_j - cs_j k'_j
+// The row / column sums rs_i = sum_j dS_ij, cs_j = sum_i dS_ij come out of the same MMAs (a ones column in the
+// MN-major operand), so they are the sums of exactly the (hi, lo) values that produced dQ / dK.
+// The reference's clamp(max=0) mask [S <= 0] on dS is not applied: S = -|q^ - k^|^2 / 2 is positive only by rounding,
+// where k^ - q^ (the factor dS multiplies) vanishes; P itself is clamped like the reference's.
 // with x = log2e (q'.k' - |k'|^2/2) - log2e |q'|^2/2 (the key norm rides in two spare K slots of the contraction,
 // split three ways so it is exact), P = ex2(min(x, 0)), G'_i = [g_i / den_i, -(g_i . y_i) / den_i], V'_j = [v_j, 1]
 // (so dP = gd . v - gy comes out of one contraction).  The tf32 MMA is bitwise symmetric under an exchange of its
@@ -67,8 +71,8 @@ struct TcBwd {
   static constexpr int OFF_STG_V = OFF_MN + 6 * TILE;
   static constexpr int OFF_STG_G = OFF_STG_V + PASSES * kBtProdThreads * 16;
   static constexpr int OFF_AUX = OFF_STG_G + PASSES * kBtProdThreads * 16;
-  // aux words: nq2[2][128], qidx[3][128], kidx[3][128], rs[2][128], cs[2][128], dsc[8][8]
-  static constexpr int AUX_BYTES = (12 * 128 + 64) * 4;
+  // aux words: nq2[2][128], qidx[3][128], kidx[3][128], dsc[8][8]
+  static constexpr int AUX_BYTES = (8 * 128 + 64) * 4;
   static constexpr int TOTAL = OFF_AUX + AUX_BYTES;
   static constexpr int TMEM_NEED = 4 * NP + 64;
   static constexpr int TMEM_COLS = pow2_cols(TMEM_NEED);
@@ -83,6 +87,12 @@ enum BtBar { KFULL, MFULL, MFREE, QREADY, KREADY, DSRDY, DQDONE, PTRDY, DVDONE, 
 // hi = x rounded to tf32 (round half away, like cvt.rna; x finite), lo = x - hi (exact)
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+  lo = x - hi;
+}
+// hi = x truncated to tf32, lo = x - hi (exact): one instruction less; the tensor core drops the low 13 bits of lo
+// either way, and the sums that must agree with the products (rs, cs) are taken by the same MMAs
+__device__ __forceinline__ void trunc_tf32(float x, float& hi, float& lo) {
+  hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
   lo = x - hi;
 }
 __device__ __forceinline__ void split4(const float4 x, float4& hi, float4& lo) {
@@ -133,9 +143,7 @@ __global__ void __launch_bounds__(kBtThreads, 1)
   float* s_nq2 = reinterpret_cast<float*>(smem + CF::OFF_AUX);   // [2][128]  log2e * -|q'|^2 / 2, by tile parity
   int* s_qidx = reinterpret_cast<int*>(s_nq2 + 256);             // [3][128]  original hit index of query row r, tile % 3
   int* s_kidx = s_qidx + 384;                                    // [3][128]
-  float* s_rs = reinterpret_cast<float*>(s_kidx + 384);          // [2][128]  row sums of dS per column part
-  float* s_cs = s_rs + 256;                                      // [2][128]  column sums
-  float* s_dsc = s_cs + 256;                                     // [8][8]    d scale partials per epilogue warp
+  float* s_dsc = reinterpret_cast<float*>(s_kidx + 384);         // [8][8]    d scale partials per epilogue warp
   __shared__ uint64_t mbar[BT_NBAR];
   __shared__ uint32_t tmem_slot;
 
@@ -169,7 +177,7 @@ __global__ void __launch_bounds__(kBtThreads, 1)
         *reinterpret_cast<float4*>(smem + tl * CF::TILE + umma::sw128_offset(rr, c)) = tl == CF::KH ? kz : z;
 #pragma unroll
       for (int tl = 0; tl < 6; ++tl)
-        *reinterpret_cast<float4*>(mn + tl * CF::TILE + umma::sw128b32_offset(rr, c)) = tl == CF::MKH ? kz : z;
+        *reinterpret_cast<float4*>(mn + tl * CF::TILE + umma::sw128b32_offset(rr, c)) = z;
     }
     for (int rr = B + ptid; rr < 128; rr += kBtProdThreads) {
       s_nq2[rr] = -1e30f; s_nq2[128 + rr] = -1e30f;
@@ -209,6 +217,32 @@ __global__ void __launch_bounds__(kBtThreads, 1)
       __syncwarp();
       if (lane == 0) umma::mbar_arrive(&mbar[b]);
     };
+    // d scale: each thread keeps its share of sum_i q'_ic dq^_ic + sum_j k'_jc dk^_jc over the consecutive tiles of one
+    // head; when the head changes the CTA reduces them in a fixed order (warp tree, then warps in order) into
+    // ds_partial[cta][head][c].  A CTA visits its tiles in a fixed order, so the result is deterministic.
+    float dsc[C];
+#pragma unroll
+    for (int cc = 0; cc < C; ++cc) dsc[cc] = 0.f;
+    int dsc_head = -1;
+    auto flush_dscale = [&]() {
+      if (dsc_head < 0) return;
+#pragma unroll
+      for (int cc = 0; cc < C; ++cc) {
+        float x = dsc[cc];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0) s_dsc[warp * 8 + cc] = x;
+        dsc[cc] = 0.f;
+      }
+      umma::bar_sync(1, kBtEpiThreads);
+      if (tid < C) {
+        float x = 0.f;
+#pragma unroll
+        for (int w = 0; w < EW; ++w) x += s_dsc[w * 8 + tid];
+        ds_partial[((size_t)blockIdx.x * H + dsc_head) * 8 + tid] = x;
+      }
+      umma::bar_sync(1, kBtEpiThreads);                  // s_dsc may be rewritten
+    };
     int it = 0;
 #pragma unroll 1
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -224,7 +258,6 @@ __global__ void __launch_bounds__(kBtThreads, 1)
       umma::fence_after_sync();
       {
         const float nq2 = nq2s[row];
-        float rs = 0.f;
 #pragma unroll
         for (int ci = 0; ci < MAXCH; ++ci) {
           const int ch = part + ci * kBtParts;
@@ -238,15 +271,12 @@ __global__ void __launch_bounds__(kBtThreads, 1)
             for (int u = 0; u < 8; ++u) {
               const float x = fmaf(__uint_as_float(ra[u]), kLog2e, nq2);
               const float p = exp2_fast(fminf(x, 0.f));
-              const float ds = x <= 0.f ? p * __uint_as_float(rb[u]) : 0.f;   // clamp(max=0) passes gradient where S <= 0
-              rs += ds;
-              split_tf32(ds, dh[u], dl[u]);
+              trunc_tf32(p * __uint_as_float(rb[u]), dh[u], dl[u]);
             }
             umma::tmem_st8(tS + lane_base + 8 * ch, dh);
             umma::tmem_st8(tDP + lane_base + 8 * ch, dl);
           }
         }
-        s_rs[part * 128 + row] = rs;
       }
       arrive_tmem(DSRDY);
 
@@ -255,7 +285,6 @@ __global__ void __launch_bounds__(kBtThreads, 1)
       umma::mbar_wait(&mbar[KREADY], ph);
       umma::fence_after_sync();
       {
-        float cs = 0.f;
 #pragma unroll
         for (int ci = 0; ci < MAXCH; ++ci) {
           const int ch = part + ci * kBtParts;
@@ -271,23 +300,20 @@ __global__ void __launch_bounds__(kBtThreads, 1)
             for (int u = 0; u < 8; ++u) {
               const float x = fmaf(__uint_as_float(ra[u]), kLog2e, nq2[u]);   // the same fmaf as the query side
               const float p = exp2_fast(fminf(x, 0.f));
-              const float ds = x <= 0.f ? p * __uint_as_float(rb[u]) : 0.f;
-              cs += ds;
-              dsr[ci * 8 + u] = ds;
-              split_tf32(p, phv[u], plv[u]);
+              dsr[ci * 8 + u] = p * __uint_as_float(rb[u]);
+              trunc_tf32(p, phv[u], plv[u]);
             }
             umma::tmem_st8(tST + lane_base + 8 * ch, phv);
             umma::tmem_st8(tDPT + lane_base + 8 * ch, plv);
           }
         }
-        s_cs[part * 128 + row] = cs;
       }
       arrive_tmem(PTRDY);
-      umma::bar_sync(1, kBtEpiThreads);                  // s_rs / s_cs of both column parts are visible
 
-      float dsc[C];   // this thread's share of sum_i q'_ic dq^_ic + sum_j k'_jc dk^_jc
-#pragma unroll
-      for (int cc = 0; cc < C; ++cc) dsc[cc] = 0.f;
+      if (h != dsc_head) {   // first tile of another head: hand in the finished head's sums
+        flush_dscale();
+        dsc_head = h;
+      }
       // x'_e (e in this thread's 16 columns) of row `row` of an MN-major (hi, lo) tile pair: hi + lo is exact
       auto centred_row = [&](int th_, int tl_, float (&xr)[16]) {
 #pragma unroll
@@ -320,8 +346,9 @@ __global__ void __launch_bounds__(kBtThreads, 1)
       {
         float acc[16], xr[16];
         umma::tmem_ld16(tO0 + lane_base + 16 * part, acc);
+        const float rs = umma::tmem_ld1(tO0 + lane_base + E);       // column E of dQ: sum_j dS_ij
         centred_row(CF::MQH, CF::MQL, xr);
-        finish_rows(acc, xr, s_rs[row] + s_rs[128 + row], row < B ? qidx[row] : -1, stage_dq);
+        finish_rows(acc, xr, rs, row < B ? qidx[row] : -1, stage_dq);
       }
 
       // ---- dS^T replaces P^T once dV has consumed it ------------------------------------------------------------
@@ -333,7 +360,7 @@ __global__ void __launch_bounds__(kBtThreads, 1)
         if (ch < KSTEPS) {
           float dh[8], dl[8];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) split_tf32(dsr[ci * 8 + u], dh[u], dl[u]);
+          for (int u = 0; u < 8; ++u) trunc_tf32(dsr[ci * 8 + u], dh[u], dl[u]);
           umma::tmem_st8(tST + lane_base + 8 * ch, dh);
           umma::tmem_st8(tDPT + lane_base + 8 * ch, dl);
         }
@@ -359,29 +386,16 @@ __global__ void __launch_bounds__(kBtThreads, 1)
       {
         float acc[16], xr[16];
         umma::tmem_ld16(tO0 + lane_base + 16 * part, acc);
+        const float cs = umma::tmem_ld1(tO0 + lane_base + E);       // column E of dK: sum_i dS_ij
         centred_row(CF::MKH, CF::MKL, xr);
-        finish_rows(acc, xr, s_cs[row] + s_cs[128 + row], row < B ? kidx[row] : -1, stage_dk);
+        finish_rows(acc, xr, cs, row < B ? kidx[row] : -1, stage_dk);
       }
       umma::fence_before_sync();                         // the TMEM loads above precede the next tile's MMAs into tO0 / tO1
       __syncwarp();
       if (lane == 0) umma::mbar_arrive(&mbar[MFREE]);    // this warp is done with the MN-major tiles
 
-      // ---- d scale partials of this tile: fixed-order warp tree, then warps in order ------------------------------
-#pragma unroll
-      for (int cc = 0; cc < C; ++cc) {
-        float x = dsc[cc];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-        if (lane == 0) s_dsc[warp * 8 + cc] = x;
-      }
-      umma::bar_sync(1, kBtEpiThreads);
-      if (tid < C) {
-        float x = 0.f;
-#pragma unroll
-        for (int w = 0; w < EW; ++w) x += s_dsc[w * 8 + tid];
-        ds_partial[(size_t)tile * 8 + tid] = x;
-      }
     }
+    flush_dscale();
   } else if (warp < EW + PW) {
     // =========================================== producer warps =================================================
     umma::setmaxnreg_dec<kBtRegsProd>();
@@ -517,8 +531,14 @@ __global__ void __launch_bounds__(kBtThreads, 1)
           const uint32_t okm = umma::sw128_offset(r, c), omn = umma::sw128b32_offset(r, c);
           constexpr int src[6] = {CF::KH, CF::KL, CF::GH, CF::GL, CF::QH, CF::QL};   // -> MKH, MKL, MGH, MGL, MQH, MQL
 #pragma unroll
-          for (int tl = 0; tl < 6; ++tl)
-            *reinterpret_cast<float4*>(mn + tl * CF::TILE + omn) = *reinterpret_cast<const float4*>(smem + src[tl] * CF::TILE + okm);
+          for (int tl = 0; tl < 6; ++tl) {
+            float4 x = *reinterpret_cast<const float4*>(smem + src[tl] * CF::TILE + okm);
+            if (tl < 2 && c == CF::SLOT_CH) {   // the MN-major K^ carries (1, 0) in the side slots: column E of dQ = sum_j dS_ij
+              umma::elem<CF::SLOT_U>(x) = tl == 0 ? 1.f : 0.f;
+              umma::elem<CF::SLOT_U + 1>(x) = 0.f;
+            }
+            *reinterpret_cast<float4*>(mn + tl * CF::TILE + omn) = x;
+          }
         }
       }
       umma::fence_async_smem();
@@ -597,17 +617,6 @@ __global__ void __launch_bounds__(kBtThreads, 1)
     for (; tile < total_tiles; tile += gridDim.x, ++it) {
       const uint32_t ph = it & 1;
       const bool more = tile + (int)gridDim.x < total_tiles;
-      // The next tile's query-side scores go out as soon as its operands are there and dQ has drained tS / tDP, but
-      // this tile's MMAs never wait for the producer: probe between them, block only at the end.
-      bool next_q_issued = !more;
-      auto next_query_scores = [&](bool block) {
-        if (next_q_issued) return;
-        if (!block && !umma::mbar_test(&mbar[KFULL], ph ^ 1)) return;
-        wait(KFULL, ph ^ 1);
-        wait(DQDONE, ph);
-        scores_query_side();
-        next_q_issued = true;
-      };
       wait(DSRDY, ph);
       wait(MFULL, ph);
       if (umma::elect_one()) {
@@ -615,14 +624,12 @@ __global__ void __launch_bounds__(kBtThreads, 1)
         umma::commit(&mbar[DQDONE]);
       }
       __syncwarp();
-      next_query_scores(false);
       wait(PTRDY, ph);
       if (umma::elect_one()) {
         ts_product(tO1, tST, tDPT, CF::MGH, CF::MGL);   // dV = P^T G'
         umma::commit(&mbar[DVDONE]);
       }
       __syncwarp();
-      next_query_scores(false);
       wait(DSTRDY, ph);
       if (umma::elect_one()) {
         ts_product(tO0, tST, tDPT, CF::MQH, CF::MQL);   // dK = dS^T Q^
@@ -630,7 +637,12 @@ __global__ void __launch_bounds__(kBtThreads, 1)
         umma::commit(&mbar[MFREE]);
       }
       __syncwarp();
-      next_query_scores(true);
+      // The tensor pipe runs in issue order: the next tile's score MMAs (0.7 us per side) go behind this tile's last
+      // product, where nothing waits for them — the epilogue still has dv / dk rows to write out.
+      if (more) {
+        wait(KFULL, ph ^ 1);
+        scores_query_side();                            // tS / tDP were drained by dQ long ago
+      }
       if (more) {                                       // next tile's key-side scores once dK has drained tST / tDPT
         wait(DKDONE, ph);
         scores_key_side();
@@ -677,13 +689,13 @@ __global__ void __launch_bounds__(256) bwd_table_sum_kernel(const float* __restr
   sum_tables(sv, dv);
 }
 
-// dscale[h,c] = (sum over the head's tiles of partial[tile][c]) / scale[h,c]; fixed-order tree -> deterministic.
+// dscale[h,c] = (sum over CTAs of partial[cta][h][c]) / scale[h,c]; fixed-order tree -> deterministic.
 __global__ void __launch_bounds__(256) dscale_tiles_kernel(const float* __restrict__ partial, const float* __restrict__ scale,
-                                                           int tiles_per_head, int C, float* __restrict__ dscale) {
+                                                           int ctas, int H, int C, float* __restrict__ dscale) {
   __shared__ float red[256];
   const int h = blockIdx.x / C, c = blockIdx.x % C;
   float x = 0.f;
-  for (int b = threadIdx.x; b < tiles_per_head; b += 256) x += partial[((size_t)h * tiles_per_head + b) * 8 + c];
+  for (int b = threadIdx.x; b < ctas; b += 256) x += partial[((size_t)b * H + h) * 8 + c];
   red[threadIdx.x] = x;
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) {
@@ -696,6 +708,7 @@ __global__ void __launch_bounds__(256) dscale_tiles_kernel(const float* __restri
   }
 }
 
+constexpr int kBtMaxCtas = 1024;
 struct BwdTcPlan {
   size_t hat_bytes, grow_bytes, stage_bytes, partial_bytes, total;
   int tiles;
@@ -706,7 +719,7 @@ static BwdTcPlan plan_bwd_tc(const hept_shape* s) {
   p.hat_bytes = align_up(sizeof(float) * (size_t)s->N * s->H * 8, 256);
   p.grow_bytes = align_up(sizeof(float) * (size_t)s->N * s->H * 32, 256);
   p.stage_bytes = align_up(sizeof(float) * (size_t)s->H * s->N * s->T * s->D, 256);
-  p.partial_bytes = align_up(sizeof(float) * (size_t)p.tiles * 8, 256);
+  p.partial_bytes = align_up(sizeof(float) * (size_t)kBtMaxCtas * s->H * 8, 256);
   p.total = p.hat_bytes + p.grow_bytes + 3 * p.stage_bytes + p.partial_bytes;
   return p;
 }
@@ -744,8 +757,11 @@ static int launch_bwd_tc(const hept_shape* s, const float* q, const float* k, co
   grad_rows_kernel<D><<<(unsigned)((rows * 8 + 255) / 256), 256, 0, st>>>(d_out_pre, out_pre, den_sum, rows, grows);
   HEPT_CHECK_LAUNCH("grad_rows");
   const int mask = bwd_stage_mask();
+  int grid = p.tiles < sms ? p.tiles : sms;             // one CTA per SM (the tile uses all 512 TMEM columns)
+  if (grid > kBtMaxCtas) grid = kBtMaxCtas;
   if (mask & 3) {
-    const int grid = p.tiles < sms ? p.tiles : sms;   // one CTA per SM (the tile uses all 512 TMEM columns)
+    cudaError_t e = cudaMemsetAsync(partial, 0, sizeof(float) * (size_t)grid * s->H * 8, st);   // heads a CTA never visits
+    HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "block_attn_bwd_tc: memset failed: %s", cudaGetErrorString(e));
     kern<<<grid, kBtThreads, smem, st>>>(q, k, v, hat, grows, positions, s->N, s->H, s->T, s->raw_size, p.tiles, sq, sk,
                                          sv, partial);
     HEPT_CHECK_LAUNCH("block_attn_bwd_tc");
@@ -754,7 +770,7 @@ static int launch_bwd_tc(const hept_shape* s, const float* q, const float* k, co
   const size_t total = rows * (D / 4);
   bwd_table_sum_kernel<D><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(sq, sk, sv, s->N, s->H, s->T, s->raw_size, dq, dk, dv);
   HEPT_CHECK_LAUNCH("bwd_table_sum");
-  dscale_tiles_kernel<<<s->H * C, 256, 0, st>>>(partial, scale, s->T * (s->N / s->B), C, dscale);
+  dscale_tiles_kernel<<<s->H * C, 256, 0, st>>>(partial, scale, grid, s->H, C, dscale);
   HEPT_CHECK_LAUNCH("dscale_tiles");
   return HEPT_OK;
 }

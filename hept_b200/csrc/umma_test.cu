@@ -1,6 +1,8 @@
 // Self-test of the tcgen05 building blocks (umma.cuh) on exactly representable data: an SS MMA with both
 // operands K-major (S = A B^T, 128 x 112 x 32) followed by a TS MMA whose A operand is read back from
 // TMEM and whose B operand is MN-major (O = S V, 128 x 32 x 112).  Used by tests/test_gpu_umma.py.
+#include <type_traits>
+
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -176,5 +178,106 @@ extern "C" int hept_debug_umma_selftest(const float* A, const float* Bm, const f
   if (kmajor_base32) umma_selftest_kernel<true><<<1, 128, smem, (cudaStream_t)stream>>>(A, Bm, V, S_out, O_out);
   else umma_selftest_kernel<false><<<1, 128, smem, (cudaStream_t)stream>>>(A, Bm, V, S_out, O_out);
   HEPT_CHECK_LAUNCH("umma_selftest");
+  return HEPT_OK;
+}
+
+// ---- timing probe: cycles for a burst of tcgen05.mma (tf32, M = 128) from issue to mbarrier completion -----------
+// mode 0: `count` TS MMAs (A from TMEM, N = 32) accumulating into ONE accumulator
+// mode 1: the same MMAs alternating between TWO accumulators
+// mode 2: `count` SS MMAs, N = 112, one accumulator
+// mode 3: `count` SS MMAs, N = 112, alternating between two accumulators
+// mode 4: TS MMAs, N = 32, round-robin over FOUR accumulators
+namespace hept {
+__global__ void __launch_bounds__(128, 1) umma_timing_kernel(int mode, int count, long long* __restrict__ cycles) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = umma::align1024(smem_raw);
+  __shared__ uint64_t mbar;
+  __shared__ uint32_t tmem_base_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 5 * 128 * 32; i += 128) reinterpret_cast<float*>(smem)[i] = 0.f;
+  if (tid == 0) umma::mbar_init(&mbar, 1);
+  if (warp == 0) umma::tmem_alloc<512>(&tmem_base_slot);
+  umma::fence_async_smem();
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem = tmem_base_slot;
+  {  // defined A operand in TMEM
+    float z[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) z[i] = 0.f;
+    for (int c0 = 0; c0 < 256; c0 += 16) umma::tmem_st16(tmem + ((uint32_t)(warp * 32) << 16) + c0, z);
+    umma::tmem_wait_st();
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  uint32_t phase = 0;
+  for (int rep = 0; rep < 3; ++rep) {   // the last repetition is reported
+    long long t0 = 0;
+    if (tid == 0) {
+      const uint32_t sA = umma::smem_u32(smem), sB = sA + 128 * 128, sV = sB + 128 * 128;
+      constexpr uint32_t id_ts = umma::idesc_tf32(128, 32, false, true);
+      constexpr uint32_t id_ss = umma::idesc_tf32(128, 112, false, false);
+      const uint64_t dA = umma::smem_desc_sw128(sA, 1024, 16), dB = umma::smem_desc_sw128(sB, 1024, 16);
+      const uint64_t dV = umma::smem_desc(sV, 512, 1024, umma::kLayoutSw128Base32);
+      const uint32_t acc0 = tmem + 256;
+      t0 = clock64();
+      // straight-line issue (descriptor = base + constant), so the burst is paced by the tensor pipe, not by the loop
+      auto burst = [&](auto mode_c) {
+        constexpr int M = decltype(mode_c)::value;
+#pragma unroll
+        for (int i = 0; i < 39; ++i) {
+          if (i >= count) break;
+          if constexpr (M >= 5 && M <= 7) {        // TS, one accumulator, N = 64 / 96 / 128: B spans N / 32 row-per-k tiles, LBO apart
+            constexpr int NN = M == 5 ? 64 : (M == 6 ? 96 : 128);
+            const uint64_t dW = umma::smem_desc(sA, 512, 13 * 1024, umma::kLayoutSw128Base32);
+            umma::mma_ts(acc0, tmem + 8 * (i % 13), dW + 64 * (i % 13), umma::idesc_tf32(128, NN, false, true), i >= 1);
+          } else if constexpr (M == 8) {           // SS, N = 32
+            umma::mma_ss(acc0, dA + 2 * (i & 3), dB + 2 * (i & 3), umma::idesc_tf32(128, 32, false, false), i >= 1);
+          } else if constexpr (M == 0 || M == 1 || M == 4) {
+            constexpr int nacc = M == 0 ? 1 : (M == 1 ? 2 : 4);
+            umma::mma_ts(acc0 + 32 * (i % nacc), tmem + 8 * (i % 13), dV + 64 * (i % 13), id_ts, i >= nacc);
+          } else {
+            umma::mma_ss(acc0 + (M == 3 ? 112 * (i & 1) : 0), dA + 2 * (i & 3), dB + 2 * (i & 3), id_ss, i >= (M == 3 ? 2 : 1));
+          }
+        }
+      };
+      switch (mode) {
+        case 0: burst(std::integral_constant<int, 0>{}); break;
+        case 1: burst(std::integral_constant<int, 1>{}); break;
+        case 2: burst(std::integral_constant<int, 2>{}); break;
+        case 3: burst(std::integral_constant<int, 3>{}); break;
+        case 4: burst(std::integral_constant<int, 4>{}); break;
+        case 5: burst(std::integral_constant<int, 5>{}); break;
+        case 6: burst(std::integral_constant<int, 6>{}); break;
+        case 7: burst(std::integral_constant<int, 7>{}); break;
+        default: burst(std::integral_constant<int, 8>{}); break;
+      }
+      umma::commit(&mbar);
+    }
+    umma::mbar_wait(&mbar, phase);
+    phase ^= 1;
+    umma::fence_after_sync();
+    if (tid == 0) cycles[0] = clock64() - t0;
+    __syncthreads();
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc<512>(tmem);
+}
+}  // namespace hept
+
+extern "C" int hept_debug_umma_timing(int mode, int count, long long* cycles, void* stream) {
+  HEPT_REQUIRE(cycles && count > 0, HEPT_EINVAL, "umma_timing: bad argument");
+  const size_t smem = (size_t)5 * 128 * 128 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(hept::umma_timing_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "umma_timing: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  hept::umma_timing_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(mode, count, cycles);
+  HEPT_CHECK_LAUNCH("umma_timing");
   return HEPT_OK;
 }

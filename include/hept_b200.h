@@ -147,6 +147,11 @@ int hept_debug_umma_selftest(const float* A, const float* Bm, const float* V, fl
  * whether the tf32 MMA is bitwise symmetric under an exchange of its operands (tests/test_gpu_umma.py). */
 int hept_debug_umma_symmetry(const float* X, const float* Y, float* S_xy, float* S_yx, void* stream);
 
+/* cycles (clock64 of the issuing thread) from the first tcgen05.mma of a burst of `count` tf32 M = 128 MMAs to the
+ * completion of its commit.  mode 0 / 1 / 4: TS MMAs with N = 32 into 1 / 2 / 4 accumulators; mode 2 / 3: SS MMAs with
+ * N = 112 into 1 / 2 accumulators.  cycles is a device pointer to one int64.  Used by tools/umma_timing.py. */
+int hept_debug_umma_timing(int mode, int count, long long* cycles, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

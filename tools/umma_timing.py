@@ -1,0 +1,28 @@
+"""Cost model of small tcgen05.mma bursts on this GPU (cycles from first issue to commit completion).
+
+    python tools/umma_timing.py      -> gpurun_out/umma_timing.json
+"""
+import ctypes
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from hept_b200 import _lib
+
+lib = _lib.load()
+out = torch.zeros(1, dtype=torch.int64, device="cuda:0")
+res = {}
+names = {0: "ts_n32_1acc", 1: "ts_n32_2acc", 5: "ts_n64", 6: "ts_n96", 7: "ts_n128", 8: "ss_n32", 2: "ss_n112_1acc"}
+for mode, name in names.items():
+    for count in (1, 13, 39):
+        _lib.check(lib.hept_debug_umma_timing(mode, count, ctypes.c_void_p(out.data_ptr()),
+                                              ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "umma_timing")
+        torch.cuda.synchronize()
+        res[f"{name}_x{count}"] = int(out.item())
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(res, open("gpurun_out/umma_timing.json", "w"), indent=1)
+for k, v in res.items():
+    print(k, v)
