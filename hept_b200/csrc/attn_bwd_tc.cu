@@ -84,20 +84,9 @@ struct TcBwd {
 
 enum BtBar { KFULL, MFULL, MFREE, QREADY, KREADY, DSRDY, DQDONE, PTRDY, DVDONE, DSTRDY, DKDONE, BT_NBAR };
 
-// hi = x rounded to tf32 (round half away, like cvt.rna; x finite), lo = x - hi (exact)
-__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-  hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
-  lo = x - hi;
-}
-// hi = x truncated to tf32, lo = x - hi (exact): one instruction less; the tensor core drops the low 13 bits of lo
-// either way, and the sums that must agree with the products (rs, cs) are taken by the same MMAs
-__device__ __forceinline__ void trunc_tf32(float x, float& hi, float& lo) {
-  hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
-  lo = x - hi;
-}
-__device__ __forceinline__ void split4(const float4 x, float4& hi, float4& lo) {
-  split_tf32(x.x, hi.x, lo.x); split_tf32(x.y, hi.y, lo.y); split_tf32(x.z, hi.z, lo.z); split_tf32(x.w, hi.w, lo.w);
-}
+using umma::split4;
+using umma::split_tf32;
+using umma::trunc_tf32;
 
 // ---------------------------------------------------------------------------------------------------------------
 // G' rows (N, H, 32): [g / den (D), -(g . y) / den, 0 ...] — the gradient arriving at numerator and normaliser of

@@ -1,321 +1,442 @@
-// a8-a11 on the 5th-generation tensor cores: the same fused gather -> block attention -> scatter as
-// attn_fwd.cu, with both contractions of a tile issued as tcgen05.mma (kind::tf32, M = 128) and the
-// accumulators in TMEM.
+// a8-a11 on the 5th-generation tensor cores: the fused gather -> block attention -> scatter of attn_fwd.cu with both
+// contractions of a tile issued as tcgen05.mma (kind::tf32, M = 128) and the accumulators in TMEM, as a persistent,
+// warp-specialised pipeline: one CTA per SM walks the tiles, two tiles are in flight at any time.
 //
 // fp32 fidelity from tf32 tensor cores: every operand x is split as x = hi + lo with hi = rn_tf32(x) and
 // lo = x - hi (exact), and each product is evaluated as hi*hi + hi*lo + lo*hi ("3xTF32", fp32 accumulate);
 // the dropped lo*lo term is 2^-22 relative.  The split only works because rows are re-centred on the
-// block's last key first (tile.cuh): |q'|, |k'| are block-sized, not detector-sized.
+// block's last key first: |q'|, |k'| are block-sized, not detector-sized.
 //
-// One tile = one block of B <= 100 sorted hits of one (table, head):
-//   S2[i,j] = log2e * (q'_i . k'_j + nk_j)         SS MMAs, K = 32: slots [0,E) carry q' log2e / k',
-//                                                   slots 30, 31 carry 1 / (nk hi, nk mid) so the key-side
-//                                                   norm rides along in the contraction (3-way split, exact)
-//   P[i,j]  = ex2(min(S2 + nq2_i, 0))              one thread per TMEM lane (= query row), written back to
-//                                                   TMEM as (hi, lo)
-//   O[i,:]  = P V                                   TS MMAs (A = P from TMEM, B = V MN-major), K = 112
+// One tile = one block of B <= 104 sorted hits of one (table, head):
+//   S[i,j]  = q'_i . k'_j + nk_j                    SS MMAs: K slots [0,E) carry q' / k', slots E, E+1 carry 1 /
+//                                                   (nk hi, nk mid) so the key-side norm nk = -|k'|^2 / 2 rides along in
+//                                                   the contraction (3-way split, exact)
+//   P[i,j]  = ex2(min(log2e S + nq2_i, 0))          one thread per TMEM lane (= query row), written back to TMEM as (hi, lo)
+//   O[i,:]  = P [V | 1]                             TS MMAs (A = P from TMEM, B = V MN-major); column D is the row sum
 // Padded key rows get nk = -1e30 (P = 0), padded value rows are zero, padded query rows are never stored.
+//
+// The tensor-core accumulator truncates after every MMA and q'.k' is far larger than the score it cancels to, so the
+// small cross terms are accumulated first and the hi*hi steps are split over two accumulators that the epilogue adds
+// in fp32 (S0: cross terms + first half of the k-steps, S1: the rest).
+//
+// Warp roles (640 threads = 5 warpgroups, register budgets rebalanced with setmaxnreg):
+//   warps 0-7   epilogue: TMEM lane = (warp & 3) * 32 + lane, columns split in two parts (warp >> 2); software
+//               pipelined: P of tile n+1 is produced before the output rows of tile n are read and scattered, so the
+//               P V MMAs of tile n run under SIMT work
+//   warps 8-15  producer: gather rows through the sort permutation into registers (one tile ahead), centre, split,
+//               write the operand tiles of stage n & 1 (q^ / k^ K-major as soon as the score MMAs of tile n-2 are
+//               done, V MN-major once its P V MMAs are done)
+//   warp 16     one elected lane issues every tcgen05.mma: S(n+1), then P V(n)
+// TMEM: two tile slots of 256 columns (S0 | S1 | O).  Hand-offs are mbarriers that complete once per use of a slot /
+// stage, so the wait parity is bit 1 of the tile counter.
 #include "tile.cuh"
 #include "umma.cuh"
 
 namespace hept {
 
-constexpr int kTcM = 128;    // UMMA M: query rows, padded
-constexpr int kTcN = 112;    // key rows, padded to a multiple of 16
-constexpr int kTcVN = 32;    // value columns, padded
+using umma::split4;
+using umma::split_tf32;
+using umma::trunc_tf32;
+
+constexpr int kFtEpiThreads = 256, kFtProdThreads = 256;
+constexpr int kFtThreads = kFtEpiThreads + kFtProdThreads + 128;
+constexpr int kFtParts = kFtEpiThreads / 128;
+// Launch budget 65536 / 640 -> 96 registers per thread = 61440 per CTA; setmaxnreg moves registers inside that pool.
+constexpr int kFtRegsEpi = 120, kFtRegsProd = 96, kFtRegsMma = 40;
+static_assert(kFtEpiThreads * kFtRegsEpi + kFtProdThreads * kFtRegsProd + 128 * kFtRegsMma <= kFtThreads * 96, "register pool");
 
 template <int D, int C, int B>
-struct TcFwdSmem {
-  static constexpr int A_BYTES = kTcM * 128;   // one 128-row K-major tile
-  static constexpr int K_BYTES = kTcN * 128;
-  static constexpr int OFF_AH = 0, OFF_AL = A_BYTES, OFF_KH = 2 * A_BYTES, OFF_KL = OFF_KH + K_BYTES,
-                       OFF_VH = OFF_KL + K_BYTES, OFF_VL = OFF_VH + K_BYTES, OFF_NQ = OFF_VL + K_BYTES,
-                       TOTAL = OFF_NQ + kTcM * 4;
+struct TcFwd {
+  static constexpr int E = D + C;
+  static constexpr int NP = (B + 15) / 16 * 16;   // N of the score MMAs (multiple of 16 at M = 128)
+  static constexpr int KC = (B + 7) / 8 * 8;      // contraction length of the TS MMAs
+  static constexpr int KSTEPS = KC / 8;
+  static constexpr int SK = (E + 2 + 7) / 8;      // k-steps of Q^ K^^T (two side slots at E, E + 1)
+  static constexpr int SK0 = (SK + 1) / 2;        // hi*hi k-steps that go to the first accumulator
+  static constexpr int VCH = D / 4;
+  static constexpr int SLOT_CH = E / 4, SLOT_U = E % 4;
+  // Operand tiles hold KC rows of 128 B.  The MMAs read M = 128 (A) or NP (B) rows: what lies past row KC belongs to
+  // the next tile and only reaches TMEM lanes / columns >= KC, which nothing reads.
+  static constexpr int TILE = KC * 128;
+  static constexpr int QH = 0, QL = 1, KH = 2, KL = 3;    // K-major tiles of a stage
+  static constexpr int OFF_V = 2 * 4 * TILE;              // then per stage VH, VL (MN-major)
+  static constexpr int OFF_AUX = OFF_V + 2 * 2 * TILE;
+  static constexpr int AUX_BYTES = (4 * 128 + 8 * 128) * 4;   // nq2[4][128], qidx[8][128]
+  static constexpr int TOTAL = OFF_AUX + AUX_BYTES;
+  static constexpr int RPP = kFtProdThreads / 8;
+  static constexpr int PASSES = (B + RPP - 1) / RPP;
+  static constexpr int SLOT_COLS = 2 * NP + 32;
+  static constexpr int TMEM_COLS = SLOT_COLS <= 64 ? 128 : (SLOT_COLS <= 128 ? 256 : 512);   // two slots, power of two
+  static constexpr int SLOT_STRIDE = TMEM_COLS / 2;
+  static_assert(E % 2 == 0 && E + 2 <= 32 && D + 1 <= 32 && D % 4 == 0, "row shapes");
+  static_assert(B <= 128 && NP <= 128 && SLOT_COLS <= 256, "tile shape");
+  static_assert(7 * TILE + 128 * 128 <= TOTAL, "the M = 128 overrun of the last K-major tile stays inside the allocation");
+  static_assert(TOTAL + 1024 <= 227 * 1024, "shared memory");
 };
 
-constexpr int kTcThreads = 256;   // warps 0-3 and 4-7 both map onto TMEM lanes 0-127; they split the columns
+// barriers, two of each (stage / slot = tile & 1)
+enum FtBar { QKFULL = 0, VFULL = 2, QKFREE = 4, VFREE = 6, SREADY = 8, PREADY = 10, ODONE = 12, FT_NBAR = 14 };
 
-template <int D, int C, int B, int TILES>
-__global__ void __launch_bounds__(kTcThreads, 2)
+template <int D, int C, int B>
+__global__ void __launch_bounds__(kFtThreads, 1)
     block_attn_fwd_tc_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
                              const float* __restrict__ hatc, const int32_t* __restrict__ positions, int N, int H, int T,
-                             int raw_size, float* __restrict__ stage) {
-  constexpr int E = D + C;
-  static_assert(E + 2 <= 32 && D % 4 == 0 && D <= kTcVN && B <= kTcN && B <= kTcM, "tile shape");
-  using SM = TcFwdSmem<D, C, B>;
+                             int raw_size, int total_tiles, float* __restrict__ stage) {
+  using CF = TcFwd<D, C, B>;
+  constexpr int E = CF::E, NP = CF::NP, KSTEPS = CF::KSTEPS, VCH = CF::VCH, PASSES = CF::PASSES, RPP = CF::RPP;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = umma::align1024(smem_raw);
-  float* s_nq = reinterpret_cast<float*>(smem + SM::OFF_NQ);
-  __shared__ uint64_t mbar;
+  float* s_nq2 = reinterpret_cast<float*>(smem + CF::OFF_AUX);   // [4][128]  log2e * -|q'|^2 / 2, by tile & 3
+  int* s_qidx = reinterpret_cast<int*>(s_nq2 + 512);             // [8][128]  original hit index of query row r, by tile & 7
+  __shared__ uint64_t mbar[FT_NBAR];
   __shared__ uint32_t tmem_slot;
-  __shared__ float s_l[kTcM];               // row sums of the upper column half
 
-  const int h = blockIdx.y / T, t = blockIdx.y % T, th = t * H + h;  // tables of one head run back to back: its q/k/v slices stay in L2
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nb = N / B;
-  const int32_t* qpos = positions + (size_t)th * N;
-  const int32_t* kpos = positions + ((size_t)T * H + th) * N;
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int sub = tid >> 3, c = tid & 7;                 // gather role: 8 lanes per row, 32 rows per pass
-  const int row = (warp & 3) * 32 + (tid & 31);          // epilogue role: TMEM lane = query row
-  const int half = warp >> 2;                            //                column half of that row
+  constexpr int EW = kFtEpiThreads / 32, PW = kFtProdThreads / 32;
 
-  if (tid == 0) umma::mbar_init(&mbar, 1);
-  if (warp == 0) umma::tmem_alloc<256>(&tmem_slot);
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      umma::mbar_init(&mbar[QKFULL + s], PW);
+      umma::mbar_init(&mbar[VFULL + s], PW);
+      umma::mbar_init(&mbar[QKFREE + s], 1);
+      umma::mbar_init(&mbar[VFREE + s], 1);
+      umma::mbar_init(&mbar[SREADY + s], 1);
+      umma::mbar_init(&mbar[PREADY + s], EW);
+      umma::mbar_init(&mbar[ODONE + s], 1);
+    }
+  }
+  if (warp == EW + PW) umma::tmem_alloc<CF::TMEM_COLS>(&tmem_slot);
+  if (warp >= EW && warp < EW + PW) {
+    // rows that never hold data are written once: zero operands, key norm -1e30 (P = ex2(-1e30) = 0)
+    const int ptid = tid - kFtEpiThreads, sub = ptid >> 3, c = ptid & 7;
+    for (int rr = B + sub; rr < CF::KC; rr += RPP) {
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 kz = z;
+      if (c == CF::SLOT_CH) umma::elem<CF::SLOT_U>(kz) = umma::tf32_hi(-1e30f);
+#pragma unroll
+      for (int st = 0; st < 2; ++st) {
+#pragma unroll
+        for (int tl = 0; tl < 4; ++tl)
+          *reinterpret_cast<float4*>(smem + (st * 4 + tl) * CF::TILE + umma::sw128_offset(rr, c)) = tl == CF::KH ? kz : z;
+#pragma unroll
+        for (int tl = 0; tl < 2; ++tl)
+          *reinterpret_cast<float4*>(smem + CF::OFF_V + (st * 2 + tl) * CF::TILE + umma::sw128b32_offset(rr, c)) = z;
+      }
+    }
+    for (int i = ptid; i < 4 * 128; i += kFtProdThreads) s_nq2[i] = 0.f;
+    for (int i = ptid; i < 8 * 128; i += kFtProdThreads) s_qidx[i] = -1;
+  }
+  umma::fence_async_smem();
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
   const uint32_t tmem = tmem_slot;
-  const uint32_t tS = tmem, tPl = tmem + kTcN, tO = tmem + 2 * kTcN;   // columns [0,112) [112,224) [224,256)
-  const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
   const uint32_t sbase = umma::smem_u32(smem);
-  uint32_t phase = 0;
 
-  // chunk c of a hat row: feature columns come from q / k, the coordinate columns from hat_coords (already scaled)
-  constexpr int XCH = D / 4;
-  auto hat_chunk = [&](const float* __restrict__ x, int n) -> float4 {
-    const float* src = c < XCH ? x + ((size_t)n * H + h) * D + 4 * c : hatc + ((size_t)n * H + h) * 8 + 4 * (c - XCH);
-    return (c < XCH + 2 && n < raw_size) ? ldg4(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+  // tiles are ordered (head, table, block): the CTAs of a wave work on one head's rows, which stay in L2
+  auto decode = [&](int tile, int& h, int& t, int& blk) {
+    const int hl = tile / nb;
+    blk = tile - hl * nb;
+    h = hl / T;
+    t = hl - h * T;
   };
 
-  // rows that never hold data are written once: query rows [B,128) zero, key rows [B,112) zero with nk = -1e30
-  // (P = ex2(-1e30) = 0), value rows [B,112) zero
-  for (int rr = B + sub; rr < kTcM; rr += kTcThreads / 8) {
-    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    *reinterpret_cast<float4*>(smem + SM::OFF_AH + umma::sw128_offset(rr, c)) = z;
-    *reinterpret_cast<float4*>(smem + SM::OFF_AL + umma::sw128_offset(rr, c)) = z;
-    if (rr < kTcN) {
-      *reinterpret_cast<float4*>(smem + SM::OFF_KH + umma::sw128_offset(rr, c)) =
-          c == 7 ? make_float4(0.f, 0.f, umma::tf32_hi(-1e30f), 0.f) : z;
-      *reinterpret_cast<float4*>(smem + SM::OFF_KL + umma::sw128_offset(rr, c)) = z;
-      *reinterpret_cast<float4*>(smem + SM::OFF_VH + umma::sw128b32_offset(rr, c)) = z;
-      *reinterpret_cast<float4*>(smem + SM::OFF_VL + umma::sw128b32_offset(rr, c)) = z;
-    }
-    if (c == 0) s_nq[rr] = 0.f;
-  }
+  if (warp < EW) {
+    // =========================================== epilogue warps =================================================
+    umma::setmaxnreg_inc<kFtRegsEpi>();
+    const int row = (warp & 3) * 32 + lane;                // TMEM lane
+    const int part = warp >> 2;                            // column part of that lane
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    constexpr int MAXCH = (KSTEPS + kFtParts - 1) / kFtParts;   // 8-column chunks per thread
 
+    // P of tile number `it` (slot it & 1): S0 + S1 -> (P hi, P lo) in place
+    auto make_p = [&](int it) {
+      const int sl = it & 1;
+      const uint32_t tS0 = tmem + sl * CF::SLOT_STRIDE, tS1 = tS0 + NP;
+      umma::mbar_wait(&mbar[SREADY + sl], (it >> 1) & 1);
+      umma::fence_after_sync();
+      const float nq2 = s_nq2[(it & 3) * 128 + row];
+#pragma unroll
+      for (int ci = 0; ci < MAXCH; ++ci) {
+        const int ch = part + ci * kFtParts;
+        if (ch < KSTEPS) {
+          uint32_t ra[8], rb[8];
+          umma::tmem_ld8_nowait(tS0 + lane_base + 8 * ch, ra);
+          umma::tmem_ld8_nowait(tS1 + lane_base + 8 * ch, rb);
+          umma::tmem_wait_ld(ra, rb);
+          float ph[8], pl[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const float x = fmaf(__uint_as_float(ra[u]) + __uint_as_float(rb[u]), kLog2e, nq2);
+            trunc_tf32(exp2_fast(fminf(x, 0.f)), ph[u], pl[u]);   // exp(min(S, 0)), example/hept.py:12
+          }
+          umma::tmem_st8(tS0 + lane_base + 8 * ch, ph);
+          umma::tmem_st8(tS1 + lane_base + 8 * ch, pl);
+        }
+      }
+      umma::tmem_wait_st();
+      umma::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) umma::mbar_arrive(&mbar[PREADY + sl]);
+    };
+
+    int it = 0;
+    if ((int)blockIdx.x < total_tiles) make_p(0);
 #pragma unroll 1
-  for (int it = 0; it < TILES; ++it) {
-    const int blk = blockIdx.x * TILES + it;
-    if (blk >= nb) break;
-
-    // ---- gather: all indices, then all rows (every load of the tile is in flight before the first use) ------
-    constexpr int PASSES = (B + 31) / 32;                 // 32 rows per pass; the last pass is partial
-    int nk_idx[PASSES], nq_idx[PASSES];
-    const int n0 = __ldg(kpos + (size_t)blk * B + (B - 1));
-#pragma unroll
-    for (int ps = 0; ps < PASSES; ++ps) {
-      const int r = ps * 32 + sub;
-      nk_idx[ps] = r < B ? __ldg(kpos + (size_t)blk * B + r) : -1;
-      nq_idx[ps] = r < B ? __ldg(qpos + (size_t)blk * B + r) : -1;
-    }
-    const float4 ctr = hat_chunk(k, n0);
-    float4 dk[PASSES], vk[PASSES], dq[PASSES];
-#pragma unroll
-    for (int ps = 0; ps < PASSES; ++ps) {
-      const int nkk = nk_idx[ps], nqq = nq_idx[ps];
-      dk[ps] = nkk >= 0 ? hat_chunk(k, nkk) : make_float4(0.f, 0.f, 0.f, 0.f);
-      dq[ps] = nqq >= 0 ? hat_chunk(q, nqq) : make_float4(0.f, 0.f, 0.f, 0.f);
-      vk[ps] = (nkk >= 0 && c < XCH && nkk < raw_size) ? ldg4(v + ((size_t)nkk * H + h) * D + 4 * c)
-                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-#pragma unroll
-    for (int ps = 0; ps < PASSES; ++ps) {
-      const int r = ps * 32 + sub;
-      // the last pass covers rows [32*(PASSES-1), B): warps whose 4 rows are all past B skip it
-      if (ps == PASSES - 1 && (ps * 32 + (warp << 2)) >= B) continue;
-      const bool in = r < B;
-      // ---- key + value row r -> Kh, Kl, Vh, Vl
-      {
-        float4 d = dk[ps];
-        d.x -= ctr.x; d.y -= ctr.y; d.z -= ctr.z; d.w -= ctr.w;
-        const float sq = tree8_lanes(chunk_sq<E>(d, c));
-        const float nk2 = kLog2e * (-0.5f * sq);
-        float hi[4], lo[4];
-        const float dv[4] = {d.x, d.y, d.z, d.w};
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const float x = (4 * c + u < E) ? dv[u] : 0.f;
-          hi[u] = umma::tf32_hi(x);
-          lo[u] = x - hi[u];
-        }
-        if (c == 7) {  // K slots 30, 31 carry the key-side norm, split three ways: nk2 = h0 + h1 + l0
-          const float h0 = umma::tf32_hi(nk2);
-          const float r1 = nk2 - h0;
-          const float h1 = umma::tf32_hi(r1);
-          hi[2] = h0; hi[3] = h1;
-          lo[2] = r1 - h1; lo[3] = 0.f;
-        }
-        if (in) {
-          const uint32_t off = umma::sw128_offset(r, c);
-          *reinterpret_cast<float4*>(smem + SM::OFF_KH + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<float4*>(smem + SM::OFF_KL + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-          const float4 vv = vk[ps];
-          const float vh[4] = {umma::tf32_hi(vv.x), umma::tf32_hi(vv.y), umma::tf32_hi(vv.z), umma::tf32_hi(vv.w)};
-          const uint32_t voff = umma::sw128b32_offset(r, c);
-          *reinterpret_cast<float4*>(smem + SM::OFF_VH + voff) = make_float4(vh[0], vh[1], vh[2], vh[3]);
-          *reinterpret_cast<float4*>(smem + SM::OFF_VL + voff) = make_float4(vv.x - vh[0], vv.y - vh[1], vv.z - vh[2], vv.w - vh[3]);
-        }
-      }
-      // ---- query row r -> Ah, Al, nq2
-      {
-        float4 d = dq[ps];
-        d.x -= ctr.x; d.y -= ctr.y; d.z -= ctr.z; d.w -= ctr.w;
-        const float nq2 = kLog2e * (-0.5f * tree8_lanes(chunk_sq<E>(d, c)));
-        float hi[4], lo[4];
-        const float dv[4] = {d.x, d.y, d.z, d.w};
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int e = 4 * c + u;
-          const float x = e < E ? dv[u] * kLog2e : 0.f;
-          hi[u] = umma::tf32_hi(x);
-          lo[u] = x - hi[u];
-          if (e == 30 || e == 31) { hi[u] = 1.f; lo[u] = 0.f; }
-        }
-        if (in) {
-          if (c == 0) s_nq[r] = nq2;
-          const uint32_t off = umma::sw128_offset(r, c);
-          *reinterpret_cast<float4*>(smem + SM::OFF_AH + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<float4*>(smem + SM::OFF_AL + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-        }
-      }
-    }
-    umma::fence_async_smem();
-    umma::fence_before_sync();
-    __syncthreads();
-    umma::fence_after_sync();
-
-    // ---- S2 = A K^T, 3xTF32 -----------------------------------------------------------------------------
-    if (tid == 0) {
-      constexpr uint32_t idesc = umma::idesc_tf32(kTcM, kTcN, false, false);
-      // The accumulator is truncated (not rounded) after every MMA and q'.k' is far larger than the score it
-      // cancels to, so: small cross terms first, and the four hi*hi steps split over two accumulators
-      // (tS: cross terms + k-steps 0,1; tPl: k-steps 2,3) that are added in fp32 in the epilogue.
-      bool acc = false;
-#pragma unroll
-      for (int part = 0; part < 2; ++part) {
-        const uint32_t a_off = part == 1 ? SM::OFF_AL : SM::OFF_AH;
-        const uint32_t b_off = part == 0 ? SM::OFF_KL : SM::OFF_KH;
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          umma::mma_ss(tS, umma::smem_desc_sw128(sbase + a_off + 32 * kk, 1024, 16),
-                       umma::smem_desc_sw128(sbase + b_off + 32 * kk, 1024, 16), idesc, acc);
-          acc = true;
-        }
-      }
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk)
-        umma::mma_ss(kk < 2 ? tS : tPl, umma::smem_desc_sw128(sbase + SM::OFF_AH + 32 * kk, 1024, 16),
-                     umma::smem_desc_sw128(sbase + SM::OFF_KH + 32 * kk, 1024, 16), idesc, kk != 2);
-      umma::commit(&mbar);
-    }
-    umma::mbar_wait(&mbar, phase);
-    phase ^= 1;
-    umma::fence_after_sync();
-
-    // ---- P = ex2(min(S2 + nq2, 0)), row sums, split back into TMEM; each warp-half owns 56 columns --------
-    const float nq2 = s_nq[row];
-    float l = 0.f;
-    {
-      constexpr int HC = kTcN / 2;   // 56 columns per half, 7 chunks of 8
-      const uint32_t col0 = half * HC;
-#pragma unroll
-      for (int cc = 0; cc < HC / 8; ++cc) {
-        uint32_t ra[8], rb[8];
-        umma::tmem_ld8_nowait(tS + lane_base + col0 + 8 * cc, ra);
-        umma::tmem_ld8_nowait(tPl + lane_base + col0 + 8 * cc, rb);
-        umma::tmem_wait_ld();
-        float ph[8], pl[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const float p = exp2_fast(fminf((__uint_as_float(ra[u]) + __uint_as_float(rb[u])) + nq2, 0.f));
-          l += p;
-          ph[u] = umma::tf32_hi(p);
-          pl[u] = p - ph[u];
-        }
-        umma::tmem_st8(tS + lane_base + col0 + 8 * cc, ph);
-        umma::tmem_st8(tPl + lane_base + col0 + 8 * cc, pl);
-      }
-    }
-    if (half == 1) s_l[row] = l;
-    umma::tmem_wait_st();
-    umma::fence_before_sync();
-    __syncthreads();
-    umma::fence_after_sync();
-
-    // ---- O = P V, 3xTF32 ----------------------------------------------------------------------------------
-    if (tid == 0) {
-      constexpr uint32_t idesc = umma::idesc_tf32(kTcM, kTcVN, false, true);
-      bool acc = false;
-#pragma unroll
-      for (int part = 0; part < 3; ++part) {
-        const uint32_t a_t = part == 1 ? tPl : tS;
-        const uint32_t b_off = part == 0 ? SM::OFF_VL : SM::OFF_VH;
-#pragma unroll
-        for (int kk = 0; kk < kTcN / 8; ++kk) {
-          umma::mma_ts(tO, a_t + 8 * kk, umma::smem_desc(sbase + b_off + 1024 * kk, 512, 1024, umma::kLayoutSw128Base32),
-                       idesc, acc);
-          acc = true;
-        }
-      }
-      umma::commit(&mbar);
-    }
-    umma::mbar_wait(&mbar, phase);
-    phase ^= 1;
-    umma::fence_after_sync();
-
-    // ---- scatter numerator and normaliser back to original order: half 0 writes columns [0,16), half 1 the rest ---
-    {
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      if (tile + (int)gridDim.x < total_tiles) make_p(it + 1);   // the other slot: runs while P V of this tile executes
+      const int sl = it & 1;
+      int h, t, blk;
+      decode(tile, h, t, blk);
+      // ---- numerator and normaliser back to original hit order: part 0 writes columns [0,16), part 1 the rest ------
+      umma::mbar_wait(&mbar[ODONE + sl], (it >> 1) & 1);
+      umma::fence_after_sync();
       float ov[16];
-      umma::tmem_ld16(tO + lane_base + 16 * half, ov);
-      if (row < B) {
-        const int n = __ldg(qpos + (size_t)blk * B + row);
+      umma::tmem_ld16(tmem + sl * CF::SLOT_STRIDE + 2 * NP + lane_base + 16 * part, ov);
+      umma::fence_before_sync();                       // these loads precede the P V MMAs of tile it + 2 into the same columns
+      const int n = row < B ? s_qidx[(it & 7) * 128 + row] : -1;
+      if (n >= 0) {
+        if (part == D / 16) ov[D % 16] += 1e-20f;      // column D: denom = rowsum + 1e-20 (example/hept.py:14)
         float4* dst = reinterpret_cast<float4*>(stage + (((size_t)h * N + n) * T + t) * kStageRow);
-        constexpr int VCH = D / 4;
+        constexpr int USED = (D + 1 + 3) / 4;           // 16-byte chunks that carry data
+        constexpr int WR = (USED + 1) / 2 * 2;          // keep 32-byte sectors whole
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          const int chunk = 4 * half + cc;
-          if (chunk < VCH) dst[chunk] = make_float4(ov[4 * cc], ov[4 * cc + 1], ov[4 * cc + 2], ov[4 * cc + 3]);
-        }
-        if (half == 0) {
-          dst[VCH] = make_float4((l + s_l[row]) + 1e-20f, 0.f, 0.f, 0.f);   // denom = rowsum + 1e-20
-          if constexpr ((VCH + 1) % 2 == 1) dst[VCH + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        for (int cc = 0; cc < 4; ++cc)
+          if (4 * part + cc < WR) dst[4 * part + cc] = make_float4(ov[4 * cc], ov[4 * cc + 1], ov[4 * cc + 2], ov[4 * cc + 3]);
       }
     }
-    umma::fence_before_sync();
-    __syncthreads();   // TMEM and shared memory are free for the next tile
-    umma::fence_after_sync();
+  } else if (warp < EW + PW) {
+    // =========================================== producer warps =================================================
+    const int ptid = tid - kFtEpiThreads, sub = ptid >> 3, c = ptid & 7;   // 8 lanes per row, RPP rows per pass
+    int nk_idx[PASSES], nq_idx[PASSES], n0 = 0;
+    float4 xq[PASSES], xk[PASSES], xv[PASSES], ctr;
+
+    auto load_indices = [&](int tile) {
+      int h, t, blk;
+      decode(tile, h, t, blk);
+      const int th = t * H + h;
+      const int32_t* qpos = positions + (size_t)th * N + (size_t)blk * B;
+      const int32_t* kpos = positions + ((size_t)T * H + th) * N + (size_t)blk * B;
+      n0 = __ldg(kpos + (B - 1));
+#pragma unroll
+      for (int ps = 0; ps < PASSES; ++ps) {
+        const int r = ps * RPP + sub;
+        nk_idx[ps] = r < B ? __ldg(kpos + r) : -1;
+        nq_idx[ps] = r < B ? __ldg(qpos + r) : -1;
+      }
+    };
+    // issue every row load of a tile (registers); chunk c of a hat row: feature columns from q / k, coordinate
+    // columns from hat_coords (already scaled)
+    auto issue_rows = [&](int tile, int it) {
+      int h, t, blk;
+      decode(tile, h, t, blk);
+      auto hat_chunk = [&](const float* __restrict__ x, int n) -> float4 {
+        const float* src = c < VCH ? x + ((size_t)n * H + h) * D + 4 * c : hatc + ((size_t)n * H + h) * 8 + 4 * (c - VCH);
+        return (c < VCH + 2 && n >= 0 && n < raw_size) ? ldg4(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+      };
+      ctr = hat_chunk(k, n0);
+#pragma unroll
+      for (int ps = 0; ps < PASSES; ++ps) {
+        const int nkk = nk_idx[ps], nqq = nq_idx[ps];
+        xk[ps] = hat_chunk(k, nkk);
+        xq[ps] = hat_chunk(q, nqq);
+        xv[ps] = (nkk >= 0 && c < VCH && nkk < raw_size) ? ldg4(v + ((size_t)nkk * H + h) * D + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const int r = ps * RPP + sub;
+        if (c == 0 && r < B) s_qidx[(it & 7) * 128 + r] = nqq;
+      }
+    };
+
+    int tile = blockIdx.x;
+    if (tile < total_tiles) {
+      load_indices(tile);
+      issue_rows(tile, 0);
+      if (tile + (int)gridDim.x < total_tiles) load_indices(tile + gridDim.x);
+    }
+    int it = 0;
+#pragma unroll 1
+    for (; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int st = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      uint8_t* km = smem + st * 4 * CF::TILE;
+      uint8_t* vm = smem + CF::OFF_V + st * 2 * CF::TILE;
+      // ---- q^ / k^ tiles of this stage: free once the score MMAs of tile it - 2 are done ---------------------------
+      if (it >= 2) umma::mbar_wait(&mbar[QKFREE + st], ph ^ 1);
+      float* nq2s = s_nq2 + (it & 3) * 128;
+#pragma unroll
+      for (int ps = 0; ps < PASSES; ++ps) {
+        const int r = ps * RPP + sub;
+        if (ps == PASSES - 1 && (ps * RPP + ((warp - EW) << 2)) >= B) continue;   // warps whose 4 rows are all past B
+        const bool in = r < B;
+        const uint32_t okm = umma::sw128_offset(r, c);
+        float4 hi, lo;
+        {  // key row: k' = k^ - centre; side slots carry nk = -|k'|^2 / 2 split three ways (exact)
+          float4 d = xk[ps];
+          d.x -= ctr.x; d.y -= ctr.y; d.z -= ctr.z; d.w -= ctr.w;
+          const float nk = -0.5f * tree8_lanes(chunk_sq<E>(d, c));
+          split4(d, hi, lo);
+          if (c == CF::SLOT_CH) {
+            const float h0 = umma::tf32_hi(nk), r1 = nk - h0, h1 = umma::tf32_hi(r1);
+            umma::elem<CF::SLOT_U>(hi) = h0; umma::elem<CF::SLOT_U + 1>(hi) = h1;
+            umma::elem<CF::SLOT_U>(lo) = r1 - h1; umma::elem<CF::SLOT_U + 1>(lo) = 0.f;
+          }
+          if (in) {
+            *reinterpret_cast<float4*>(km + CF::KH * CF::TILE + okm) = hi;
+            *reinterpret_cast<float4*>(km + CF::KL * CF::TILE + okm) = lo;
+          }
+        }
+        {  // query row: q' = q^ - centre; side slots carry 1
+          float4 d = xq[ps];
+          d.x -= ctr.x; d.y -= ctr.y; d.z -= ctr.z; d.w -= ctr.w;
+          const float nq2 = kLog2e * (-0.5f * tree8_lanes(chunk_sq<E>(d, c)));
+          split4(d, hi, lo);
+          if (c == CF::SLOT_CH) {
+            umma::elem<CF::SLOT_U>(hi) = 1.f; umma::elem<CF::SLOT_U + 1>(hi) = 1.f;
+            umma::elem<CF::SLOT_U>(lo) = 0.f; umma::elem<CF::SLOT_U + 1>(lo) = 0.f;
+          }
+          if (in) {
+            *reinterpret_cast<float4*>(km + CF::QH * CF::TILE + okm) = hi;
+            *reinterpret_cast<float4*>(km + CF::QL * CF::TILE + okm) = lo;
+            if (c == 0) nq2s[r] = nq2;
+          }
+        }
+      }
+      umma::fence_async_smem();
+      __syncwarp();
+      if (lane == 0) umma::mbar_arrive(&mbar[QKFULL + st]);
+
+      // ---- value tiles of this stage: free once the P V MMAs of tile it - 2 are done -------------------------------
+      if (it >= 2) umma::mbar_wait(&mbar[VFREE + st], ph ^ 1);
+#pragma unroll
+      for (int ps = 0; ps < PASSES; ++ps) {
+        const int r = ps * RPP + sub;
+        if (r < B) {
+          float4 d = xv[ps], hi, lo;
+          if (c == VCH) d.x = 1.f;                     // ones column: O[:, D] = row sum of P
+          split4(d, hi, lo);
+          const uint32_t omn = umma::sw128b32_offset(r, c);
+          *reinterpret_cast<float4*>(vm + omn) = hi;
+          *reinterpret_cast<float4*>(vm + CF::TILE + omn) = lo;
+        }
+      }
+      umma::fence_async_smem();
+      __syncwarp();
+      if (lane == 0) umma::mbar_arrive(&mbar[VFULL + st]);
+
+      // ---- registers are free: put the next tile's loads in flight, fetch the indices of the one after -----------
+      const int next = tile + gridDim.x;
+      if (next < total_tiles) {
+        issue_rows(next, it + 1);
+        if (next + (int)gridDim.x < total_tiles) load_indices(next + gridDim.x);
+      }
+    }
+  } else {
+    umma::setmaxnreg_dec<kFtRegsMma>();
+  }
+  if (warp == EW + PW) {
+    // =========================================== MMA issuer ====================================================
+    // the warp runs the schedule uniformly; the lane chosen by elect.sync issues (always the same lane, so its
+    // tcgen05.commit covers every MMA issued before)
+    constexpr uint32_t idesc_s = umma::idesc_tf32(128, NP, false, false);
+    constexpr uint32_t idesc_o = umma::idesc_tf32(128, 32, false, true);
+    const uint64_t kdesc0 = umma::smem_desc_sw128(sbase, 1024, 16);
+    const uint64_t vdesc0 = umma::smem_desc(sbase + CF::OFF_V, 512, 1024, umma::kLayoutSw128Base32);
+    auto wait = [&](int b, uint32_t parity) {
+      umma::mbar_wait(&mbar[b], parity);
+      umma::fence_after_sync();
+    };
+    // S = Q^ K^^T of tile number `it`: cross terms and the first SK0 hi*hi k-steps into S0, the rest into S1
+    auto scores = [&](int it) {
+      const int st = it & 1;
+      const uint32_t tS0 = tmem + st * CF::SLOT_STRIDE, tS1 = tS0 + NP;
+      if (umma::elect_one()) {
+        uint64_t base = kdesc0 + (uint64_t)((st * 4 * CF::TILE) >> 4);
+        asm volatile("" : "+l"(base));   // opaque: descriptors are re-derived here (one add each), not hoisted and spilled
+        const uint64_t qh = base + ((CF::QH * CF::TILE) >> 4), ql = base + ((CF::QL * CF::TILE) >> 4),
+                       kh = base + ((CF::KH * CF::TILE) >> 4), kl = base + ((CF::KL * CF::TILE) >> 4);
+#pragma unroll
+        for (int kk = 0; kk < CF::SK; ++kk) umma::mma_ss(tS0, qh + 2 * kk, kl + 2 * kk, idesc_s, kk != 0);
+#pragma unroll
+        for (int kk = 0; kk < CF::SK; ++kk) umma::mma_ss(tS0, ql + 2 * kk, kh + 2 * kk, idesc_s, true);
+#pragma unroll
+        for (int kk = 0; kk < CF::SK; ++kk)
+          umma::mma_ss(kk < CF::SK0 ? tS0 : tS1, qh + 2 * kk, kh + 2 * kk, idesc_s, kk != CF::SK0);
+        umma::commit(&mbar[SREADY + st]);
+        umma::commit(&mbar[QKFREE + st]);
+      }
+      __syncwarp();
+    };
+    int it = 0;
+    int tile = blockIdx.x;
+    if (tile < total_tiles) {
+      wait(QKFULL + 0, 0);
+      scores(0);
+    }
+#pragma unroll 1
+    for (; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int st = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      if (tile + (int)gridDim.x < total_tiles) {
+        // S of the next tile goes into the other slot: its P (tile it - 1) must have been consumed by P V(it - 1)
+        wait(QKFULL + (st ^ 1), ((it + 1) >> 1) & 1);
+        if (it >= 1) wait(ODONE + (st ^ 1), ((it - 1) >> 1) & 1);
+        scores(it + 1);
+      }
+      wait(PREADY + st, ph);
+      wait(VFULL + st, ph);
+      if (umma::elect_one()) {
+        const uint32_t tS0 = tmem + st * CF::SLOT_STRIDE, tS1 = tS0 + NP, tO = tS0 + 2 * NP;
+        uint64_t base = vdesc0 + (uint64_t)((st * 2 * CF::TILE) >> 4);
+        asm volatile("" : "+l"(base));
+#pragma unroll
+        for (int p3 = 0; p3 < 3; ++p3) {                 // P_hi V_lo, P_lo V_hi, P_hi V_hi
+          const uint32_t a = p3 == 1 ? tS1 : tS0;
+          const uint64_t db = base + (p3 == 0 ? (uint64_t)(CF::TILE >> 4) : 0);
+#pragma unroll
+          for (int kk = 0; kk < KSTEPS; ++kk) umma::mma_ts(tO, a + 8 * kk, db + 64 * kk, idesc_o, (p3 | kk) != 0);
+        }
+        umma::commit(&mbar[ODONE + st]);
+        umma::commit(&mbar[VFREE + st]);
+      }
+      __syncwarp();
+    }
   }
 
+  umma::fence_before_sync();
   __syncthreads();
-  if (warp == 0) umma::tmem_dealloc<256>(tmem);
+  if (warp == EW + PW) umma::tmem_dealloc<CF::TMEM_COLS>(tmem);
 }
 
-template <int D, int C, int B, int TILES>
+template <int D, int C, int B>
 static int launch_fwd_tc(const hept_shape* s, const float* q, const float* k, const float* v, const float* hatc,
                          const int32_t* positions, float* stage, cudaStream_t st) {
-  using SM = TcFwdSmem<D, C, B>;
-  auto kern = block_attn_fwd_tc_kernel<D, C, B, TILES>;
-  const size_t smem = SM::TOTAL + 1024;
-  static bool configured = false;
-  if (!configured) {
+  using CF = TcFwd<D, C, B>;
+  auto kern = block_attn_fwd_tc_kernel<D, C, B>;
+  const size_t smem = CF::TOTAL + 1024;
+  static int sms = 0;
+  if (!sms) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "block_attn_fwd_tc: cannot reserve %zu B of shared memory: %s", smem,
                  cudaGetErrorString(e));
-    configured = true;
+    int dev = 0, n = 0;
+    cudaGetDevice(&dev);
+    e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    HEPT_REQUIRE(e == cudaSuccess && n > 0, HEPT_ECUDA, "block_attn_fwd_tc: cannot read the SM count");
+    sms = n;
   }
-  const int nb = s->N / s->B;
-  dim3 grid((nb + TILES - 1) / TILES, s->T * s->H);
-  kern<<<grid, kTcThreads, smem, st>>>(q, k, v, hatc, positions, s->N, s->H, s->T, s->raw_size, stage);
+  const int tiles = s->T * s->H * (s->N / s->B);
+  const int grid = tiles < sms ? tiles : sms;   // one CTA per SM (two tiles in flight use all 512 TMEM columns)
+  kern<<<grid, kFtThreads, smem, st>>>(q, k, v, hatc, positions, s->N, s->H, s->T, s->raw_size, tiles, stage);
   HEPT_CHECK_LAUNCH("block_attn_fwd_tc");
   return HEPT_OK;
 }
 
 int block_attention_fwd_tc(const hept_shape* s, const float* q, const float* k, const float* v, const float* hatc,
                            const int32_t* positions, float* stage, cudaStream_t st) {
-  if (s->D == 24 && s->C == 6 && s->B == 100) return launch_fwd_tc<24, 6, 100, 4>(s, q, k, v, hatc, positions, stage, st);
-  if (s->D == 24 && s->C == 4 && s->B == 100) return launch_fwd_tc<24, 4, 100, 4>(s, q, k, v, hatc, positions, stage, st);
-  if (s->D == 8 && s->C == 6 && s->B == 10) return launch_fwd_tc<8, 6, 10, 4>(s, q, k, v, hatc, positions, stage, st);
+  if (s->D == 24 && s->C == 6 && s->B == 100) return launch_fwd_tc<24, 6, 100>(s, q, k, v, hatc, positions, stage, st);
+  if (s->D == 24 && s->C == 4 && s->B == 100) return launch_fwd_tc<24, 4, 100>(s, q, k, v, hatc, positions, stage, st);
+  if (s->D == 8 && s->C == 6 && s->B == 10) return launch_fwd_tc<8, 6, 10>(s, q, k, v, hatc, positions, stage, st);
   set_error("block_attention_fwd (tensor-core engine): (D=%d, C=%d, B=%d) not compiled in", s->D, s->C, s->B);
   return HEPT_EUNSUPPORTED;
 }

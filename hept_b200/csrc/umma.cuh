@@ -230,6 +230,21 @@ __device__ __forceinline__ float tf32_hi(float x) {
   return __uint_as_float(u);
 }
 
+// hi = x rounded to tf32 (round half away, like cvt.rna; x finite), lo = x - hi (exact)
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+  lo = x - hi;
+}
+// hi = x truncated to tf32, lo = x - hi (exact): one instruction less; the tensor core drops the low 13 bits of lo
+// either way
+__device__ __forceinline__ void trunc_tf32(float x, float& hi, float& lo) {
+  hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+  lo = x - hi;
+}
+__device__ __forceinline__ void split4(const float4 x, float4& hi, float4& lo) {
+  split_tf32(x.x, hi.x, lo.x); split_tf32(x.y, hi.y, lo.y); split_tf32(x.z, hi.z, lo.z); split_tf32(x.w, hi.w, lo.w);
+}
+
 // byte offset of 16-byte chunk `chunk` of row `row` inside a SWIZZLE_128B_BASE32B tile with 128-byte rows
 __device__ __forceinline__ uint32_t sw128b32_offset(int row, int chunk) {
   return (uint32_t)row * 128u + (uint32_t)(((((chunk >> 1) ^ (row & 3)) << 1) | (chunk & 1)) << 4);
