@@ -10,7 +10,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhept_sm100.so")
+LIB_PATH = os.environ.get("HEPT_LIB") or os.path.join(_HERE, "libhept_sm100.so")   # HEPT_LIB: tools/pipeline_trace.py
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "hept_b200.h")
 
 HEPT_OK, HEPT_EINVAL, HEPT_EUNSUPPORTED, HEPT_ECUDA, HEPT_EWORKSPACE = 0, -1, -2, -3, -4
@@ -32,6 +32,7 @@ SIGNATURES = {
     "hept_shape_supported": (C.c_int, [_i32, _i32, _i32]),
     "hept_coord_scale_fwd": (C.c_int, [_p, _i32, _i32, _i32, _i32, _p, _p]),
     "hept_coord_scale_bwd": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _i32, _p, _p]),
+    "hept_hash_workspace_bytes": (_sz, [_SP]),
     "hept_hash_project": (C.c_int, [_SP, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "hept_keys_from_packed_shifts": (C.c_int, [_SP, _p, _p, _p, _p, _p]),
     "hept_keys_from_region_indices": (C.c_int, [_SP, _p, _p, _p, _p, _p, _p, _p]),

@@ -28,7 +28,7 @@ struct FwdPlan {
 static FwdPlan plan_fwd(const hept_shape* s) {
   FwdPlan p;
   const size_t th = (size_t)s->T * s->H, thn = th * s->N;
-  p.ext_bytes = align_up(sizeof(uint32_t) * 2 * th, 256);
+  p.ext_bytes = align_up(hept_hash_workspace_bytes(s), 256);
   p.span_bytes = align_up(sizeof(float) * th, 256);
   p.hat_bytes = align_up(sizeof(float) * (size_t)s->N * s->H * 8, 256);
   p.proj_bytes = align_up(sizeof(float) * 2 * thn, 256);

@@ -36,6 +36,7 @@
 // CENTRED rows, sum_i q'_ic dq^_ic + sum_j k'_jc dk^_jc = scale_c * (the tile's share of d scale_c): no large
 // terms, nothing to cancel.  Per-tile partials are reduced in a fixed order (deterministic).
 #include "tile.cuh"
+#include "trace.cuh"
 #include "umma.cuh"
 
 namespace hept {
@@ -81,6 +82,11 @@ struct TcBwd {
   static_assert(7 * TILE + 128 * 128 <= TOTAL, "the M = 128 overrun of the last K-major tile stays inside the allocation");
   static_assert(TOTAL + 1024 <= 227 * 1024, "shared memory");
 };
+
+// timeline probe events (trace.cuh)
+enum BtEv { BE_QREADY, BE_DSRDY, BE_KREADY, BE_PTRDY, BE_DQDONE, BE_DQOUT, BE_DVDONE, BE_DSTRDY, BE_DVOUT, BE_DKDONE, BE_END,
+            BP_KFREE, BP_KFULL, BP_ISSUED, BP_MFREE, BP_MFULL, BM_DQ_GO, BM_DV_GO, BM_DK_GO, BM_SQ_GO, BM_SK_GO, BM_END };
+HEPT_TRACE_SETTER(hept_debug_trace_bwd)
 
 enum BtBar { KFULL, MFULL, MFREE, QREADY, KREADY, DSRDY, DQDONE, PTRDY, DVDONE, DSTRDY, DKDONE, BT_NBAR };
 
@@ -245,6 +251,7 @@ __global__ void __launch_bounds__(kBtThreads, 1)
       // ---- query side: dS -> TMEM (hi over S, lo over dP), row sums ---------------------------------------------
       umma::mbar_wait(&mbar[QREADY], ph);
       umma::fence_after_sync();
+      if (warp == 0) HEPT_TRACE_EVENT(BE_QREADY, it);
       {
         const float nq2 = nq2s[row];
 #pragma unroll
@@ -268,11 +275,13 @@ __global__ void __launch_bounds__(kBtThreads, 1)
         }
       }
       arrive_tmem(DSRDY);
+      if (warp == 0) HEPT_TRACE_EVENT(BE_DSRDY, it);
 
       // ---- key side: P^T -> TMEM (hi over S^T, lo over dP^T), dS^T kept in registers, column sums ---------------
       float dsr[MAXCH * 8];
       umma::mbar_wait(&mbar[KREADY], ph);
       umma::fence_after_sync();
+      if (warp == 0) HEPT_TRACE_EVENT(BE_KREADY, it);
       {
 #pragma unroll
         for (int ci = 0; ci < MAXCH; ++ci) {
@@ -298,6 +307,7 @@ __global__ void __launch_bounds__(kBtThreads, 1)
         }
       }
       arrive_tmem(PTRDY);
+      if (warp == 0) HEPT_TRACE_EVENT(BE_PTRDY, it);
 
       if (h != dsc_head) {   // first tile of another head: hand in the finished head's sums
         flush_dscale();
@@ -332,6 +342,7 @@ __global__ void __launch_bounds__(kBtThreads, 1)
       // ---- dq^ rows ---------------------------------------------------------------------------------------------
       umma::mbar_wait(&mbar[DQDONE], ph);
       umma::fence_after_sync();
+      if (warp == 0) HEPT_TRACE_EVENT(BE_DQDONE, it);
       {
         float acc[16], xr[16];
         umma::tmem_ld16(tO0 + lane_base + 16 * part, acc);
@@ -340,9 +351,11 @@ __global__ void __launch_bounds__(kBtThreads, 1)
         finish_rows(acc, xr, rs, row < B ? qidx[row] : -1, stage_dq);
       }
 
+      if (warp == 0) HEPT_TRACE_EVENT(BE_DQOUT, it);
       // ---- dS^T replaces P^T once dV has consumed it ------------------------------------------------------------
       umma::mbar_wait(&mbar[DVDONE], ph);
       umma::fence_after_sync();
+      if (warp == 0) HEPT_TRACE_EVENT(BE_DVDONE, it);
 #pragma unroll
       for (int ci = 0; ci < MAXCH; ++ci) {
         const int ch = part + ci * kBtParts;
@@ -355,6 +368,7 @@ __global__ void __launch_bounds__(kBtThreads, 1)
         }
       }
       arrive_tmem(DSTRDY);                               // also: this warp has read dQ out of tO0
+      if (warp == 0) HEPT_TRACE_EVENT(BE_DSTRDY, it);
 
       // ---- dv rows ----------------------------------------------------------------------------------------------
       {
@@ -369,9 +383,11 @@ __global__ void __launch_bounds__(kBtThreads, 1)
         }
       }
 
+      if (warp == 0) HEPT_TRACE_EVENT(BE_DVOUT, it);
       // ---- dk^ rows ---------------------------------------------------------------------------------------------
       umma::mbar_wait(&mbar[DKDONE], ph);
       umma::fence_after_sync();
+      if (warp == 0) HEPT_TRACE_EVENT(BE_DKDONE, it);
       {
         float acc[16], xr[16];
         umma::tmem_ld16(tO0 + lane_base + 16 * part, acc);
@@ -382,6 +398,7 @@ __global__ void __launch_bounds__(kBtThreads, 1)
       umma::fence_before_sync();                         // the TMEM loads above precede the next tile's MMAs into tO0 / tO1
       __syncwarp();
       if (lane == 0) umma::mbar_arrive(&mbar[MFREE]);    // this warp is done with the MN-major tiles
+      if (warp == 0) HEPT_TRACE_EVENT(BE_END, it);
 
     }
     flush_dscale();
@@ -444,6 +461,7 @@ __global__ void __launch_bounds__(kBtThreads, 1)
       const uint32_t ph = it & 1;
       // ---- K-major operand tiles: free once the previous tile's score MMAs (both sides) are done ------------------
       if (it > 0) umma::mbar_wait(&mbar[KREADY], ph ^ 1);
+      if (warp == EW) HEPT_TRACE_EVENT(BP_KFREE, it);
       umma::cp_async_wait_all();
       float* nq2s = s_nq2 + ph * 128;
 #pragma unroll
@@ -503,6 +521,7 @@ __global__ void __launch_bounds__(kBtThreads, 1)
       umma::fence_async_smem();
       __syncwarp();
       if (lane == 0) umma::mbar_arrive(&mbar[KFULL]);
+      if (warp == EW) HEPT_TRACE_EVENT(BP_KFULL, it);
 
       // ---- registers and staging are free: put the next tile's loads in flight, fetch the indices of the one after -
       const int next = tile + gridDim.x;
@@ -512,7 +531,9 @@ __global__ void __launch_bounds__(kBtThreads, 1)
       }
 
       // ---- MN-major copies: free once the previous tile's last MMA is done and its epilogue has read them ---------
+      if (warp == EW) HEPT_TRACE_EVENT(BP_ISSUED, it);
       if (it > 0) umma::mbar_wait(&mbar[MFREE], ph ^ 1);
+      if (warp == EW) HEPT_TRACE_EVENT(BP_MFREE, it);
 #pragma unroll
       for (int ps = 0; ps < PASSES; ++ps) {
         const int r = ps * RPP + sub;
@@ -533,6 +554,7 @@ __global__ void __launch_bounds__(kBtThreads, 1)
       umma::fence_async_smem();
       __syncwarp();
       if (lane == 0) umma::mbar_arrive(&mbar[MFULL]);
+      if (warp == EW) HEPT_TRACE_EVENT(BP_MFULL, it);
     }
   } else {
     umma::setmaxnreg_dec<kBtRegsMma>();
@@ -608,18 +630,21 @@ __global__ void __launch_bounds__(kBtThreads, 1)
       const bool more = tile + (int)gridDim.x < total_tiles;
       wait(DSRDY, ph);
       wait(MFULL, ph);
+      HEPT_TRACE_EVENT(BM_DQ_GO, it);
       if (umma::elect_one()) {
         ts_product(tO0, tS, tDP, CF::MKH, CF::MKL);     // dQ = dS K^
         umma::commit(&mbar[DQDONE]);
       }
       __syncwarp();
       wait(PTRDY, ph);
+      HEPT_TRACE_EVENT(BM_DV_GO, it);
       if (umma::elect_one()) {
         ts_product(tO1, tST, tDPT, CF::MGH, CF::MGL);   // dV = P^T G'
         umma::commit(&mbar[DVDONE]);
       }
       __syncwarp();
       wait(DSTRDY, ph);
+      HEPT_TRACE_EVENT(BM_DK_GO, it);
       if (umma::elect_one()) {
         ts_product(tO0, tST, tDPT, CF::MQH, CF::MQL);   // dK = dS^T Q^
         umma::commit(&mbar[DKDONE]);
@@ -630,12 +655,15 @@ __global__ void __launch_bounds__(kBtThreads, 1)
       // product, where nothing waits for them — the epilogue still has dv / dk rows to write out.
       if (more) {
         wait(KFULL, ph ^ 1);
+        HEPT_TRACE_EVENT(BM_SQ_GO, it + 1);
         scores_query_side();                            // tS / tDP were drained by dQ long ago
       }
       if (more) {                                       // next tile's key-side scores once dK has drained tST / tDPT
         wait(DKDONE, ph);
+        HEPT_TRACE_EVENT(BM_SK_GO, it + 1);
         scores_key_side();
       }
+      HEPT_TRACE_EVENT(BM_END, it);
     }
   }
 

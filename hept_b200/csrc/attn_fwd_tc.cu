@@ -19,17 +19,18 @@
 // small cross terms are accumulated first and the hi*hi steps are split over two accumulators that the epilogue adds
 // in fp32 (S0: cross terms + first half of the k-steps, S1: the rest).
 //
-// Warp roles (640 threads = 5 warpgroups, register budgets rebalanced with setmaxnreg):
+// Warp roles (896 threads = 7 warpgroups, register budgets rebalanced with setmaxnreg):
 //   warps 0-7   epilogue: TMEM lane = (warp & 3) * 32 + lane, columns split in two parts (warp >> 2); software
 //               pipelined: P of tile n+1 is produced before the output rows of tile n are read and scattered, so the
 //               P V MMAs of tile n run under SIMT work
-//   warps 8-15  producer: gather rows through the sort permutation into registers (one tile ahead), centre, split,
+//   warps 8-23  producer: gather rows through the sort permutation into registers (one tile ahead), centre, split,
 //               write the operand tiles of stage n & 1 (q^ / k^ K-major as soon as the score MMAs of tile n-2 are
 //               done, V MN-major once its P V MMAs are done)
-//   warp 16     one elected lane issues every tcgen05.mma: S(n+1), then P V(n)
+//   warp 24     one elected lane issues every tcgen05.mma: S(n+1), then P V(n)
 // TMEM: two tile slots of 256 columns (S0 | S1 | O).  Hand-offs are mbarriers that complete once per use of a slot /
 // stage, so the wait parity is bit 1 of the tile counter.
 #include "tile.cuh"
+#include "trace.cuh"
 #include "umma.cuh"
 
 namespace hept {
@@ -38,12 +39,15 @@ using umma::split4;
 using umma::split_tf32;
 using umma::trunc_tf32;
 
-constexpr int kFtEpiThreads = 256, kFtProdThreads = 256;
+constexpr int kFtEpiThreads = 256, kFtProdThreads = 512;
 constexpr int kFtThreads = kFtEpiThreads + kFtProdThreads + 128;
 constexpr int kFtParts = kFtEpiThreads / 128;
-// Launch budget 65536 / 640 -> 96 registers per thread = 61440 per CTA; setmaxnreg moves registers inside that pool.
-constexpr int kFtRegsEpi = 120, kFtRegsProd = 96, kFtRegsMma = 40;
-static_assert(kFtEpiThreads * kFtRegsEpi + kFtProdThreads * kFtRegsProd + 128 * kFtRegsMma <= kFtThreads * 96, "register pool");
+// Launch budget 65536 / 896 -> 72 registers per thread = 64512 per CTA; setmaxnreg moves registers inside that pool.
+// The gather / centre / split work of the producer is latency bound (ncu: every producer warp busy or stalled on its
+// own loads the whole time, the epilogue waiting for scores), so it gets 16 warps: two 64-row passes per tile.
+constexpr int kFtLaunchRegs = 72;
+constexpr int kFtRegsEpi = 104, kFtRegsProd = 64, kFtRegsMma = 24;
+static_assert(kFtEpiThreads * kFtRegsEpi + kFtProdThreads * kFtRegsProd + 128 * kFtRegsMma <= kFtThreads * kFtLaunchRegs, "register pool");
 
 template <int D, int C, int B>
 struct TcFwd {
@@ -73,6 +77,11 @@ struct TcFwd {
   static_assert(7 * TILE + 128 * 128 <= TOTAL, "the M = 128 overrun of the last K-major tile stays inside the allocation");
   static_assert(TOTAL + 1024 <= 227 * 1024, "shared memory");
 };
+
+// timeline probe events (trace.cuh)
+enum FtEv { EV_E_SREADY, EV_E_PREADY, EV_E_ODONE, EV_E_OUT, EV_P_QKFREE, EV_P_QKFULL, EV_P_VFREE, EV_P_VFULL, EV_P_ISSUED,
+            EV_M_S_GO, EV_M_S_ISSUED, EV_M_PV_GO, EV_M_PV_ISSUED };
+HEPT_TRACE_SETTER(hept_debug_trace_fwd)
 
 // barriers, two of each (stage / slot = tile & 1)
 enum FtBar { QKFULL = 0, VFULL = 2, QKFREE = 4, VFREE = 6, SREADY = 8, PREADY = 10, ODONE = 12, FT_NBAR = 14 };
@@ -157,6 +166,7 @@ __global__ void __launch_bounds__(kFtThreads, 1)
       const uint32_t tS0 = tmem + sl * CF::SLOT_STRIDE, tS1 = tS0 + NP;
       umma::mbar_wait(&mbar[SREADY + sl], (it >> 1) & 1);
       umma::fence_after_sync();
+      if (warp == 0) HEPT_TRACE_EVENT(EV_E_SREADY, it);
       const float nq2 = s_nq2[(it & 3) * 128 + row];
 #pragma unroll
       for (int ci = 0; ci < MAXCH; ++ci) {
@@ -180,6 +190,7 @@ __global__ void __launch_bounds__(kFtThreads, 1)
       umma::fence_before_sync();
       __syncwarp();
       if (lane == 0) umma::mbar_arrive(&mbar[PREADY + sl]);
+      if (warp == 0) HEPT_TRACE_EVENT(EV_E_PREADY, it);
     };
 
     int it = 0;
@@ -193,6 +204,7 @@ __global__ void __launch_bounds__(kFtThreads, 1)
       // ---- numerator and normaliser back to original hit order: part 0 writes columns [0,16), part 1 the rest ------
       umma::mbar_wait(&mbar[ODONE + sl], (it >> 1) & 1);
       umma::fence_after_sync();
+      if (warp == 0) HEPT_TRACE_EVENT(EV_E_ODONE, it);
       float ov[16];
       umma::tmem_ld16(tmem + sl * CF::SLOT_STRIDE + 2 * NP + lane_base + 16 * part, ov);
       umma::fence_before_sync();                       // these loads precede the P V MMAs of tile it + 2 into the same columns
@@ -206,9 +218,11 @@ __global__ void __launch_bounds__(kFtThreads, 1)
         for (int cc = 0; cc < 4; ++cc)
           if (4 * part + cc < WR) dst[4 * part + cc] = make_float4(ov[4 * cc], ov[4 * cc + 1], ov[4 * cc + 2], ov[4 * cc + 3]);
       }
+      if (warp == 0) HEPT_TRACE_EVENT(EV_E_OUT, it);
     }
   } else if (warp < EW + PW) {
     // =========================================== producer warps =================================================
+    umma::setmaxnreg_dec<kFtRegsProd>();
     const int ptid = tid - kFtEpiThreads, sub = ptid >> 3, c = ptid & 7;   // 8 lanes per row, RPP rows per pass
     int nk_idx[PASSES], nq_idx[PASSES], n0 = 0;
     float4 xq[PASSES], xk[PASSES], xv[PASSES], ctr;
@@ -263,6 +277,7 @@ __global__ void __launch_bounds__(kFtThreads, 1)
       uint8_t* vm = smem + CF::OFF_V + st * 2 * CF::TILE;
       // ---- q^ / k^ tiles of this stage: free once the score MMAs of tile it - 2 are done ---------------------------
       if (it >= 2) umma::mbar_wait(&mbar[QKFREE + st], ph ^ 1);
+      if (warp == EW) HEPT_TRACE_EVENT(EV_P_QKFREE, it);
       float* nq2s = s_nq2 + (it & 3) * 128;
 #pragma unroll
       for (int ps = 0; ps < PASSES; ++ps) {
@@ -305,9 +320,11 @@ __global__ void __launch_bounds__(kFtThreads, 1)
       umma::fence_async_smem();
       __syncwarp();
       if (lane == 0) umma::mbar_arrive(&mbar[QKFULL + st]);
+      if (warp == EW) HEPT_TRACE_EVENT(EV_P_QKFULL, it);
 
       // ---- value tiles of this stage: free once the P V MMAs of tile it - 2 are done -------------------------------
       if (it >= 2) umma::mbar_wait(&mbar[VFREE + st], ph ^ 1);
+      if (warp == EW) HEPT_TRACE_EVENT(EV_P_VFREE, it);
 #pragma unroll
       for (int ps = 0; ps < PASSES; ++ps) {
         const int r = ps * RPP + sub;
@@ -323,6 +340,7 @@ __global__ void __launch_bounds__(kFtThreads, 1)
       umma::fence_async_smem();
       __syncwarp();
       if (lane == 0) umma::mbar_arrive(&mbar[VFULL + st]);
+      if (warp == EW) HEPT_TRACE_EVENT(EV_P_VFULL, it);
 
       // ---- registers are free: put the next tile's loads in flight, fetch the indices of the one after -----------
       const int next = tile + gridDim.x;
@@ -330,6 +348,7 @@ __global__ void __launch_bounds__(kFtThreads, 1)
         issue_rows(next, it + 1);
         if (next + (int)gridDim.x < total_tiles) load_indices(next + gridDim.x);
       }
+      if (warp == EW) HEPT_TRACE_EVENT(EV_P_ISSUED, it);
     }
   } else {
     umma::setmaxnreg_dec<kFtRegsMma>();
@@ -381,10 +400,13 @@ __global__ void __launch_bounds__(kFtThreads, 1)
         // S of the next tile goes into the other slot: its P (tile it - 1) must have been consumed by P V(it - 1)
         wait(QKFULL + (st ^ 1), ((it + 1) >> 1) & 1);
         if (it >= 1) wait(ODONE + (st ^ 1), ((it - 1) >> 1) & 1);
+        HEPT_TRACE_EVENT(EV_M_S_GO, it + 1);
         scores(it + 1);
+        HEPT_TRACE_EVENT(EV_M_S_ISSUED, it + 1);
       }
       wait(PREADY + st, ph);
       wait(VFULL + st, ph);
+      HEPT_TRACE_EVENT(EV_M_PV_GO, it);
       if (umma::elect_one()) {
         const uint32_t tS0 = tmem + st * CF::SLOT_STRIDE, tS1 = tS0 + NP, tO = tS0 + 2 * NP;
         uint64_t base = vdesc0 + (uint64_t)((st * 2 * CF::TILE) >> 4);
@@ -400,6 +422,7 @@ __global__ void __launch_bounds__(kFtThreads, 1)
         umma::commit(&mbar[VFREE + st]);
       }
       __syncwarp();
+      HEPT_TRACE_EVENT(EV_M_PV_ISSUED, it);
     }
   }
 

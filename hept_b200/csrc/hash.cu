@@ -150,10 +150,6 @@ __global__ void hat_coords_kernel(const float* __restrict__ coords, const float*
   hat[i] = (c < C && (int)n < raw_size) ? __fmul_rn(scale[h * C + c], coords[n * C + c]) : 0.f;
 }
 
-__global__ void finish_span_kernel(const uint32_t* __restrict__ ext, int th, float* __restrict__ span) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < th) span[i] = __fsub_rn(from_ordered_bits(ext[2 * i + 1]), from_ordered_bits(ext[2 * i + 0]));
-}
 
 // ---------------------------------------------------------------------------------------------------
 // keys.  Explicit round-to-nearest multiply and add: an FMA contraction would not match eager torch.
@@ -184,6 +180,183 @@ __global__ void keys_regions_kernel(const float* __restrict__ proj, const float*
   float pk = n < raw_size ? proj[thn + i] : inf;
   keys[i] = __fadd_rn(pq, shift);
   keys[thn + i] = __fadd_rn(pk, shift);
+}
+
+// Second generation, T known at compile time (T <= 4).
+//  * persistent grid: a CTA walks groups of 32 hits and keeps the running min / max of its warps in registers; it
+//    writes ONE partial per (table, head) at the end and finish_span reduces the partials.  The first generation issued
+//    2 T atomics per warp on 2 T H addresses that share four cache lines: 90 k serialised L2 atomics were the whole
+//    75 us of the kernel (a rewrite of the arithmetic alone did not move it).  No atomics: the span is deterministic.
+//  * the q / k rows go to shared memory with cp.async (no registers, no issue slots while they fly) and a thread walks
+//    its row four elements at a time with every table's accumulator live: a step is 2 + T LDS.128 for 8 T FMAs.
+//    alpha is re-laid as (H, EP = 32, T) with zero rows past E, so the T 16-byte chunks of a step are aligned.
+// The per-table FMA chain runs over e = 0 .. E-1 in order, exactly like the first generation: same bits.
+constexpr int kHashMaxCtas = HEPT_HASH_MAX_CTAS;
+
+template <int D, int C, int T>
+__global__ void __launch_bounds__(256) hash_project_v2_kernel(const float* __restrict__ q, const float* __restrict__ k,
+                                                              const float* __restrict__ coords,
+                                                              const float* __restrict__ scale,
+                                                              const float* __restrict__ alpha, int N, int H, int raw_size,
+                                                              float* __restrict__ proj, uint32_t* __restrict__ partial) {
+  constexpr int E = D + C, EP = 32;
+  static_assert(E <= EP && D % 4 == 0 && T <= 4 && C <= 8, "row shapes");
+  extern __shared__ __align__(16) float s_dyn[];
+  const int HD = H * D, stride = HD + 4;
+  float* s_alpha = s_dyn;                         // (H, EP, T), 16-byte aligned chunks of 4 e x T
+  float* s_scale = s_alpha + H * EP * T;          // (H, C)
+  float* s_q = s_scale + ((H * C + 3) & ~3);      // 32 rows x stride
+  float* s_k = s_q + 32 * stride;
+  for (int i = threadIdx.x; i < H * EP * T; i += blockDim.x) {
+    const int t = i % T, e = (i / T) % EP, h = i / (T * EP);
+    s_alpha[i] = e < E ? alpha[(h * E + e) * T + t] : 0.f;
+  }
+  for (int i = threadIdx.x; i < H * C; i += blockDim.x) s_scale[i] = scale[i];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int warps = blockDim.x >> 5;
+  const int vec_per_row = HD / 4;
+  const int groups = (N + 31) / 32;
+  // running extrema of the heads this warp owns (h = warp, warp + warps, ...): lane-private until the end
+  constexpr int HPW = 4;                          // heads per warp covered without spilling (H <= warps * HPW)
+  uint32_t lo[HPW][T], hi[HPW][T];
+#pragma unroll
+  for (int j = 0; j < HPW; ++j)
+#pragma unroll
+    for (int t = 0; t < T; ++t) { lo[j][t] = 0xffffffffu; hi[j][t] = 0u; }
+
+  for (int g = blockIdx.x; g < groups; g += gridDim.x) {
+    const int n0 = g * 32;
+    const int rows = min(32, N - n0);
+    __syncthreads();                              // the previous group's rows have been consumed
+    for (int i = threadIdx.x; i < rows * vec_per_row; i += blockDim.x) {
+      const int r = i / vec_per_row, c4 = i - r * vec_per_row;
+      const size_t gi = ((size_t)(n0 + r) * HD) / 4 + c4;
+      cp_async16_ca(s_q + r * stride + 4 * c4, reinterpret_cast<const float4*>(q) + gi);
+      cp_async16_ca(s_k + r * stride + 4 * c4, reinterpret_cast<const float4*>(k) + gi);
+    }
+    const int n = n0 + lane;
+    const bool live = n < N;
+    const bool real = live && n < raw_size;
+    float cc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) cc[c] = 0.f;
+    if (real) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) cc[c] = __ldg(coords + (size_t)n * C + c);
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+
+#pragma unroll
+    for (int j = 0; j < HPW; ++j) {
+      const int h = warp + j * warps;
+      if (h >= H) break;
+      float pq[T], pk[T];
+#pragma unroll
+      for (int t = 0; t < T; ++t) { pq[t] = 0.f; pk[t] = 0.f; }
+      const float* al = s_alpha + h * EP * T;
+#pragma unroll
+      for (int c4 = 0; c4 < EP / 4; ++c4) {
+        if (4 * c4 >= E) break;
+        float xq[4], xk[4];
+        if (4 * c4 < D) {
+          const float4 a = real ? *reinterpret_cast<const float4*>(s_q + lane * stride + h * D + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 b = real ? *reinterpret_cast<const float4*>(s_k + lane * stride + h * D + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          xq[0] = a.x; xq[1] = a.y; xq[2] = a.z; xq[3] = a.w;
+          xk[0] = b.x; xk[1] = b.y; xk[2] = b.z; xk[3] = b.w;
+        } else {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int c = 4 * c4 + u - D;
+            const float v = (c < C && real) ? __fmul_rn(s_scale[h * C + (c < C ? c : 0)], cc[c < C ? c : 0]) : 0.f;
+            xq[u] = v; xk[u] = v;
+          }
+        }
+        float av[4 * T];                                  // alpha[e = 4 c4 + u][t] at av[u * T + t]
+#pragma unroll
+        for (int jj = 0; jj < T; ++jj) {
+          const float4 a4 = *reinterpret_cast<const float4*>(al + 4 * c4 * T + 4 * jj);
+          av[4 * jj] = a4.x; av[4 * jj + 1] = a4.y; av[4 * jj + 2] = a4.z; av[4 * jj + 3] = a4.w;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (4 * c4 + u < E) {
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+              pq[t] = fmaf(xq[u], av[u * T + t], pq[t]);
+              pk[t] = fmaf(xk[u], av[u * T + t], pk[t]);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        const size_t th_n = (size_t)(t * H + h) * N;
+        if (live) {
+          proj[th_n + n] = pq[t];
+          proj[(size_t)T * H * N + th_n + n] = pk[t];
+          lo[j][t] = min(lo[j][t], min(ordered_bits(pq[t]), ordered_bits(pk[t])));
+          hi[j][t] = max(hi[j][t], max(ordered_bits(pq[t]), ordered_bits(pk[t])));
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < HPW; ++j) {
+    const int h = warp + j * warps;
+    if (h >= H) break;
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      const uint32_t l = __reduce_min_sync(0xffffffffu, lo[j][t]), m = __reduce_max_sync(0xffffffffu, hi[j][t]);
+      if (lane == 0) {
+        partial[((size_t)blockIdx.x * T * H + t * H + h) * 2 + 0] = l;
+        partial[((size_t)blockIdx.x * T * H + t * H + h) * 2 + 1] = m;
+      }
+    }
+  }
+}
+
+// span[th] = max - min over the per-CTA partials (first generation: ctas == 1, the atomically maintained pair)
+__global__ void finish_span_kernel(const uint32_t* __restrict__ partial, int ctas, int th, float* __restrict__ span) {
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (i >= th) return;
+  uint32_t lo = 0xffffffffu, hi = 0u;
+  for (int b = lane; b < ctas; b += 32) {
+    lo = min(lo, partial[((size_t)b * th + i) * 2 + 0]);
+    hi = max(hi, partial[((size_t)b * th + i) * 2 + 1]);
+  }
+  lo = __reduce_min_sync(0xffffffffu, lo);
+  hi = __reduce_max_sync(0xffffffffu, hi);
+  if (lane == 0) span[i] = __fsub_rn(from_ordered_bits(hi), from_ordered_bits(lo));
+}
+
+template <int D, int C, int T>
+static int launch_project_v2(const hept_shape* s, const float* q, const float* k, const float* coords, const float* scale,
+                             const float* alpha, float* proj, uint32_t* partial, int* ctas, cudaStream_t st) {
+  const size_t smem = sizeof(float) * ((size_t)s->H * 32 * T + (((size_t)s->H * C + 3) & ~(size_t)3) +
+                                       2 * 32 * ((size_t)s->H * D + 4));
+  static int sms = 0, per_sm = 0;
+  if (!sms) {
+    cudaError_t e = cudaFuncSetAttribute(hash_project_v2_kernel<D, C, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "hash_project: %s", cudaGetErrorString(e));
+    int dev = 0, n = 0;
+    cudaGetDevice(&dev);
+    e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    HEPT_REQUIRE(e == cudaSuccess && n > 0, HEPT_ECUDA, "hash_project: cannot read the SM count");
+    sms = n;
+  }
+  HEPT_REQUIRE(smem <= 100 * 1024, HEPT_EUNSUPPORTED, "hash_project: H*D=%d too wide for the staging buffer", s->H * D);
+  HEPT_REQUIRE(s->H <= 8 * 4, HEPT_EUNSUPPORTED, "hash_project: more than 32 heads");
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hash_project_v2_kernel<D, C, T>, 256, smem);
+  HEPT_REQUIRE(e == cudaSuccess && per_sm > 0, HEPT_ECUDA, "hash_project: occupancy query failed");
+  const int groups = (s->N + 31) / 32;
+  int grid = sms * per_sm;                       // one resident wave
+  if (grid > groups) grid = groups;
+  if (grid > kHashMaxCtas) grid = kHashMaxCtas;
+  *ctas = grid;
+  hash_project_v2_kernel<D, C, T><<<grid, 256, smem, st>>>(q, k, coords, scale, alpha, s->N, s->H, s->raw_size, proj, partial);
+  HEPT_CHECK_LAUNCH("hash_project");
+  return HEPT_OK;
 }
 
 template <int D, int C>
@@ -226,6 +399,11 @@ extern "C" int hept_coord_scale_bwd(const float* w, const float* scale, const fl
   return HEPT_OK;
 }
 
+extern "C" size_t hept_hash_workspace_bytes(const hept_shape* s) {
+  if (!s || s->T <= 0 || s->H <= 0) return 0;
+  return sizeof(uint32_t) * 2 * (size_t)s->T * s->H * kHashMaxCtas;
+}
+
 extern "C" int hept_hash_project(const hept_shape* s, const float* q, const float* k, const float* coords,
                                  const float* scale, const float* alpha, float* proj, float* span, void* workspace,
                                  size_t workspace_bytes, void* stream) {
@@ -233,22 +411,28 @@ extern "C" int hept_hash_project(const hept_shape* s, const float* q, const floa
   HEPT_REQUIRE(q && k && coords && scale && alpha && proj && span && workspace, HEPT_EINVAL,
                "hash_project: null pointer");
   const int th = s->T * s->H;
-  HEPT_REQUIRE(workspace_bytes >= sizeof(uint32_t) * 2 * (size_t)th, HEPT_EWORKSPACE,
-               "hash_project: workspace needs %zu bytes", sizeof(uint32_t) * 2 * (size_t)th);
+  HEPT_REQUIRE(workspace_bytes >= hept_hash_workspace_bytes(s), HEPT_EWORKSPACE,
+               "hash_project: workspace needs %zu bytes", hept_hash_workspace_bytes(s));
   cudaStream_t st = (cudaStream_t)stream;
   uint32_t* ext = (uint32_t*)workspace;
-  init_extrema_kernel<<<(th + 127) / 128, 128, 0, st>>>(ext, th);
-  HEPT_CHECK_LAUNCH("init_extrema");
-  int rc;
-  if (s->D == 24 && s->C == 6) rc = launch_project<24, 6>(s, q, k, coords, scale, alpha, proj, ext, st);
-  else if (s->D == 24 && s->C == 4) rc = launch_project<24, 4>(s, q, k, coords, scale, alpha, proj, ext, st);
-  else if (s->D == 8 && s->C == 6) rc = launch_project<8, 6>(s, q, k, coords, scale, alpha, proj, ext, st);
+  int rc, ctas = 1;
+  if (s->D == 24 && s->C == 6 && s->T == 3) rc = launch_project_v2<24, 6, 3>(s, q, k, coords, scale, alpha, proj, ext, &ctas, st);
+  else if (s->D == 24 && s->C == 4 && s->T == 3) rc = launch_project_v2<24, 4, 3>(s, q, k, coords, scale, alpha, proj, ext, &ctas, st);
+  else if (s->D == 8 && s->C == 6 && s->T == 2) rc = launch_project_v2<8, 6, 2>(s, q, k, coords, scale, alpha, proj, ext, &ctas, st);
   else {
-    set_error("hash_project: (D=%d, C=%d) not compiled in", s->D, s->C);
-    return HEPT_EUNSUPPORTED;
+    // any other table count: the first-generation kernel with one atomically maintained (min, max) pair per (table, head)
+    init_extrema_kernel<<<(th + 127) / 128, 128, 0, st>>>(ext, th);
+    HEPT_CHECK_LAUNCH("init_extrema");
+    if (s->D == 24 && s->C == 6) rc = launch_project<24, 6>(s, q, k, coords, scale, alpha, proj, ext, st);
+    else if (s->D == 24 && s->C == 4) rc = launch_project<24, 4>(s, q, k, coords, scale, alpha, proj, ext, st);
+    else if (s->D == 8 && s->C == 6) rc = launch_project<8, 6>(s, q, k, coords, scale, alpha, proj, ext, st);
+    else {
+      set_error("hash_project: (D=%d, C=%d) not compiled in", s->D, s->C);
+      return HEPT_EUNSUPPORTED;
+    }
   }
   if (rc) return rc;
-  finish_span_kernel<<<(th + 127) / 128, 128, 0, st>>>(ext, th, span);
+  finish_span_kernel<<<(th + 7) / 8, 256, 0, st>>>(ext, ctas, th, span);
   HEPT_CHECK_LAUNCH("finish_span");
   return HEPT_OK;
 }

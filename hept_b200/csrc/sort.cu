@@ -16,7 +16,13 @@ constexpr int kRadixBits = 8;
 constexpr int kRadix = 1 << kRadixBits;
 constexpr int kSortThreads = 256;
 constexpr int kSortWarps = kSortThreads / 32;
-constexpr int kItemsPerThread = 16;
+#ifndef HEPT_SORT_ITEMS
+#define HEPT_SORT_ITEMS 16
+#endif
+#ifndef HEPT_SORT_BLOCKS
+#define HEPT_SORT_BLOCKS 3
+#endif
+constexpr int kItemsPerThread = HEPT_SORT_ITEMS;
 constexpr int kTile = kSortThreads * kItemsPerThread;  // 4096 keys per CTA
 
 // lanes of the warp whose (valid, 8-bit digit) equals mine, from nine ballots.  __match_any_sync gives the same mask
@@ -60,7 +66,7 @@ __global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const void* __
 
 // keys_in/idx_in -> keys_out/idx_out.  idx_in == nullptr means the identity (first pass);
 // keys_out == nullptr means the keys are no longer needed (last pass).
-__global__ void __launch_bounds__(kSortThreads, 3) radix_scatter_kernel(const void* __restrict__ keys_in, bool as_float,
+__global__ void __launch_bounds__(kSortThreads, HEPT_SORT_BLOCKS) radix_scatter_kernel(const void* __restrict__ keys_in, bool as_float,
                                                                       const int32_t* __restrict__ idx_in, int n,
                                                                       int tiles, int shift,
                                                                       const uint32_t* __restrict__ tile_hist,

@@ -104,8 +104,8 @@ def hash_project(d: Dims, q, k, coords, scale, alpha) -> Tuple[torch.Tensor, tor
     alpha = _need(alpha, "e2lsh.alpha", torch.float32, (d.H, d.E, d.T))
     proj = torch.empty(2, d.T, d.H, d.N, dtype=torch.float32, device=q.device)
     span = torch.empty(d.T, d.H, dtype=torch.float32, device=q.device)
-    ws = _workspace(8 * d.T * d.H, q)
     s = d.struct()
+    ws = _workspace(lib.hept_hash_workspace_bytes(C.byref(s)), q)
     _lib.check(lib.hept_hash_project(C.byref(s), _ptr(q), _ptr(k), _ptr(coords), _ptr(scale), _ptr(alpha), _ptr(proj),
                                      _ptr(span), _ptr(ws), ws.numel(), _stream(q)), "hept_hash_project")
     return proj, span

@@ -59,7 +59,11 @@ int hept_coord_scale_bwd(const float* w_rpe_weight, const float* scale, const fl
 
 /* ---- a4+a5  E2LSH.forward x2 + lsh_mapping (example/hept_utils.py:45-47, 64-71) ---------------
  * q,k (N, H*D); coords (N, C); scale (H, C); alpha (H, E, T).
- * proj (2, T, H, N): [0] = queries, [1] = keys.  span (T, H) = max - min over both. */
+ * proj (2, T, H, N): [0] = queries, [1] = keys.  span (T, H) = max - min over both.
+ * workspace: hept_hash_workspace_bytes(s) = one (min, max) pair per (CTA, table, head), at most HEPT_HASH_MAX_CTAS CTAs
+ * (the persistent grid keeps extrema in registers; no atomics, so the span is deterministic). */
+#define HEPT_HASH_MAX_CTAS 1024
+size_t hept_hash_workspace_bytes(const hept_shape* s);
 int hept_hash_project(const hept_shape* s, const float* q, const float* k, const float* coords,
                       const float* scale, const float* alpha, float* proj, float* span,
                       void* workspace, size_t workspace_bytes, void* stream);

@@ -1,0 +1,64 @@
+"""Timeline of the warp-specialised tile kernels: clock64 stamps of every hand-off of CTA 0 (trace.cuh), first 64 tiles.
+
+    make -C hept_b200/csrc TRACE=1 && python tools/pipeline_trace.py
+
+Prints, per tile, each event's offset from the first stamp and the steady-state period / phases; writes
+gpurun_out/pipeline_trace.json."""
+import ctypes
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+os.environ.setdefault("HEPT_LIB", os.path.join(ROOT, "hept_b200", "libhept_sm100_trace.so"))
+import torch
+
+import bench
+from hept_b200 import _lib, ops
+
+FWD = ["E_SREADY", "E_PREADY", "E_ODONE", "E_OUT", "P_QKFREE", "P_QKFULL", "P_VFREE", "P_VFULL", "P_ISSUED",
+       "M_S_GO", "M_S_ISSUED", "M_PV_GO", "M_PV_ISSUED"]
+BWD = ["E_QREADY", "E_DSRDY", "E_KREADY", "E_PTRDY", "E_DQDONE", "E_DQOUT", "E_DVDONE", "E_DSTRDY", "E_DVOUT", "E_DKDONE",
+       "E_END", "P_KFREE", "P_KFULL", "P_ISSUED", "P_MFREE", "P_MFULL", "M_DQ_GO", "M_DV_GO", "M_DK_GO", "M_SQ_GO",
+       "M_SK_GO", "M_END"]
+TILES, EVENTS = 64, 32
+
+lib = _lib.load()
+lib.hept_set_engine(1)
+lib.hept_set_bwd_variant(3)
+cfg, params, inp, g = bench.make_event(7, 60000)
+dev = torch.device("cuda:0")
+inp = {k: v.to(dev) for k, v in inp.items()}
+n = inp["query"].shape[0]
+d = ops.Dims(N=n, H=cfg["num_heads"], D=cfg["h_dim"], C=cfg["coords_dim"], T=cfg["n_hashes"], B=cfg["block_size"], raw_size=n)
+w, al = params["w_rpe.weight"].to(dev), params["e2lsh.alpha"].to(dev)
+gpre = torch.randn(n, d.H * d.D, device=dev)
+tf = torch.zeros(EVENTS * TILES, dtype=torch.int64, device=dev)
+tb = torch.zeros(EVENTS * TILES, dtype=torch.int64, device=dev)
+for fn, buf in (("hept_debug_trace_fwd", tf), ("hept_debug_trace_bwd", tb)):
+    f = getattr(lib, fn)       # only the TRACE build exports these
+    f.argtypes, f.restype = [ctypes.c_void_p], ctypes.c_int
+    assert f(ctypes.c_void_p(buf.data_ptr())) == 0
+for _ in range(3):
+    tf.zero_(); tb.zero_()
+    out, den, scale, pos = ops.attention_fwd(d, inp["query"], inp["key"], inp["value"], inp["coords"], w,
+                                             cfg["num_w_per_dist"], al, combined_shifts=inp["combined_shifts"])
+    ops.attention_bwd(d, inp["query"], inp["key"], inp["value"], inp["coords"], scale, pos, out, den, gpre)
+torch.cuda.synchronize()
+res = {}
+for name, ev, buf in (("fwd", FWD, tf), ("bwd", BWD, tb)):
+    t = buf.cpu().view(EVENTS, TILES)[: len(ev)]
+    t0 = int(t[t > 0].min())
+    rel = (t - t0).clamp_min(-1)
+    print(f"==== {name}: cycles since the first stamp; rows = tiles of CTA 0")
+    print("tile " + " ".join(f"{e:>10}" for e in ev))
+    for it in range(8, 20):
+        print(f"{it:4d} " + " ".join(f"{int(rel[e, it]):>10}" for e in range(len(ev))))
+    lo, hi = 10, 60
+    period = float(t[0, hi] - t[0, lo]) / (hi - lo)
+    phase = {e: float((t[i, lo:hi] - t[0, lo:hi]).double().mean()) for i, e in enumerate(ev)}
+    print(f"period {period:.0f} cycles/tile; mean offset from {ev[0]}: " + ", ".join(f"{k}={v:.0f}" for k, v in phase.items()))
+    res[name] = {"period_cycles": period, "phase": phase, "events": ev, "stamps": rel[:, :40].tolist()}
+os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+json.dump(res, open(os.path.join(ROOT, "gpurun_out", "pipeline_trace.json"), "w"))

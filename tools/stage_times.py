@@ -1,0 +1,71 @@
+"""CUDA-event time of every native stage of one tracking-60k fwd+bwd (inputs rotate over 4 events, far beyond L2).
+
+    python tools/stage_times.py [n_hits]     -> gpurun_out/stage_times.json
+"""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+
+import bench
+from hept_b200 import _lib, ops
+
+n_raw = int(sys.argv[1]) if len(sys.argv) > 1 else 60000
+lib = _lib.load()
+dev = torch.device("cuda:0")
+sets = []
+for i in range(4):
+    cfg, params, inp, g = bench.make_event(7 + i, n_raw)
+    inp = {k: v.to(dev) for k, v in inp.items()}
+    sets.append(inp)
+n = sets[0]["query"].shape[0]
+d = ops.Dims(N=n, H=cfg["num_heads"], D=cfg["h_dim"], C=cfg["coords_dim"], T=cfg["n_hashes"], B=cfg["block_size"], raw_size=n)
+K = cfg["num_w_per_dist"]
+w, al = params["w_rpe.weight"].to(dev), params["e2lsh.alpha"].to(dev)
+scale = ops.coord_scale(w, d.H, d.D, K)
+mid = []
+for s in sets:
+    proj, span = ops.hash_project(d, s["query"], s["key"], s["coords"], scale, al)
+    keys = ops.keys_from_packed_shifts(d, proj, span, s["combined_shifts"])
+    pos = ops.segmented_argsort(keys)
+    stage = ops.block_attention_fwd(d, s["query"], s["key"], s["value"], s["coords"], scale, pos)
+    out, den = ops.or_combine(d, stage)
+    mid.append(dict(proj=proj, span=span, keys=keys, pos=pos, stage=stage, out=out, den=den, g=torch.randn_like(out)))
+
+
+def ev(fn, reps=12):
+    for i in range(3):
+        fn(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(reps):
+        fn(i)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e3
+
+
+S = lambda i: sets[i % 4]
+M = lambda i: mid[i % 4]
+t = {}
+t["hash_project"] = ev(lambda i: ops.hash_project(d, S(i)["query"], S(i)["key"], S(i)["coords"], scale, al))
+t["keys"] = ev(lambda i: ops.keys_from_packed_shifts(d, M(i)["proj"], M(i)["span"], S(i)["combined_shifts"]))
+t["argsort"] = ev(lambda i: ops.segmented_argsort(M(i)["keys"]))
+t["hat+tiles_fwd"] = ev(lambda i: ops.block_attention_fwd(d, S(i)["query"], S(i)["key"], S(i)["value"], S(i)["coords"], scale, M(i)["pos"]))
+t["or_combine"] = ev(lambda i: ops.or_combine(d, M(i)["stage"]))
+t["fwd_call"] = ev(lambda i: ops.attention_fwd(d, S(i)["query"], S(i)["key"], S(i)["value"], S(i)["coords"], w, K, al,
+                                               combined_shifts=S(i)["combined_shifts"]))
+t["bwd_call"] = ev(lambda i: ops.attention_bwd(d, S(i)["query"], S(i)["key"], S(i)["value"], S(i)["coords"], scale,
+                                               M(i)["pos"], M(i)["out"], M(i)["den"], M(i)["g"]))
+lib.hept_set_bwd_stage_mask(3)
+t["bwd_pre+tiles"] = ev(lambda i: ops.attention_bwd(d, S(i)["query"], S(i)["key"], S(i)["value"], S(i)["coords"], scale,
+                                                    M(i)["pos"], M(i)["out"], M(i)["den"], M(i)["g"]))
+lib.hept_set_bwd_stage_mask(7)
+t = {k: round(v, 1) for k, v in t.items()}
+print(json.dumps(t))
+os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+json.dump(t, open(os.path.join(ROOT, "gpurun_out", "stage_times.json"), "w"))
