@@ -41,6 +41,9 @@ SIGNATURES = {
     "hept_hat_coords": (C.c_int, [_SP, _p, _p, _p, _p]),
     "hept_block_attention_fwd": (C.c_int, [_SP, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "hept_or_combine": (C.c_int, [_SP, _p, _p, _p, _p]),
+    "hept_out_linear_fwd": (C.c_int, [_SP, _p, _p, _p, _p, _p]),
+    "hept_out_linear_bwd_workspace_bytes": (_sz, [_SP]),
+    "hept_out_linear_bwd": (C.c_int, [_SP, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "hept_attention_bwd_workspace_bytes": (_sz, [_SP]),
     "hept_block_attention_bwd": (C.c_int, [_SP] + [_p] * 14 + [_sz, _p]),
     "hept_attention_fwd_workspace_bytes": (_sz, [_SP]),

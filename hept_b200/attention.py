@@ -10,8 +10,9 @@ returning ``(N, h_dim)``, same state_dict keys (``out_linear.weight``, ``out_lin
 ``e2lsh.alpha``, plus ``e2lsh.beta`` when a src/ checkpoint carries it), so
 ``load_state_dict(strict=True)`` works on both checkpoint flavours.
 
-Everything between the q/k/v inputs and ``out_linear`` runs in libhept_sm100.so (one native call
-forward, one backward); ``out_linear`` itself is a plain library GEMM (torch / cuBLAS).  There is no
+Everything from the q/k/v inputs to the module output runs in libhept_sm100.so: one native call for
+a3..a12 forward and one for its backward, and ``out_linear`` (whose parameters stay in an ``nn.Linear``
+for state_dict compatibility) on the library's streaming kernels, forward and backward.  There is no
 CPU path: CPU tensors raise, a missing library raises.
 
 Documented deviation: the src/ reference zeroes ``value[raw_size:]`` IN the caller's tensor
@@ -73,6 +74,24 @@ class _HeptCore(torch.autograd.Function):
         return dq, dk, dv, dw, None, None, None, None, None, None, None, None
 
 
+class _OutLinear(torch.autograd.Function):
+    """out_pre (N, H*D), weight (D, H*D), bias (D) -> out (N, D): ``out_linear`` of example/hept.py:80 on the library's own
+    streaming kernels (csrc/out_linear.cu) instead of three library GEMMs."""
+
+    @staticmethod
+    def forward(ctx, out_pre, weight, bias, dims: ops.Dims):
+        w, b = weight.contiguous(), bias.contiguous()
+        ctx.save_for_backward(out_pre, w)
+        ctx.dims = dims
+        return ops.out_linear_fwd(dims, out_pre, w, b)
+
+    @staticmethod
+    def backward(ctx, d_out):
+        out_pre, w = ctx.saved_tensors
+        dx, dw, db = ops.out_linear_bwd(ctx.dims, d_out.contiguous(), w, out_pre, need_input_grad=ctx.needs_input_grad[0])
+        return dx, dw, db, None
+
+
 class HEPTAttention(nn.Module):
     def __init__(self, hash_dim: int, **kwargs):
         super().__init__()
@@ -89,6 +108,9 @@ class HEPTAttention(nn.Module):
     # -- the hot path ---------------------------------------------------------------------------
     def attend(self, query, key, value, **kwargs) -> torch.Tensor:
         """Everything up to (not including) out_linear -> (N, H*D)."""
+        return self._attend(query, key, value, **kwargs)[0]
+
+    def _attend(self, query, key, value, **kwargs):
         if not query.is_cuda:
             raise RuntimeError(
                 "hept_b200.HEPTAttention runs on CUDA (sm_100a) only; there is no CPU path. "
@@ -116,9 +138,11 @@ class HEPTAttention(nn.Module):
             eta, phi = eta.contiguous(), phi.contiguous()
         dims = ops.Dims(N=n, H=H, D=D, C=C, T=self.n_hashes, B=self.block_size, raw_size=raw)
         f32 = lambda t: t if t.dtype == torch.float32 else t.float()
-        return _HeptCore.apply(f32(query).reshape(n, H * D), f32(key).reshape(n, H * D), f32(value).reshape(n, H * D),
-                               w, self.e2lsh.alpha, f32(coords), shifts, eta, phi, regions_h, dims,
-                               self.num_w_per_dist)
+        out_pre = _HeptCore.apply(f32(query).reshape(n, H * D), f32(key).reshape(n, H * D), f32(value).reshape(n, H * D),
+                                  w, self.e2lsh.alpha, f32(coords), shifts, eta, phi, regions_h, dims,
+                                  self.num_w_per_dist)
+        return out_pre, dims
 
     def forward(self, query, key, value, **kwargs):
-        return self.out_linear(self.attend(query, key, value, **kwargs))
+        out_pre, dims = self._attend(query, key, value, **kwargs)
+        return _OutLinear.apply(out_pre, self.out_linear.weight, self.out_linear.bias, dims)

@@ -1,12 +1,14 @@
 // Error plumbing, launch accounting and the one-call forward (a3..a12) of the C ABI.
 #include <stdarg.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace hept {
 
 static thread_local char g_error[512] = "";
-static thread_local int g_launches = 0;
+static std::atomic<int> g_launches{0};   // process-wide: autograd runs the backward on its own thread
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -14,7 +16,7 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_error, sizeof(g_error), fmt, ap);
   va_end(ap);
 }
-void count_launch(int n) { g_launches += n; }
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 static int g_bwd_mask = 7;
 int bwd_stage_mask() { return g_bwd_mask; }
 static int g_engine = 1;  // tcgen05 tiles by default (faster, same tolerance contract); 0 = fp32 CUDA-core tiles
@@ -48,9 +50,7 @@ using namespace hept;
 extern "C" int hept_abi_version(void) { return 1; }
 extern "C" const char* hept_last_error(void) { return g_error; }
 extern "C" int hept_launch_count(int reset) {
-  int n = g_launches;
-  if (reset) g_launches = 0;
-  return n;
+  return reset ? g_launches.exchange(0, std::memory_order_relaxed) : g_launches.load(std::memory_order_relaxed);
 }
 
 extern "C" void hept_set_bwd_stage_mask(int mask) { g_bwd_mask = mask & 7; }

@@ -189,6 +189,34 @@ def or_combine(d: Dims, stage) -> Tuple[torch.Tensor, torch.Tensor]:
     return out_pre, den
 
 
+def out_linear_fwd(d: Dims, out_pre, weight, bias) -> torch.Tensor:
+    """out (N, D) = out_pre (N, H*D) weight^T + bias   (example/hept.py:80)."""
+    lib = _lib.load()
+    x = _need(out_pre, "out_pre", torch.float32, (d.N, d.H * d.D))
+    w = _need(weight, "out_linear.weight", torch.float32, (d.D, d.H * d.D))
+    b = _need(bias, "out_linear.bias", torch.float32, (d.D,))
+    out = torch.empty(d.N, d.D, dtype=torch.float32, device=x.device)
+    s = d.struct()
+    _lib.check(lib.hept_out_linear_fwd(C.byref(s), _ptr(x), _ptr(w), _ptr(b), _ptr(out), _stream(x)), "hept_out_linear_fwd")
+    return out
+
+
+def out_linear_bwd(d: Dims, d_out, weight, out_pre, need_input_grad: bool = True):
+    """-> d_out_pre (N, H*D) or None, d_weight (D, H*D), d_bias (D)."""
+    lib = _lib.load()
+    g = _need(d_out, "d_out", torch.float32, (d.N, d.D))
+    w = _need(weight, "out_linear.weight", torch.float32, (d.D, d.H * d.D))
+    x = _need(out_pre, "out_pre", torch.float32, (d.N, d.H * d.D))
+    dx = torch.empty_like(x) if need_input_grad else None
+    dw = torch.empty_like(w)
+    db = torch.empty(d.D, dtype=torch.float32, device=x.device)
+    s = d.struct()
+    ws = _workspace(lib.hept_out_linear_bwd_workspace_bytes(C.byref(s)), x)
+    _lib.check(lib.hept_out_linear_bwd(C.byref(s), _ptr(g), _ptr(w), _ptr(x), _ptr(dx), _ptr(dw), _ptr(db), _ptr(ws),
+                                       ws.numel(), _stream(x)), "hept_out_linear_bwd")
+    return dx, dw, db
+
+
 # --------------------------------------------------------------------------------------- whole path
 def attention_fwd(d: Dims, q, k, v, coords, w_rpe_weight, K: int, alpha, combined_shifts=None, region_indices=None,
                   regions_h=None):

@@ -102,6 +102,19 @@ int hept_block_attention_fwd(const hept_shape* s, const float* q, const float* k
  * out_pre (N, H*D) = sum_t numer / sum_t denom ; den_sum (N, H) kept for backward. */
 int hept_or_combine(const hept_shape* s, const float* stage, float* out_pre, float* den_sum, void* stream);
 
+/* ---- a12, second half: out_linear (example/hept.py:80; nn.Linear(H*D, D)) ------------------------
+ * out (N, D) = out_pre (N, H*D) weight^T (D, H*D) + bias (D), fp32 FMA, no library GEMM. */
+int hept_out_linear_fwd(const hept_shape* s, const float* out_pre, const float* weight, const float* bias,
+                        float* out, void* stream);
+/* its backward: d_out (N, D) -> d_out_pre (N, H*D) = d_out weight (skipped when d_out_pre is null),
+ * d_weight (D, H*D) = d_out^T out_pre, d_bias (D) = column sums of d_out.  The parameter gradients are summed per
+ * CTA over slabs of hits, then over at most HEPT_OUT_LINEAR_MAX_CTAS CTAs in a fixed order: deterministic. */
+#define HEPT_OUT_LINEAR_MAX_CTAS 1024
+size_t hept_out_linear_bwd_workspace_bytes(const hept_shape* s);
+int hept_out_linear_bwd(const hept_shape* s, const float* d_out, const float* weight, const float* out_pre,
+                        float* d_out_pre, float* d_weight, float* d_bias, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
 /* ---- a18  backward of a8..a12 and of the coordinate scale's use in a3 --------------------------
  * d_out_pre (N, H*D) is the gradient arriving from out_linear.  Writes dq, dk, dv (N, H*D) and
  * dscale (H, C).  Deterministic (no floating-point atomics). */
@@ -122,7 +135,7 @@ int hept_attention_fwd(const hept_shape* s, const float* q, const float* k, cons
                        const float* regions_h, float* scale, int32_t* positions, float* out_pre,
                        float* den_sum, void* workspace, size_t workspace_bytes, void* stream);
 
-/* kernel launches this library enqueued from the calling thread since the counter was last reset
+/* kernel launches this library enqueued (any thread of the process) since the counter was last reset
  * (bench.py's gpu_launches); reset != 0 zeroes the counter after reading it. */
 int hept_launch_count(int reset);
 

@@ -124,6 +124,33 @@ def test_coord_scale_forward_backward(name):
     assert rel_err(dw.cpu(), w.grad) < 1e-5
 
 
+@pytest.mark.parametrize("shape", [(1300, 8, 24), (60000, 8, 24), (70, 2, 8), (6437, 8, 24)])
+def test_out_linear_forward_backward(shape):
+    """a12 projection (example/hept.py:80) on the library's streaming kernels vs a float64 evaluation: an fp32 dot product
+    of H*D terms; 2e-6 relative (Frobenius) is ~10 ulp of headroom over sqrt(192) * 2^-24.  Deterministic bit for bit."""
+    from hept_b200 import ops
+
+    n, H, D = shape
+    g = torch.Generator().manual_seed(n)
+    x = torch.randn(n, H * D, generator=g)
+    w = torch.randn(D, H * D, generator=g) / (H * D) ** 0.5
+    b = torch.randn(D, generator=g)
+    go = torch.randn(n, D, generator=g)
+    d = ops.Dims(N=n, H=H, D=D, C=6, T=3, B=n, raw_size=n)
+    xd, wd, bd, gd = (t.to(dev()) for t in (x, w, b, go))
+    out = ops.out_linear_fwd(d, xd, wd, bd)
+    ref = x.double() @ w.double().T + b.double()
+    assert rel_err(out.cpu(), ref) < 2e-6
+    dx, dw, db = ops.out_linear_bwd(d, gd, wd, xd)
+    assert rel_err(dx.cpu(), go.double() @ w.double()) < 2e-6
+    assert rel_err(dw.cpu(), go.double().T @ x.double()) < 2e-6
+    assert rel_err(db.cpu(), go.double().sum(0)) < 2e-6
+    dx2, dw2, db2 = ops.out_linear_bwd(d, gd, wd, xd)
+    assert torch.equal(dw, dw2) and torch.equal(db, db2) and torch.equal(dx, dx2)
+    none, dw3, _ = ops.out_linear_bwd(d, gd, wd, xd, need_input_grad=False)
+    assert none is None and torch.equal(dw, dw3)
+
+
 @pytest.mark.parametrize("name", CASES)
 def test_projection_span_keys(name):
     from hept_b200 import ops

@@ -61,6 +61,11 @@ t["fwd_call"] = ev(lambda i: ops.attention_fwd(d, S(i)["query"], S(i)["key"], S(
                                                combined_shifts=S(i)["combined_shifts"]))
 t["bwd_call"] = ev(lambda i: ops.attention_bwd(d, S(i)["query"], S(i)["key"], S(i)["value"], S(i)["coords"], scale,
                                                M(i)["pos"], M(i)["out"], M(i)["den"], M(i)["g"]))
+wo, bo = params["out_linear.weight"].to(dev), params["out_linear.bias"].to(dev)
+go = torch.randn(n, d.D, device=dev)
+t["out_linear_fwd"] = ev(lambda i: ops.out_linear_fwd(d, M(i)["out"], wo, bo))
+t["out_linear_bwd"] = ev(lambda i: ops.out_linear_bwd(d, go, wo, M(i)["out"]))
+t["out_linear_bwd_params_only"] = ev(lambda i: ops.out_linear_bwd(d, go, wo, M(i)["out"], need_input_grad=False))
 lib.hept_set_bwd_stage_mask(3)
 t["bwd_pre+tiles"] = ev(lambda i: ops.attention_bwd(d, S(i)["query"], S(i)["key"], S(i)["value"], S(i)["coords"], scale,
                                                     M(i)["pos"], M(i)["out"], M(i)["den"], M(i)["g"]))
