@@ -7,9 +7,9 @@
 //   query side (TMEM lane = query i)                     key side (TMEM lane = key j)
 //   S   = Q^ K^^T            SS, N = NP                   S^T  = K^ Q^^T            SS (operands exchanged)
 //   dP  = G' V'^T            SS                           dP^T = V' G'^T            SS
-//   dS  = P dP  -> TMEM (hi, lo)                          P^T -> TMEM (hi, lo), dS^T kept in registers
+//   dS  = P dP  -> TMEM (hi, lo)                          P^T -> TMEM (hi, lo), dS^T kept in registers, then written
 //   dQ  = dS [K^ | 1]        TS, B = K^ MN-major          dV   = P^T G'             TS, B = G' MN-major
-//   dq^_i = dQ_i - rs_i q'_i                              dK   = dS^T [Q^ | 1]      TS (after dS^T replaced P^T)
+//   dq^_i = dQ_i - rs_i q'_i                              dK   = dS^T [Q^ | 1]      TS (dS^T where dS was, once dQ is done)
 //                                                         dk^_j = dK_j - cs_j k'_j
 // The row / column sums rs_i = sum_j dS_ij, cs_j = sum_i dS_ij come out of the same MMAs (a ones column in the
 // MN-major operand), so they are the sums of exactly the (hi, lo) values that produced dQ / dK.
@@ -88,7 +88,7 @@ enum BtEv { BE_QREADY, BE_DSRDY, BE_KREADY, BE_PTRDY, BE_DQDONE, BE_DQOUT, BE_DV
             BP_KFREE, BP_KFULL, BP_ISSUED, BP_MFREE, BP_MFULL, BM_DQ_GO, BM_DV_GO, BM_DK_GO, BM_SQ_GO, BM_SK_GO, BM_END };
 HEPT_TRACE_SETTER(hept_debug_trace_bwd)
 
-enum BtBar { KFULL, MFULL, MFREE, QREADY, KREADY, DSRDY, DQDONE, PTRDY, DVDONE, DSTRDY, DKDONE, BT_NBAR };
+enum BtBar { KFULL, MFULL, MFREE, QREADY, KREADY, DSRDY, DQDONE, PTRDY, DVDONE, DSTRDY, DKDONE, STFREE, BT_NBAR };
 
 using umma::split4;
 using umma::split_tf32;
@@ -158,6 +158,7 @@ __global__ void __launch_bounds__(kBtThreads, 1)
     umma::mbar_init(&mbar[DVDONE], 1);
     umma::mbar_init(&mbar[DSTRDY], EW);
     umma::mbar_init(&mbar[DKDONE], 1);
+    umma::mbar_init(&mbar[STFREE], EW);
   }
   if (warp == EW + PW) umma::tmem_alloc<CF::TMEM_COLS>(&tmem_slot);
   if (warp >= EW && warp < EW + PW) {
@@ -254,8 +255,8 @@ __global__ void __launch_bounds__(kBtThreads, 1)
       if (warp == 0) HEPT_TRACE_EVENT(BE_QREADY, it);
       {
         const float nq2 = nq2s[row];
-#pragma unroll
-        for (int ci = 0; ci < MAXCH; ++ci) {
+#pragma unroll 1                                   // nothing is carried between chunks: rolled, the kernel's code has to stay
+        for (int ci = 0; ci < MAXCH; ++ci) {      // inside the instruction cache (see the note on code size in DESIGN.md)
           const int ch = part + ci * kBtParts;
           if (ch < KSTEPS) {
             uint32_t ra[8], rb[8];
@@ -339,23 +340,10 @@ __global__ void __launch_bounds__(kBtThreads, 1)
         }
       };
 
-      // ---- dq^ rows ---------------------------------------------------------------------------------------------
+      // ---- dS^T goes where dS was, as soon as dQ has consumed dS: dK can then follow dV on the tensor pipe at once -----
       umma::mbar_wait(&mbar[DQDONE], ph);
       umma::fence_after_sync();
       if (warp == 0) HEPT_TRACE_EVENT(BE_DQDONE, it);
-      {
-        float acc[16], xr[16];
-        umma::tmem_ld16(tO0 + lane_base + 16 * part, acc);
-        const float rs = umma::tmem_ld1(tO0 + lane_base + E);       // column E of dQ: sum_j dS_ij
-        centred_row(CF::MQH, CF::MQL, xr);
-        finish_rows(acc, xr, rs, row < B ? qidx[row] : -1, stage_dq);
-      }
-
-      if (warp == 0) HEPT_TRACE_EVENT(BE_DQOUT, it);
-      // ---- dS^T replaces P^T once dV has consumed it ------------------------------------------------------------
-      umma::mbar_wait(&mbar[DVDONE], ph);
-      umma::fence_after_sync();
-      if (warp == 0) HEPT_TRACE_EVENT(BE_DVDONE, it);
 #pragma unroll
       for (int ci = 0; ci < MAXCH; ++ci) {
         const int ch = part + ci * kBtParts;
@@ -363,14 +351,27 @@ __global__ void __launch_bounds__(kBtThreads, 1)
           float dh[8], dl[8];
 #pragma unroll
           for (int u = 0; u < 8; ++u) trunc_tf32(dsr[ci * 8 + u], dh[u], dl[u]);
-          umma::tmem_st8(tST + lane_base + 8 * ch, dh);
-          umma::tmem_st8(tDPT + lane_base + 8 * ch, dl);
+          umma::tmem_st8(tS + lane_base + 8 * ch, dh);
+          umma::tmem_st8(tDP + lane_base + 8 * ch, dl);
         }
       }
-      arrive_tmem(DSTRDY);                               // also: this warp has read dQ out of tO0
+      arrive_tmem(DSTRDY);
       if (warp == 0) HEPT_TRACE_EVENT(BE_DSTRDY, it);
 
+      // ---- dq^ rows (dK accumulates elsewhere, so tO0 stays valid) ------------------------------------------------
+      {
+        float acc[16], xr[16];
+        umma::tmem_ld16(tO0 + lane_base + 16 * part, acc);
+        const float rs = umma::tmem_ld1(tO0 + lane_base + E);       // column E of dQ: sum_j dS_ij
+        centred_row(CF::MQH, CF::MQL, xr);
+        finish_rows(acc, xr, rs, row < B ? qidx[row] : -1, stage_dq);
+      }
+      if (warp == 0) HEPT_TRACE_EVENT(BE_DQOUT, it);
+
       // ---- dv rows ----------------------------------------------------------------------------------------------
+      umma::mbar_wait(&mbar[DVDONE], ph);
+      umma::fence_after_sync();
+      if (warp == 0) HEPT_TRACE_EVENT(BE_DVDONE, it);
       {
         float acc[16];
         umma::tmem_ld16(tO1 + lane_base + 16 * part, acc);
@@ -382,16 +383,19 @@ __global__ void __launch_bounds__(kBtThreads, 1)
             if (4 * (4 * part + cc) < D) dst[4 * part + cc] = make_float4(acc[4 * cc], acc[4 * cc + 1], acc[4 * cc + 2], acc[4 * cc + 3]);
         }
       }
-
       if (warp == 0) HEPT_TRACE_EVENT(BE_DVOUT, it);
-      // ---- dk^ rows ---------------------------------------------------------------------------------------------
+
+      // ---- dk^ rows: dK was accumulated over the first columns of the (consumed) P^T region -----------------------
       umma::mbar_wait(&mbar[DKDONE], ph);
       umma::fence_after_sync();
       if (warp == 0) HEPT_TRACE_EVENT(BE_DKDONE, it);
       {
         float acc[16], xr[16];
-        umma::tmem_ld16(tO0 + lane_base + 16 * part, acc);
-        const float cs = umma::tmem_ld1(tO0 + lane_base + E);       // column E of dK: sum_i dS_ij
+        umma::tmem_ld16(tST + lane_base + 16 * part, acc);
+        const float cs = umma::tmem_ld1(tST + lane_base + E);       // column E of dK: sum_i dS_ij
+        umma::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) umma::mbar_arrive(&mbar[STFREE]);            // the next tile's key-side scores may overwrite tST
         centred_row(CF::MKH, CF::MKL, xr);
         finish_rows(acc, xr, cs, row < B ? kidx[row] : -1, stage_dk);
       }
@@ -577,9 +581,8 @@ __global__ void __launch_bounds__(kBtThreads, 1)
       for (int p3 = 0; p3 < 3; ++p3) {
         const int x = p3 == 1 ? xl : xh, y = p3 == 0 ? yl : yh;
         const uint64_t dx = base + (uint64_t)((x * CF::TILE) >> 4), dy = base + (uint64_t)((y * CF::TILE) >> 4);
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          if (kk >= ksteps) break;
+#pragma unroll 1
+        for (int kk = 0; kk < ksteps; ++kk) {
           if (swap) umma::mma_ss(d, dy + 2 * kk, dx + 2 * kk, idesc_s, (p3 | kk) != 0);
           else umma::mma_ss(d, dx + 2 * kk, dy + 2 * kk, idesc_s, (p3 | kk) != 0);
         }
@@ -593,7 +596,7 @@ __global__ void __launch_bounds__(kBtThreads, 1)
       for (int p3 = 0; p3 < 3; ++p3) {
         const uint32_t a = p3 == 1 ? a_lo : a_hi;
         const uint64_t db = base + (uint64_t)(((p3 == 0 ? bl : bh) * CF::TILE) >> 4);
-#pragma unroll
+#pragma unroll 1
         for (int kk = 0; kk < KSTEPS; ++kk) umma::mma_ts(d, a + 8 * kk, db + 64 * kk, idesc_o, (p3 | kk) != 0);
       }
     };
@@ -619,6 +622,8 @@ __global__ void __launch_bounds__(kBtThreads, 1)
     };
     int it = 0;
     int tile = blockIdx.x;
+    HEPT_TRACE_CTA(0);
+    HEPT_TRACE_CTA(2);
     if (tile < total_tiles) {
       wait(KFULL, 0);
       scores_query_side();
@@ -646,25 +651,24 @@ __global__ void __launch_bounds__(kBtThreads, 1)
       wait(DSTRDY, ph);
       HEPT_TRACE_EVENT(BM_DK_GO, it);
       if (umma::elect_one()) {
-        ts_product(tO0, tST, tDPT, CF::MQH, CF::MQL);   // dK = dS^T Q^
+        ts_product(tST, tS, tDP, CF::MQH, CF::MQL);     // dK = dS^T Q^: A where dS was, accumulator over the consumed P^T
         umma::commit(&mbar[DKDONE]);
         umma::commit(&mbar[MFREE]);
       }
       __syncwarp();
-      // The tensor pipe runs in issue order: the next tile's score MMAs (0.7 us per side) go behind this tile's last
-      // product, where nothing waits for them — the epilogue still has dv / dk rows to write out.
+      // The tensor pipe runs in issue order: the next tile's query-side scores go right behind dK (which reads tS / tDP);
+      // the key-side scores overwrite tST / tDPT, where dK accumulated, so they wait for the epilogue to read dk out.
       if (more) {
         wait(KFULL, ph ^ 1);
         HEPT_TRACE_EVENT(BM_SQ_GO, it + 1);
-        scores_query_side();                            // tS / tDP were drained by dQ long ago
-      }
-      if (more) {                                       // next tile's key-side scores once dK has drained tST / tDPT
-        wait(DKDONE, ph);
+        scores_query_side();
+        wait(STFREE, ph);
         HEPT_TRACE_EVENT(BM_SK_GO, it + 1);
         scores_key_side();
       }
       HEPT_TRACE_EVENT(BM_END, it);
     }
+    HEPT_TRACE_CTA(1);
   }
 
   umma::fence_before_sync();

@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(kFtThreads, 1)
     auto make_p = [&](int it) {
       const int sl = it & 1;
       const uint32_t tS0 = tmem + sl * CF::SLOT_STRIDE, tS1 = tS0 + NP;
-      umma::mbar_wait(&mbar[SREADY + sl], (it >> 1) & 1);
+      umma::mbar_wait_parked(&mbar[SREADY + sl], (it >> 1) & 1);
       umma::fence_after_sync();
       if (warp == 0) HEPT_TRACE_EVENT(EV_E_SREADY, it);
       const float nq2 = s_nq2[(it & 3) * 128 + row];
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(kFtThreads, 1)
       int h, t, blk;
       decode(tile, h, t, blk);
       // ---- numerator and normaliser back to original hit order: part 0 writes columns [0,16), part 1 the rest ------
-      umma::mbar_wait(&mbar[ODONE + sl], (it >> 1) & 1);
+      umma::mbar_wait_parked(&mbar[ODONE + sl], (it >> 1) & 1);
       umma::fence_after_sync();
       if (warp == 0) HEPT_TRACE_EVENT(EV_E_ODONE, it);
       float ov[16];
@@ -243,7 +243,9 @@ __global__ void __launch_bounds__(kFtThreads, 1)
     };
     // issue every row load of a tile (registers); chunk c of a hat row: feature columns from q / k, coordinate
     // columns from hat_coords (already scaled)
-    auto issue_rows = [&](int tile, int it) {
+    // The q^ / k^ loads of the next tile are issued as soon as this tile's have been consumed (before the value phase and
+    // its wait), the value loads after the value phase: every load gets as much flight time as its registers allow.
+    auto issue_qk = [&](int tile, int it) {
       int h, t, blk;
       decode(tile, h, t, blk);
       auto hat_chunk = [&](const float* __restrict__ x, int n) -> float4 {
@@ -256,16 +258,25 @@ __global__ void __launch_bounds__(kFtThreads, 1)
         const int nkk = nk_idx[ps], nqq = nq_idx[ps];
         xk[ps] = hat_chunk(k, nkk);
         xq[ps] = hat_chunk(q, nqq);
-        xv[ps] = (nkk >= 0 && c < VCH && nkk < raw_size) ? ldg4(v + ((size_t)nkk * H + h) * D + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
         const int r = ps * RPP + sub;
         if (c == 0 && r < B) s_qidx[(it & 7) * 128 + r] = nqq;
+      }
+    };
+    auto issue_v = [&](int tile) {
+      int h, t, blk;
+      decode(tile, h, t, blk);
+#pragma unroll
+      for (int ps = 0; ps < PASSES; ++ps) {
+        const int nkk = nk_idx[ps];
+        xv[ps] = (nkk >= 0 && c < VCH && nkk < raw_size) ? ldg4(v + ((size_t)nkk * H + h) * D + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
 
     int tile = blockIdx.x;
     if (tile < total_tiles) {
       load_indices(tile);
-      issue_rows(tile, 0);
+      issue_qk(tile, 0);
+      issue_v(tile);
       if (tile + (int)gridDim.x < total_tiles) load_indices(tile + gridDim.x);
     }
     int it = 0;
@@ -276,7 +287,7 @@ __global__ void __launch_bounds__(kFtThreads, 1)
       uint8_t* km = smem + st * 4 * CF::TILE;
       uint8_t* vm = smem + CF::OFF_V + st * 2 * CF::TILE;
       // ---- q^ / k^ tiles of this stage: free once the score MMAs of tile it - 2 are done ---------------------------
-      if (it >= 2) umma::mbar_wait(&mbar[QKFREE + st], ph ^ 1);
+      if (it >= 2) umma::mbar_wait_parked(&mbar[QKFREE + st], ph ^ 1);
       if (warp == EW) HEPT_TRACE_EVENT(EV_P_QKFREE, it);
       float* nq2s = s_nq2 + (it & 3) * 128;
 #pragma unroll
@@ -321,9 +332,11 @@ __global__ void __launch_bounds__(kFtThreads, 1)
       __syncwarp();
       if (lane == 0) umma::mbar_arrive(&mbar[QKFULL + st]);
       if (warp == EW) HEPT_TRACE_EVENT(EV_P_QKFULL, it);
+      const int next = tile + gridDim.x;
+      if (next < total_tiles) issue_qk(next, it + 1);
 
       // ---- value tiles of this stage: free once the P V MMAs of tile it - 2 are done -------------------------------
-      if (it >= 2) umma::mbar_wait(&mbar[VFREE + st], ph ^ 1);
+      if (it >= 2) umma::mbar_wait_parked(&mbar[VFREE + st], ph ^ 1);
       if (warp == EW) HEPT_TRACE_EVENT(EV_P_VFREE, it);
 #pragma unroll
       for (int ps = 0; ps < PASSES; ++ps) {
@@ -343,9 +356,8 @@ __global__ void __launch_bounds__(kFtThreads, 1)
       if (warp == EW) HEPT_TRACE_EVENT(EV_P_VFULL, it);
 
       // ---- registers are free: put the next tile's loads in flight, fetch the indices of the one after -----------
-      const int next = tile + gridDim.x;
       if (next < total_tiles) {
-        issue_rows(next, it + 1);
+        issue_v(next);
         if (next + (int)gridDim.x < total_tiles) load_indices(next + gridDim.x);
       }
       if (warp == EW) HEPT_TRACE_EVENT(EV_P_ISSUED, it);
@@ -362,7 +374,7 @@ __global__ void __launch_bounds__(kFtThreads, 1)
     const uint64_t kdesc0 = umma::smem_desc_sw128(sbase, 1024, 16);
     const uint64_t vdesc0 = umma::smem_desc(sbase + CF::OFF_V, 512, 1024, umma::kLayoutSw128Base32);
     auto wait = [&](int b, uint32_t parity) {
-      umma::mbar_wait(&mbar[b], parity);
+      umma::mbar_wait_parked(&mbar[b], parity);
       umma::fence_after_sync();
     };
     // S = Q^ K^^T of tile number `it`: cross terms and the first SK0 hi*hi k-steps into S0, the rest into S1
@@ -388,6 +400,8 @@ __global__ void __launch_bounds__(kFtThreads, 1)
     };
     int it = 0;
     int tile = blockIdx.x;
+    HEPT_TRACE_CTA(0);
+    HEPT_TRACE_CTA(2);
     if (tile < total_tiles) {
       wait(QKFULL + 0, 0);
       scores(0);
@@ -424,6 +438,7 @@ __global__ void __launch_bounds__(kFtThreads, 1)
       __syncwarp();
       HEPT_TRACE_EVENT(EV_M_PV_ISSUED, it);
     }
+    HEPT_TRACE_CTA(1);
   }
 
   umma::fence_before_sync();

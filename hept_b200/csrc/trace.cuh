@@ -9,10 +9,18 @@ namespace hept {
 constexpr int kTraceTiles = 64, kTraceEvents = 32;
 #ifdef HEPT_TRACE
 static __device__ long long* g_trace_ptr;
+__device__ __forceinline__ unsigned __smid_for_trace() { unsigned r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
 #define HEPT_TRACE_EVENT(ev, it)                                                                      \
   do {                                                                                                \
     if (blockIdx.x == 0 && (it) < ::hept::kTraceTiles && (threadIdx.x & 31) == 0 && g_trace_ptr)      \
       g_trace_ptr[(ev) * ::hept::kTraceTiles + (it)] = clock64();                                     \
+  } while (0)
+// per-CTA stamp (slot 0 = start, 1 = end), stored behind the event table
+#define HEPT_TRACE_CTA(slot)                                                                          \
+  do {                                                                                                \
+    if ((threadIdx.x & 31) == 0 && g_trace_ptr)                                                       \
+      g_trace_ptr[::hept::kTraceEvents * ::hept::kTraceTiles + 4 * blockIdx.x + (slot)] =            \
+          (slot) == 2 ? (long long)__smid_for_trace() : clock64();                                    \
   } while (0)
 #define HEPT_TRACE_SETTER(name)                                                                       \
   extern "C" int name(long long* buf) {                                                               \
@@ -20,6 +28,7 @@ static __device__ long long* g_trace_ptr;
   }
 #else
 #define HEPT_TRACE_EVENT(ev, it) do { } while (0)
+#define HEPT_TRACE_CTA(slot) do { } while (0)
 #define HEPT_TRACE_SETTER(name)
 #endif
 }  // namespace hept

@@ -176,11 +176,28 @@ __device__ __forceinline__ void mbar_init(uint64_t* mbar, uint32_t count) {
 // Bounded wait: a descriptor or protocol bug must trap, not hang the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
   const uint32_t addr = smem_u32(mbar);
+#pragma unroll 1
   for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
     uint32_t done;
     asm volatile(
         "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
         : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+// The same with a suspend-time hint: the hardware parks the warp until the phase completes instead of returning after
+// its short default limit, so a waiting warp stops spending issue slots on TRYWAIT / BRA pairs.  Waking up from the
+// parked state is slower, though (measured, any hint value): good for the forward tiles (two tiles in flight, -2 %),
+// bad for the backward tiles, whose eleven hand-offs per tile are all on the critical path (+11 %).
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* mbar, uint32_t parity) {
+  const uint32_t addr = smem_u32(mbar);
+#pragma unroll 1
+  for (uint32_t spin = 0; spin < (1u << 16); ++spin) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(done) : "r"(addr), "r"(parity), "r"(100000u) : "memory");
     if (done) return;
   }
   __trap();

@@ -34,8 +34,8 @@ n = inp["query"].shape[0]
 d = ops.Dims(N=n, H=cfg["num_heads"], D=cfg["h_dim"], C=cfg["coords_dim"], T=cfg["n_hashes"], B=cfg["block_size"], raw_size=n)
 w, al = params["w_rpe.weight"].to(dev), params["e2lsh.alpha"].to(dev)
 gpre = torch.randn(n, d.H * d.D, device=dev)
-tf = torch.zeros(EVENTS * TILES, dtype=torch.int64, device=dev)
-tb = torch.zeros(EVENTS * TILES, dtype=torch.int64, device=dev)
+tf = torch.zeros(EVENTS * TILES + 4 * 1024, dtype=torch.int64, device=dev)
+tb = torch.zeros(EVENTS * TILES + 4 * 1024, dtype=torch.int64, device=dev)
 for fn, buf in (("hept_debug_trace_fwd", tf), ("hept_debug_trace_bwd", tb)):
     f = getattr(lib, fn)       # only the TRACE build exports these
     f.argtypes, f.restype = [ctypes.c_void_p], ctypes.c_int
@@ -48,7 +48,7 @@ for _ in range(3):
 torch.cuda.synchronize()
 res = {}
 for name, ev, buf in (("fwd", FWD, tf), ("bwd", BWD, tb)):
-    t = buf.cpu().view(EVENTS, TILES)[: len(ev)]
+    t = buf.cpu()[: EVENTS * TILES].view(EVENTS, TILES)[: len(ev)]
     t0 = int(t[t > 0].min())
     rel = (t - t0).clamp_min(-1)
     print(f"==== {name}: cycles since the first stamp; rows = tiles of CTA 0")
@@ -60,5 +60,19 @@ for name, ev, buf in (("fwd", FWD, tf), ("bwd", BWD, tb)):
     phase = {e: float((t[i, lo:hi] - t[0, lo:hi]).double().mean()) for i, e in enumerate(ev)}
     print(f"period {period:.0f} cycles/tile; mean offset from {ev[0]}: " + ", ".join(f"{k}={v:.0f}" for k, v in phase.items()))
     res[name] = {"period_cycles": period, "phase": phase, "events": ev, "stamps": rel[:, :40].tolist()}
+per_sm = {}
+for name, buf in (("fwd", tf), ("bwd", tb)):
+    cta = buf.cpu()[EVENTS * TILES:].view(-1, 4)
+    cta = cta[cta[:, 1] > 0]
+    dur = (cta[:, 1] - cta[:, 0]).double()
+    print(f"{name} per-CTA duration (cycles): n={len(cta)} min={dur.min():.0f} median={dur.median():.0f} max={dur.max():.0f}")
+    res[name + "_cta_cycles"] = dur.tolist()
+    res[name + "_cta_smid"] = cta[:, 2].tolist()
+    per_sm[name] = {int(sm): float(d) for sm, d in zip(cta[:, 2], dur)}
+common = sorted(set(per_sm["fwd"]) & set(per_sm["bwd"]))
+f = torch.tensor([per_sm["fwd"][k] for k in common]); b = torch.tensor([per_sm["bwd"][k] for k in common])
+print("fwd/bwd per-SM duration correlation:", float(torch.corrcoef(torch.stack([f, b]))[0, 1]))
+order = sorted(common, key=lambda k: per_sm["bwd"][k])
+print("fastest SMs (bwd):", order[:12], " slowest:", order[-12:])
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump(res, open(os.path.join(ROOT, "gpurun_out", "pipeline_trace.json"), "w"))
