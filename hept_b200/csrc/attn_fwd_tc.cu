@@ -248,8 +248,12 @@ __global__ void __launch_bounds__(kFtThreads, 1)
     auto issue_qk = [&](int tile, int it) {
       int h, t, blk;
       decode(tile, h, t, blk);
+      // chunk c of a hat row: feature columns from q / k, coordinate columns from hat_coords.  The per-lane base and
+      // row stride are fixed for the tile, so a load is one multiply-add and one predicated LDG (no divergent paths).
+      const size_t hstride = c < VCH ? (size_t)H * D : (size_t)H * 8;
+      const size_t hoff = c < VCH ? (size_t)h * D + 4 * c : (size_t)h * 8 + 4 * (c - VCH);
       auto hat_chunk = [&](const float* __restrict__ x, int n) -> float4 {
-        const float* src = c < VCH ? x + ((size_t)n * H + h) * D + 4 * c : hatc + ((size_t)n * H + h) * 8 + 4 * (c - VCH);
+        const float* src = (c < VCH ? x : hatc) + hoff + (size_t)(n < 0 ? 0 : n) * hstride;
         return (c < VCH + 2 && n >= 0 && n < raw_size) ? ldg4(src) : make_float4(0.f, 0.f, 0.f, 0.f);
       };
       ctr = hat_chunk(k, n0);

@@ -8,37 +8,44 @@ namespace hept {
 // ---------------------------------------------------------------------------------------------------
 // coordinate scale: one small CTA; H*R*K sums of D terms.
 // ---------------------------------------------------------------------------------------------------
+// thread <-> (h, r, k): wbar = sum_d w[h*D+d, r*K+k] (D independent loads), e = exp(min(wbar, 50)); then thread <-> (h, r)
+// adds the K terms in order.  One CTA of H*R*K threads (400 for the tracking model).
 __global__ void coord_scale_fwd_kernel(const float* __restrict__ w, int H, int D, int R, int K,
                                        float* __restrict__ scale) {
-  // thread <-> (h, r); qw = sum_k exp(min(sum_d w[h*D+d, r*K+k], 50))
+  extern __shared__ float s_e[];                   // (H*R, K)
+  const int n = H * R * K;
+  for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+    const int h = idx / (R * K), rk = idx - h * (R * K);
+    float s = 0.f;
+    for (int d = 0; d < D; ++d) s += __ldg(w + (size_t)(h * D + d) * (R * K) + rk);
+    s_e[idx] = expf(fminf(s, 50.f));
+  }
+  __syncthreads();
   for (int idx = threadIdx.x; idx < H * R; idx += blockDim.x) {
-    int h = idx / R, r = idx % R;
+    const int h = idx / R, r = idx % R;
     float qw = 0.f;
-    for (int kk = 0; kk < K; ++kk) {
-      float s = 0.f;
-      for (int d = 0; d < D; ++d) s += w[(size_t)(h * D + d) * (R * K) + r * K + kk];
-      qw += expf(fminf(s, 50.f));
-    }
-    float sc = sqrtf(2.f * qw);
+    for (int kk = 0; kk < K; ++kk) qw += s_e[idx * K + kk];
+    const float sc = sqrtf(2.f * qw);
     scale[h * (R + 1) + r + 1] = sc;
     if (r == 0) scale[h * (R + 1)] = sc;  // eta and phi share weight 0 (example/hept.py:23)
   }
 }
 
+// thread <-> (h, r, k), any number of CTAs
 __global__ void coord_scale_bwd_kernel(const float* __restrict__ w, const float* __restrict__ scale,
                                        const float* __restrict__ dscale, int H, int D, int R, int K,
                                        float* __restrict__ dw) {
   // d scale / d qw = 1 / scale ; d qw / d wbar = exp(wbar) * [wbar <= 50] ; d wbar / d w[h,d,r,k] = 1
   const int C = R + 1;
-  for (int idx = threadIdx.x; idx < H * R * K; idx += blockDim.x) {
-    int h = idx / (R * K), r = (idx / K) % R, kk = idx % K;
-    float s = 0.f;
-    for (int d = 0; d < D; ++d) s += w[(size_t)(h * D + d) * (R * K) + r * K + kk];
-    float dqw = dscale[h * C + r + 1] / scale[h * C + r + 1];
-    if (r == 0) dqw += dscale[h * C] / scale[h * C];
-    float g = (s <= 50.f) ? dqw * expf(s) : 0.f;
-    for (int d = 0; d < D; ++d) dw[(size_t)(h * D + d) * (R * K) + r * K + kk] = g;
-  }
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= H * R * K) return;
+  const int h = idx / (R * K), r = (idx / K) % R, kk = idx % K;
+  float s = 0.f;
+  for (int d = 0; d < D; ++d) s += __ldg(w + (size_t)(h * D + d) * (R * K) + r * K + kk);
+  float dqw = dscale[h * C + r + 1] / scale[h * C + r + 1];
+  if (r == 0) dqw += dscale[h * C] / scale[h * C];
+  const float g = (s <= 50.f) ? dqw * expf(s) : 0.f;
+  for (int d = 0; d < D; ++d) dw[(size_t)(h * D + d) * (R * K) + r * K + kk] = g;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -385,7 +392,10 @@ using namespace hept;
 extern "C" int hept_coord_scale_fwd(const float* w, int32_t H, int32_t D, int32_t R, int32_t K, float* scale,
                                     void* stream) {
   HEPT_REQUIRE(w && scale && H > 0 && D > 0 && R > 0 && K > 0, HEPT_EINVAL, "coord_scale_fwd: bad argument");
-  coord_scale_fwd_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(w, H, D, R, K, scale);
+  const int items = H * R * K;
+  HEPT_REQUIRE(items * sizeof(float) <= 48 * 1024, HEPT_EUNSUPPORTED, "coord_scale_fwd: H*R*K=%d too large", items);
+  const int threads = items < 1024 ? (items + 31) / 32 * 32 : 1024;
+  coord_scale_fwd_kernel<<<1, threads, items * sizeof(float), (cudaStream_t)stream>>>(w, H, D, R, K, scale);
   HEPT_CHECK_LAUNCH("coord_scale_fwd");
   return HEPT_OK;
 }
@@ -394,7 +404,7 @@ extern "C" int hept_coord_scale_bwd(const float* w, const float* scale, const fl
                                     int32_t R, int32_t K, float* dw, void* stream) {
   HEPT_REQUIRE(w && scale && dscale && dw && H > 0 && D > 0 && R > 0 && K > 0, HEPT_EINVAL,
                "coord_scale_bwd: bad argument");
-  coord_scale_bwd_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(w, scale, dscale, H, D, R, K, dw);
+  coord_scale_bwd_kernel<<<(H * R * K + 127) / 128, 128, 0, (cudaStream_t)stream>>>(w, scale, dscale, H, D, R, K, dw);
   HEPT_CHECK_LAUNCH("coord_scale_bwd");
   return HEPT_OK;
 }
