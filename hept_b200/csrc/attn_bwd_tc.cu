@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(kBtThreads, 1)
     block_attn_bwd_tc_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
                              const float* __restrict__ hatc, const float* __restrict__ grows,
                              const int32_t* __restrict__ positions, int N, int H, int T, int raw_size, int total_tiles,
-                             float* __restrict__ stage_dq, float* __restrict__ stage_dk, float* __restrict__ stage_dv,
+                             TileDecoder dec, float* __restrict__ stage_dq, float* __restrict__ stage_dk, float* __restrict__ stage_dv,
                              float* __restrict__ ds_partial) {
   using CF = TcBwd<D, C, B>;
   constexpr int E = CF::E, NP = CF::NP, KSTEPS = CF::KSTEPS, VCH = CF::VCH, PASSES = CF::PASSES;
@@ -143,7 +143,6 @@ __global__ void __launch_bounds__(kBtThreads, 1)
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int nb = N / B;
   constexpr int EW = kBtEpiThreads / 32, PW = kBtProdThreads / 32;
 
   if (tid == 0) {
@@ -191,12 +190,7 @@ __global__ void __launch_bounds__(kBtThreads, 1)
   const uint32_t sbase = umma::smem_u32(smem), mbase = sbase + CF::OFF_MN;
 
   // tiles are ordered (head, table, block): the CTAs of a wave work on one head's rows, which stay in L2
-  auto decode = [&](int tile, int& h, int& t, int& blk) {
-    const int hl = tile / nb;
-    blk = tile - hl * nb;
-    h = hl / T;
-    t = hl - h * T;
-  };
+  const TileDecoder decode = dec;
 
   if (warp < EW) {
     // =========================================== epilogue warps =================================================
@@ -787,8 +781,9 @@ static int launch_bwd_tc(const hept_shape* s, const float* q, const float* k, co
   if (mask & 3) {
     cudaError_t e = cudaMemsetAsync(partial, 0, sizeof(float) * (size_t)grid * s->H * 8, st);   // heads a CTA never visits
     HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "block_attn_bwd_tc: memset failed: %s", cudaGetErrorString(e));
-    kern<<<grid, kBtThreads, smem, st>>>(q, k, v, hat, grows, positions, s->N, s->H, s->T, s->raw_size, p.tiles, sq, sk,
-                                         sv, partial);
+    HEPT_REQUIRE(TileDecoder::exact_for(p.tiles, s->N / s->B, s->T), HEPT_EUNSUPPORTED, "block_attn_bwd_tc: too many tiles (%d)", p.tiles);
+    kern<<<grid, kBtThreads, smem, st>>>(q, k, v, hat, grows, positions, s->N, s->H, s->T, s->raw_size, p.tiles,
+                                         TileDecoder::make(s->N / s->B, s->T), sq, sk, sv, partial);
     HEPT_CHECK_LAUNCH("block_attn_bwd_tc");
   }
   if (!(mask & 4)) return HEPT_OK;

@@ -90,7 +90,7 @@ template <int D, int C, int B>
 __global__ void __launch_bounds__(kFtThreads, 1)
     block_attn_fwd_tc_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
                              const float* __restrict__ hatc, const int32_t* __restrict__ positions, int N, int H, int T,
-                             int raw_size, int total_tiles, float* __restrict__ stage) {
+                             int raw_size, int total_tiles, TileDecoder dec, float* __restrict__ stage) {
   using CF = TcFwd<D, C, B>;
   constexpr int E = CF::E, NP = CF::NP, KSTEPS = CF::KSTEPS, VCH = CF::VCH, PASSES = CF::PASSES, RPP = CF::RPP;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -101,7 +101,6 @@ __global__ void __launch_bounds__(kFtThreads, 1)
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int nb = N / B;
   constexpr int EW = kFtEpiThreads / 32, PW = kFtProdThreads / 32;
 
   if (tid == 0) {
@@ -145,12 +144,7 @@ __global__ void __launch_bounds__(kFtThreads, 1)
   const uint32_t sbase = umma::smem_u32(smem);
 
   // tiles are ordered (head, table, block): the CTAs of a wave work on one head's rows, which stay in L2
-  auto decode = [&](int tile, int& h, int& t, int& blk) {
-    const int hl = tile / nb;
-    blk = tile - hl * nb;
-    h = hl / T;
-    t = hl - h * T;
-  };
+  const TileDecoder decode = dec;
 
   if (warp < EW) {
     // =========================================== epilogue warps =================================================
@@ -469,7 +463,9 @@ static int launch_fwd_tc(const hept_shape* s, const float* q, const float* k, co
   }
   const int tiles = s->T * s->H * (s->N / s->B);
   const int grid = tiles < sms ? tiles : sms;   // one CTA per SM (two tiles in flight use all 512 TMEM columns)
-  kern<<<grid, kFtThreads, smem, st>>>(q, k, v, hatc, positions, s->N, s->H, s->T, s->raw_size, tiles, stage);
+  HEPT_REQUIRE(TileDecoder::exact_for(tiles, s->N / s->B, s->T), HEPT_EUNSUPPORTED, "block_attn_fwd_tc: too many tiles (%d)", tiles);
+  kern<<<grid, kFtThreads, smem, st>>>(q, k, v, hatc, positions, s->N, s->H, s->T, s->raw_size, tiles,
+                                       TileDecoder::make(s->N / s->B, s->T), stage);
   HEPT_CHECK_LAUNCH("block_attn_fwd_tc");
   return HEPT_OK;
 }

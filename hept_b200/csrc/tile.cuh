@@ -28,6 +28,26 @@
 
 namespace hept {
 
+// tile -> (head, table, block) for tiles ordered (head, table, block) without integer division on the device: the
+// quotients come from one IMAD.HI each with multipliers computed on the host (a runtime `/` costs ~40 instructions, and
+// the persistent tile kernels decode several tiles per iteration in every warp role).
+// magic(d) = floor(2^32 / d) + 1 gives floor(x / d) = umulhi(x, magic) for x * d < 2^32; d == 1 is flagged by magic 0.
+struct TileDecoder {
+  uint32_t nb, T, magic_nb, magic_T;
+  static uint32_t magic(uint32_t d) { return d <= 1 ? 0u : (uint32_t)((1ull << 32) / d) + 1u; }
+  static TileDecoder make(int nb, int T) { return TileDecoder{(uint32_t)nb, (uint32_t)T, magic((uint32_t)nb), magic((uint32_t)T)}; }
+  // largest tile count the multipliers are exact for
+  static bool exact_for(long long tiles, int nb, int T) { return tiles * (long long)nb < (1ll << 32) && tiles * (long long)T < (1ll << 32); }
+  __device__ __forceinline__ void operator()(int tile, int& h, int& t, int& blk) const {
+    const uint32_t hl = magic_nb ? __umulhi((uint32_t)tile, magic_nb) : (uint32_t)tile;
+    blk = (int)((uint32_t)tile - hl * nb);
+    const uint32_t hh = magic_T ? __umulhi(hl, magic_T) : hl;
+    h = (int)hh;
+    t = (int)(hl - hh * T);
+  }
+};
+
+
 template <int D_, int C_, int B_, int G_, int R_>
 struct TileLayout {
   static constexpr int D = D_, C = C_, B = B_, G = G_, R = R_;
