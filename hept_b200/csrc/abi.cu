@@ -91,12 +91,13 @@ extern "C" int hept_attention_fwd(const hept_shape* s, const float* q, const flo
   void* sort_ws = w;
   int rc;
   if ((rc = hept_coord_scale_fwd(w_rpe_weight, s->H, s->D, s->C - 1, K, scale, stream))) return rc;
-  if ((rc = hept_hash_project(s, q, k, coords, scale, alpha, proj, span, ext, p.ext_bytes, stream))) return rc;
+  bool hat_done = false;   // the fused projection kernel emits the scaled coordinates as a by-product
+  if ((rc = hash_project_impl(s, q, k, coords, scale, alpha, proj, span, ext, p.ext_bytes, hat, &hat_done, stream))) return rc;
   if (packed) rc = hept_keys_from_packed_shifts(s, proj, span, combined_shifts, keys, stream);
   else rc = hept_keys_from_region_indices(s, proj, span, region_eta, region_phi, regions_h, keys, stream);
   if (rc) return rc;
   if ((rc = hept_segmented_argsort(keys, 2 * s->T * s->H, s->N, positions, sort_ws, p.sort_bytes, stream))) return rc;
-  if ((rc = hept_hat_coords(s, coords, scale, hat, stream))) return rc;
+  if (!hat_done && (rc = hept_hat_coords(s, coords, scale, hat, stream))) return rc;
   if ((rc = hept_block_attention_fwd(s, q, k, v, coords, scale, hat, positions, stage, stream))) return rc;
   return hept_or_combine(s, stage, out_pre, den_sum, stream);
 }

@@ -14,7 +14,10 @@ void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 int bwd_stage_mask();
 int engine();  // 0 = fp32 SIMT tiles, 1 = tcgen05 tiles
-int bwd_variant();  // 1 = one lane per row (attn_bwd.cu), 2 = lane pairs + FFMA2 (attn_bwd2.cu), 3 = tcgen05 (attn_bwd_tc.cu)
+int bwd_variant();
+int hash_project_impl(const hept_shape* s, const float* q, const float* k, const float* coords, const float* scale,
+                      const float* alpha, float* proj, float* span, void* workspace, size_t workspace_bytes, float* hat,
+                      bool* hat_done, void* stream);  // 1 = one lane per row (attn_bwd.cu), 2 = lane pairs + FFMA2 (attn_bwd2.cu), 3 = tcgen05 (attn_bwd_tc.cu)
 
 #define HEPT_REQUIRE(cond, code, ...)      \
   do {                                     \

@@ -205,7 +205,8 @@ __global__ void __launch_bounds__(256) hash_project_v2_kernel(const float* __res
                                                               const float* __restrict__ coords,
                                                               const float* __restrict__ scale,
                                                               const float* __restrict__ alpha, int N, int H, int raw_size,
-                                                              float* __restrict__ proj, uint32_t* __restrict__ partial) {
+                                                              float* __restrict__ proj, uint32_t* __restrict__ partial,
+                                                              float* __restrict__ hat) {
   constexpr int E = D + C, EP = 32;
   static_assert(E <= EP && D % 4 == 0 && T <= 4 && C <= 8, "row shapes");
   extern __shared__ __align__(16) float s_dyn[];
@@ -278,6 +279,9 @@ __global__ void __launch_bounds__(256) hash_project_v2_kernel(const float* __res
             const float v = (c < C && real) ? __fmul_rn(s_scale[h * C + (c < C ? c : 0)], cc[c < C ? c : 0]) : 0.f;
             xq[u] = v; xk[u] = v;
           }
+          // by-product: the scaled coordinates are the hat_coords rows the tile kernels gather (saves hat_coords_kernel)
+          if (hat != nullptr && live && 4 * c4 - D < 8)
+            *reinterpret_cast<float4*>(hat + ((size_t)n * H + h) * 8 + (4 * c4 - D)) = make_float4(xq[0], xq[1], xq[2], xq[3]);
         }
         float av[4 * T];                                  // alpha[e = 4 c4 + u][t] at av[u * T + t]
 #pragma unroll
@@ -295,6 +299,9 @@ __global__ void __launch_bounds__(256) hash_project_v2_kernel(const float* __res
             }
           }
         }
+      }
+      if constexpr (C <= 4) {                        // the second hat chunk holds no coordinate: zero it
+        if (hat != nullptr && live) *reinterpret_cast<float4*>(hat + ((size_t)n * H + h) * 8 + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
       for (int t = 0; t < T; ++t) {
@@ -339,7 +346,7 @@ __global__ void finish_span_kernel(const uint32_t* __restrict__ partial, int cta
 
 template <int D, int C, int T>
 static int launch_project_v2(const hept_shape* s, const float* q, const float* k, const float* coords, const float* scale,
-                             const float* alpha, float* proj, uint32_t* partial, int* ctas, cudaStream_t st) {
+                             const float* alpha, float* proj, uint32_t* partial, int* ctas, float* hat, cudaStream_t st) {
   const size_t smem = sizeof(float) * ((size_t)s->H * 32 * T + (((size_t)s->H * C + 3) & ~(size_t)3) +
                                        2 * 32 * ((size_t)s->H * D + 4));
   static int sms = 0, per_sm = 0;
@@ -361,7 +368,7 @@ static int launch_project_v2(const hept_shape* s, const float* q, const float* k
   if (grid > groups) grid = groups;
   if (grid > kHashMaxCtas) grid = kHashMaxCtas;
   *ctas = grid;
-  hash_project_v2_kernel<D, C, T><<<grid, 256, smem, st>>>(q, k, coords, scale, alpha, s->N, s->H, s->raw_size, proj, partial);
+  hash_project_v2_kernel<D, C, T><<<grid, 256, smem, st>>>(q, k, coords, scale, alpha, s->N, s->H, s->raw_size, proj, partial, hat);
   HEPT_CHECK_LAUNCH("hash_project");
   return HEPT_OK;
 }
@@ -414,9 +421,12 @@ extern "C" size_t hept_hash_workspace_bytes(const hept_shape* s) {
   return sizeof(uint32_t) * 2 * (size_t)s->T * s->H * kHashMaxCtas;
 }
 
-extern "C" int hept_hash_project(const hept_shape* s, const float* q, const float* k, const float* coords,
-                                 const float* scale, const float* alpha, float* proj, float* span, void* workspace,
-                                 size_t workspace_bytes, void* stream) {
+namespace hept {
+// hat != nullptr: also emit hat_coords (N, H, 8) when the fused kernel is used; *hat_done tells whether it was
+int hash_project_impl(const hept_shape* s, const float* q, const float* k, const float* coords, const float* scale,
+                      const float* alpha, float* proj, float* span, void* workspace, size_t workspace_bytes, float* hat,
+                      bool* hat_done, void* stream) {
+  if (hat_done) *hat_done = false;
   if (int rc = validate_shape(s)) return rc;
   HEPT_REQUIRE(q && k && coords && scale && alpha && proj && span && workspace, HEPT_EINVAL,
                "hash_project: null pointer");
@@ -426,10 +436,12 @@ extern "C" int hept_hash_project(const hept_shape* s, const float* q, const floa
   cudaStream_t st = (cudaStream_t)stream;
   uint32_t* ext = (uint32_t*)workspace;
   int rc, ctas = 1;
-  if (s->D == 24 && s->C == 6 && s->T == 3) rc = launch_project_v2<24, 6, 3>(s, q, k, coords, scale, alpha, proj, ext, &ctas, st);
-  else if (s->D == 24 && s->C == 4 && s->T == 3) rc = launch_project_v2<24, 4, 3>(s, q, k, coords, scale, alpha, proj, ext, &ctas, st);
-  else if (s->D == 8 && s->C == 6 && s->T == 2) rc = launch_project_v2<8, 6, 2>(s, q, k, coords, scale, alpha, proj, ext, &ctas, st);
+  bool fused = true;
+  if (s->D == 24 && s->C == 6 && s->T == 3) rc = launch_project_v2<24, 6, 3>(s, q, k, coords, scale, alpha, proj, ext, &ctas, hat, st);
+  else if (s->D == 24 && s->C == 4 && s->T == 3) rc = launch_project_v2<24, 4, 3>(s, q, k, coords, scale, alpha, proj, ext, &ctas, hat, st);
+  else if (s->D == 8 && s->C == 6 && s->T == 2) rc = launch_project_v2<8, 6, 2>(s, q, k, coords, scale, alpha, proj, ext, &ctas, hat, st);
   else {
+    fused = false;
     // any other table count: the first-generation kernel with one atomically maintained (min, max) pair per (table, head)
     init_extrema_kernel<<<(th + 127) / 128, 128, 0, st>>>(ext, th);
     HEPT_CHECK_LAUNCH("init_extrema");
@@ -444,7 +456,15 @@ extern "C" int hept_hash_project(const hept_shape* s, const float* q, const floa
   if (rc) return rc;
   finish_span_kernel<<<(th + 7) / 8, 256, 0, st>>>(ext, ctas, th, span);
   HEPT_CHECK_LAUNCH("finish_span");
+  if (hat_done) *hat_done = fused && hat != nullptr;
   return HEPT_OK;
+}
+}  // namespace hept
+
+extern "C" int hept_hash_project(const hept_shape* s, const float* q, const float* k, const float* coords,
+                                 const float* scale, const float* alpha, float* proj, float* span, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+  return hept::hash_project_impl(s, q, k, coords, scale, alpha, proj, span, workspace, workspace_bytes, nullptr, nullptr, stream);
 }
 
 extern "C" int hept_hat_coords(const hept_shape* s, const float* coords, const float* scale, float* hat_coords,
