@@ -8,7 +8,8 @@
 //   S   = Q^ K^^T            SS, N = NP                   S^T  = K^ Q^^T            SS (operands exchanged)
 //   dP  = G' V'^T            SS                           dP^T = V' G'^T            SS
 //   dS  = P dP  -> TMEM (hi, lo)                          P^T -> TMEM (hi, lo), dS^T kept in registers, then written
-//   dQ  = dS [K^ | 1]        TS, B = K^ MN-major          dV   = P^T G'             TS, B = G' MN-major
+//   dQ  = dS [K^ | 1]        TS, B = K^ MN-major          dV   = P^T G'             TS, B = G' MN-major   (TS products: N = 64,
+//                                                                                                            [hi | lo] tiles)
 //   dq^_i = dQ_i - rs_i q'_i                              dK   = dS^T [Q^ | 1]      TS (dS^T where dS was, once dQ is done)
 //                                                         dk^_j = dK_j - cs_j k'_j
 // The row / column sums rs_i = sum_j dS_ij, cs_j = sum_i dS_ij come out of the same MMAs (a ones column in the
@@ -185,8 +186,7 @@ __global__ void __launch_bounds__(kBtThreads, 1)
   __syncthreads();
   umma::fence_after_sync();
   const uint32_t tmem = tmem_slot;
-  const uint32_t tS = tmem, tDP = tmem + NP, tST = tmem + 2 * NP, tDPT = tmem + 3 * NP, tO0 = tmem + 4 * NP,
-                 tO1 = tmem + 4 * NP + 32;
+  const uint32_t tS = tmem, tDP = tmem + NP, tST = tmem + 2 * NP, tDPT = tmem + 3 * NP, tO = tmem + 4 * NP;
   const uint32_t sbase = umma::smem_u32(smem), mbase = sbase + CF::OFF_MN;
 
   // tiles are ordered (head, table, block): the CTAs of a wave work on one head's rows, which stay in L2
@@ -243,36 +243,7 @@ __global__ void __launch_bounds__(kBtThreads, 1)
       const int* qidx = s_qidx + (it % 3) * 128;
       const int* kidx = s_kidx + (it % 3) * 128;
 
-      // ---- query side: dS -> TMEM (hi over S, lo over dP), row sums ---------------------------------------------
-      umma::mbar_wait(&mbar[QREADY], ph);
-      umma::fence_after_sync();
-      if (warp == 0) HEPT_TRACE_EVENT(BE_QREADY, it);
-      {
-        const float nq2 = nq2s[row];
-#pragma unroll 1                                   // nothing is carried between chunks: rolled, the kernel's code has to stay
-        for (int ci = 0; ci < MAXCH; ++ci) {      // inside the instruction cache (see the note on code size in DESIGN.md)
-          const int ch = part + ci * kBtParts;
-          if (ch < KSTEPS) {
-            uint32_t ra[8], rb[8];
-            umma::tmem_ld8_nowait(tS + lane_base + 8 * ch, ra);
-            umma::tmem_ld8_nowait(tDP + lane_base + 8 * ch, rb);
-            umma::tmem_wait_ld(ra, rb);
-            float dh[8], dl[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const float x = fmaf(__uint_as_float(ra[u]), kLog2e, nq2);
-              const float p = exp2_fast(fminf(x, 0.f));
-              trunc_tf32(p * __uint_as_float(rb[u]), dh[u], dl[u]);
-            }
-            umma::tmem_st8(tS + lane_base + 8 * ch, dh);
-            umma::tmem_st8(tDP + lane_base + 8 * ch, dl);
-          }
-        }
-      }
-      arrive_tmem(DSRDY);
-      if (warp == 0) HEPT_TRACE_EVENT(BE_DSRDY, it);
-
-      // ---- key side: P^T -> TMEM (hi over S^T, lo over dP^T), dS^T kept in registers, column sums ---------------
+      // ---- key side first: P^T -> TMEM (hi over S^T, lo over dP^T), dS^T kept in registers ---------------------------
       float dsr[MAXCH * 8];
       umma::mbar_wait(&mbar[KREADY], ph);
       umma::fence_after_sync();
@@ -304,6 +275,35 @@ __global__ void __launch_bounds__(kBtThreads, 1)
       arrive_tmem(PTRDY);
       if (warp == 0) HEPT_TRACE_EVENT(BE_PTRDY, it);
 
+      // ---- query side: dS -> TMEM (hi over S, lo over dP) -----------------------------------------------------------
+      umma::mbar_wait(&mbar[QREADY], ph);
+      umma::fence_after_sync();
+      if (warp == 0) HEPT_TRACE_EVENT(BE_QREADY, it);
+      {
+        const float nq2 = nq2s[row];
+#pragma unroll 1                                   // nothing is carried between chunks: rolled, the kernel's code has to stay
+        for (int ci = 0; ci < MAXCH; ++ci) {      // inside the instruction cache (see the note on code size in DESIGN.md)
+          const int ch = part + ci * kBtParts;
+          if (ch < KSTEPS) {
+            uint32_t ra[8], rb[8];
+            umma::tmem_ld8_nowait(tS + lane_base + 8 * ch, ra);
+            umma::tmem_ld8_nowait(tDP + lane_base + 8 * ch, rb);
+            umma::tmem_wait_ld(ra, rb);
+            float dh[8], dl[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const float x = fmaf(__uint_as_float(ra[u]), kLog2e, nq2);
+              const float p = exp2_fast(fminf(x, 0.f));
+              trunc_tf32(p * __uint_as_float(rb[u]), dh[u], dl[u]);
+            }
+            umma::tmem_st8(tS + lane_base + 8 * ch, dh);
+            umma::tmem_st8(tDP + lane_base + 8 * ch, dl);
+          }
+        }
+      }
+      arrive_tmem(DSRDY);
+      if (warp == 0) HEPT_TRACE_EVENT(BE_DSRDY, it);
+
       if (h != dsc_head) {   // first tile of another head: hand in the finished head's sums
         flush_dscale();
         dsc_head = h;
@@ -333,8 +333,34 @@ __global__ void __launch_bounds__(kBtThreads, 1)
             if (part == (D + cc) / 16) dsc[cc] = fmaf(xr[(D + cc) % 16], o[(D + cc) % 16], dsc[cc]);
         }
       };
+      // a 64-column accumulator = [hi*hi | hi*lo + lo*hi]: this thread's 16 columns of the sum of the two halves
+      auto ld_acc = [&](uint32_t taddr, float (&acc)[16]) {
+        float lo[16];
+        umma::tmem_ld16(taddr + lane_base + 16 * part, acc);
+        umma::tmem_ld16(taddr + 32 + lane_base + 16 * part, lo);
+#pragma unroll
+        for (int u = 0; u < 16; ++u) acc[u] += lo[u];
+      };
+      auto ld_sum = [&](uint32_t taddr) { return umma::tmem_ld1(taddr + lane_base + E) + umma::tmem_ld1(taddr + 32 + lane_base + E); };
 
-      // ---- dS^T goes where dS was, as soon as dQ has consumed dS: dK can then follow dV on the tensor pipe at once -----
+      // ---- dv rows (dV was the first product into tO) ------------------------------------------------------------------
+      umma::mbar_wait(&mbar[DVDONE], ph);
+      umma::fence_after_sync();
+      if (warp == 0) HEPT_TRACE_EVENT(BE_DVDONE, it);
+      {
+        float acc[16];
+        ld_acc(tO, acc);
+        const int n = row < B ? kidx[row] : -1;
+        if (n >= 0) {
+          float4* dst = reinterpret_cast<float4*>(stage_dv + (((size_t)h * N + n) * T + t) * D);
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc)
+            if (4 * (4 * part + cc) < D) dst[4 * part + cc] = make_float4(acc[4 * cc], acc[4 * cc + 1], acc[4 * cc + 2], acc[4 * cc + 3]);
+        }
+      }
+      if (warp == 0) HEPT_TRACE_EVENT(BE_DVOUT, it);
+
+      // ---- dS^T goes where dS was, as soon as dQ has consumed dS; dK then accumulates into tO (dv rows are out) --------
       umma::mbar_wait(&mbar[DQDONE], ph);
       umma::fence_after_sync();
       if (warp == 0) HEPT_TRACE_EVENT(BE_DQDONE, it);
@@ -349,51 +375,34 @@ __global__ void __launch_bounds__(kBtThreads, 1)
           umma::tmem_st8(tDP + lane_base + 8 * ch, dl);
         }
       }
-      arrive_tmem(DSTRDY);
+      arrive_tmem(DSTRDY);                               // also: this warp has read dV out of tO
       if (warp == 0) HEPT_TRACE_EVENT(BE_DSTRDY, it);
 
-      // ---- dq^ rows (dK accumulates elsewhere, so tO0 stays valid) ------------------------------------------------
+      // ---- dq^ rows: dQ was accumulated over the first columns of the (consumed) P^T region ---------------------------
       {
         float acc[16], xr[16];
-        umma::tmem_ld16(tO0 + lane_base + 16 * part, acc);
-        const float rs = umma::tmem_ld1(tO0 + lane_base + E);       // column E of dQ: sum_j dS_ij
+        ld_acc(tST, acc);
+        const float rs = ld_sum(tST);                              // column E of dQ: sum_j dS_ij
+        umma::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) umma::mbar_arrive(&mbar[STFREE]);           // the next tile's key-side scores may overwrite tST
         centred_row(CF::MQH, CF::MQL, xr);
         finish_rows(acc, xr, rs, row < B ? qidx[row] : -1, stage_dq);
       }
       if (warp == 0) HEPT_TRACE_EVENT(BE_DQOUT, it);
 
-      // ---- dv rows ----------------------------------------------------------------------------------------------
-      umma::mbar_wait(&mbar[DVDONE], ph);
-      umma::fence_after_sync();
-      if (warp == 0) HEPT_TRACE_EVENT(BE_DVDONE, it);
-      {
-        float acc[16];
-        umma::tmem_ld16(tO1 + lane_base + 16 * part, acc);
-        const int n = row < B ? kidx[row] : -1;
-        if (n >= 0) {
-          float4* dst = reinterpret_cast<float4*>(stage_dv + (((size_t)h * N + n) * T + t) * D);
-#pragma unroll
-          for (int cc = 0; cc < 4; ++cc)
-            if (4 * (4 * part + cc) < D) dst[4 * part + cc] = make_float4(acc[4 * cc], acc[4 * cc + 1], acc[4 * cc + 2], acc[4 * cc + 3]);
-        }
-      }
-      if (warp == 0) HEPT_TRACE_EVENT(BE_DVOUT, it);
-
-      // ---- dk^ rows: dK was accumulated over the first columns of the (consumed) P^T region -----------------------
+      // ---- dk^ rows ---------------------------------------------------------------------------------------------------
       umma::mbar_wait(&mbar[DKDONE], ph);
       umma::fence_after_sync();
       if (warp == 0) HEPT_TRACE_EVENT(BE_DKDONE, it);
       {
         float acc[16], xr[16];
-        umma::tmem_ld16(tST + lane_base + 16 * part, acc);
-        const float cs = umma::tmem_ld1(tST + lane_base + E);       // column E of dK: sum_i dS_ij
-        umma::fence_before_sync();
-        __syncwarp();
-        if (lane == 0) umma::mbar_arrive(&mbar[STFREE]);            // the next tile's key-side scores may overwrite tST
+        ld_acc(tO, acc);
+        const float cs = ld_sum(tO);                               // column E of dK: sum_i dS_ij
         centred_row(CF::MKH, CF::MKL, xr);
         finish_rows(acc, xr, cs, row < B ? kidx[row] : -1, stage_dk);
       }
-      umma::fence_before_sync();                         // the TMEM loads above precede the next tile's MMAs into tO0 / tO1
+      umma::fence_before_sync();                         // the TMEM loads above precede the next tile's MMAs into tO
       __syncwarp();
       if (lane == 0) umma::mbar_arrive(&mbar[MFREE]);    // this warp is done with the MN-major tiles
       if (warp == 0) HEPT_TRACE_EVENT(BE_END, it);
@@ -462,7 +471,7 @@ __global__ void __launch_bounds__(kBtThreads, 1)
     for (; tile < total_tiles; tile += gridDim.x, ++it) {
       const uint32_t ph = it & 1;
       // ---- K-major operand tiles: free once the previous tile's score MMAs (both sides) are done ------------------
-      if (it > 0) umma::mbar_wait(&mbar[KREADY], ph ^ 1);
+      if (it > 0) umma::mbar_wait(&mbar[QREADY], ph ^ 1);   // the commit after the later (query-side) scores covers both sides
       if (warp == EW) HEPT_TRACE_EVENT(BP_KFREE, it);
       umma::cp_async_wait_all();
       float* nq2s = s_nq2 + ph * 128;
@@ -567,9 +576,11 @@ __global__ void __launch_bounds__(kBtThreads, 1)
     // tcgen05.commit covers every MMA issued before)
     constexpr uint32_t idesc_s = umma::idesc_tf32(128, NP, false, false);
     constexpr uint32_t idesc_o = umma::idesc_tf32(128, 32, false, true);
+    constexpr uint32_t idesc_o64 = umma::idesc_tf32(128, 64, false, true);
     // descriptors differ only in their start-address field (bits [0,14), 16-byte units): base + offset / 16
     const uint64_t kdesc0 = umma::smem_desc_sw128(sbase, 1024, 16);
-    const uint64_t mdesc0 = umma::smem_desc(mbase, 512, 1024, umma::kLayoutSw128Base32);
+    // MN-major B: LBO = the distance between the 32-column tiles of an N = 64 operand, i.e. from a hi tile to its lo tile
+    const uint64_t mdesc0 = umma::smem_desc(mbase, 512, CF::TILE, umma::kLayoutSw128Base32);
     // D = A B^T, both K-major, 3xTF32 (small cross terms first).  `swap` exchanges the operand roles while keeping the
     // product order, so D^T comes out bit-identical.  Called by the elected lane only.
     auto ss_product = [&](uint32_t d, int xh, int xl, int yh, int yl, int ksteps, bool swap) {
@@ -586,16 +597,19 @@ __global__ void __launch_bounds__(kBtThreads, 1)
         }
       }
     };
-    // D = A[tmem hi/lo] * B[MN-major hi/lo], 3xTF32.  Called by the elected lane only.
-    auto ts_product = [&](uint32_t d, uint32_t a_hi, uint32_t a_lo, int bh, int bl) {
+    // D[64 columns] = A[tmem hi/lo] * B[MN-major hi/lo], 3xTF32 with two MMAs per k-step instead of three: A_hi meets
+    // [B_hi | B_lo] in ONE N = 64 MMA (columns [0,32) = hi*hi, [32,64) = hi*lo) and A_lo meets B_hi in an N = 32 MMA that
+    // accumulates into the upper half; the epilogue adds the halves in fp32.  A third fewer MMAs and a third fewer reads
+    // of A from TMEM, whose read bandwidth bounds this kernel.  `bh` = the hi tile; its lo tile follows it.
+    // Called by the elected lane only.
+    auto ts_product = [&](uint32_t d, uint32_t a_hi, uint32_t a_lo, int bh) {
       uint64_t base = mdesc0;
       asm volatile("" : "+l"(base));
-#pragma unroll
-      for (int p3 = 0; p3 < 3; ++p3) {
-        const uint32_t a = p3 == 1 ? a_lo : a_hi;
-        const uint64_t db = base + (uint64_t)(((p3 == 0 ? bl : bh) * CF::TILE) >> 4);
+      const uint64_t db = base + (uint64_t)((bh * CF::TILE) >> 4);
 #pragma unroll 1
-        for (int kk = 0; kk < KSTEPS; ++kk) umma::mma_ts(d, a + 8 * kk, db + 64 * kk, idesc_o, (p3 | kk) != 0);
+      for (int kk = 0; kk < KSTEPS; ++kk) {
+        umma::mma_ts(d, a_hi + 8 * kk, db + 64 * kk, idesc_o64, kk != 0);
+        umma::mma_ts(d + 32, a_lo + 8 * kk, db + 64 * kk, idesc_o, true);
       }
     };
     auto wait = [&](BtBar b, uint32_t parity) {
@@ -624,45 +638,45 @@ __global__ void __launch_bounds__(kBtThreads, 1)
     HEPT_TRACE_CTA(2);
     if (tile < total_tiles) {
       wait(KFULL, 0);
-      scores_query_side();
       scores_key_side();
+      scores_query_side();
     }
 #pragma unroll 1
     for (; tile < total_tiles; tile += gridDim.x, ++it) {
       const uint32_t ph = it & 1;
       const bool more = tile + (int)gridDim.x < total_tiles;
-      wait(DSRDY, ph);
-      wait(MFULL, ph);
-      HEPT_TRACE_EVENT(BM_DQ_GO, it);
-      if (umma::elect_one()) {
-        ts_product(tO0, tS, tDP, CF::MKH, CF::MKL);     // dQ = dS K^
-        umma::commit(&mbar[DQDONE]);
-      }
-      __syncwarp();
       wait(PTRDY, ph);
+      wait(MFULL, ph);
       HEPT_TRACE_EVENT(BM_DV_GO, it);
       if (umma::elect_one()) {
-        ts_product(tO1, tST, tDPT, CF::MGH, CF::MGL);   // dV = P^T G'
+        ts_product(tO, tST, tDPT, CF::MGH);             // dV = P^T G'
         umma::commit(&mbar[DVDONE]);
+      }
+      __syncwarp();
+      wait(DSRDY, ph);
+      HEPT_TRACE_EVENT(BM_DQ_GO, it);
+      if (umma::elect_one()) {
+        ts_product(tST, tS, tDP, CF::MKH);              // dQ = dS K^: accumulator over the P^T columns dV has consumed
+        umma::commit(&mbar[DQDONE]);
       }
       __syncwarp();
       wait(DSTRDY, ph);
       HEPT_TRACE_EVENT(BM_DK_GO, it);
       if (umma::elect_one()) {
-        ts_product(tST, tS, tDP, CF::MQH, CF::MQL);     // dK = dS^T Q^: A where dS was, accumulator over the consumed P^T
+        ts_product(tO, tS, tDP, CF::MQH);               // dK = dS^T Q^: A where dS was, accumulator where dV was (read out)
         umma::commit(&mbar[DKDONE]);
         umma::commit(&mbar[MFREE]);
       }
       __syncwarp();
-      // The tensor pipe runs in issue order: the next tile's query-side scores go right behind dK (which reads tS / tDP);
-      // the key-side scores overwrite tST / tDPT, where dK accumulated, so they wait for the epilogue to read dk out.
+      // The next tile's key-side scores (the epilogue starts with them) overwrite tST / tDPT, where dQ accumulated: they
+      // wait for the epilogue to read dq out; the query-side scores follow (tS / tDP: behind dK in pipe order).
       if (more) {
         wait(KFULL, ph ^ 1);
-        HEPT_TRACE_EVENT(BM_SQ_GO, it + 1);
-        scores_query_side();
         wait(STFREE, ph);
         HEPT_TRACE_EVENT(BM_SK_GO, it + 1);
         scores_key_side();
+        HEPT_TRACE_EVENT(BM_SQ_GO, it + 1);
+        scores_query_side();
       }
       HEPT_TRACE_EVENT(BM_END, it);
     }

@@ -12,6 +12,8 @@ constexpr int kTM = 128, kTN = 112, kTK = 32, kTV = 32;
 
 // KM_B32 == true: the K-major operands A and Bm are stored with the SWIZZLE_128B_BASE32B pattern as well (the pattern
 // the MN-major operand needs), i.e. one shared-memory image of a row-per-hit tile serves both roles.
+// O_out (128, 96): columns [0, 32) = S V from an N = 32 MMA; columns [32, 96) = S [V | V2] from ONE N = 64 MMA per k-step whose
+// MN-major B operand spans two 32-column tiles LBO bytes apart (V2 = 2 V + 1 elementwise).
 template <bool KM_B32>
 __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ Bm,
                                                                const float* __restrict__ V, float* __restrict__ S_out,
@@ -21,6 +23,7 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* __re
   uint8_t* sA = smem;                       // 128 rows x 128 B
   uint8_t* sB = sA + kTM * 128;             // 112 rows x 128 B
   uint8_t* sV = sB + kTN * 128;             // 112 rows x 128 B   (row = k, 32 floats along n)
+  uint8_t* sV2 = sV + kTN * 128;            // the second 32-column tile of the N = 64 operand
   __shared__ uint64_t mbar;
   __shared__ uint32_t tmem_base_slot;
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -34,7 +37,9 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* __re
     const int r = idx >> 3, c = idx & 7;
     *reinterpret_cast<float4*>(sB + (KM_B32 ? umma::sw128b32_offset(r, c) : umma::sw128_offset(r, c))) =
         *reinterpret_cast<const float4*>(Bm + r * kTK + 4 * c);
-    *reinterpret_cast<float4*>(sV + umma::sw128b32_offset(r, c)) = *reinterpret_cast<const float4*>(V + r * kTV + 4 * c);
+    const float4 vv = *reinterpret_cast<const float4*>(V + r * kTV + 4 * c);
+    *reinterpret_cast<float4*>(sV + umma::sw128b32_offset(r, c)) = vv;
+    *reinterpret_cast<float4*>(sV2 + umma::sw128b32_offset(r, c)) = make_float4(2.f * vv.x + 1.f, 2.f * vv.y + 1.f, 2.f * vv.z + 1.f, 2.f * vv.w + 1.f);
   }
   if (tid == 0) umma::mbar_init(&mbar, 1);
   if (warp == 0) umma::tmem_alloc<256>(&tmem_base_slot);
@@ -77,17 +82,19 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const float* __re
     for (int k = 0; k < kTN / 8; ++k) {
       const uint64_t db = umma::smem_desc(umma::smem_u32(sV) + 1024 * k, 512, 1024, umma::kLayoutSw128Base32);
       umma::mma_ts(tO, tS + 8 * k, db, idesc, k > 0);
+      const uint64_t db2 = umma::smem_desc(umma::smem_u32(sV) + 1024 * k, 512, kTN * 128, umma::kLayoutSw128Base32);
+      umma::mma_ts(tO + 32, tS + 8 * k, db2, umma::idesc_tf32(kTM, 64, false, true), k > 0);
     }
     umma::commit(&mbar);
   }
   umma::mbar_wait(&mbar, 1);
   umma::fence_after_sync();
 #pragma unroll 1
-  for (int c0 = 0; c0 < kTV; c0 += 16) {
+  for (int c0 = 0; c0 < 3 * kTV; c0 += 16) {
     float v[16];
     umma::tmem_ld16(tO + lane_base + c0, v);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) O_out[tid * kTV + c0 + i] = v[i];
+    for (int i = 0; i < 16; ++i) O_out[tid * 3 * kTV + c0 + i] = v[i];
   }
   umma::fence_before_sync();
   __syncthreads();
@@ -166,7 +173,7 @@ extern "C" int hept_debug_umma_symmetry(const float* X, const float* Y, float* S
 extern "C" int hept_debug_umma_selftest(const float* A, const float* Bm, const float* V, float* S_out, float* O_out,
                                         int kmajor_base32, void* stream) {
   HEPT_REQUIRE(A && Bm && V && S_out && O_out, HEPT_EINVAL, "umma_selftest: null pointer");
-  const size_t smem = (size_t)(kTM + 2 * kTN) * 128 + 1024;
+  const size_t smem = (size_t)(kTM + 3 * kTN) * 128 + 1024;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(umma_selftest_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

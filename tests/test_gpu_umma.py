@@ -19,7 +19,7 @@ def test_umma_selftest_exact_on_small_integers(kmajor_base32):   # image) faults
     B = torch.randint(-4, 5, (112, 32), generator=g).float()
     V = torch.randint(-3, 4, (112, 32), generator=g).float()
     S = torch.empty(128, 112, device=dev)
-    O = torch.empty(128, 32, device=dev)
+    O = torch.empty(128, 96, device=dev)
     Ad, Bd, Vd = A.to(dev), B.to(dev), V.to(dev)
     p = lambda t: ctypes.c_void_p(t.data_ptr())
     rc = lib.hept_debug_umma_selftest(p(Ad), p(Bd), p(Vd), p(S), p(O), kmajor_base32,
@@ -29,7 +29,10 @@ def test_umma_selftest_exact_on_small_integers(kmajor_base32):   # image) faults
     S_ref = A.double() @ B.double().T
     O_ref = S_ref @ V.double()
     assert torch.equal(S.cpu().double(), S_ref), (S.cpu()[:2, :8], S_ref[:2, :8])
-    assert torch.equal(O.cpu().double(), O_ref), (O.cpu()[:2, :8], O_ref[:2, :8])
+    assert torch.equal(O.cpu()[:, :32].double(), O_ref), (O.cpu()[:2, :8], O_ref[:2, :8])
+    # one N = 64 MMA per k-step over two 32-column tiles LBO apart: [S V | S (2 V + 1)]
+    O2_ref = torch.cat([O_ref, S_ref @ (2 * V.double() + 1)], dim=1)
+    assert torch.equal(O.cpu()[:, 32:].double(), O2_ref), (O.cpu()[:2, 32:40], O2_ref[:2, :8])
 
 
 def test_tf32_mma_is_symmetric_under_operand_exchange():
