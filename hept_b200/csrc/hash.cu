@@ -200,8 +200,8 @@ __global__ void keys_regions_kernel(const float* __restrict__ proj, const float*
 // The per-table FMA chain runs over e = 0 .. E-1 in order, exactly like the first generation: same bits.
 constexpr int kHashMaxCtas = HEPT_HASH_MAX_CTAS;
 
-template <int D, int C, int T>
-__global__ void __launch_bounds__(256) hash_project_v2_kernel(const float* __restrict__ q, const float* __restrict__ k,
+template <int D, int C, int T, int HPW>
+__global__ void __launch_bounds__(256, HPW == 1 ? 4 : 2) hash_project_v2_kernel(const float* __restrict__ q, const float* __restrict__ k,
                                                               const float* __restrict__ coords,
                                                               const float* __restrict__ scale,
                                                               const float* __restrict__ alpha, int N, int H, int raw_size,
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(256) hash_project_v2_kernel(const float* __res
   const int vec_per_row = HD / 4;
   const int groups = (N + 31) / 32;
   // running extrema of the heads this warp owns (h = warp, warp + warps, ...): lane-private until the end
-  constexpr int HPW = 4;                          // heads per warp covered without spilling (H <= warps * HPW)
+  // HPW = heads per warp (H <= warps * HPW): 1 for the shipped 8-head shapes, which keeps the kernel at 4 CTAs per SM
   uint32_t lo[HPW][T], hi[HPW][T];
 #pragma unroll
   for (int j = 0; j < HPW; ++j)
@@ -350,8 +350,11 @@ static int launch_project_v2(const hept_shape* s, const float* q, const float* k
   const size_t smem = sizeof(float) * ((size_t)s->H * 32 * T + (((size_t)s->H * C + 3) & ~(size_t)3) +
                                        2 * 32 * ((size_t)s->H * D + 4));
   static int sms = 0, per_sm = 0;
+  const bool wide = s->H > 8;                     // more than one head per warp
   if (!sms) {
-    cudaError_t e = cudaFuncSetAttribute(hash_project_v2_kernel<D, C, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(hash_project_v2_kernel<D, C, T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(hash_project_v2_kernel<D, C, T, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "hash_project: %s", cudaGetErrorString(e));
     int dev = 0, n = 0;
     cudaGetDevice(&dev);
@@ -361,14 +364,16 @@ static int launch_project_v2(const hept_shape* s, const float* q, const float* k
   }
   HEPT_REQUIRE(smem <= 100 * 1024, HEPT_EUNSUPPORTED, "hash_project: H*D=%d too wide for the staging buffer", s->H * D);
   HEPT_REQUIRE(s->H <= 8 * 4, HEPT_EUNSUPPORTED, "hash_project: more than 32 heads");
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hash_project_v2_kernel<D, C, T>, 256, smem);
+  cudaError_t e = wide ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hash_project_v2_kernel<D, C, T, 4>, 256, smem)
+                       : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hash_project_v2_kernel<D, C, T, 1>, 256, smem);
   HEPT_REQUIRE(e == cudaSuccess && per_sm > 0, HEPT_ECUDA, "hash_project: occupancy query failed");
   const int groups = (s->N + 31) / 32;
   int grid = sms * per_sm;                       // one resident wave
   if (grid > groups) grid = groups;
   if (grid > kHashMaxCtas) grid = kHashMaxCtas;
   *ctas = grid;
-  hash_project_v2_kernel<D, C, T><<<grid, 256, smem, st>>>(q, k, coords, scale, alpha, s->N, s->H, s->raw_size, proj, partial, hat);
+  if (wide) hash_project_v2_kernel<D, C, T, 4><<<grid, 256, smem, st>>>(q, k, coords, scale, alpha, s->N, s->H, s->raw_size, proj, partial, hat);
+  else hash_project_v2_kernel<D, C, T, 1><<<grid, 256, smem, st>>>(q, k, coords, scale, alpha, s->N, s->H, s->raw_size, proj, partial, hat);
   HEPT_CHECK_LAUNCH("hash_project");
   return HEPT_OK;
 }
