@@ -27,7 +27,10 @@ def load_case(name: str):
     for nm, t in (("q", q), ("k", k), ("v", v), ("alpha", params["e2lsh.alpha"])):
         want = float(z["meta_chk_" + nm])
         got = float(t.double().sum())
-        assert got == want, f"synthetic generator drifted for {name}:{nm} ({got} vs {want}); regenerate the fixtures"
+        # the float64 sum is taken by torch on whatever host runs the test: its reduction order (vector width, threads)
+        # moves the last bits, a drifted generator moves the leading ones
+        assert abs(got - want) <= 1e-9 * max(1.0, abs(want)), \
+            f"synthetic generator drifted for {name}:{nm} ({got} vs {want}); regenerate the fixtures"
     inputs: Dict[str, torch.Tensor] = {"query": q, "key": k, "value": v, "coords": gold["coords"]}
     if flavour == "example":
         inputs["combined_shifts"] = gold["combined_shifts"]
