@@ -205,6 +205,221 @@ __global__ void __launch_bounds__(kOlThreads) out_linear_bwd_params_kernel(const
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Register-tiled versions for IN = 8 OUT (the shipped H = 8 shapes).  The row-per-lane kernels above are bound by the
+// L1 tag stage (a warp's 16-byte accesses touch 32 lines) and by the 128 B/clk shared-memory return path (one
+// LDS.128 — broadcast or not — delivers 512 B per warp for 4 FMAs per lane).  Here the rows travel global -> shared
+// with fully coalesced cp.async (double-buffered), and a thread owns a 4-hit x 6-output (forward), 4-hit x 8-column
+// (input gradient) or 8 x 8 (weight gradient) register tile, so a 16-byte shared-memory load feeds 16-32 FMAs.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kTlHits = 128;                       // hits per CTA tile (forward, input gradient)
+constexpr int kTlThreads = 128;
+
+// forward: thread = (q = tid / 4, og = tid % 4): hits q, q+32, q+64, q+96 x outputs [6 og, 6 og + 6)
+template <int OUT, int IN>
+__global__ void __launch_bounds__(kTlThreads) out_linear_fwd_tiled_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                          const float* __restrict__ b, int N, float* __restrict__ out) {
+  constexpr int KC = 48, NCH = IN / KC, XS = KC + 4, WS = IN + 4, PER = OUT / 4;
+  static_assert(IN % KC == 0 && OUT % 4 == 0 && PER % 2 == 0, "tile shape");
+  extern __shared__ __align__(16) float s_dyn[];
+  float* s_w = s_dyn;                              // (OUT, WS)
+  float* s_x = s_w + OUT * WS;                     // (kTlHits, XS): one buffer; 45 KB per CTA -> 5 CTAs per SM, so the 469 tiles
+                                                   // of a 60k-hit event are ONE wave and other CTAs cover a CTA's load latency
+  const int tid = threadIdx.x, q = tid >> 2, og = tid & 3;
+  const int n0 = blockIdx.x * kTlHits;
+  const int rows = min(kTlHits, N - n0);
+  auto load_chunk = [&](int kc) {
+    float* dst = s_x;
+    for (int i = tid; i < kTlHits * (KC / 4); i += kTlThreads) {
+      const int r = i / (KC / 4), c4 = i - r * (KC / 4);
+      if (r < rows) cp_async16_cg(dst + r * XS + 4 * c4, x + (size_t)(n0 + r) * IN + kc * KC + 4 * c4);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  load_chunk(0);
+  for (int i = tid; i < OUT * (IN / 4); i += kTlThreads) {
+    const int j = i / (IN / 4), c4 = i - j * (IN / 4);
+    *reinterpret_cast<float4*>(s_w + j * WS + 4 * c4) = ldg4(w + (size_t)j * IN + 4 * c4);
+  }
+  float acc[4][PER];
+#pragma unroll
+  for (int u = 0; u < PER; ++u) {
+    const float bu = __ldg(b + og * PER + u);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) acc[t][u] = bu;
+  }
+#pragma unroll 1
+  for (int kc = 0; kc < NCH; ++kc) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    const float* xs = s_x + q * XS;
+    const float* ws = s_w + og * PER * WS + kc * KC;
+#pragma unroll 4
+    for (int c4 = 0; c4 < KC / 4; ++c4) {
+      float4 xv[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) xv[t] = *reinterpret_cast<const float4*>(xs + 32 * t * XS + 4 * c4);
+#pragma unroll
+      for (int u = 0; u < PER; ++u) {
+        const float4 wv = *reinterpret_cast<const float4*>(ws + u * WS + 4 * c4);
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+          acc[t][u] = fmaf(xv[t].w, wv.w, fmaf(xv[t].z, wv.z, fmaf(xv[t].y, wv.y, fmaf(xv[t].x, wv.x, acc[t][u]))));
+      }
+    }
+    __syncthreads();
+    if (kc + 1 < NCH) load_chunk(kc + 1);
+  }
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int r = q + 32 * t;
+    if (r < rows) {
+      float2* dst = reinterpret_cast<float2*>(out + (size_t)(n0 + r) * OUT + og * PER);
+#pragma unroll
+      for (int u2 = 0; u2 < PER / 2; ++u2) dst[u2] = make_float2(acc[t][2 * u2], acc[t][2 * u2 + 1]);
+    }
+  }
+}
+
+// input gradient: thread = (q = tid / 4, cg = tid % 4 + 4 i): hits q + 32 u x columns [8 cg, 8 cg + 8), i < IN / 32
+template <int OUT, int IN>
+__global__ void __launch_bounds__(kTlThreads, 4) out_linear_bwd_input_tiled_kernel(const float* __restrict__ g,
+                                                                                const float* __restrict__ w, int N,
+                                                                                float* __restrict__ dx) {
+  constexpr int GS = OUT + 4;
+  static_assert(OUT % 4 == 0 && IN % 32 == 0, "tile shape");
+  extern __shared__ __align__(16) float s_dyn[];
+  float* s_w = s_dyn;                              // (OUT, IN)
+  float* s_g = s_w + OUT * IN;                     // (kTlHits, GS)
+  const int tid = threadIdx.x, q = tid >> 2, c0 = tid & 3;
+  const int n0 = blockIdx.x * kTlHits;
+  const int rows = min(kTlHits, N - n0);
+  for (int i = tid; i < OUT * IN / 4; i += kTlThreads) reinterpret_cast<float4*>(s_w)[i] = __ldg(reinterpret_cast<const float4*>(w) + i);
+  for (int i = tid; i < kTlHits * (OUT / 4); i += kTlThreads) {
+    const int r = i / (OUT / 4), j4 = i - r * (OUT / 4);
+    *reinterpret_cast<float4*>(s_g + r * GS + 4 * j4) =
+        r < rows ? ldg4(g + (size_t)(n0 + r) * OUT + 4 * j4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int i = 0; i < IN / 32; ++i) {
+    const int cg = c0 + 4 * i;
+    float4 a0[4], a1[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) { a0[t] = make_float4(0.f, 0.f, 0.f, 0.f); a1[t] = a0[t]; }
+#pragma unroll
+    for (int j4 = 0; j4 < OUT / 4; ++j4) {
+      float4 gv[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) gv[t] = *reinterpret_cast<const float4*>(s_g + (q + 32 * t) * GS + 4 * j4);
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const float4 w0 = *reinterpret_cast<const float4*>(s_w + (4 * j4 + jj) * IN + 8 * cg);
+        const float4 w1 = *reinterpret_cast<const float4*>(s_w + (4 * j4 + jj) * IN + 8 * cg + 4);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float gj = jj == 0 ? gv[t].x : (jj == 1 ? gv[t].y : (jj == 2 ? gv[t].z : gv[t].w));
+          a0[t].x = fmaf(gj, w0.x, a0[t].x); a0[t].y = fmaf(gj, w0.y, a0[t].y); a0[t].z = fmaf(gj, w0.z, a0[t].z); a0[t].w = fmaf(gj, w0.w, a0[t].w);
+          a1[t].x = fmaf(gj, w1.x, a1[t].x); a1[t].y = fmaf(gj, w1.y, a1[t].y); a1[t].z = fmaf(gj, w1.z, a1[t].z); a1[t].w = fmaf(gj, w1.w, a1[t].w);
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int r = q + 32 * t;
+      if (r < rows) {
+        float4* dst = reinterpret_cast<float4*>(dx + (size_t)(n0 + r) * IN + 8 * cg);
+        dst[0] = a0[t];
+        dst[1] = a1[t];
+      }
+    }
+  }
+}
+
+// weight / bias gradient, stage 1: a CTA = kPgGroups hit groups x (OUT / 8) x (IN / 8) threads; a thread owns an 8 x 8 tile
+// of dW; slabs of kPgRows hits are staged in shared memory (double-buffered cp.async); group p takes the hits p, p + G, ...
+// of a slab.  The groups' tiles are added through shared memory in group order (deterministic), db by the ct == 0 threads.
+constexpr int kPgGroups = 4, kPgRows = 32;
+template <int OUT, int IN>
+__global__ void __launch_bounds__(kPgGroups * (OUT / 8) * (IN / 8), 2) out_linear_bwd_params_tiled_kernel(
+    const float* __restrict__ g, const float* __restrict__ x, int N, float* __restrict__ partial) {
+  constexpr int JT = OUT / 8, CT = IN / 8, PER = JT * CT, THREADS = kPgGroups * PER;
+  constexpr int XS = IN + 4, GS = OUT + 4, SLAB = kPgRows * (XS + GS);
+  static_assert(2 * SLAB >= (OUT + 1) * IN, "the staging buffers double as the reduction buffer");
+  extern __shared__ __align__(16) float s_dyn[];   // 2 x [ (kPgRows, XS) | (kPgRows, GS) ]
+  const int tid = threadIdx.x, p = tid / PER, u = tid % PER;
+  const int jt = u / CT, ct = u % CT;
+  float acc[8][8], bsum[8];
+#pragma unroll
+  for (int a = 0; a < 8; ++a) {
+    bsum[a] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[a][c] = 0.f;
+  }
+  const int slabs = (N + kPgRows - 1) / kPgRows;
+  auto load_slab = [&](int slab, int buf) {
+    float* xs = s_dyn + buf * SLAB;
+    float* gs = xs + kPgRows * XS;
+    const int n0 = slab * kPgRows, rows = min(kPgRows, N - n0);
+    for (int i = tid; i < kPgRows * (IN / 4); i += THREADS) {
+      const int r = i / (IN / 4), c4 = i - r * (IN / 4);
+      if (r < rows) cp_async16_cg(xs + r * XS + 4 * c4, x + (size_t)(n0 + r) * IN + 4 * c4);
+    }
+    for (int i = tid; i < kPgRows * (OUT / 4); i += THREADS) {
+      const int r = i / (OUT / 4), j4 = i - r * (OUT / 4);
+      if (r < rows) cp_async16_cg(gs + r * GS + 4 * j4, g + (size_t)(n0 + r) * OUT + 4 * j4);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  int slab = blockIdx.x, it = 0;
+  if (slab < slabs) load_slab(slab, 0);
+#pragma unroll 1
+  for (; slab < slabs; slab += gridDim.x, ++it) {
+    const int next = slab + gridDim.x;
+    if (next < slabs) {
+      load_slab(next, (it + 1) & 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const float* xs = s_dyn + (it & 1) * SLAB;
+    const float* gs = xs + kPgRows * XS;
+    const int rows = min(kPgRows, N - slab * kPgRows);
+#pragma unroll 2
+    for (int r = p; r < rows; r += kPgGroups) {
+      const float4 g0 = *reinterpret_cast<const float4*>(gs + r * GS + 8 * jt), g1 = *reinterpret_cast<const float4*>(gs + r * GS + 8 * jt + 4);
+      const float4 x0 = *reinterpret_cast<const float4*>(xs + r * XS + 8 * ct), x1 = *reinterpret_cast<const float4*>(xs + r * XS + 8 * ct + 4);
+      const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+      for (int a = 0; a < 8; ++a) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[a][c] = fmaf(gv[a], xv[c], acc[a][c]);
+        bsum[a] += gv[a];                          // only the ct == 0 threads' sums are used
+      }
+    }
+    __syncthreads();
+  }
+  // groups add their tiles in order 0, 1, ... through shared memory (the staging buffers are free now)
+  float* s_acc = s_dyn;                            // (OUT + 1, IN)
+#pragma unroll 1
+  for (int turn = 0; turn < kPgGroups; ++turn) {
+    if (p == turn) {
+#pragma unroll
+      for (int a = 0; a < 8; ++a) {
+        float* dst = s_acc + (8 * jt + a) * IN + 8 * ct;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) dst[c] = turn == 0 ? acc[a][c] : dst[c] + acc[a][c];
+        if (ct == 0) s_acc[OUT * IN + 8 * jt + a] = turn == 0 ? bsum[a] : s_acc[OUT * IN + 8 * jt + a] + bsum[a];
+      }
+    }
+    __syncthreads();
+  }
+  float* dstp = partial + (size_t)blockIdx.x * (OUT + 1) * IN;
+  for (int i = tid; i < OUT * IN + OUT; i += THREADS) dstp[i] = s_acc[i];
+}
+
 // Stage 2: fixed-order sum over CTAs.  A CTA of 256 threads = 32 entries of (OUT + 1, IN) x 8 parts; part p sums the
 // partials p, p + 8, ... in order, then the eight sums are added in order.  Entries [OUT][OUT..IN) are unused.
 __global__ void __launch_bounds__(256) out_linear_reduce_kernel(const float* __restrict__ partial, int ctas, int OUT, int IN,
@@ -249,6 +464,19 @@ static int launch_ol_fwd(const hept_shape* s, const float* x, const float* w, co
     configured = true;
   }
   HEPT_REQUIRE(smem <= 96 * 1024 && IN % 4 == 0, HEPT_EUNSUPPORTED, "out_linear_fwd: H*D=%d not supported", IN);
+  if constexpr (OUT == 24) if (IN == OUT * 8) {    // the shipped H = 8, D = 24 shape: staged, register-tiled
+    constexpr int TIN = OUT * 8;
+    const size_t tsmem = sizeof(float) * ((size_t)OUT * (TIN + 4) + (size_t)kTlHits * (48 + 4));
+    static bool tconfigured = false;
+    if (!tconfigured) {
+      cudaError_t e = cudaFuncSetAttribute(out_linear_fwd_tiled_kernel<OUT, TIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem);
+      HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "out_linear_fwd: %s", cudaGetErrorString(e));
+      tconfigured = true;
+    }
+    out_linear_fwd_tiled_kernel<OUT, TIN><<<(s->N + kTlHits - 1) / kTlHits, kTlThreads, tsmem, st>>>(x, w, b, s->N, out);
+    HEPT_CHECK_LAUNCH("out_linear_fwd");
+    return HEPT_OK;
+  }
   const int units = (s->N + 32 * HT - 1) / (32 * HT) * (OUT / OUTS);
   out_linear_fwd_kernel<OUT, OUTS, HT><<<(units + kOlWarps - 1) / kOlWarps, 32 * kOlWarps, smem, st>>>(x, w, b, s->N, IN, out);
   HEPT_CHECK_LAUNCH("out_linear_fwd");
@@ -272,17 +500,50 @@ static int launch_ol_bwd(const hept_shape* s, const float* g, const float* w, co
       configured = true;
     }
     HEPT_REQUIRE(smem <= 96 * 1024, HEPT_EUNSUPPORTED, "out_linear_bwd: H*D=%d too wide", IN);
-    const int units = (s->N + 63) / 64 * SPLIT;
-    const unsigned grid = (unsigned)((units + kOlWarps - 1) / kOlWarps);
-    out_linear_bwd_input_kernel<OUT, SPLIT><<<grid, 32 * kOlWarps, smem, st>>>(g, w, s->N, IN, dx);
+    bool tiled = false;
+    if constexpr (OUT == 24) if (IN == OUT * 8) {
+      tiled = true;
+      constexpr int TIN = OUT * 8;
+      const size_t tsmem = sizeof(float) * ((size_t)OUT * TIN + (size_t)kTlHits * (OUT + 4));
+      static bool tconfigured = false;
+      if (!tconfigured) {
+        cudaError_t e = cudaFuncSetAttribute(out_linear_bwd_input_tiled_kernel<OUT, TIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem);
+        HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "out_linear_bwd: %s", cudaGetErrorString(e));
+        tconfigured = true;
+      }
+      out_linear_bwd_input_tiled_kernel<OUT, TIN><<<(s->N + kTlHits - 1) / kTlHits, kTlThreads, tsmem, st>>>(g, w, s->N, dx);
+    }
+    if (!tiled) {
+      const int units = (s->N + 63) / 64 * SPLIT;
+      const unsigned grid = (unsigned)((units + kOlWarps - 1) / kOlWarps);
+      out_linear_bwd_input_kernel<OUT, SPLIT><<<grid, 32 * kOlWarps, smem, st>>>(g, w, s->N, IN, dx);
+    }
     HEPT_CHECK_LAUNCH("out_linear_bwd_input");
   }
   const int slabs = (s->N + kOlRows - 1) / kOlRows;
   int ctas = sms * 4;
   if (ctas > slabs) ctas = slabs;
   if (ctas > kOlMaxCtas) ctas = kOlMaxCtas;
-  const size_t psmem = sizeof(float) * ((size_t)kOlRows * OUT + (size_t)OUT * IN);
-  out_linear_bwd_params_kernel<OUT><<<ctas, kOlThreads, psmem, st>>>(g, x, s->N, IN, partial);
+  bool ptiled = false;
+  if constexpr (OUT == 24) if (IN == OUT * 8) {
+    ptiled = true;
+    constexpr int TIN = OUT * 8, THREADS = kPgGroups * (OUT / 8) * (TIN / 8);
+    const size_t tsmem = sizeof(float) * 2 * (size_t)kPgRows * (TIN + 4 + OUT + 4);
+    static bool tconfigured = false;
+    if (!tconfigured) {
+      cudaError_t e = cudaFuncSetAttribute(out_linear_bwd_params_tiled_kernel<OUT, TIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem);
+      HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "out_linear_bwd: %s", cudaGetErrorString(e));
+      tconfigured = true;
+    }
+    const int tslabs = (s->N + kPgRows - 1) / kPgRows;
+    ctas = sms * 2 < tslabs ? sms * 2 : tslabs;
+    if (ctas > kOlMaxCtas) ctas = kOlMaxCtas;
+    out_linear_bwd_params_tiled_kernel<OUT, TIN><<<ctas, THREADS, tsmem, st>>>(g, x, s->N, partial);
+  }
+  if (!ptiled) {
+    const size_t psmem = sizeof(float) * ((size_t)kOlRows * OUT + (size_t)OUT * IN);
+    out_linear_bwd_params_kernel<OUT><<<ctas, kOlThreads, psmem, st>>>(g, x, s->N, IN, partial);
+  }
   HEPT_CHECK_LAUNCH("out_linear_bwd_params");
   const int entries = (OUT + 1) * IN;
   out_linear_reduce_kernel<<<(entries + 31) / 32, 256, 0, st>>>(partial, ctas, OUT, IN, dw, db);
