@@ -99,15 +99,30 @@ using umma::trunc_tf32;
 // G' rows (N, H, 32): [g / den (D), -(g . y) / den, 0 ...] — the gradient arriving at numerator and normaliser of
 // every table (d so_t = g / den, d denom_t = -(g . y) / den, attn_bwd.cu).  Eight lanes per row.
 // ---------------------------------------------------------------------------------------------------------------
+// The same launch also writes hat_coords (N, H, 8) = scale[h,c] * coords[n,c] (hash.cu, hat_coords_kernel): lanes 0 and 1
+// of a row write its two 16-byte chunks, which saves a 15 us streaming launch per backward.
 template <int D>
 __global__ void __launch_bounds__(256) grad_rows_kernel(const float* __restrict__ g, const float* __restrict__ y,
                                                         const float* __restrict__ den, size_t rows,
-                                                        float* __restrict__ out) {
+                                                        float* __restrict__ out, const float* __restrict__ coords,
+                                                        const float* __restrict__ scale, int H, int C, int raw_size,
+                                                        float* __restrict__ hat) {
   constexpr int VCH = D / 4;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t r = idx >> 3;
   const int c = (int)(idx & 7);
   const bool live = r < rows;
+  if (live && c < 2) {
+    const size_t n = r / H;
+    const int h = (int)(r - n * H);
+    float hv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int cc = 4 * c + u;
+      hv[u] = (cc < C && (int)n < raw_size) ? __fmul_rn(__ldg(scale + h * C + cc), __ldg(coords + n * C + cc)) : 0.f;
+    }
+    *reinterpret_cast<float4*>(hat + r * 8 + 4 * c) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+  }
   float4 gd = make_float4(0.f, 0.f, 0.f, 0.f);
   float part = 0.f;
   if (live && c < VCH) {
@@ -784,10 +799,10 @@ static int launch_bwd_tc(const hept_shape* s, const float* q, const float* k, co
   float* sk = (float*)((char*)sq + p.stage_bytes);
   float* sv = (float*)((char*)sk + p.stage_bytes);
   float* partial = (float*)((char*)sv + p.stage_bytes);
-  int rc;
-  if ((rc = hept_hat_coords(s, coords, scale, hat, st))) return rc;
+  HEPT_REQUIRE(s->C <= 8, HEPT_EUNSUPPORTED, "block_attn_bwd_tc: more than 8 coordinates");
   const size_t rows = (size_t)s->N * s->H;
-  grad_rows_kernel<D><<<(unsigned)((rows * 8 + 255) / 256), 256, 0, st>>>(d_out_pre, out_pre, den_sum, rows, grows);
+  grad_rows_kernel<D><<<(unsigned)((rows * 8 + 255) / 256), 256, 0, st>>>(d_out_pre, out_pre, den_sum, rows, grows, coords, scale,
+                                                                         s->H, s->C, s->raw_size, hat);
   HEPT_CHECK_LAUNCH("grad_rows");
   const int mask = bwd_stage_mask();
   int grid = p.tiles < sms ? p.tiles : sms;             // one CTA per SM (the tile uses all 512 TMEM columns)
