@@ -89,6 +89,9 @@ enum BtEv { BE_QREADY, BE_DSRDY, BE_KREADY, BE_PTRDY, BE_DQDONE, BE_DQOUT, BE_DV
             BP_KFREE, BP_KFULL, BP_ISSUED, BP_MFREE, BP_MFULL, BM_DQ_GO, BM_DV_GO, BM_DK_GO, BM_SQ_GO, BM_SK_GO, BM_END };
 HEPT_TRACE_SETTER(hept_debug_trace_bwd)
 
+#ifndef HEPT_BWD_PROD_WAIT
+#define HEPT_BWD_PROD_WAIT DVDONE
+#endif
 enum BtBar { KFULL, MFULL, MFREE, QREADY, KREADY, DSRDY, DQDONE, PTRDY, DVDONE, DSTRDY, DKDONE, STFREE, BT_NBAR };
 
 using umma::split4;
@@ -486,7 +489,7 @@ __global__ void __launch_bounds__(kBtThreads, 1)
     for (; tile < total_tiles; tile += gridDim.x, ++it) {
       const uint32_t ph = it & 1;
       // ---- K-major operand tiles: free once the previous tile's score MMAs (both sides) are done ------------------
-      if (it > 0) umma::mbar_wait(&mbar[QREADY], ph ^ 1);   // the commit after the later (query-side) scores covers both sides
+      if (it > 0) umma::mbar_wait(&mbar[HEPT_BWD_PROD_WAIT], ph ^ 1);   // dV done (hence both sides' score MMAs): see DESIGN.md on contention
       if (warp == EW) HEPT_TRACE_EVENT(BP_KFREE, it);
       umma::cp_async_wait_all();
       float* nq2s = s_nq2 + ph * 128;

@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(128, 1) umma_timing_kernel(int mode, int count
     float z[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) z[i] = 0.f;
-    for (int c0 = 0; c0 < 256; c0 += 16) umma::tmem_st16(tmem + ((uint32_t)(warp * 32) << 16) + c0, z);
+    for (int c0 = 0; c0 < 512; c0 += 16) umma::tmem_st16(tmem + ((uint32_t)(warp * 32) << 16) + c0, z);
     umma::tmem_wait_st();
   }
   umma::fence_before_sync();
@@ -234,9 +234,16 @@ __global__ void __launch_bounds__(128, 1) umma_timing_kernel(int mode, int count
       auto burst = [&](auto mode_c) {
         constexpr int M = decltype(mode_c)::value;
 #pragma unroll
-        for (int i = 0; i < 39; ++i) {
+        for (int i = 0; i < 52; ++i) {
           if (i >= count) break;
-          if constexpr (M >= 5 && M <= 7) {        // TS, one accumulator, N = 64 / 96 / 128: B spans N / 32 row-per-k tiles, LBO apart
+          if constexpr (M >= 9 && M <= 11) {       // the backward's TS product: N = 64 (A hi) + N = 32 (A lo) per k-step, at its TMEM columns:
+            // 9: A at 224 / 336, D at 448 (dV);  10: A at 0 / 112, D at 448 (dK);  11: A at 0 / 112, D at 224 (dQ)
+            constexpr uint32_t a_hi = M == 9 ? 224 : 0, a_lo = M == 9 ? 336 : 112, dcol = M == 11 ? 224 : 448;
+            const uint64_t dW = umma::smem_desc(sA, 512, 13 * 1024, umma::kLayoutSw128Base32);
+            const int kk = (i >> 1) % 13;
+            if ((i & 1) == 0) umma::mma_ts(tmem + dcol, tmem + a_hi + 8 * kk, dW + 64 * kk, umma::idesc_tf32(128, 64, false, true), i >= 2);
+            else umma::mma_ts(tmem + dcol + 32, tmem + a_lo + 8 * kk, dW + 64 * kk, id_ts, true);
+          } else if constexpr (M >= 5 && M <= 7) {        // TS, one accumulator, N = 64 / 96 / 128: B spans N / 32 row-per-k tiles, LBO apart
             constexpr int NN = M == 5 ? 64 : (M == 6 ? 96 : 128);
             const uint64_t dW = umma::smem_desc(sA, 512, 13 * 1024, umma::kLayoutSw128Base32);
             umma::mma_ts(acc0, tmem + 8 * (i % 13), dW + 64 * (i % 13), umma::idesc_tf32(128, NN, false, true), i >= 1);
@@ -259,6 +266,9 @@ __global__ void __launch_bounds__(128, 1) umma_timing_kernel(int mode, int count
         case 5: burst(std::integral_constant<int, 5>{}); break;
         case 6: burst(std::integral_constant<int, 6>{}); break;
         case 7: burst(std::integral_constant<int, 7>{}); break;
+        case 9: burst(std::integral_constant<int, 9>{}); break;
+        case 10: burst(std::integral_constant<int, 10>{}); break;
+        case 11: burst(std::integral_constant<int, 11>{}); break;
         default: burst(std::integral_constant<int, 8>{}); break;
       }
       umma::commit(&mbar);
