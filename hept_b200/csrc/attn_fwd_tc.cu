@@ -20,7 +20,7 @@
 // in fp32 (S0: cross terms + first half of the k-steps, S1: the rest).
 //
 // Warp roles (896 threads = 7 warpgroups, register budgets rebalanced with setmaxnreg):
-//   warps 0-7   epilogue: TMEM lane = (warp & 3) * 32 + lane, columns split in two parts (warp >> 2); software
+//   warps 0-7   epilogue (and the value operand: v rows via cp.async, split, MN-major value tiles of tile n+2): TMEM lane = (warp & 3) * 32 + lane, columns split in two parts (warp >> 2); software
 //               pipelined: P of tile n+1 is produced before the output rows of tile n are read and scattered, so the
 //               P V MMAs of tile n run under SIMT work
 //   warps 8-23  producer: gather rows through the sort permutation into registers (one tile ahead), centre, split,
@@ -64,7 +64,9 @@ struct TcFwd {
   static constexpr int TILE = KC * 128;
   static constexpr int QH = 0, QL = 1, KH = 2, KL = 3;    // K-major tiles of a stage
   static constexpr int OFF_V = 2 * 4 * TILE;              // then per stage VH, VL (MN-major)
-  static constexpr int OFF_AUX = OFF_V + 2 * 2 * TILE;
+  static constexpr int OFF_VSTG = OFF_V + 2 * 2 * TILE;    // raw value rows, two sets of B x (D / 4) 16-byte chunks
+  static constexpr int VSTG = (B * (D / 4) * 16 + 127) / 128 * 128;
+  static constexpr int OFF_AUX = OFF_VSTG + 2 * VSTG;
   static constexpr int AUX_BYTES = (4 * 128 + 8 * 128) * 4;   // nq2[4][128], qidx[8][128]
   static constexpr int TOTAL = OFF_AUX + AUX_BYTES;
   static constexpr int RPP = kFtProdThreads / 8;
@@ -107,7 +109,7 @@ __global__ void __launch_bounds__(kFtThreads, 1)
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
       umma::mbar_init(&mbar[QKFULL + s], PW);
-      umma::mbar_init(&mbar[VFULL + s], PW);
+      umma::mbar_init(&mbar[VFULL + s], EW);           // the epilogue warps own the value operand
       umma::mbar_init(&mbar[QKFREE + s], 1);
       umma::mbar_init(&mbar[VFREE + s], 1);
       umma::mbar_init(&mbar[SREADY + s], 1);
@@ -131,6 +133,18 @@ __global__ void __launch_bounds__(kFtThreads, 1)
 #pragma unroll
         for (int tl = 0; tl < 2; ++tl)
           *reinterpret_cast<float4*>(smem + CF::OFF_V + (st * 2 + tl) * CF::TILE + umma::sw128b32_offset(rr, c)) = z;
+      }
+    }
+    // value tiles: only chunks [0, D / 4) of a row change from tile to tile; chunk D / 4 holds the ones column
+    // (O[:, D] = row sum of P) and the rest is zero
+    for (int rr = sub; rr < B; rr += kFtProdThreads / 8) {
+      if (c >= VCH) {
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f), one = make_float4(c == VCH ? 1.f : 0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int st = 0; st < 2; ++st) {
+          *reinterpret_cast<float4*>(smem + CF::OFF_V + (st * 2 + 0) * CF::TILE + umma::sw128b32_offset(rr, c)) = one;
+          *reinterpret_cast<float4*>(smem + CF::OFF_V + (st * 2 + 1) * CF::TILE + umma::sw128b32_offset(rr, c)) = z;
+        }
       }
     }
     for (int i = ptid; i < 4 * 128; i += kFtProdThreads) s_nq2[i] = 0.f;
@@ -187,6 +201,75 @@ __global__ void __launch_bounds__(kFtThreads, 1)
       if (warp == 0) HEPT_TRACE_EVENT(EV_E_PREADY, it);
     };
 
+    // ---- the value operand is the epilogue's job: it waits on S for a good third of a tile, the producer warps, which
+    // bound the kernel, do not.  Raw v rows travel global -> shared with cp.async (no registers) four tiles before they
+    // are used; thread <-> items (row r, chunk c < D / 4) idx = tid, tid + 256, ...; a thread splits its own items into
+    // (hi, lo) and writes the MN-major tiles of stage it & 1 right after it has read O of tile it - 2 out (P V done).
+    constexpr int ITEMS = B * VCH, VPER = (ITEMS + kFtEpiThreads - 1) / kFtEpiThreads;
+    const int g = (int)gridDim.x;
+    int hit[VPER];                                     // key-side hit index of this thread's items, loaded one step before `v_issue`
+    auto v_hits = [&](int tile) {
+      int h, t, blk;
+      decode(tile, h, t, blk);
+      const int32_t* kpos = positions + ((size_t)T * H + t * H + h) * N + (size_t)blk * B;
+#pragma unroll
+      for (int u = 0; u < VPER; ++u) {
+        const int idx = tid + u * kFtEpiThreads;
+        hit[u] = idx < ITEMS ? __ldg(kpos + idx / VCH) : -1;
+      }
+    };
+    auto v_issue = [&](int tile, int set) {            // uses hit[] loaded for `tile`; always commits one group
+      if (tile < total_tiles) {
+        int h, t, blk;
+        decode(tile, h, t, blk);
+        float4* stg = reinterpret_cast<float4*>(smem + CF::OFF_VSTG + set * CF::VSTG);
+        const float* vh = v + (size_t)h * D;
+#pragma unroll
+        for (int u = 0; u < VPER; ++u) {
+          const int idx = tid + u * kFtEpiThreads;
+          if (idx < ITEMS) {
+            const int n = hit[u];
+            const bool ok = n < raw_size;
+            umma::cp_async16(stg + idx, ok ? vh + (size_t)n * H * D + 4 * (idx % VCH) : v, ok ? 16 : 0);
+          }
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto v_write = [&](int vit) {                      // value tiles of tile number `vit` (stage vit & 1) from staging set vit & 1
+      const int st = vit & 1;
+      uint8_t* vm = smem + CF::OFF_V + st * 2 * CF::TILE;
+      const float4* stg = reinterpret_cast<const float4*>(smem + CF::OFF_VSTG + st * CF::VSTG);
+#pragma unroll
+      for (int u = 0; u < VPER; ++u) {
+        const int idx = tid + u * kFtEpiThreads;
+        if (idx < ITEMS) {
+          float4 hi, lo;
+          split4(stg[idx], hi, lo);
+          const uint32_t omn = umma::sw128b32_offset(idx / VCH, idx % VCH);
+          *reinterpret_cast<float4*>(vm + omn) = hi;
+          *reinterpret_cast<float4*>(vm + CF::TILE + omn) = lo;
+        }
+      }
+      umma::fence_async_smem();
+      __syncwarp();
+      if (lane == 0) umma::mbar_arrive(&mbar[VFULL + st]);
+      if (warp == 0) HEPT_TRACE_EVENT(EV_P_VFULL, vit);
+    };
+    // prologue: rows of tiles 0, 1 (written before the loop), 2, 3 (in flight); groups are committed in tile order
+    const int tile0 = blockIdx.x;
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+      if (tile0 + j * g < total_tiles) v_hits(tile0 + j * g);
+      if (j == 2) {                                    // sets are reused: tiles 0 and 1 must be out of them first
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (tile0 < total_tiles) v_write(0);
+        if (tile0 + g < total_tiles) v_write(1);
+      }
+      v_issue(tile0 + j * g, j & 1);
+    }
+    if (tile0 + 4 * g < total_tiles) v_hits(tile0 + 4 * g);
+
     int it = 0;
     if ((int)blockIdx.x < total_tiles) make_p(0);
 #pragma unroll 1
@@ -213,13 +296,21 @@ __global__ void __launch_bounds__(kFtThreads, 1)
           if (4 * part + cc < WR) dst[4 * part + cc] = make_float4(ov[4 * cc], ov[4 * cc + 1], ov[4 * cc + 2], ov[4 * cc + 3]);
       }
       if (warp == 0) HEPT_TRACE_EVENT(EV_E_OUT, it);
+      // ---- P V of this tile is done (ODONE): its value tiles are free -> write those of tile it + 2, refill the set -----
+      if (tile + 2 * g < total_tiles) {
+        asm volatile("cp.async.wait_group 1;" ::: "memory");     // rows of tile it + 2 have landed (it + 3 may be in flight)
+        v_write(it + 2);
+      }
+      v_issue(tile + 4 * g, it & 1);                             // hit[] holds tile it + 4
+      if (tile + 5 * g < total_tiles) v_hits(tile + 5 * g);
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
   } else if (warp < EW + PW) {
     // =========================================== producer warps =================================================
     umma::setmaxnreg_dec<kFtRegsProd>();
     const int ptid = tid - kFtEpiThreads, sub = ptid >> 3, c = ptid & 7;   // 8 lanes per row, RPP rows per pass
     int nk_idx[PASSES], nq_idx[PASSES], n0 = 0;
-    float4 xq[PASSES], xk[PASSES], xv[PASSES], ctr;
+    float4 xq[PASSES], xk[PASSES], ctr;
 
     auto load_indices = [&](int tile) {
       int h, t, blk;
@@ -260,21 +351,10 @@ __global__ void __launch_bounds__(kFtThreads, 1)
         if (c == 0 && r < B) s_qidx[(it & 7) * 128 + r] = nqq;
       }
     };
-    auto issue_v = [&](int tile) {
-      int h, t, blk;
-      decode(tile, h, t, blk);
-#pragma unroll
-      for (int ps = 0; ps < PASSES; ++ps) {
-        const int nkk = nk_idx[ps];
-        xv[ps] = (nkk >= 0 && c < VCH && nkk < raw_size) ? ldg4(v + ((size_t)nkk * H + h) * D + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    };
-
     int tile = blockIdx.x;
     if (tile < total_tiles) {
       load_indices(tile);
       issue_qk(tile, 0);
-      issue_v(tile);
       if (tile + (int)gridDim.x < total_tiles) load_indices(tile + gridDim.x);
     }
     int it = 0;
@@ -283,7 +363,6 @@ __global__ void __launch_bounds__(kFtThreads, 1)
       const int st = it & 1;
       const uint32_t ph = (it >> 1) & 1;
       uint8_t* km = smem + st * 4 * CF::TILE;
-      uint8_t* vm = smem + CF::OFF_V + st * 2 * CF::TILE;
       // ---- q^ / k^ tiles of this stage: free once the score MMAs of tile it - 2 are done ---------------------------
       if (it >= 2) umma::mbar_wait_parked(&mbar[QKFREE + st], ph ^ 1);
       if (warp == EW) HEPT_TRACE_EVENT(EV_P_QKFREE, it);
@@ -333,31 +412,8 @@ __global__ void __launch_bounds__(kFtThreads, 1)
       const int next = tile + gridDim.x;
       if (next < total_tiles) issue_qk(next, it + 1);
 
-      // ---- value tiles of this stage: free once the P V MMAs of tile it - 2 are done -------------------------------
-      if (it >= 2) umma::mbar_wait_parked(&mbar[VFREE + st], ph ^ 1);
-      if (warp == EW) HEPT_TRACE_EVENT(EV_P_VFREE, it);
-#pragma unroll
-      for (int ps = 0; ps < PASSES; ++ps) {
-        const int r = ps * RPP + sub;
-        if (r < B) {
-          float4 d = xv[ps], hi, lo;
-          if (c == VCH) d.x = 1.f;                     // ones column: O[:, D] = row sum of P
-          split4(d, hi, lo);
-          const uint32_t omn = umma::sw128b32_offset(r, c);
-          *reinterpret_cast<float4*>(vm + omn) = hi;
-          *reinterpret_cast<float4*>(vm + CF::TILE + omn) = lo;
-        }
-      }
-      umma::fence_async_smem();
-      __syncwarp();
-      if (lane == 0) umma::mbar_arrive(&mbar[VFULL + st]);
-      if (warp == EW) HEPT_TRACE_EVENT(EV_P_VFULL, it);
-
-      // ---- registers are free: put the next tile's loads in flight, fetch the indices of the one after -----------
-      if (next < total_tiles) {
-        issue_v(next);
-        if (next + (int)gridDim.x < total_tiles) load_indices(next + gridDim.x);
-      }
+      // ---- registers are free: fetch the indices of the tile after the next (its rows are already in flight) ------
+      if (next < total_tiles && next + (int)gridDim.x < total_tiles) load_indices(next + gridDim.x);
       if (warp == EW) HEPT_TRACE_EVENT(EV_P_ISSUED, it);
     }
   } else {
