@@ -185,10 +185,18 @@ __global__ void __launch_bounds__(kFtThreads, 1)
           umma::tmem_ld8_nowait(tS1 + lane_base + 8 * ch, rb);
           umma::tmem_wait_ld(ra, rb);
           float ph[8], pl[8];
+          // two elements per issue slot where the ISA has packed fp32 (add, fma: sm_100); same IEEE results per element
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const float x = fmaf(__uint_as_float(ra[u]) + __uint_as_float(rb[u]), kLog2e, nq2);
-            trunc_tf32(exp2_fast(fminf(x, 0.f)), ph[u], pl[u]);   // exp(min(S, 0)), example/hept.py:12
+          for (int u = 0; u < 8; u += 2) {
+            const float2 s2 = __fadd2_rn(make_float2(__uint_as_float(ra[u]), __uint_as_float(ra[u + 1])),
+                                         make_float2(__uint_as_float(rb[u]), __uint_as_float(rb[u + 1])));
+            const float2 x2 = __ffma2_rn(s2, make_float2(kLog2e, kLog2e), make_float2(nq2, nq2));
+            const float p0 = exp2_fast(fminf(x2.x, 0.f)), p1 = exp2_fast(fminf(x2.y, 0.f));   // exp(min(S, 0)), example/hept.py:12
+            ph[u] = __uint_as_float(__float_as_uint(p0) & 0xffffe000u);
+            ph[u + 1] = __uint_as_float(__float_as_uint(p1) & 0xffffe000u);
+            const float2 l2 = __ffma2_rn(make_float2(ph[u], ph[u + 1]), make_float2(-1.f, -1.f), make_float2(p0, p1));   // p - hi, exact
+            pl[u] = l2.x;
+            pl[u + 1] = l2.y;
           }
           umma::tmem_st8(tS0 + lane_base + 8 * ch, ph);
           umma::tmem_st8(tS1 + lane_base + 8 * ch, pl);
