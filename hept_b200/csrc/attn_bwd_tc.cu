@@ -7,11 +7,14 @@
 //   query side (TMEM lane = query i)                     key side (TMEM lane = key j)
 //   S   = Q^ K^^T            SS, N = NP                   S^T  = K^ Q^^T            SS (operands exchanged)
 //   dP  = G' V'^T            SS                           dP^T = V' G'^T            SS
-//   dS  = P dP  -> TMEM (hi, lo)                          P^T -> TMEM (hi, lo), dS^T kept in registers, then written
-//   dQ  = dS [K^ | 1]        TS, B = K^ MN-major          dV   = P^T G'             TS, B = G' MN-major   (TS products: N = 64,
-//                                                                                                            [hi | lo] tiles)
-//   dq^_i = dQ_i - rs_i q'_i                              dK   = dS^T [Q^ | 1]      TS (dS^T where dS was, once dQ is done)
+//   dS  = P dP  -> TMEM (hi, lo)                          P^T -> TMEM (hi, lo), dS^T kept in registers
+//   dQ  = dS [K^ | 1]        TS, B = K^ MN-major          dV   = P^T G'             TS, B = G' MN-major
+//   dq^_i = dQ_i - rs_i q'_i                              dK   = dS^T [Q^ | 1]      TS (dS^T written where dS was, once dQ is done)
 //                                                         dk^_j = dK_j - cs_j k'_j
+// The TS products are N = 64 MMAs over [hi | lo] operand tiles: per k-step A_hi meets [B_hi | B_lo] once (columns [0,32) =
+// hi*hi, [32,64) = hi*lo) and A_lo meets B_hi in an N = 32 MMA into the upper half; the epilogue adds the halves.
+// Order on the tensor pipe: dV (accumulator tO), dQ (accumulator over the P^T columns dV has consumed), dK (A = dS^T in
+// the dS columns, accumulator tO again once dv has been read out), then the next tile's scores.
 // The row / column sums rs_i = sum_j dS_ij, cs_j = sum_i dS_ij come out of the same MMAs (a ones column in the
 // MN-major operand), so they are the sums of exactly the (hi, lo) values that produced dQ / dK.
 // The reference's clamp(max=0) mask [S <= 0] on dS is not applied: S = -|q^ - k^|^2 / 2 is positive only by rounding,
@@ -24,11 +27,11 @@
 // Warp roles (640 threads = 5 warpgroups, register budgets rebalanced with setmaxnreg):
 //   warps 0-7   epilogue: TMEM lane = (warp & 3) * 32 + lane, columns split in two parts (warp >> 2)
 //   warps 8-15  producer: gather rows through the sort permutation (q^, k^ into registers, v and G' with cp.async into
-//               a staging buffer, all issued one tile ahead), centre, split, write the K-major operand tiles as soon
-//               as the previous tile's score MMAs have consumed theirs, copy them to the MN-major tiles once the
-//               previous tile's last MMA is done
-//   warp 16     one thread issues every tcgen05.mma (warps 17-19 only give their registers away); the next tile's score MMAs are issued as soon as their TMEM
-//               columns are free, so the tensor pipe runs under the epilogue of the current tile
+//               a staging buffer, all issued one tile ahead), centre, split, write the K-major operand tiles once the
+//               previous tile's dV is done (earlier would be legal, but the conversion and the TS MMAs contend for
+//               shared memory), copy them to the MN-major tiles once the previous tile's last MMA is done
+//   warp 16     one thread issues every tcgen05.mma (warps 17-19 only give their registers away); the next tile's
+//               score MMAs are issued as soon as their TMEM columns are free
 // Hand-offs are mbarriers (tcgen05.commit on the MMA side, one arrive per warp on the others); each completes once
 // per tile, so the wait parity is the tile counter's low bit.
 //

@@ -20,12 +20,14 @@
 // in fp32 (S0: cross terms + first half of the k-steps, S1: the rest).
 //
 // Warp roles (896 threads = 7 warpgroups, register budgets rebalanced with setmaxnreg):
-//   warps 0-7   epilogue (and the value operand: v rows via cp.async, split, MN-major value tiles of tile n+2): TMEM lane = (warp & 3) * 32 + lane, columns split in two parts (warp >> 2); software
+//   warps 0-7   epilogue: TMEM lane = (warp & 3) * 32 + lane, columns split in two parts (warp >> 2); software
 //               pipelined: P of tile n+1 is produced before the output rows of tile n are read and scattered, so the
-//               P V MMAs of tile n run under SIMT work
-//   warps 8-23  producer: gather rows through the sort permutation into registers (one tile ahead), centre, split,
-//               write the operand tiles of stage n & 1 (q^ / k^ K-major as soon as the score MMAs of tile n-2 are
-//               done, V MN-major once its P V MMAs are done)
+//               P V MMAs of tile n run under SIMT work.  The same warps own the value operand: raw v rows travel
+//               global -> shared with cp.async four tiles ahead, and right after O of tile n has been read out (its
+//               P V MMAs are done, so the value tiles of that stage are free) each thread splits its own chunks into
+//               the MN-major (hi, lo) value tiles of tile n+2
+//   warps 8-23  producer: gather q^ / k^ rows through the sort permutation into registers (one tile ahead), centre,
+//               split, write the K-major operand tiles of stage n & 1 as soon as the score MMAs of tile n-2 are done
 //   warp 24     one elected lane issues every tcgen05.mma: S(n+1), then P V(n)
 // TMEM: two tile slots of 256 columns (S0 | S1 | O).  Hand-offs are mbarriers that complete once per use of a slot /
 // stage, so the wait parity is bit 1 of the tile counter.
