@@ -303,6 +303,8 @@ __global__ void __launch_bounds__(kTlThreads, 4) out_linear_bwd_input_tiled_kern
   __syncthreads();
 #pragma unroll 1
   for (int i = 0; i < IN / 32; ++i) {
+    asm volatile("" ::: "memory");                 // keep the gradient rows in shared memory: hoisting their loads out of
+                                                   // this loop costs 96 registers (spills, one CTA less per SM)
     const int cg = c0 + 4 * i;
     float4 a0[4], a1[4];
 #pragma unroll
