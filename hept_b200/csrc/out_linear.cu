@@ -241,12 +241,14 @@ __global__ void __launch_bounds__(kTlThreads) out_linear_fwd_tiled_kernel(const 
     const int j = i / (IN / 4), c4 = i - j * (IN / 4);
     *reinterpret_cast<float4*>(s_w + j * WS + 4 * c4) = ldg4(w + (size_t)j * IN + 4 * c4);
   }
-  float acc[4][PER];
+  // packed fp32 FMAs (fma.rn.f32x2, sm_100): an accumulator pair holds the sums over the even and the odd k of a
+  // 16-byte chunk pair; two FMAs per issue slot, the halves are added at the end
+  float2 acc[4][PER];
 #pragma unroll
   for (int u = 0; u < PER; ++u) {
     const float bu = __ldg(b + og * PER + u);
 #pragma unroll
-    for (int t = 0; t < 4; ++t) acc[t][u] = bu;
+    for (int t = 0; t < 4; ++t) acc[t][u] = make_float2(bu, 0.f);
   }
 #pragma unroll 1
   for (int kc = 0; kc < NCH; ++kc) {
@@ -263,8 +265,10 @@ __global__ void __launch_bounds__(kTlThreads) out_linear_fwd_tiled_kernel(const 
       for (int u = 0; u < PER; ++u) {
         const float4 wv = *reinterpret_cast<const float4*>(ws + u * WS + 4 * c4);
 #pragma unroll
-        for (int t = 0; t < 4; ++t)
-          acc[t][u] = fmaf(xv[t].w, wv.w, fmaf(xv[t].z, wv.z, fmaf(xv[t].y, wv.y, fmaf(xv[t].x, wv.x, acc[t][u]))));
+        for (int t = 0; t < 4; ++t) {
+          acc[t][u] = __ffma2_rn(make_float2(xv[t].x, xv[t].y), make_float2(wv.x, wv.y), acc[t][u]);
+          acc[t][u] = __ffma2_rn(make_float2(xv[t].z, xv[t].w), make_float2(wv.z, wv.w), acc[t][u]);
+        }
       }
     }
     __syncthreads();
@@ -276,7 +280,8 @@ __global__ void __launch_bounds__(kTlThreads) out_linear_fwd_tiled_kernel(const 
     if (r < rows) {
       float2* dst = reinterpret_cast<float2*>(out + (size_t)(n0 + r) * OUT + og * PER);
 #pragma unroll
-      for (int u2 = 0; u2 < PER / 2; ++u2) dst[u2] = make_float2(acc[t][2 * u2], acc[t][2 * u2 + 1]);
+      for (int u2 = 0; u2 < PER / 2; ++u2)
+        dst[u2] = make_float2(acc[t][2 * u2].x + acc[t][2 * u2].y, acc[t][2 * u2 + 1].x + acc[t][2 * u2 + 1].y);
     }
   }
 }
@@ -321,8 +326,12 @@ __global__ void __launch_bounds__(kTlThreads, 4) out_linear_bwd_input_tiled_kern
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           const float gj = jj == 0 ? gv[t].x : (jj == 1 ? gv[t].y : (jj == 2 ? gv[t].z : gv[t].w));
-          a0[t].x = fmaf(gj, w0.x, a0[t].x); a0[t].y = fmaf(gj, w0.y, a0[t].y); a0[t].z = fmaf(gj, w0.z, a0[t].z); a0[t].w = fmaf(gj, w0.w, a0[t].w);
-          a1[t].x = fmaf(gj, w1.x, a1[t].x); a1[t].y = fmaf(gj, w1.y, a1[t].y); a1[t].z = fmaf(gj, w1.z, a1[t].z); a1[t].w = fmaf(gj, w1.w, a1[t].w);
+          const float2 g2 = make_float2(gj, gj);     // packed fp32 FMAs: two columns per issue slot, same sums per element
+          float2 r;
+          r = __ffma2_rn(g2, make_float2(w0.x, w0.y), make_float2(a0[t].x, a0[t].y)); a0[t].x = r.x; a0[t].y = r.y;
+          r = __ffma2_rn(g2, make_float2(w0.z, w0.w), make_float2(a0[t].z, a0[t].w)); a0[t].z = r.x; a0[t].w = r.y;
+          r = __ffma2_rn(g2, make_float2(w1.x, w1.y), make_float2(a1[t].x, a1[t].y)); a1[t].x = r.x; a1[t].y = r.y;
+          r = __ffma2_rn(g2, make_float2(w1.z, w1.w), make_float2(a1[t].z, a1[t].w)); a1[t].z = r.x; a1[t].w = r.y;
         }
       }
     }
@@ -351,12 +360,13 @@ __global__ void __launch_bounds__(kPgGroups * (OUT / 8) * (IN / 8), 2) out_linea
   extern __shared__ __align__(16) float s_dyn[];   // 2 x [ (kPgRows, XS) | (kPgRows, GS) ]
   const int tid = threadIdx.x, p = tid / PER, u = tid % PER;
   const int jt = u / CT, ct = u % CT;
-  float acc[8][8], bsum[8];
+  float2 acc[8][4];                                // 8 x 8 tile as column pairs: packed fp32 FMAs, two columns per issue slot
+  float bsum[8];
 #pragma unroll
   for (int a = 0; a < 8; ++a) {
     bsum[a] = 0.f;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) acc[a][c] = 0.f;
+    for (int c = 0; c < 4; ++c) acc[a][c] = make_float2(0.f, 0.f);
   }
   const int slabs = (N + kPgRows - 1) / kPgRows;
   auto load_slab = [&](int slab, int buf) {
@@ -393,11 +403,12 @@ __global__ void __launch_bounds__(kPgGroups * (OUT / 8) * (IN / 8), 2) out_linea
       const float4 g0 = *reinterpret_cast<const float4*>(gs + r * GS + 8 * jt), g1 = *reinterpret_cast<const float4*>(gs + r * GS + 8 * jt + 4);
       const float4 x0 = *reinterpret_cast<const float4*>(xs + r * XS + 8 * ct), x1 = *reinterpret_cast<const float4*>(xs + r * XS + 8 * ct + 4);
       const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-      const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+      const float2 xv[4] = {make_float2(x0.x, x0.y), make_float2(x0.z, x0.w), make_float2(x1.x, x1.y), make_float2(x1.z, x1.w)};
 #pragma unroll
       for (int a = 0; a < 8; ++a) {
+        const float2 g2 = make_float2(gv[a], gv[a]);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) acc[a][c] = fmaf(gv[a], xv[c], acc[a][c]);
+        for (int c = 0; c < 4; ++c) acc[a][c] = __ffma2_rn(g2, xv[c], acc[a][c]);
         bsum[a] += gv[a];                          // only the ct == 0 threads' sums are used
       }
     }
@@ -412,7 +423,10 @@ __global__ void __launch_bounds__(kPgGroups * (OUT / 8) * (IN / 8), 2) out_linea
       for (int a = 0; a < 8; ++a) {
         float* dst = s_acc + (8 * jt + a) * IN + 8 * ct;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) dst[c] = turn == 0 ? acc[a][c] : dst[c] + acc[a][c];
+        for (int c = 0; c < 4; ++c) {
+          dst[2 * c] = turn == 0 ? acc[a][c].x : dst[2 * c] + acc[a][c].x;
+          dst[2 * c + 1] = turn == 0 ? acc[a][c].y : dst[2 * c + 1] + acc[a][c].y;
+        }
         if (ct == 0) s_acc[OUT * IN + 8 * jt + a] = turn == 0 ? bsum[a] : s_acc[OUT * IN + 8 * jt + a] + bsum[a];
       }
     }
