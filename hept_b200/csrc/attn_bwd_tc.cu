@@ -732,9 +732,18 @@ __global__ void __launch_bounds__(256) bwd_table_sum_kernel(const float* __restr
       return;
     }
     float4 s = ldg4(in + src);
-    for (int t = 1; t < T; ++t) {   // table order, like the reference's sum over dim 0
-      const float4 x = ldg4(in + src + (size_t)t * D);
-      s.x += x.x; s.y += x.y; s.z += x.z; s.w += x.w;
+    if (T <= 4) {                   // every load in flight before the first add (T is a run-time value)
+      float4 x[3];
+#pragma unroll
+      for (int t = 1; t < 4; ++t) x[t - 1] = t < T ? ldg4(in + src + (size_t)t * D) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int t = 1; t < 4; ++t)   // table order, like the reference's sum over dim 0
+        if (t < T) { s.x += x[t - 1].x; s.y += x[t - 1].y; s.z += x[t - 1].z; s.w += x[t - 1].w; }
+    } else {
+      for (int t = 1; t < T; ++t) {
+        const float4 x = ldg4(in + src + (size_t)t * D);
+        s.x += x.x; s.y += x.y; s.z += x.z; s.w += x.w;
+      }
     }
     *reinterpret_cast<float4*>(out + dst) = s;
   };

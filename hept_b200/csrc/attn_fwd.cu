@@ -105,10 +105,27 @@ __global__ void __launch_bounds__(256) or_combine_kernel(const float* __restrict
   const float* rows = stage + ((size_t)h * N + n) * T * kStageRow;
   float4 num = make_float4(0.f, 0.f, 0.f, 0.f);
   float den = 0.f;
-  for (int t = 0; t < T; ++t) {  // sum over tables in table order, like Tensor.sum(dim=0)
-    const float4 x = ldg4(rows + t * kStageRow + 4 * c);
-    num.x += x.x; num.y += x.y; num.z += x.z; num.w += x.w;
-    den += __ldg(rows + t * kStageRow + D);
+  if (T <= 4) {   // every load in flight before the first add (T is a run-time value: the plain loop serialises them)
+    float4 x[4];
+    float dn[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      x[t] = t < T ? ldg4(rows + t * kStageRow + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      dn[t] = t < T ? __ldg(rows + t * kStageRow + D) : 0.f;
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {  // sum over tables in table order, like Tensor.sum(dim=0)
+      if (t < T) {
+        num.x += x[t].x; num.y += x[t].y; num.z += x[t].z; num.w += x[t].w;
+        den += dn[t];
+      }
+    }
+  } else {
+    for (int t = 0; t < T; ++t) {
+      const float4 x = ldg4(rows + t * kStageRow + 4 * c);
+      num.x += x.x; num.y += x.y; num.z += x.z; num.w += x.w;
+      den += __ldg(rows + t * kStageRow + D);
+    }
   }
   float4 y = make_float4(num.x / den, num.y / den, num.z / den, num.w / den);
   *reinterpret_cast<float4*>(out_pre + (n * H + h) * D + 4 * c) = y;
