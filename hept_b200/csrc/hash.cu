@@ -330,18 +330,26 @@ __global__ void __launch_bounds__(256, HPW == 1 ? 4 : 2) hash_project_v2_kernel(
   }
 }
 
-// span[th] = max - min over the per-CTA partials (first generation: ctas == 1, the atomically maintained pair)
-__global__ void finish_span_kernel(const uint32_t* __restrict__ partial, int ctas, int th, float* __restrict__ span) {
-  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (i >= th) return;
+// span[th] = max - min over the per-CTA partials (first generation: ctas == 1, the atomically maintained pair).
+// One CTA of 128 threads per (table, head).
+__global__ void __launch_bounds__(128) finish_span_kernel(const uint32_t* __restrict__ partial, int ctas, int th,
+                                                          float* __restrict__ span) {
+  __shared__ uint32_t s_lo[4], s_hi[4];
+  const int i = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t lo = 0xffffffffu, hi = 0u;
-  for (int b = lane; b < ctas; b += 32) {
+  for (int b = threadIdx.x; b < ctas; b += 128) {
     lo = min(lo, partial[((size_t)b * th + i) * 2 + 0]);
     hi = max(hi, partial[((size_t)b * th + i) * 2 + 1]);
   }
   lo = __reduce_min_sync(0xffffffffu, lo);
   hi = __reduce_max_sync(0xffffffffu, hi);
-  if (lane == 0) span[i] = __fsub_rn(from_ordered_bits(hi), from_ordered_bits(lo));
+  if (lane == 0) { s_lo[warp] = lo; s_hi[warp] = hi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    lo = min(min(s_lo[0], s_lo[1]), min(s_lo[2], s_lo[3]));
+    hi = max(max(s_hi[0], s_hi[1]), max(s_hi[2], s_hi[3]));
+    span[i] = __fsub_rn(from_ordered_bits(hi), from_ordered_bits(lo));
+  }
 }
 
 template <int D, int C, int T>
@@ -459,7 +467,7 @@ int hash_project_impl(const hept_shape* s, const float* q, const float* k, const
     }
   }
   if (rc) return rc;
-  finish_span_kernel<<<(th + 7) / 8, 256, 0, st>>>(ext, ctas, th, span);
+  finish_span_kernel<<<th, 128, 0, st>>>(ext, ctas, th, span);
   HEPT_CHECK_LAUNCH("finish_span");
   if (hat_done) *hat_done = fused && hat != nullptr;
   return HEPT_OK;
