@@ -158,3 +158,21 @@ def test_gradient_allreduce_two_ranks_gloo():
     for rank, gw, gb, nbytes in got:
         assert torch.allclose(gw, lin.weight.grad) and torch.allclose(gb, lin.bias.grad)
         assert nbytes == (15 + 3) * 4
+
+
+def test_trace_variant_of_the_library_builds():
+    """The pipeline timeline probe (csrc/trace.cuh, `make TRACE=1`) is compiled out of the product library; this keeps the
+    instrumented variant building (it exports the two setters tools/pipeline_trace.py binds)."""
+    import ctypes
+    import os
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    csrc = os.path.join(root, "hept_b200", "csrc")
+    subprocess.run(["make", "-C", csrc, f"-j{os.cpu_count() or 4}", "TRACE=1"], check=True, capture_output=True)
+    lib = ctypes.CDLL(os.path.join(root, "hept_b200", "libhept_sm100_trace.so"))
+    for name in ("hept_debug_trace_fwd", "hept_debug_trace_bwd", "hept_attention_fwd"):
+        assert hasattr(lib, name), name
+    from hept_b200 import _lib
+
+    assert not hasattr(_lib.load(), "hept_debug_trace_fwd"), "the product library must not carry the probe"
