@@ -70,7 +70,7 @@ def attention_problem(sizes, seed):
 
 results = []
 if world == 1:
-    for name, sizes in (("attention fwd+bwd, 60000 hits", [60000]), ("attention fwd+bwd, 61237 hits (padded to 61300)", [61237]),
+    for name, sizes in (("attention fwd+bwd, 6037 hits (tracking-6k)", [6037]), ("attention fwd+bwd, 60000 hits", [60000]), ("attention fwd+bwd, 61237 hits (padded to 61300)", [61237]),
                         ("attention fwd+bwd, 8 imbalanced events, 60187 hits", synthetic.event_sizes("batched-imbalanced"))):
         step, n = attention_problem(sizes, 3)
         ms = timeit(step)
@@ -105,5 +105,8 @@ results.append({"config": f"tracking Transformer training step, 60000 hits/rank,
                 "hits_per_s": world * 60000 / ms * 1e3, "allreduce_bytes": grad_bytes[0]})
 if rank == 0:
     print(json.dumps(results, indent=1))
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open(f"gpurun_out/configs_{world}gpu.json", "w") as f:
+        json.dump(results, f, indent=1)
 if world > 1:
     dist.destroy_process_group()
