@@ -167,6 +167,13 @@ def run_ours(args):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    try:   # pin this rank to the CPUs next to its GPU before any pinned host buffer exists: with 8 ranks the H2D copies of the
+        import pynvml   # e2e leg otherwise cross the socket interconnect
+
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
+    except Exception:
+        pass
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
