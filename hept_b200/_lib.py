@@ -53,6 +53,8 @@ SIGNATURES = {
     "hept_set_engine": (None, [C.c_int]),
     "hept_get_engine": (C.c_int, []),
     "hept_set_bwd_variant": (None, [C.c_int]),
+    "hept_set_sort_variant": (None, [C.c_int]),
+    "hept_get_sort_variant": (C.c_int, []),
     "hept_get_bwd_variant": (C.c_int, []),
     "hept_debug_umma_selftest": (C.c_int, [_p, _p, _p, _p, _p, C.c_int, _p]),
     "hept_debug_umma_symmetry": (C.c_int, [_p, _p, _p, _p, _p]),

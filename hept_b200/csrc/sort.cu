@@ -8,7 +8,17 @@
 // combined by exclusive prefix sums in index order.  Equal keys therefore keep ascending original index,
 // the tie-break the oracle pins (torch.argsort(stable=True)).  The tile is reordered in shared memory
 // first so that the global writes of a digit run are contiguous.
+//
+// Segments that fit the shared memory of one thread-block cluster take the cluster-resident path below instead: one
+// global read of the keys, four passes through distributed shared memory, one global write of the positions.
+#include <cooperative_groups.h>
+
+#include <atomic>
+#include <cstdlib>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace hept {
 
@@ -189,6 +199,147 @@ __global__ void __launch_bounds__(kSortThreads, HEPT_SORT_BLOCKS) radix_scatter_
   }
 }
 
+// ---- cluster-resident path --------------------------------------------------------------------------------------
+// One cluster of `cs` CTAs per segment; CTA r keeps slots [r * cap, (r + 1) * cap) of the segment's current order (keys and
+// original indices) in its shared memory.  A pass counts digits per warp (ballots, as above), publishes the CTA's digit
+// totals, reads the totals of the whole cluster through DSMEM after a cluster barrier, and scatters every (key, index)
+// straight into the slot it belongs to in the shared memory of the CTA that owns that slot.  Order inside a CTA is
+// warp run, then iteration, then lane; CTAs are combined in rank order: the same stable order as the global path.
+#ifndef HEPT_CS_THREADS
+#define HEPT_CS_THREADS 512
+#endif
+constexpr int kCsThreads = HEPT_CS_THREADS;
+constexpr int kCsWarps = kCsThreads / 32;
+constexpr int kCsMaxCap = 12288;   // slots per CTA: 4 buffers x 4 B x cap + 17.5 KB of counters <= 227 KB
+
+static size_t cluster_sort_smem(int cap) { return (size_t)cap * 16 + (size_t)(kCsWarps * kRadix + kRadix + 32) * 4; }
+
+__global__ void __launch_bounds__(kCsThreads, 1) cluster_sort_kernel(const float* __restrict__ keys, int n, int cap,
+                                                                      int32_t* __restrict__ positions) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int cs = (int)cluster.num_blocks(), r = (int)cluster.block_rank();
+  const int seg = blockIdx.x / cs;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  extern __shared__ __align__(16) uint8_t smem[];
+  // two (keys, indices) orders: order b lives at kbuf + b * cap, ibuf + b * cap
+  uint32_t* kbuf = reinterpret_cast<uint32_t*>(smem);
+  int32_t* ibuf = reinterpret_cast<int32_t*>(kbuf + 2 * cap);
+  uint32_t (*warp_off)[kRadix] = reinterpret_cast<uint32_t (*)[kRadix]>(ibuf + 2 * cap);
+  uint32_t* hist_pub = &warp_off[kCsWarps - 1][kRadix - 1] + 1;   // digit totals of this CTA, read by the whole cluster
+  uint32_t* scan_tmp = hist_pub + kRadix;
+  const size_t base = (size_t)seg * n;
+  const int lo = r * cap;
+  const int cnt = max(0, min(cap, n - lo));
+  for (int e = tid; e < cnt; e += kCsThreads) {
+    kbuf[e] = ordered_bits(keys[base + lo + e]);
+    ibuf[e] = lo + e;
+  }
+  // contiguous run of every warp, a multiple of 32 long
+  const int per = (((cnt + kCsWarps - 1) / kCsWarps) + 31) & ~31;
+  const int wlo = min(cnt, warp * per), whi = min(cnt, wlo + per);
+  int cur = 0;
+#pragma unroll 1
+  for (int shift = 0; shift < 32; shift += kRadixBits) {
+    const uint32_t* ck = kbuf + cur * cap;
+    const int32_t* ci = ibuf + cur * cap;
+    for (int d = tid; d < kCsWarps * kRadix; d += kCsThreads) (&warp_off[0][0])[d] = 0;
+    __syncthreads();
+    // (1) digit counts of every warp's run
+#pragma unroll 1
+    for (int e0 = wlo; e0 < whi; e0 += 32) {
+      const int e = e0 + lane;
+      const bool ok = e < whi;
+      const uint32_t dg = ok ? (ck[e] >> shift) & (kRadix - 1) : 0u;
+      const uint32_t peers = same_digit_lanes(dg, ok);
+      if (ok && lane == __ffs(peers) - 1) warp_off[warp][dg] += __popc(peers);
+      __syncwarp();
+    }
+    __syncthreads();
+    // (2) exclusive prefix over the warps, CTA totals published for the cluster
+    if (tid < kRadix) {
+      uint32_t run = 0;
+#pragma unroll
+      for (int w = 0; w < kCsWarps; ++w) {
+        const uint32_t c = warp_off[w][tid];
+        warp_off[w][tid] = run;
+        run += c;
+      }
+      hist_pub[tid] = run;
+    }
+    cluster.sync();
+    // (3) digit `tid`: count in the whole segment and in the CTAs before this one; exclusive scan over the digits
+    uint32_t total = 0, before = 0;
+    if (tid < kRadix) {
+      for (int q = 0; q < cs; ++q) {
+        const uint32_t c = *cluster.map_shared_rank(hist_pub + tid, q);
+        total += c;
+        before += q < r ? c : 0u;
+      }
+    }
+    uint32_t inc = total;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const uint32_t a = __shfl_up_sync(0xffffffffu, inc, off);
+      if (lane >= off) inc += a;
+    }
+    if (lane == 31) scan_tmp[warp] = inc;
+    __syncthreads();
+    if (tid < kRadix) {
+      uint32_t pre = 0;
+#pragma unroll
+      for (int w = 0; w < kRadix / 32; ++w) pre += w < warp ? scan_tmp[w] : 0u;
+      const uint32_t first = pre + inc - total + before;     // slot of this CTA's first key with digit `tid`
+#pragma unroll
+      for (int w = 0; w < kCsWarps; ++w) warp_off[w][tid] += first;
+    }
+    __syncthreads();
+    // (4) rank in the same order; every (key, index) goes to the CTA that owns its slot
+    uint32_t* nk = kbuf + (cur ^ 1) * cap;
+    int32_t* ni = ibuf + (cur ^ 1) * cap;
+#pragma unroll 1
+    for (int e0 = wlo; e0 < whi; e0 += 32) {
+      const int e = e0 + lane;
+      const bool ok = e < whi;
+      const uint32_t key = ok ? ck[e] : 0u;
+      const int32_t idx = ok ? ci[e] : 0;
+      const uint32_t dg = (key >> shift) & (kRadix - 1);
+      const uint32_t peers = same_digit_lanes(ok ? dg : 0u, ok);
+      const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+      uint32_t pos = 0;
+      if (ok) pos = warp_off[warp][dg] + rank;
+      __syncwarp();
+      if (ok && lane == __ffs(peers) - 1) warp_off[warp][dg] += __popc(peers);
+      __syncwarp();
+      if (ok) {
+        const uint32_t q = pos / (uint32_t)cap, off = pos - q * (uint32_t)cap;
+        *cluster.map_shared_rank(nk + off, q) = key;
+        *cluster.map_shared_rank(ni + off, q) = idx;
+      }
+    }
+    cluster.sync();     // every slot of the next order is written; nobody reads the old order any more
+    cur ^= 1;
+  }
+  for (int e = tid; e < cnt; e += kCsThreads) positions[base + lo + e] = ibuf[cur * cap + e];
+}
+
+// process-wide: 0 = cluster-resident path when the segment fits (default), 1 = global passes always
+static std::atomic<int> g_sort_variant{0};
+
+// cluster size for `segments` sorts of n keys, or 0 when the global passes take them.  Measured on B200 with 48 segments
+// (us, cluster / global): n = 1 300: 21 / 51, 6 100: 32 / 54, 12 000: 47 / 58, 20 000: 71 / 69, 60 000: 200 / 128 -- both
+// paths spend ~3 SM cycles per key and pass on ranking; the cluster path saves the seven extra launches and the
+// histogram reads, which is what short segments are made of, and loses once its clusters no longer fit one wave.
+// HEPT_SORT_CLUSTER=cs forces a cluster size (experiments), HEPT_SORT_CLUSTER=-1 the global passes.
+static int cluster_size_for(int segments, int n) {
+  static const int forced = [] { const char* e = getenv("HEPT_SORT_CLUSTER"); return e ? atoi(e) : 0; }();
+  if (g_sort_variant.load(std::memory_order_relaxed) == 1 || forced < 0) return 0;
+  const int need = (n + kCsMaxCap - 1) / kCsMaxCap;
+  if (forced > 0) return need > 8 ? 0 : max(min(forced, 8), need);
+  if (n > 16384) return 0;
+  const int cs = n <= 2048 ? 1 : 2;
+  return (long long)segments * cs <= 2 * 148 ? cs : 0;
+}
+
 struct SortPlan {
   int tiles;
   size_t hist_bytes, keys_bytes, idx_bytes, total;
@@ -208,6 +359,9 @@ static SortPlan plan_sort(int segments, int n) {
 
 using namespace hept;
 
+extern "C" void hept_set_sort_variant(int variant) { g_sort_variant.store(variant == 1 ? 1 : 0, std::memory_order_relaxed); }
+extern "C" int hept_get_sort_variant(void) { return g_sort_variant.load(std::memory_order_relaxed); }
+
 extern "C" size_t hept_argsort_workspace_bytes(int32_t num_segments, int32_t n) {
   if (num_segments <= 0 || n <= 0) return 0;
   return plan_sort(num_segments, n).total;
@@ -222,6 +376,34 @@ extern "C" int hept_segmented_argsort(const float* keys, int32_t num_segments, i
                p.total, workspace_bytes);
   HEPT_REQUIRE(num_segments <= 65535, HEPT_EINVAL, "segmented_argsort: too many segments (%d)", num_segments);
   cudaStream_t st = (cudaStream_t)stream;
+  if (const int cs = cluster_size_for(num_segments, n)) {
+    const int cap = (n + cs - 1) / cs;
+    const size_t smem = cluster_sort_smem(cap);
+    static std::atomic<size_t> opted{0};
+    if (opted.load() < smem) {
+      HEPT_REQUIRE(cudaFuncSetAttribute(cluster_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cluster_sort_smem(kCsMaxCap)) == cudaSuccess,
+                   HEPT_ECUDA, "segmented_argsort: cannot opt in to %zu bytes of shared memory", cluster_sort_smem(kCsMaxCap));
+      opted.store(cluster_sort_smem(kCsMaxCap));
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)num_segments * cs);
+    cfg.blockDim = dim3(kCsThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, cluster_sort_kernel, keys, (int)n, cap, positions);
+    if (e == cudaSuccess) {
+      count_launch(1);
+      return HEPT_OK;
+    }
+    (void)cudaGetLastError();     // a cluster shape this device cannot place: the global passes take it
+  }
   char* w = (char*)workspace;
   uint32_t* hist = (uint32_t*)w;            w += p.hist_bytes;
   uint32_t* kbuf[2] = {(uint32_t*)w, (uint32_t*)(w + p.keys_bytes)};  w += 2 * p.keys_bytes;

@@ -148,6 +148,12 @@ void hept_set_bwd_stage_mask(int mask);
 void hept_set_engine(int engine);
 int hept_get_engine(void);
 
+/* a7 segmented argsort: 0 = cluster-resident sort (one thread-block cluster per segment, passes through distributed
+ * shared memory) whenever a segment fits, global passes otherwise (default); 1 = global passes always.  Process-wide;
+ * both produce the same positions. */
+void hept_set_sort_variant(int variant);
+int hept_get_sort_variant(void);
+
 /* backward tile kernels: 1 = one lane per row (attn_bwd.cu), 2 = lane pairs + packed FFMA2 (attn_bwd2.cu). */
 void hept_set_bwd_variant(int variant);
 int hept_get_bwd_variant(void);

@@ -191,9 +191,44 @@ def test_projection_span_keys(name):
     assert float((keys.cpu()[fin] - kref[fin]).abs().max()) <= 1e-5 * float(scale_k)
 
 
-@pytest.mark.parametrize("segs,n", [(1, 1), (3, 31), (2, 4096), (5, 4097), (48, 6100), (4, 70001)])
-def test_segmented_argsort_is_stable_argsort(segs, n):
-    from hept_b200 import ops
+@pytest.mark.parametrize("variant", [0, 1], ids=["cluster", "global"])
+@pytest.mark.parametrize("segs,n", [(1, 1), (3, 31), (2, 4096), (5, 4097), (48, 6100), (4, 70001), (48, 60000), (7, 12289),
+                                    (2, 98304), (1, 98305), (200, 1500)])
+def test_segmented_argsort_is_stable_argsort(segs, n, variant):
+    """Both sorts (cluster-resident through distributed shared memory, and the global passes that take segments too long
+    for a cluster) against torch's stable argsort, bit for bit."""
+    from hept_b200 import _lib, ops
+
+    lib = _lib.load()
+    lib.hept_set_sort_variant(variant)
+    try:
+        _check_segmented_argsort(ops, segs, n)
+    finally:
+        lib.hept_set_sort_variant(0)
+
+
+@pytest.mark.parametrize("cs,segs,n", [(3, 5, 30001), (5, 8, 60000), (8, 3, 98304), (7, 2, 1000)])
+def test_cluster_sort_at_forced_cluster_sizes(cs, segs, n):
+    """The cluster-resident sort at cluster sizes the dispatch rule does not pick by itself (HEPT_SORT_CLUSTER is read
+    once per process, hence the child process)."""
+    import subprocess
+    import sys
+
+    code = (
+        "import torch; from hept_b200 import ops\n"
+        f"g = torch.Generator().manual_seed({cs * 7 + n})\n"
+        f"keys = torch.randn({segs}, {n}, generator=g) * 1e3\n"
+        "keys[:, ::3] = torch.round(keys[:, ::3])\n"
+        "pos = ops.segmented_argsort(keys.cuda())\n"
+        "assert torch.equal(pos.cpu().long(), torch.argsort(keys, dim=-1, stable=True))\n"
+        "print('sorted')\n")
+    env = dict(os.environ, HEPT_SORT_CLUSTER=str(cs))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "sorted" in r.stdout, r.stderr[-2000:]
+
+
+def _check_segmented_argsort(ops, segs, n):
 
     g = torch.Generator().manual_seed(segs * 100003 + n)
     keys = torch.randn(segs, n, generator=g) * 1e3
