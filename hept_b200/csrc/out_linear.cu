@@ -436,23 +436,35 @@ __global__ void __launch_bounds__(kPgGroups * (OUT / 8) * (IN / 8), 2) out_linea
   for (int i = tid; i < OUT * IN + OUT; i += THREADS) dstp[i] = s_acc[i];
 }
 
-// Stage 2: fixed-order sum over CTAs.  A CTA of 256 threads = 32 entries of (OUT + 1, IN) x 8 parts; part p sums the
-// partials p, p + 8, ... in order, then the eight sums are added in order.  Entries [OUT][OUT..IN) are unused.
-__global__ void __launch_bounds__(256) out_linear_reduce_kernel(const float* __restrict__ partial, int ctas, int OUT, int IN,
-                                                                float* __restrict__ dw, float* __restrict__ db) {
-  __shared__ float red[8][32];
+// Stage 2: fixed-order sum over CTAs.  A CTA of 512 threads = 32 entries of (OUT + 1, IN) x 16 parts; part p sums the
+// partials p, p + 16, ... in order (eight loads in flight ahead of the adds), then the sixteen sums are added in order.
+// Entries [OUT][OUT..IN) are unused.
+constexpr int kOlParts = 16;
+__global__ void __launch_bounds__(32 * kOlParts) out_linear_reduce_kernel(const float* __restrict__ partial, int ctas, int OUT,
+                                                                          int IN, float* __restrict__ dw, float* __restrict__ db) {
+  __shared__ float red[kOlParts][32];
   const int e = threadIdx.x & 31, part = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + e;
   const int entries = (OUT + 1) * IN;
   float s = 0.f;
-  if (i < entries)
-    for (int b = part; b < ctas; b += 8) s += partial[(size_t)b * entries + i];
+  if (i < entries) {
+    const float* src = partial + i;
+    int b = part;
+    for (; b + 7 * kOlParts < ctas; b += 8 * kOlParts) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = src[(size_t)(b + u * kOlParts) * entries];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s += v[u];
+    }
+    for (; b < ctas; b += kOlParts) s += src[(size_t)b * entries];
+  }
   red[part][e] = s;
   __syncthreads();
   if (part == 0 && i < entries) {
     float t = red[0][e];
 #pragma unroll
-    for (int p = 1; p < 8; ++p) t += red[p][e];
+    for (int p = 1; p < kOlParts; ++p) t += red[p][e];
     const int j = i / IN, c = i - j * IN;
     if (j < OUT) dw[i] = t;
     else if (c < OUT) db[c] = t;
@@ -562,7 +574,7 @@ static int launch_ol_bwd(const hept_shape* s, const float* g, const float* w, co
   }
   HEPT_CHECK_LAUNCH("out_linear_bwd_params");
   const int entries = (OUT + 1) * IN;
-  out_linear_reduce_kernel<<<(entries + 31) / 32, 256, 0, st>>>(partial, ctas, OUT, IN, dw, db);
+  out_linear_reduce_kernel<<<(entries + 31) / 32, 32 * kOlParts, 0, st>>>(partial, ctas, OUT, IN, dw, db);
   HEPT_CHECK_LAUNCH("out_linear_reduce");
   return HEPT_OK;
 }
