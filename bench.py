@@ -362,7 +362,7 @@ def kernel_roofline(resident, gouts, cfg, mod, w_rpe, peak, peak_src, n_sets):
              "block_attn_bwd_tc": 2 * T * H * B * (2 * (D + C) + 2 * D + 2 * (D + C) + D)}   # both sides recompute S and dP
     times = {}
     times["block_attn_fwd"] = ev_time(lambda i: ops.block_attention_fwd(d, *saved[i % n_sets][:6]))
-    if variant == 3:
+    if variant >= 3:
         lib.hept_set_bwd_stage_mask(3)
         t_all = ev_time(lambda i: ops.attention_bwd(d, *saved[i % n_sets]))
         lib.hept_set_bwd_stage_mask(7)
@@ -386,7 +386,7 @@ def kernel_roofline(resident, gouts, cfg, mod, w_rpe, peak, peak_src, n_sets):
                  "block_attn_bwd_tc": "block_attn_bwd_tc_kernel"}
         if names[top] in tj:
             traffic, tsrc = tj[names[top]]["dram_bytes_per_launch"], "profiles/r1c_traffic.json (" + tj[names[top]]["source"] + ")"
-    tensor = variant == 3 or lib.hept_get_engine()
+    tensor = variant >= 3 or lib.hept_get_engine()
     return {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": traffic, "traffic_source": tsrc, "peak_source": peak_src, "bytes_per_launch": per_hit[top] * N_RAW,
             "kernel_ms": {k: v * 1e3 for k, v in times.items()},

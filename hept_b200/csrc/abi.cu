@@ -56,7 +56,7 @@ extern "C" int hept_launch_count(int reset) {
 extern "C" void hept_set_bwd_stage_mask(int mask) { g_bwd_mask = mask & 7; }
 extern "C" void hept_set_engine(int engine) { g_engine = engine ? 1 : 0; }
 extern "C" int hept_get_engine(void) { return g_engine; }
-extern "C" void hept_set_bwd_variant(int variant) { g_bwd_variant = (variant == 2 || variant == 3) ? variant : 1; }
+extern "C" void hept_set_bwd_variant(int variant) { g_bwd_variant = (variant >= 2 && variant <= 5) ? variant : 1; }
 extern "C" int hept_get_bwd_variant(void) { return g_bwd_variant; }
 
 extern "C" size_t hept_attention_fwd_workspace_bytes(const hept_shape* s) {

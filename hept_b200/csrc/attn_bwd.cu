@@ -367,7 +367,7 @@ extern "C" int hept_block_attention_bwd(const hept_shape* s, const float* q, con
                "block_attention_bwd: workspace needs %zu bytes", hept_attention_bwd_workspace_bytes(s));
   cudaStream_t st = (cudaStream_t)stream;
   char* ws = (char*)workspace;
-  if (bwd_variant() == 3)
+  if (bwd_variant() >= 3)
     return block_attention_bwd_tc(s, q, k, v, coords, scale, positions, out_pre, den_sum, d_out_pre, dq, dk, dv, dscale, ws, st);
   if (s->D == 24 && s->C == 6 && s->B == 100)
     return launch_bwd<24, 6, 100, 5, 1, 3, 1>(s, q, k, v, coords, scale, positions, out_pre, den_sum, d_out_pre, dq, dk, dv, dscale, ws, st);

@@ -79,7 +79,10 @@ struct TcBwd {
   // aux words: nq2[2][128], qidx[3][128], kidx[3][128], dsc[8][8]
   static constexpr int AUX_BYTES = (8 * 128 + 64) * 4;
   static constexpr int TOTAL = OFF_AUX + AUX_BYTES;
-  static constexpr int TMEM_NEED = 4 * NP + 64;
+  // dQ accumulates over 64 columns from the start of the P^T region (2 NP): the dV / dK accumulator must start past it, or
+  // dQ lands on dV before the epilogue has read it (NP < 32, i.e. blocks of at most 16 hits)
+  static constexpr int O_COL = 4 * NP > 2 * NP + 64 ? 4 * NP : 2 * NP + 64;
+  static constexpr int TMEM_NEED = O_COL + 64;
   static constexpr int TMEM_COLS = pow2_cols(TMEM_NEED);
   static_assert(E % 2 == 0 && E + 2 <= 32 && D + 1 <= 32 && D % 4 == 0, "row shapes");
   static_assert(B <= 128 && NP <= 128 && TMEM_NEED <= 512, "tile shape");
@@ -145,13 +148,13 @@ __global__ void __launch_bounds__(256) grad_rows_kernel(const float* __restrict_
 // ---------------------------------------------------------------------------------------------------------------
 // the tile kernel
 // ---------------------------------------------------------------------------------------------------------------
-template <int D, int C, int B>
+template <int D, int C, int B, bool DIRECT>
 __global__ void __launch_bounds__(kBtThreads, 1)
     block_attn_bwd_tc_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
                              const float* __restrict__ hatc, const float* __restrict__ grows,
                              const int32_t* __restrict__ positions, int N, int H, int T, int raw_size, int total_tiles,
                              TileDecoder dec, float* __restrict__ stage_dq, float* __restrict__ stage_dk, float* __restrict__ stage_dv,
-                             float* __restrict__ ds_partial) {
+                             float* __restrict__ ds_partial, int* __restrict__ done) {
   using CF = TcBwd<D, C, B>;
   constexpr int E = CF::E, NP = CF::NP, KSTEPS = CF::KSTEPS, VCH = CF::VCH, PASSES = CF::PASSES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -207,7 +210,7 @@ __global__ void __launch_bounds__(kBtThreads, 1)
   __syncthreads();
   umma::fence_after_sync();
   const uint32_t tmem = tmem_slot;
-  const uint32_t tS = tmem, tDP = tmem + NP, tST = tmem + 2 * NP, tDPT = tmem + 3 * NP, tO = tmem + 4 * NP;
+  const uint32_t tS = tmem, tDP = tmem + NP, tST = tmem + 2 * NP, tDPT = tmem + 3 * NP, tO = tmem + CF::O_COL;
   const uint32_t sbase = umma::smem_u32(smem), mbase = sbase + CF::OFF_MN;
 
   // tiles are ordered (head, table, block): the CTAs of a wave work on one head's rows, which stay in L2
@@ -235,6 +238,7 @@ __global__ void __launch_bounds__(kBtThreads, 1)
 #pragma unroll
     for (int cc = 0; cc < C; ++cc) dsc[cc] = 0.f;
     int dsc_head = -1;
+    int pend = -1, grp_tiles = 0, ready = -1, cur_grp = -1;   // DIRECT: see below
     auto flush_dscale = [&]() {
       if (dsc_head < 0) return;
 #pragma unroll
@@ -246,13 +250,29 @@ __global__ void __launch_bounds__(kBtThreads, 1)
         dsc[cc] = 0.f;
       }
       umma::bar_sync(1, kBtEpiThreads);
+      if (DIRECT && tid == 0 && pend >= 0)               // every epilogue warp has issued the rows of the finished group
+        asm volatile("red.release.gpu.global.add.s32 [%0], %1;" :: "l"(done + pend), "r"(grp_tiles) : "memory");
+      grp_tiles = 0;
       if (tid < C) {
         float x = 0.f;
 #pragma unroll
         for (int w = 0; w < EW; ++w) x += s_dsc[w * 8 + tid];
-        ds_partial[((size_t)blockIdx.x * H + dsc_head) * 8 + tid] = x;
+        float* dst = ds_partial + ((size_t)blockIdx.x * H + dsc_head) * 8 + tid;
+        *dst = DIRECT ? *dst + x : x;                    // paired order: a head comes back T times (the buffer starts at zero)
       }
       umma::bar_sync(1, kBtEpiThreads);                  // s_dsc may be rewritten
+    };
+    // DIRECT: rows go straight into dq / dk / dv (n, h, D): table 0 stores, later tables add (16-byte vector atomics), so
+    // the per-table staging rows and the kernel that sums them are gone.  Order of the adds = table order, enforced, so
+    // the sums are the same bits every run and the same as the staged sum: when a CTA leaves a (table, head) group -- with
+    // the paired tile order that is where flush_dscale already synchronises the epilogue warps -- one thread adds the CTA's
+    // number of tiles of the group to done[t * H + h] with release semantics (the barrier orders the other warps' rows
+    // before it; a fence per warp and tile instead costs 10 % of the kernel, a __threadfence per lane 40 %), and a tile of
+    // table t >= 1 writes its first row once done[(t - 1) * H + h] has reached the group's nb tiles.  That group ended a
+    // whole group ago, so with groups of at least two waves of tiles nobody ever waits.
+    auto put_chunk = [&](float4* dst, const float4 x, bool live, int t_) {
+      if (!DIRECT || t_ == 0) *dst = live ? x : make_float4(0.f, 0.f, 0.f, 0.f);
+      else if (live) atomicAdd(dst, x);
     };
     int it = 0;
 #pragma unroll 1
@@ -325,9 +345,12 @@ __global__ void __launch_bounds__(kBtThreads, 1)
       arrive_tmem(DSRDY);
       if (warp == 0) HEPT_TRACE_EVENT(BE_DSRDY, it);
 
-      if (h != dsc_head) {   // first tile of another head: hand in the finished head's sums
+      // first tile of another head (DIRECT: of another (table, head) group -- a CTA that skips groups can come back to the
+      // same head): hand in the finished group's sums and, DIRECT, its tile count
+      if (DIRECT ? t * H + h != cur_grp : h != dsc_head) {
         flush_dscale();
         dsc_head = h;
+        cur_grp = t * H + h;
       }
       // x'_e (e in this thread's 16 columns) of row `row` of an MN-major (hi, lo) tile pair: hi + lo is exact
       auto centred_row = [&](int th_, int tl_, float (&xr)[16]) {
@@ -345,10 +368,12 @@ __global__ void __launch_bounds__(kBtThreads, 1)
 #pragma unroll
         for (int u = 0; u < 16; ++u) o[u] = fmaf(-sum, xr[u], acc[u]);
         if (n >= 0) {
-          float4* dst = reinterpret_cast<float4*>(stage + (((size_t)h * N + n) * T + t) * D);
+          float4* dst = reinterpret_cast<float4*>(stage + (DIRECT ? ((size_t)n * H + h) * D : (((size_t)h * N + n) * T + t) * D));
+          const bool live = !DIRECT || n < raw_size;
 #pragma unroll
           for (int cc = 0; cc < 4; ++cc)
-            if (4 * (4 * part + cc) < D) dst[4 * part + cc] = make_float4(o[4 * cc], o[4 * cc + 1], o[4 * cc + 2], o[4 * cc + 3]);
+            if (4 * (4 * part + cc) < D)
+              put_chunk(dst + 4 * part + cc, make_float4(o[4 * cc], o[4 * cc + 1], o[4 * cc + 2], o[4 * cc + 3]), live, t);
 #pragma unroll
           for (int cc = 0; cc < C; ++cc)     // coordinate column D + cc lives in part (D + cc) / 16 (part is warp-uniform)
             if (part == (D + cc) / 16) dsc[cc] = fmaf(xr[(D + cc) % 16], o[(D + cc) % 16], dsc[cc]);
@@ -368,15 +393,37 @@ __global__ void __launch_bounds__(kBtThreads, 1)
       umma::mbar_wait(&mbar[DVDONE], ph);
       umma::fence_after_sync();
       if (warp == 0) HEPT_TRACE_EVENT(BE_DVDONE, it);
+      if (DIRECT) {
+        if (t > 0 && ready != (t - 1) * H + h) {         // the rows of table t - 1 of this head are all in place?
+          ready = (t - 1) * H + h;
+          const int want = (int)decode.nb;
+          if (lane == 0) {
+            // poll relaxed (an acquire load invalidates the SM's L1 every time), acquire once the count is there
+            auto count = [&]() {
+              int c;
+              asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(c) : "l"(done + ready) : "memory");
+              return c;
+            };
+            int spins = 0;
+            while (count() < want && ++spins < (1 << 24)) __nanosleep(32);
+            int c;
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(c) : "l"(done + ready) : "memory");
+            if (c < want) __trap();                      // a second of waiting: the launch is broken, do not add out of order
+          }
+          __syncwarp();                                  // the other lanes' adds are ordered after lane 0's acquire
+        }
+      }
       {
         float acc[16];
         ld_acc(tO, acc);
         const int n = row < B ? kidx[row] : -1;
         if (n >= 0) {
-          float4* dst = reinterpret_cast<float4*>(stage_dv + (((size_t)h * N + n) * T + t) * D);
+          float4* dst = reinterpret_cast<float4*>(stage_dv + (DIRECT ? ((size_t)n * H + h) * D : (((size_t)h * N + n) * T + t) * D));
+          const bool live = !DIRECT || n < raw_size;
 #pragma unroll
           for (int cc = 0; cc < 4; ++cc)
-            if (4 * (4 * part + cc) < D) dst[4 * part + cc] = make_float4(acc[4 * cc], acc[4 * cc + 1], acc[4 * cc + 2], acc[4 * cc + 3]);
+            if (4 * (4 * part + cc) < D)
+              put_chunk(dst + 4 * part + cc, make_float4(acc[4 * cc], acc[4 * cc + 1], acc[4 * cc + 2], acc[4 * cc + 3]), live, t);
         }
       }
       if (warp == 0) HEPT_TRACE_EVENT(BE_DVOUT, it);
@@ -426,6 +473,18 @@ __global__ void __launch_bounds__(kBtThreads, 1)
       umma::fence_before_sync();                         // the TMEM loads above precede the next tile's MMAs into tO
       __syncwarp();
       if (lane == 0) umma::mbar_arrive(&mbar[MFREE]);    // this warp is done with the MN-major tiles
+      if (DIRECT) {
+        pend = t + 1 < T ? t * H + h : -1;               // the last table's count is never read
+        ++grp_tiles;
+        // last tile of this CTA in the group: hand the count in now rather than at the next group's first tile
+        int hn = -1, tn = 0, bn;
+        if (tile + (int)gridDim.x < total_tiles) decode(tile + (int)gridDim.x, hn, tn, bn);
+        if (hn < 0 || tn * H + hn != cur_grp) {
+          flush_dscale();
+          dsc_head = hn;
+          cur_grp = tn * H + hn;
+        }
+      }
       if (warp == 0) HEPT_TRACE_EVENT(BE_END, it);
 
     }
@@ -782,7 +841,7 @@ static BwdTcPlan plan_bwd_tc(const hept_shape* s) {
   p.hat_bytes = align_up(sizeof(float) * (size_t)s->N * s->H * 8, 256);
   p.grow_bytes = align_up(sizeof(float) * (size_t)s->N * s->H * 32, 256);
   p.stage_bytes = align_up(sizeof(float) * (size_t)s->H * s->N * s->T * s->D, 256);
-  p.partial_bytes = align_up(sizeof(float) * (size_t)kBtMaxCtas * s->H * 8, 256);
+  p.partial_bytes = align_up(sizeof(float) * (size_t)kBtMaxCtas * s->H * 8 + sizeof(int) * (size_t)s->T * s->H, 256);
   p.total = p.hat_bytes + p.grow_bytes + 3 * p.stage_bytes + p.partial_bytes;
   return p;
 }
@@ -794,11 +853,13 @@ static int launch_bwd_tc(const hept_shape* s, const float* q, const float* k, co
                          const float* d_out_pre, float* dq, float* dk, float* dv, float* dscale, char* ws,
                          cudaStream_t st) {
   using CF = TcBwd<D, C, B>;
-  auto kern = block_attn_bwd_tc_kernel<D, C, B>;
+  auto kern = block_attn_bwd_tc_kernel<D, C, B, false>;
+  auto kern_direct = block_attn_bwd_tc_kernel<D, C, B, true>;
   const size_t smem = CF::TOTAL + 1024;
   static int sms = 0;
   if (!sms) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kern_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "block_attn_bwd_tc: cannot reserve %zu B of shared memory: %s", smem,
                  cudaGetErrorString(e));
     int dev = 0, n = 0;
@@ -822,18 +883,33 @@ static int launch_bwd_tc(const hept_shape* s, const float* q, const float* k, co
   const int mask = bwd_stage_mask();
   int grid = p.tiles < sms ? p.tiles : sms;             // one CTA per SM (the tile uses all 512 TMEM columns)
   if (grid > kBtMaxCtas) grid = kBtMaxCtas;
+  // Rows of the T tables: added straight into dq / dk / dv in table order by the tile kernel (needs the paired tile order,
+  // i.e. an even number of heads; variant 3 does it when a (head, table) group is at least two waves of tiles, so that
+  // no tile ever waits for the previous table; 4 = whenever possible, 5 = never), or staged per table and summed by
+  // bwd_table_sum.  Same bits either way.
+  const int nb = s->N / s->B;
+  const int variant = bwd_variant();
+  const bool direct = s->H % 2 == 0 && variant != 5 && (variant == 4 || nb >= 2 * grid) && (mask & 3) == 3;
   if (mask & 3) {
-    cudaError_t e = cudaMemsetAsync(partial, 0, sizeof(float) * (size_t)grid * s->H * 8, st);   // heads a CTA never visits
+    // partial sums of heads a CTA never visits, and the per-(table, head) tile counts of the direct path
+    int* done = (int*)(partial + (size_t)grid * s->H * 8);
+    cudaError_t e = cudaMemsetAsync(partial, 0, sizeof(float) * (size_t)grid * s->H * 8 + sizeof(int) * (size_t)s->T * s->H, st);
     HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "block_attn_bwd_tc: memset failed: %s", cudaGetErrorString(e));
-    HEPT_REQUIRE(TileDecoder::exact_for(p.tiles, s->N / s->B, s->T), HEPT_EUNSUPPORTED, "block_attn_bwd_tc: too many tiles (%d)", p.tiles);
-    kern<<<grid, kBtThreads, smem, st>>>(q, k, v, hat, grows, positions, s->N, s->H, s->T, s->raw_size, p.tiles,
-                                         TileDecoder::make(s->N / s->B, s->T), sq, sk, sv, partial);
+    HEPT_REQUIRE(TileDecoder::exact_for(p.tiles, nb, s->T), HEPT_EUNSUPPORTED, "block_attn_bwd_tc: too many tiles (%d)", p.tiles);
+    if (direct)
+      kern_direct<<<grid, kBtThreads, smem, st>>>(q, k, v, hat, grows, positions, s->N, s->H, s->T, s->raw_size, p.tiles,
+                                                  TileDecoder::make(nb, s->T, true), dq, dk, dv, partial, done);
+    else
+      kern<<<grid, kBtThreads, smem, st>>>(q, k, v, hat, grows, positions, s->N, s->H, s->T, s->raw_size, p.tiles,
+                                           TileDecoder::make(nb, s->T), sq, sk, sv, partial, done);
     HEPT_CHECK_LAUNCH("block_attn_bwd_tc");
   }
   if (!(mask & 4)) return HEPT_OK;
-  const size_t total = rows * (D / 4);
-  bwd_table_sum_kernel<D><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(sq, sk, sv, s->N, s->H, s->T, s->raw_size, dq, dk, dv);
-  HEPT_CHECK_LAUNCH("bwd_table_sum");
+  if (!direct) {
+    const size_t total = rows * (D / 4);
+    bwd_table_sum_kernel<D><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(sq, sk, sv, s->N, s->H, s->T, s->raw_size, dq, dk, dv);
+    HEPT_CHECK_LAUNCH("bwd_table_sum");
+  }
   dscale_tiles_kernel<<<s->H * C, 256, 0, st>>>(partial, scale, grid, s->H, C, dscale);
   HEPT_CHECK_LAUNCH("dscale_tiles");
   return HEPT_OK;

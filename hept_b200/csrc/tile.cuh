@@ -32,18 +32,31 @@ namespace hept {
 // quotients come from one IMAD.HI each with multipliers computed on the host (a runtime `/` costs ~40 instructions, and
 // the persistent tile kernels decode several tiles per iteration in every warp role).
 // magic(d) = floor(2^32 / d) + 1 gives floor(x / d) = umulhi(x, magic) for x * d < 2^32; d == 1 is flagged by magic 0.
+// Two orders of the (head, table) groups of nb tiles each:
+//   plain  (h0,t0) (h0,t1) ... (h0,tT-1) (h1,t0) ...           one head's rows stay in L2 for its T tables;
+//   paired (h0,t0) (h1,t0) (h0,t1) (h1,t1) ... (h2,t0) (h3,t0)  two heads' rows stay in L2, and the tiles of (h, t + 1)
+//          start a whole group after the last tile of (h, t) -- what the backward needs to add a table's rows onto
+//          the previous table's without waiting (attn_bwd_tc.cu).  Needs an even number of heads.
 struct TileDecoder {
-  uint32_t nb, T, magic_nb, magic_T;
+  uint32_t nb, T, magic_nb, magic_T, paired;
   static uint32_t magic(uint32_t d) { return d <= 1 ? 0u : (uint32_t)((1ull << 32) / d) + 1u; }
-  static TileDecoder make(int nb, int T) { return TileDecoder{(uint32_t)nb, (uint32_t)T, magic((uint32_t)nb), magic((uint32_t)T)}; }
+  static TileDecoder make(int nb, int T, bool paired = false) {
+    return TileDecoder{(uint32_t)nb, (uint32_t)T, magic((uint32_t)nb), magic(paired ? 2u * (uint32_t)T : (uint32_t)T), paired ? 1u : 0u};
+  }
   // largest tile count the multipliers are exact for
-  static bool exact_for(long long tiles, int nb, int T) { return tiles * (long long)nb < (1ll << 32) && tiles * (long long)T < (1ll << 32); }
+  static bool exact_for(long long tiles, int nb, int T) { return tiles * (long long)nb < (1ll << 32) && tiles * 2ll * T < (1ll << 32); }
   __device__ __forceinline__ void operator()(int tile, int& h, int& t, int& blk) const {
     const uint32_t hl = magic_nb ? __umulhi((uint32_t)tile, magic_nb) : (uint32_t)tile;
     blk = (int)((uint32_t)tile - hl * nb);
-    const uint32_t hh = magic_T ? __umulhi(hl, magic_T) : hl;
-    h = (int)hh;
-    t = (int)(hl - hh * T);
+    if (paired) {
+      const uint32_t hp = __umulhi(hl, magic_T), r = hl - hp * 2u * T;     // 2 T >= 2: the multiplier is never the d == 1 flag
+      h = (int)(2u * hp + (r & 1u));
+      t = (int)(r >> 1);
+    } else {
+      const uint32_t hh = magic_T ? __umulhi(hl, magic_T) : hl;
+      h = (int)hh;
+      t = (int)(hl - hh * T);
+    }
   }
 };
 

@@ -154,7 +154,11 @@ int hept_get_engine(void);
 void hept_set_sort_variant(int variant);
 int hept_get_sort_variant(void);
 
-/* backward tile kernels: 1 = one lane per row (attn_bwd.cu), 2 = lane pairs + packed FFMA2 (attn_bwd2.cu). */
+/* backward tile kernels: 1 = one lane per row (attn_bwd.cu), 2 = lane pairs + packed FFMA2 (attn_bwd2.cu),
+ * 3 = tcgen05 tiles (attn_bwd_tc.cu; default).  The tcgen05 tiles either add the T tables' rows straight into dq / dk / dv in
+ * table order (no staging rows, no summing kernel; needs an even number of heads) or stage them per table: 3 picks the
+ * direct form when a (head, table) group is at least two waves of tiles, 4 = direct whenever possible, 5 = staged always.
+ * Same bits either way. */
 void hept_set_bwd_variant(int variant);
 int hept_get_bwd_variant(void);
 
