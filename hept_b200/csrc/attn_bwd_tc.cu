@@ -166,11 +166,14 @@ __global__ void __launch_bounds__(kBtThreads, 1)
   float* s_dsc = reinterpret_cast<float*>(s_kidx + 384);         // [8][8]    d scale partials per epilogue warp
   __shared__ uint64_t mbar[BT_NBAR];
   __shared__ uint32_t tmem_slot;
+  __shared__ int s_dep[2];                                       // DIRECT: (group, tile count seen) fetched at the last group change
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int EW = kBtEpiThreads / 32, PW = kBtProdThreads / 32;
 
   if (tid == 0) {
+    s_dep[0] = -1;
+    s_dep[1] = 0;
     umma::mbar_init(&mbar[KFULL], PW);
     umma::mbar_init(&mbar[MFULL], PW);
     umma::mbar_init(&mbar[MFREE], 1 + EW);
@@ -239,8 +242,10 @@ __global__ void __launch_bounds__(kBtThreads, 1)
     for (int cc = 0; cc < C; ++cc) dsc[cc] = 0.f;
     int dsc_head = -1;
     int pend = -1, grp_tiles = 0, ready = -1, cur_grp = -1;   // DIRECT: see below
-    auto flush_dscale = [&]() {
+    auto flush_dscale = [&](int dep = -1) {   // dep: the group whose count the CTA's next tiles will need (DIRECT), or -1
       if (dsc_head < 0) return;
+      int dep_cnt = 0;                         // asked for here, used after the barrier: the L2 round trip hides behind the sums
+      if (DIRECT && tid == 32 && dep >= 0) asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(dep_cnt) : "l"(done + dep) : "memory");
 #pragma unroll
       for (int cc = 0; cc < C; ++cc) {
         float x = dsc[cc];
@@ -253,6 +258,7 @@ __global__ void __launch_bounds__(kBtThreads, 1)
       if (DIRECT && tid == 0 && pend >= 0)               // every epilogue warp has issued the rows of the finished group
         asm volatile("red.release.gpu.global.add.s32 [%0], %1;" :: "l"(done + pend), "r"(grp_tiles) : "memory");
       grp_tiles = 0;
+      if (DIRECT && tid == 32) { s_dep[0] = dep; s_dep[1] = dep_cnt; }   // published by the barrier below
       if (tid < C) {
         float x = 0.f;
 #pragma unroll
@@ -397,7 +403,8 @@ __global__ void __launch_bounds__(kBtThreads, 1)
         if (t > 0 && ready != (t - 1) * H + h) {         // the rows of table t - 1 of this head are all in place?
           ready = (t - 1) * H + h;
           const int want = (int)decode.nb;
-          if (lane == 0) {
+          // usually the count was already complete when the CTA left its previous group (flush_dscale asked for it)
+          if (!(s_dep[0] == ready && s_dep[1] >= want) && lane == 0) {
             // poll relaxed (an acquire load invalidates the SM's L1 every time), acquire once the count is there
             auto count = [&]() {
               int c;
@@ -480,7 +487,7 @@ __global__ void __launch_bounds__(kBtThreads, 1)
         int hn = -1, tn = 0, bn;
         if (tile + (int)gridDim.x < total_tiles) decode(tile + (int)gridDim.x, hn, tn, bn);
         if (hn < 0 || tn * H + hn != cur_grp) {
-          flush_dscale();
+          flush_dscale(hn >= 0 && tn > 0 ? (tn - 1) * H + hn : -1);
           dsc_head = hn;
           cur_grp = tn * H + hn;
         }
@@ -889,7 +896,15 @@ static int launch_bwd_tc(const hept_shape* s, const float* q, const float* k, co
   // bwd_table_sum.  Same bits either way.
   const int nb = s->N / s->B;
   const int variant = bwd_variant();
-  const bool direct = s->H % 2 == 0 && variant != 5 && (variant == 4 || nb >= 2 * grid) && (mask & 3) == 3;
+  // heads per group: two when the number of heads is even (measured at 60k hits, 8 heads: 798 us with pairs, 806 with
+  // threes, ~826 with fours -- the rows of more heads no longer stay in L2), else the smallest group size that does not
+  // leave a last group of one head (whose tables would follow each other directly).  HEPT_BWD_GROUP overrides (experiments).
+  static const int forced_g = [] { const char* e = getenv("HEPT_BWD_GROUP"); return e ? atoi(e) : 0; }();
+  int hg = 0;
+  for (int g = 2; g <= 4 && !hg; ++g)
+    if (s->H >= g && s->H % g != 1) hg = g;
+  if (forced_g > 1 && s->H >= forced_g && s->H % forced_g != 1) hg = forced_g;
+  const bool direct = hg > 0 && variant != 5 && (variant == 4 || nb >= 2 * grid) && (mask & 3) == 3;
   if (mask & 3) {
     // partial sums of heads a CTA never visits, and the per-(table, head) tile counts of the direct path
     int* done = (int*)(partial + (size_t)grid * s->H * 8);
@@ -898,7 +913,7 @@ static int launch_bwd_tc(const hept_shape* s, const float* q, const float* k, co
     HEPT_REQUIRE(TileDecoder::exact_for(p.tiles, nb, s->T), HEPT_EUNSUPPORTED, "block_attn_bwd_tc: too many tiles (%d)", p.tiles);
     if (direct)
       kern_direct<<<grid, kBtThreads, smem, st>>>(q, k, v, hat, grows, positions, s->N, s->H, s->T, s->raw_size, p.tiles,
-                                                  TileDecoder::make(nb, s->T, true), dq, dk, dv, partial, done);
+                                                  TileDecoder::make(nb, s->T, s->H, hg), dq, dk, dv, partial, done);
     else
       kern<<<grid, kBtThreads, smem, st>>>(q, k, v, hat, grows, positions, s->N, s->H, s->T, s->raw_size, p.tiles,
                                            TileDecoder::make(nb, s->T), sq, sk, sv, partial, done);

@@ -33,25 +33,44 @@ namespace hept {
 // the persistent tile kernels decode several tiles per iteration in every warp role).
 // magic(d) = floor(2^32 / d) + 1 gives floor(x / d) = umulhi(x, magic) for x * d < 2^32; d == 1 is flagged by magic 0.
 // Two orders of the (head, table) groups of nb tiles each:
-//   plain  (h0,t0) (h0,t1) ... (h0,tT-1) (h1,t0) ...           one head's rows stay in L2 for its T tables;
-//   paired (h0,t0) (h1,t0) (h0,t1) (h1,t1) ... (h2,t0) (h3,t0)  two heads' rows stay in L2, and the tiles of (h, t + 1)
-//          start a whole group after the last tile of (h, t) -- what the backward needs to add a table's rows onto
-//          the previous table's without waiting (attn_bwd_tc.cu).  Needs an even number of heads.
+//   plain   (h0,t0) (h0,t1) ... (h0,tT-1) (h1,t0) ...                 one head's rows stay in L2 for its T tables;
+//   grouped, G heads at a time: (h0,t0) (h1,t0) (h2,t0) (h0,t1) (h1,t1) (h2,t1) ... then the next G heads; the last
+//           H % G heads form a smaller group of their own.  G heads' rows stay in L2, and the tiles of (h, t + 1) start
+//           G - 1 whole groups after the last tile of (h, t) -- what the backward needs to add a table's rows onto the
+//           previous table's without waiting (attn_bwd_tc.cu).
 struct TileDecoder {
-  uint32_t nb, T, magic_nb, magic_T, paired;
+  uint32_t nb, T, magic_nb, magic_T;
+  uint32_t G, tail_base, tail_h0, tail_G, magic_GT, magic_G, magic_tG;   // G == 0: plain order
   static uint32_t magic(uint32_t d) { return d <= 1 ? 0u : (uint32_t)((1ull << 32) / d) + 1u; }
-  static TileDecoder make(int nb, int T, bool paired = false) {
-    return TileDecoder{(uint32_t)nb, (uint32_t)T, magic((uint32_t)nb), magic(paired ? 2u * (uint32_t)T : (uint32_t)T), paired ? 1u : 0u};
+  static TileDecoder make(int nb, int T, int H = 0, int G = 0) {
+    TileDecoder d{(uint32_t)nb, (uint32_t)T, magic((uint32_t)nb), magic((uint32_t)T), 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    if (G > 1 && H > 0) {
+      d.G = (uint32_t)G;
+      d.tail_G = (uint32_t)(H % G);
+      d.tail_base = (uint32_t)((H / G) * G * T);
+      d.tail_h0 = (uint32_t)((H / G) * G);
+      d.magic_GT = magic((uint32_t)(G * T));
+      d.magic_G = magic((uint32_t)G);
+      d.magic_tG = magic(d.tail_G);
+    }
+    return d;
   }
   // largest tile count the multipliers are exact for
-  static bool exact_for(long long tiles, int nb, int T) { return tiles * (long long)nb < (1ll << 32) && tiles * 2ll * T < (1ll << 32); }
+  static bool exact_for(long long tiles, int nb, int T) { return tiles * (long long)nb < (1ll << 32) && tiles * 8ll * T < (1ll << 32); }
   __device__ __forceinline__ void operator()(int tile, int& h, int& t, int& blk) const {
     const uint32_t hl = magic_nb ? __umulhi((uint32_t)tile, magic_nb) : (uint32_t)tile;
     blk = (int)((uint32_t)tile - hl * nb);
-    if (paired) {
-      const uint32_t hp = __umulhi(hl, magic_T), r = hl - hp * 2u * T;     // 2 T >= 2: the multiplier is never the d == 1 flag
-      h = (int)(2u * hp + (r & 1u));
-      t = (int)(r >> 1);
+    if (G) {
+      uint32_t r, h0, gs, mg;                     // position in the head group, its first head, its size
+      if (hl < tail_base) {
+        const uint32_t hp = __umulhi(hl, magic_GT);
+        r = hl - hp * G * T; h0 = hp * G; gs = G; mg = magic_G;
+      } else {
+        r = hl - tail_base; h0 = tail_h0; gs = tail_G; mg = magic_tG;
+      }
+      const uint32_t tt = mg ? __umulhi(r, mg) : r;
+      t = (int)tt;
+      h = (int)(h0 + r - tt * gs);
     } else {
       const uint32_t hh = magic_T ? __umulhi(hl, magic_T) : hl;
       h = (int)hh;
