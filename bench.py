@@ -376,7 +376,7 @@ def kernel_roofline(resident, gouts, cfg, mod, w_rpe, peak, peak_src, n_sets):
     achieved = per_hit[top] * N_RAW / times[top] / 1e9
     # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (tools/ncu_summary.py)
     traffic, tsrc = None, None
-    tpath = os.path.join(ROOT, "profiles", "r1c_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r1e_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
             tj = json.load(f)
@@ -385,14 +385,15 @@ def kernel_roofline(resident, gouts, cfg, mod, w_rpe, peak, peak_src, n_sets):
                  "block_attn_bwd_dkv": "block_attn_bwd_dkv_kernel" if variant == 1 else "block_attn_bwd_pair_kernel",
                  "block_attn_bwd_tc": "block_attn_bwd_tc_kernel"}
         if names[top] in tj:
-            traffic, tsrc = tj[names[top]]["dram_bytes_per_launch"], "profiles/r1c_traffic.json (" + tj[names[top]]["source"] + ")"
+            traffic, tsrc = tj[names[top]]["dram_bytes_per_launch"], "profiles/r1e_traffic.json (" + tj[names[top]]["source"] + ")"
     tensor = variant >= 3 or lib.hept_get_engine()
     return {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": traffic, "traffic_source": tsrc, "peak_source": peak_src, "bytes_per_launch": per_hit[top] * N_RAW,
             "kernel_ms": {k: v * 1e3 for k, v in times.items()},
             "tile_tflops": {k: flops[k] * N_RAW / times[k] / 1e12 for k in times},
             "note": ("kernel_ms of block_attn_bwd_tc includes its two streaming pre-passes (scaled coordinates, gradient rows; "
-                     "~40 us); the tile kernels are bounded by the thread-side TMEM port and by contention between the warp roles "
+                     "~40 us) and, in its default direct form, the sum over the T tables (rows added into dq/dk/dv by the tile kernel: "
+                     "the 81 us bwd_table_sum launch of the staged form is gone, this kernel is ~35 us longer); the tile kernels are bounded by the thread-side TMEM port and by contention between the warp roles "
                      "(DESIGN.md 4), not by HBM: tile_tflops counts algorithmic fp32 FLOPs (each is three tf32 MMA passes)") if tensor else
                     "tile kernels are fp32-FMA bound, not HBM bound (SURVEY.md 7.3-3); tile_tflops is against ~74 TF/s SIMT peak"}
 
