@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(kBtThreads, 1)
 #pragma unroll
     for (int cc = 0; cc < C; ++cc) dsc[cc] = 0.f;
     int dsc_head = -1;
-    int pend = -1, grp_tiles = 0, ready = -1, cur_grp = -1;   // DIRECT: see below
+    int ready = -1, cur_grp = -1;                        // DIRECT: see below
     auto flush_dscale = [&](int dep = -1) {   // dep: the group whose count the CTA's next tiles will need (DIRECT), or -1
       if (dsc_head < 0) return;
       int dep_cnt = 0;                         // asked for here, used after the barrier: the L2 round trip hides behind the sums
@@ -255,9 +255,6 @@ __global__ void __launch_bounds__(kBtThreads, 1)
         dsc[cc] = 0.f;
       }
       umma::bar_sync(1, kBtEpiThreads);
-      if (DIRECT && tid == 0 && pend >= 0)               // every epilogue warp has issued the rows of the finished group
-        asm volatile("red.release.gpu.global.add.s32 [%0], %1;" :: "l"(done + pend), "r"(grp_tiles) : "memory");
-      grp_tiles = 0;
       if (DIRECT && tid == 32) { s_dep[0] = dep; s_dep[1] = dep_cnt; }   // published by the barrier below
       if (tid < C) {
         float x = 0.f;
@@ -270,12 +267,13 @@ __global__ void __launch_bounds__(kBtThreads, 1)
     };
     // DIRECT: rows go straight into dq / dk / dv (n, h, D): table 0 stores, later tables add (16-byte vector atomics), so
     // the per-table staging rows and the kernel that sums them are gone.  Order of the adds = table order, enforced, so
-    // the sums are the same bits every run and the same as the staged sum: when a CTA leaves a (table, head) group -- with
-    // the paired tile order that is where flush_dscale already synchronises the epilogue warps -- one thread adds the CTA's
-    // number of tiles of the group to done[t * H + h] with release semantics (the barrier orders the other warps' rows
-    // before it; a fence per warp and tile instead costs 10 % of the kernel, a __threadfence per lane 40 %), and a tile of
-    // table t >= 1 writes its first row once done[(t - 1) * H + h] has reached the group's nb tiles.  That group ended a
-    // whole group ago, so with groups of at least two waves of tiles nobody ever waits.
+    // the sums are the same bits every run and the same as the staged sum: the CTA's tiles of a (table, head) group are
+    // counted into done[t * H + h] with release semantics once their rows are out (by a producer thread, see there), and
+    // a tile of table t >= 1 writes its first row once done[(t - 1) * H + h] has reached the group's nb tiles.  With the
+    // grouped tile order that group ended at least a whole group ago, so with groups of two waves of tiles or more nobody
+    // waits; the count is fetched when the CTA changes group, at the barrier flush_dscale needs anyway, so a tile normally
+    // starts its rows without a global load.  (A fence per warp and tile in the epilogue costs 10 % of the kernel, a
+    // __threadfence per lane 40 %.)
     auto put_chunk = [&](float4* dst, const float4 x, bool live, int t_) {
       if (!DIRECT || t_ == 0) *dst = live ? x : make_float4(0.f, 0.f, 0.f, 0.f);
       else if (live) atomicAdd(dst, x);
@@ -481,9 +479,7 @@ __global__ void __launch_bounds__(kBtThreads, 1)
       __syncwarp();
       if (lane == 0) umma::mbar_arrive(&mbar[MFREE]);    // this warp is done with the MN-major tiles
       if (DIRECT) {
-        pend = t + 1 < T ? t * H + h : -1;               // the last table's count is never read
-        ++grp_tiles;
-        // last tile of this CTA in the group: hand the count in now rather than at the next group's first tile
+        // last tile of this CTA in the group: sums handed in, and the count the next group depends on asked for, now
         int hn = -1, tn = 0, bn;
         if (tile + (int)gridDim.x < total_tiles) decode(tile + (int)gridDim.x, hn, tn, bn);
         if (hn < 0 || tn * H + hn != cur_grp) {
@@ -553,6 +549,16 @@ __global__ void __launch_bounds__(kBtThreads, 1)
       issue_rows(tile, 0);
       if (tile + (int)gridDim.x < total_tiles) load_indices(tile + gridDim.x);
     }
+    // DIRECT: this CTA's finished tiles of a (table, head) group are counted into done[] here, not by the epilogue warps:
+    // once the producer has seen MFREE of tile it - 1, every epilogue warp has issued that tile's rows (they arrive on
+    // MFREE after their last row), so one producer thread can publish them with a release -- and its MEMBAR stalls a
+    // warp that is about to wait for the MMAs anyway instead of the epilogue, which bounds the kernel.
+    int rel_grp = -1, rel_cnt = 0;                        // group of tile it - 1 (-1: last table, nobody reads the count)
+    auto hand_in = [&]() {
+      if (rel_grp >= 0 && rel_cnt > 0 && ptid == 0)
+        asm volatile("red.release.gpu.global.add.s32 [%0], %1;" :: "l"(done + rel_grp), "r"(rel_cnt) : "memory");
+      rel_cnt = 0;
+    };
     int it = 0;
 #pragma unroll 1
     for (; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -653,6 +659,22 @@ __global__ void __launch_bounds__(kBtThreads, 1)
       __syncwarp();
       if (lane == 0) umma::mbar_arrive(&mbar[MFULL]);
       if (warp == EW) HEPT_TRACE_EVENT(BP_MFULL, it);
+      if (DIRECT && warp == EW) {
+        // MFREE of tile it - 1 was seen above: count it, and hand the count in when this tile belongs to another group
+        int h, t, blk;
+        decode(tile, h, t, blk);
+        const int g = t + 1 < T ? t * H + h : -1;
+        if (it > 0) {
+          ++rel_cnt;
+          if (g != rel_grp || t + 1 >= T) hand_in();      // (last-table groups all read -1: nothing to hand in, counter reset)
+        }
+        rel_grp = g;
+      }
+    }
+    if (DIRECT && warp == EW && it > 0) {                 // the CTA's last tile
+      umma::mbar_wait(&mbar[MFREE], (it - 1) & 1);
+      ++rel_cnt;
+      hand_in();
     }
   } else {
     umma::setmaxnreg_dec<kBtRegsMma>();
