@@ -498,6 +498,40 @@ def _backward_engines_agree_60k():
         assert err < 1e-4 and worst < 1e-3, (name, err, worst)   # 3xTF32 + truncating accumulator vs fp32 FMA chains
 
 
+@pytest.mark.parametrize("heads", [3, 5, 6, 7, 4])
+def test_direct_backward_head_groups(heads, engine):
+    """The direct form of the tcgen05 backward orders its tiles in groups of 2, 3 or 4 heads depending on the head count
+    (5 = 3 + 2, 7 = 4 + 3; 4 and 6 pair up); every grouping must give the staged form's bits, and the fp32 tiles' values."""
+    if engine != "tcgen05":
+        pytest.skip("runs once")
+    from hept_b200 import _lib, ops, synthetic
+
+    lib = _lib.load()
+    cfg = dict(synthetic.TRACKING, num_heads=heads)
+    n_raw = 2930
+    coords_raw, batch = synthetic.batched_cloud([n_raw], cfg["coords_dim"], heads)
+    params = synthetic.module_params(cfg, heads)
+    _, kw, _ = O.prepare_batched(torch.zeros(n_raw, 1), coords_raw, batch, params["regions"], cfg["block_size"], heads)
+    n = kw["coords"].shape[0]
+    q, k, v = synthetic.qkv(n, cfg, heads)
+    d = dims_of(cfg, n)
+    qd, kd, vd, cd = q.to(dev()), k.to(dev()), v.to(dev()), kw["coords"].to(dev())
+    out, den, scale, pos = ops.attention_fwd(d, qd, kd, vd, cd, params["w_rpe.weight"].to(dev()), cfg["num_w_per_dist"],
+                                             params["e2lsh.alpha"].to(dev()), combined_shifts=kw["combined_shifts"].to(dev()))
+    g = torch.randn(n, d.H * d.D, generator=torch.Generator().manual_seed(5)).to(dev())
+    res = {}
+    try:
+        for variant in (1, 4, 5):
+            lib.hept_set_bwd_variant(variant)
+            res[variant] = ops.attention_bwd(d, qd, kd, vd, cd, scale, pos, out, den, g)
+    finally:
+        lib.hept_set_bwd_variant(3)
+    for name, a, b in zip(("dq", "dk", "dv"), res[4], res[5]):
+        assert torch.equal(a, b), (heads, name)
+    for name, a, b in zip(("dq", "dk", "dv", "dscale"), res[4], res[1]):
+        assert rel_err(a.cpu(), b.cpu()) < 1e-4, (heads, name)
+
+
 # ------------------------------------------------------- BASELINE.json configs[2..3] and the prepare step on device
 def test_prepare_input_on_device_matches_cpu():
     from hept_b200 import prepare, synthetic
