@@ -117,32 +117,50 @@ __global__ void __launch_bounds__(256) grad_rows_kernel(const float* __restrict_
                                                         const float* __restrict__ scale, int H, int C, int raw_size,
                                                         float* __restrict__ hat) {
   constexpr int VCH = D / 4;
+  constexpr int RPT = 2;                                 // rows per thread: both rows' loads are in flight before the first use
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t r = idx >> 3;
+  const size_t half = (rows + RPT - 1) / RPT;
   const int c = (int)(idx & 7);
-  const bool live = r < rows;
-  if (live && c < 2) {
-    const size_t n = r / H;
-    const int h = (int)(r - n * H);
-    float hv[4];
+  size_t r[RPT];
+  bool live[RPT];
+  float dn[RPT];
+  float4 gg[RPT], yy[RPT];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int cc = 4 * c + u;
-      hv[u] = (cc < C && (int)n < raw_size) ? __fmul_rn(__ldg(scale + h * C + cc), __ldg(coords + n * C + cc)) : 0.f;
+  for (int u = 0; u < RPT; ++u) {
+    r[u] = (idx >> 3) + u * half;
+    live[u] = (idx >> 3) < half && r[u] < rows;
+    dn[u] = 1.f;
+    gg[u] = yy[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live[u] && c < VCH) {
+      dn[u] = __ldg(den + r[u]);
+      gg[u] = ldg4(g + r[u] * D + 4 * c);
+      yy[u] = ldg4(y + r[u] * D + 4 * c);
     }
-    *reinterpret_cast<float4*>(hat + r * 8 + 4 * c) = make_float4(hv[0], hv[1], hv[2], hv[3]);
   }
-  float4 gd = make_float4(0.f, 0.f, 0.f, 0.f);
-  float part = 0.f;
-  if (live && c < VCH) {
-    const float inv = 1.f / __ldg(den + r);
-    const float4 gg = ldg4(g + r * D + 4 * c), yy = ldg4(y + r * D + 4 * c);
-    gd = make_float4(gg.x * inv, gg.y * inv, gg.z * inv, gg.w * inv);
-    part = fmaf(gd.w, yy.w, fmaf(gd.z, yy.z, fmaf(gd.y, yy.y, gd.x * yy.x)));
+#pragma unroll
+  for (int u = 0; u < RPT; ++u) {
+    if (live[u] && c < 2) {
+      const size_t n = r[u] / H;
+      const int h = (int)(r[u] - n * H);
+      float hv[4];
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const int cc = 4 * c + w;
+        hv[w] = (cc < C && (int)n < raw_size) ? __fmul_rn(__ldg(scale + h * C + cc), __ldg(coords + n * C + cc)) : 0.f;
+      }
+      *reinterpret_cast<float4*>(hat + r[u] * 8 + 4 * c) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+    }
+    float4 gd = make_float4(0.f, 0.f, 0.f, 0.f);
+    float part = 0.f;
+    if (live[u] && c < VCH) {
+      const float inv = 1.f / dn[u];
+      gd = make_float4(gg[u].x * inv, gg[u].y * inv, gg[u].z * inv, gg[u].w * inv);
+      part = fmaf(gd.w, yy[u].w, fmaf(gd.z, yy[u].z, fmaf(gd.y, yy[u].y, gd.x * yy[u].x)));
+    }
+    const float gy = tree8_lanes(part);
+    if (c == VCH) gd.x = -gy;
+    if (live[u]) *reinterpret_cast<float4*>(out + r[u] * 32 + 4 * c) = gd;
   }
-  const float gy = tree8_lanes(part);
-  if (c == VCH) gd.x = -gy;
-  if (live) *reinterpret_cast<float4*>(out + r * 32 + 4 * c) = gd;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -906,7 +924,7 @@ static int launch_bwd_tc(const hept_shape* s, const float* q, const float* k, co
   float* partial = (float*)((char*)sv + p.stage_bytes);
   HEPT_REQUIRE(s->C <= 8, HEPT_EUNSUPPORTED, "block_attn_bwd_tc: more than 8 coordinates");
   const size_t rows = (size_t)s->N * s->H;
-  grad_rows_kernel<D><<<(unsigned)((rows * 8 + 255) / 256), 256, 0, st>>>(d_out_pre, out_pre, den_sum, rows, grows, coords, scale,
+  grad_rows_kernel<D><<<(unsigned)((((rows + 1) / 2) * 8 + 255) / 256), 256, 0, st>>>(d_out_pre, out_pre, den_sum, rows, grows, coords, scale,
                                                                          s->H, s->C, s->raw_size, hat);
   HEPT_CHECK_LAUNCH("grad_rows");
   const int mask = bwd_stage_mask();
