@@ -56,9 +56,6 @@ SIGNATURES = {
     "hept_set_sort_variant": (None, [C.c_int]),
     "hept_get_sort_variant": (C.c_int, []),
     "hept_get_bwd_variant": (C.c_int, []),
-    "hept_debug_umma_selftest": (C.c_int, [_p, _p, _p, _p, _p, C.c_int, _p]),
-    "hept_debug_umma_symmetry": (C.c_int, [_p, _p, _p, _p, _p]),
-    "hept_debug_umma_timing": (C.c_int, [C.c_int, C.c_int, _p, _p]),
 }
 
 _lib = None

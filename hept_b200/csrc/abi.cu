@@ -17,12 +17,13 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
-static int g_bwd_mask = 7;
-int bwd_stage_mask() { return g_bwd_mask; }
-static int g_engine = 1;  // tcgen05 tiles by default (faster, same tolerance contract); 0 = fp32 CUDA-core tiles
-int engine() { return g_engine; }
-static int g_bwd_variant = 3;  // tcgen05 backward tiles by default; 1 = fp32 CUDA-core tiles, 2 = lane-pair FFMA2 tiles
-int bwd_variant() { return g_bwd_variant; }
+// process-wide selectors (profiling / test aids); atomics: autograd calls the backward from its own thread
+static std::atomic<int> g_bwd_mask{7};
+int bwd_stage_mask() { return g_bwd_mask.load(std::memory_order_relaxed); }
+static std::atomic<int> g_engine{1};  // tcgen05 tiles by default (faster, same tolerance contract); 0 = fp32 CUDA-core tiles
+int engine() { return g_engine.load(std::memory_order_relaxed); }
+static std::atomic<int> g_bwd_variant{3};  // tcgen05 backward tiles by default; 1 = fp32 CUDA-core tiles
+int bwd_variant() { return g_bwd_variant.load(std::memory_order_relaxed); }
 
 struct FwdPlan {
   size_t ext_bytes, span_bytes, hat_bytes, proj_bytes, keys_bytes, sort_bytes, stage_bytes, total;
@@ -53,11 +54,13 @@ extern "C" int hept_launch_count(int reset) {
   return reset ? g_launches.exchange(0, std::memory_order_relaxed) : g_launches.load(std::memory_order_relaxed);
 }
 
-extern "C" void hept_set_bwd_stage_mask(int mask) { g_bwd_mask = mask & 7; }
-extern "C" void hept_set_engine(int engine) { g_engine = engine ? 1 : 0; }
-extern "C" int hept_get_engine(void) { return g_engine; }
-extern "C" void hept_set_bwd_variant(int variant) { g_bwd_variant = (variant >= 2 && variant <= 5) ? variant : 1; }
-extern "C" int hept_get_bwd_variant(void) { return g_bwd_variant; }
+extern "C" void hept_set_bwd_stage_mask(int mask) { g_bwd_mask.store(mask & 7, std::memory_order_relaxed); }
+extern "C" void hept_set_engine(int engine) { g_engine.store(engine ? 1 : 0, std::memory_order_relaxed); }
+extern "C" int hept_get_engine(void) { return engine(); }
+extern "C" void hept_set_bwd_variant(int variant) {
+  g_bwd_variant.store((variant >= 3 && variant <= 5) ? variant : 1, std::memory_order_relaxed);
+}
+extern "C" int hept_get_bwd_variant(void) { return bwd_variant(); }
 
 extern "C" size_t hept_attention_fwd_workspace_bytes(const hept_shape* s) {
   if (!s || s->N <= 0 || s->H <= 0 || s->T <= 0) return 0;

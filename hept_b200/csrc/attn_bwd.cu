@@ -272,10 +272,6 @@ __global__ void __launch_bounds__(256) dscale_finish_kernel(const float* __restr
   if (threadIdx.x == 0) dscale[col] = red[0];
 }
 
-int block_attention_bwd_tiles2(const hept_shape* s, const float* q, const float* k, const float* v, const float* coords,
-                               const float* scale, const int32_t* positions, const float* out_pre, const float* den_sum,
-                               const float* d_out_pre, float* stage_dq, float* stage_dk, float* stage_dv, int mask,
-                               cudaStream_t st);
 int block_attention_bwd_tc(const hept_shape* s, const float* q, const float* k, const float* v, const float* coords,
                            const float* scale, const int32_t* positions, const float* out_pre, const float* den_sum,
                            const float* d_out_pre, float* dq, float* dk, float* dv, float* dscale, char* ws,
@@ -305,12 +301,12 @@ static int launch_bwd(const hept_shape* s, const float* q, const float* k, const
   using LK = TileLayout<D, C, B, GK, 1>;
   auto kq = block_attn_bwd_dq_kernel<D, C, B, GQ, MINQ>;
   auto kk = block_attn_bwd_dkv_kernel<D, C, B, GK, MINK>;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.needed()) {
     cudaError_t e1 = cudaFuncSetAttribute(kq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LQ::SMEM_BYTES);
     cudaError_t e2 = cudaFuncSetAttribute(kk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LK::SMEM_BYTES);
     HEPT_REQUIRE(e1 == cudaSuccess && e2 == cudaSuccess, HEPT_ECUDA, "block_attn_bwd: cannot reserve shared memory");
-    configured = true;
+    configured.mark();
   }
   BwdPlan p = plan_bwd(s);
   float* stage_dq = (float*)ws;
@@ -319,11 +315,6 @@ static int launch_bwd(const hept_shape* s, const float* q, const float* k, const
   float* partial = (float*)(ws + 2 * p.dq_bytes + p.dv_bytes);
   const int nb = s->N / s->B;
   const int mask = bwd_stage_mask();  // profiling aid: all stages unless hept_set_bwd_stage_mask() says otherwise
-  if (bwd_variant() == 2) {
-    if (int rc = block_attention_bwd_tiles2(s, q, k, v, coords, scale, positions, out_pre, den_sum, d_out_pre, stage_dq,
-                                            stage_dk, stage_dv, mask, st))
-      return rc;
-  } else {
   if (mask & 1) {
     kq<<<dim3((nb + GQ - 1) / GQ, s->T * s->H), LQ::THREADS, LQ::SMEM_BYTES, st>>>(
         q, k, v, coords, scale, positions, out_pre, den_sum, d_out_pre, s->N, s->H, s->T, s->raw_size, stage_dq);
@@ -333,7 +324,6 @@ static int launch_bwd(const hept_shape* s, const float* q, const float* k, const
     kk<<<dim3((nb + GK - 1) / GK, s->T * s->H), LK::THREADS, LK::SMEM_BYTES, st>>>(
         q, k, v, coords, scale, positions, out_pre, den_sum, d_out_pre, s->N, s->H, s->T, s->raw_size, stage_dk, stage_dv);
     HEPT_CHECK_LAUNCH("block_attn_bwd_dkv");
-  }
   }
   if (!(mask & 4)) return HEPT_OK;
   bwd_reduce_kernel<D, C><<<p.nblk, 256, 0, st>>>(stage_dq, stage_dk, stage_dv, coords, s->N, s->H, s->T, s->raw_size,

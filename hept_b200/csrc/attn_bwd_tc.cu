@@ -17,8 +17,8 @@
 // the dS columns, accumulator tO again once dv has been read out), then the next tile's scores.
 // The row / column sums rs_i = sum_j dS_ij, cs_j = sum_i dS_ij come out of the same MMAs (a ones column in the
 // MN-major operand), so they are the sums of exactly the (hi, lo) values that produced dQ / dK.
-// The reference's clamp(max=0) mask [S <= 0] on dS is not applied: S = -|q^ - k^|^2 / 2 is positive only by rounding,
-// where k^ - q^ (the factor dS multiplies) vanishes; P itself is clamped like the reference's.
+// The reference's clamp(max=0) passes gradient only where S <= 0 (example/hept.py:12, ClampBackward): dS = [x <= 0] P dP with
+// the x this kernel computes (centred rows: x > 0 happens only by rounding, for coincident points), on both sides alike.
 // with x = log2e (q'.k' - |k'|^2/2) - log2e |q'|^2/2 (the key norm rides in two spare K slots of the contraction,
 // split three ways so it is exact), P = ex2(min(x, 0)), G'_i = [g_i / den_i, -(g_i . y_i) / den_i], V'_j = [v_j, 1]
 // (so dP = gd . v - gy comes out of one contraction).  The tf32 MMA is bitwise symmetric under an exchange of its
@@ -115,10 +115,12 @@ __global__ void __launch_bounds__(256) grad_rows_kernel(const float* __restrict_
                                                         const float* __restrict__ den, size_t rows,
                                                         float* __restrict__ out, const float* __restrict__ coords,
                                                         const float* __restrict__ scale, int H, int C, int raw_size,
-                                                        float* __restrict__ hat) {
+                                                        float* __restrict__ hat, uint32_t* __restrict__ zero, int zero_words) {
   constexpr int VCH = D / 4;
   constexpr int RPT = 2;                                 // rows per thread: both rows' loads are in flight before the first use
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // the tile kernel's per-CTA d scale partials and (table, head) tile counters start at zero (was a memset node)
+  for (size_t z = idx; z < (size_t)zero_words; z += (size_t)gridDim.x * blockDim.x) zero[z] = 0u;
   const size_t half = (rows + RPT - 1) / RPT;
   const int c = (int)(idx & 7);
   size_t r[RPT];
@@ -327,7 +329,7 @@ __global__ void __launch_bounds__(kBtThreads, 1)
             for (int u = 0; u < 8; ++u) {
               const float x = fmaf(__uint_as_float(ra[u]), kLog2e, nq2[u]);   // the same fmaf as the query side
               const float p = exp2_fast(fminf(x, 0.f));
-              dsr[ci * 8 + u] = p * __uint_as_float(rb[u]);
+              dsr[ci * 8 + u] = x <= 0.f ? p * __uint_as_float(rb[u]) : 0.f;   // clamp(max=0) backward: [S <= 0]
               trunc_tf32(p, phv[u], plv[u]);
             }
             umma::tmem_st8(tST + lane_base + 8 * ch, phv);
@@ -357,7 +359,7 @@ __global__ void __launch_bounds__(kBtThreads, 1)
             for (int u = 0; u < 8; ++u) {
               const float x = fmaf(__uint_as_float(ra[u]), kLog2e, nq2);
               const float p = exp2_fast(fminf(x, 0.f));
-              trunc_tf32(p * __uint_as_float(rb[u]), dh[u], dl[u]);
+              trunc_tf32(x <= 0.f ? p * __uint_as_float(rb[u]) : 0.f, dh[u], dl[u]);   // the same mask, the same bits
             }
             umma::tmem_st8(tS + lane_base + 8 * ch, dh);
             umma::tmem_st8(tDP + lane_base + 8 * ch, dl);
@@ -903,18 +905,16 @@ static int launch_bwd_tc(const hept_shape* s, const float* q, const float* k, co
   auto kern = block_attn_bwd_tc_kernel<D, C, B, false>;
   auto kern_direct = block_attn_bwd_tc_kernel<D, C, B, true>;
   const size_t smem = CF::TOTAL + 1024;
-  static int sms = 0;
-  if (!sms) {
+  static DeviceOnce configured;
+  if (configured.needed()) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(kern_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "block_attn_bwd_tc: cannot reserve %zu B of shared memory: %s", smem,
                  cudaGetErrorString(e));
-    int dev = 0, n = 0;
-    cudaGetDevice(&dev);
-    e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    HEPT_REQUIRE(e == cudaSuccess && n > 0, HEPT_ECUDA, "block_attn_bwd_tc: cannot read the SM count");
-    sms = n;
+    configured.mark();
   }
+  const int sms = sm_count();
+  HEPT_REQUIRE(sms > 0, HEPT_ECUDA, "block_attn_bwd_tc: cannot read the SM count");
   BwdTcPlan p = plan_bwd_tc(s);
   float* hat = (float*)ws;
   float* grows = (float*)(ws + p.hat_bytes);
@@ -924,12 +924,14 @@ static int launch_bwd_tc(const hept_shape* s, const float* q, const float* k, co
   float* partial = (float*)((char*)sv + p.stage_bytes);
   HEPT_REQUIRE(s->C <= 8, HEPT_EUNSUPPORTED, "block_attn_bwd_tc: more than 8 coordinates");
   const size_t rows = (size_t)s->N * s->H;
-  grad_rows_kernel<D><<<(unsigned)((((rows + 1) / 2) * 8 + 255) / 256), 256, 0, st>>>(d_out_pre, out_pre, den_sum, rows, grows, coords, scale,
-                                                                         s->H, s->C, s->raw_size, hat);
-  HEPT_CHECK_LAUNCH("grad_rows");
   const int mask = bwd_stage_mask();
   int grid = p.tiles < sms ? p.tiles : sms;             // one CTA per SM (the tile uses all 512 TMEM columns)
   if (grid > kBtMaxCtas) grid = kBtMaxCtas;
+  // d scale partials of heads a CTA never visits and the per-(table, head) tile counts of the direct form start at zero
+  const int zero_words = (mask & 3) ? grid * s->H * 8 + s->T * s->H : 0;
+  grad_rows_kernel<D><<<(unsigned)((((rows + 1) / 2) * 8 + 255) / 256), 256, 0, st>>>(d_out_pre, out_pre, den_sum, rows, grows, coords, scale,
+                                                                         s->H, s->C, s->raw_size, hat, (uint32_t*)partial, zero_words);
+  HEPT_CHECK_LAUNCH("grad_rows");
   // Rows of the T tables: added straight into dq / dk / dv in table order by the tile kernel (needs the paired tile order,
   // i.e. an even number of heads; variant 3 does it when a (head, table) group is at least two waves of tiles, so that
   // no tile ever waits for the previous table; 4 = whenever possible, 5 = never), or staged per table and summed by
@@ -944,17 +946,33 @@ static int launch_bwd_tc(const hept_shape* s, const float* q, const float* k, co
   for (int g = 2; g <= 4 && !hg; ++g)
     if (s->H >= g && s->H % g != 1) hg = g;
   if (forced_g > 1 && s->H >= forced_g && s->H % forced_g != 1) hg = forced_g;
-  const bool direct = hg > 0 && variant != 5 && (variant == 4 || nb >= 2 * grid) && (mask & 3) == 3;
+  bool direct = hg > 0 && variant != 5 && (variant == 4 || nb >= 2 * grid) && (mask & 3) == 3;
   if (mask & 3) {
-    // partial sums of heads a CTA never visits, and the per-(table, head) tile counts of the direct path
     int* done = (int*)(partial + (size_t)grid * s->H * 8);
-    cudaError_t e = cudaMemsetAsync(partial, 0, sizeof(float) * (size_t)grid * s->H * 8 + sizeof(int) * (size_t)s->T * s->H, st);
-    HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "block_attn_bwd_tc: memset failed: %s", cudaGetErrorString(e));
     HEPT_REQUIRE(TileDecoder::exact_for(p.tiles, nb, s->T), HEPT_EUNSUPPORTED, "block_attn_bwd_tc: too many tiles (%d)", p.tiles);
-    if (direct)
-      kern_direct<<<grid, kBtThreads, smem, st>>>(q, k, v, hat, grows, positions, s->N, s->H, s->T, s->raw_size, p.tiles,
-                                                  TileDecoder::make(nb, s->T, s->H, hg), dq, dk, dv, partial, done);
-    else
+    bool launched = false;
+    if (direct) {
+      // The direct form's CTAs wait for each other's tile counts, so every CTA of the grid must be resident at once: a
+      // COOPERATIVE launch makes the driver guarantee that (it places the whole grid or nothing, whatever other streams hold)
+      // instead of this code assuming it.  If the device cannot place `grid` CTAs together the staged form takes over.
+      const TileDecoder dec = TileDecoder::make(nb, s->T, s->H, hg);
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)grid);
+      cfg.blockDim = dim3(kBtThreads);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeCooperative;
+      attr[0].val.cooperative = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      cudaError_t e = cudaLaunchKernelEx(&cfg, kern_direct, q, k, v, (const float*)hat, (const float*)grows, positions, (int)s->N,
+                                         (int)s->H, (int)s->T, (int)s->raw_size, (int)p.tiles, dec, dq, dk, dv, partial, done);
+      if (e == cudaSuccess) launched = true;
+      else (void)cudaGetLastError();
+    }
+    direct = launched;
+    if (!launched)
       kern<<<grid, kBtThreads, smem, st>>>(q, k, v, hat, grows, positions, s->N, s->H, s->T, s->raw_size, p.tiles,
                                            TileDecoder::make(nb, s->T), sq, sk, sv, partial, done);
     HEPT_CHECK_LAUNCH("block_attn_bwd_tc");

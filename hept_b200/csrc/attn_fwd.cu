@@ -137,12 +137,12 @@ static int launch_fwd(const hept_shape* s, const float* q, const float* k, const
                       const float* scale, const int32_t* positions, float* stage, cudaStream_t st) {
   using L = TileLayout<D, C, B, G, R>;
   auto kern = block_attn_fwd_kernel<D, C, B, G, R, MINB>;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.needed()) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::SMEM_BYTES);
     HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "block_attn_fwd: cannot reserve %zu B of shared memory: %s",
                  L::SMEM_BYTES, cudaGetErrorString(e));
-    configured = true;
+    configured.mark();
   }
   const int nb = s->N / s->B;
   dim3 grid((nb + G - 1) / G, s->T * s->H);

@@ -516,17 +516,15 @@ static int launch_fwd_tc(const hept_shape* s, const float* q, const float* k, co
   using CF = TcFwd<D, C, B>;
   auto kern = block_attn_fwd_tc_kernel<D, C, B>;
   const size_t smem = CF::TOTAL + 1024;
-  static int sms = 0;
-  if (!sms) {
+  static DeviceOnce configured;
+  if (configured.needed()) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "block_attn_fwd_tc: cannot reserve %zu B of shared memory: %s", smem,
                  cudaGetErrorString(e));
-    int dev = 0, n = 0;
-    cudaGetDevice(&dev);
-    e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    HEPT_REQUIRE(e == cudaSuccess && n > 0, HEPT_ECUDA, "block_attn_fwd_tc: cannot read the SM count");
-    sms = n;
+    configured.mark();
   }
+  const int sms = sm_count();
+  HEPT_REQUIRE(sms > 0, HEPT_ECUDA, "block_attn_fwd_tc: cannot read the SM count");
   const int tiles = s->T * s->H * (s->N / s->B);
   const int grid = tiles < sms ? tiles : sms;   // one CTA per SM (two tiles in flight use all 512 TMEM columns)
   HEPT_REQUIRE(TileDecoder::exact_for(tiles, s->N / s->B, s->T), HEPT_EUNSUPPORTED, "block_attn_fwd_tc: too many tiles (%d)", tiles);

@@ -5,6 +5,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "../../include/hept_b200.h"
 
 namespace hept {
@@ -17,7 +19,33 @@ int engine();  // 0 = fp32 SIMT tiles, 1 = tcgen05 tiles
 int bwd_variant();
 int hash_project_impl(const hept_shape* s, const float* q, const float* k, const float* coords, const float* scale,
                       const float* alpha, float* proj, float* span, void* workspace, size_t workspace_bytes, float* hat,
-                      bool* hat_done, void* stream);  // 1 = one lane per row (attn_bwd.cu), 2 = lane pairs + FFMA2 (attn_bwd2.cu), 3 = tcgen05 (attn_bwd_tc.cu)
+                      bool* hat_done, void* stream);
+
+// Per-DEVICE one-time setup.  cudaFuncSetAttribute opt-ins and SM counts belong to the device that is current when a
+// call arrives (the host side makes the tensors' device current around every call), not to the process: a second GPU in
+// the same process needs its own opt-in and its own grid size.  Two threads racing through the same first use both
+// configure (idempotent) before either marks it done.
+struct DeviceOnce {
+  std::atomic<uint64_t> done{0};
+  static int device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev & 63;
+  }
+  bool needed() const { return !((done.load(std::memory_order_acquire) >> device()) & 1ull); }
+  void mark() { done.fetch_or(1ull << device(), std::memory_order_release); }
+};
+// SM count of the current device (cached per device); 0 if it cannot be read
+inline int sm_count() {
+  static std::atomic<int> cache[64];
+  const int dev = DeviceOnce::device();
+  int n = cache[dev].load(std::memory_order_relaxed);
+  if (n <= 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 0;
+    cache[dev].store(n, std::memory_order_relaxed);
+  }
+  return n;
+}
 
 #define HEPT_REQUIRE(cond, code, ...)      \
   do {                                     \

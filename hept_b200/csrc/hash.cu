@@ -357,19 +357,18 @@ static int launch_project_v2(const hept_shape* s, const float* q, const float* k
                              const float* alpha, float* proj, uint32_t* partial, int* ctas, float* hat, cudaStream_t st) {
   const size_t smem = sizeof(float) * ((size_t)s->H * 32 * T + (((size_t)s->H * C + 3) & ~(size_t)3) +
                                        2 * 32 * ((size_t)s->H * D + 4));
-  static int sms = 0, per_sm = 0;
+  static DeviceOnce configured;
+  int per_sm = 0;
   const bool wide = s->H > 8;                     // more than one head per warp
-  if (!sms) {
+  if (configured.needed()) {
     cudaError_t e = cudaFuncSetAttribute(hash_project_v2_kernel<D, C, T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(hash_project_v2_kernel<D, C, T, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "hash_project: %s", cudaGetErrorString(e));
-    int dev = 0, n = 0;
-    cudaGetDevice(&dev);
-    e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    HEPT_REQUIRE(e == cudaSuccess && n > 0, HEPT_ECUDA, "hash_project: cannot read the SM count");
-    sms = n;
+    configured.mark();
   }
+  const int sms = sm_count();
+  HEPT_REQUIRE(sms > 0, HEPT_ECUDA, "hash_project: cannot read the SM count");
   HEPT_REQUIRE(smem <= 100 * 1024, HEPT_EUNSUPPORTED, "hash_project: H*D=%d too wide for the staging buffer", s->H * D);
   HEPT_REQUIRE(s->H <= 8 * 4, HEPT_EUNSUPPORTED, "hash_project: more than 32 heads");
   cudaError_t e = wide ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hash_project_v2_kernel<D, C, T, 4>, 256, smem)
@@ -392,11 +391,11 @@ static int launch_project(const hept_shape* s, const float* q, const float* k, c
   const int E = D + C;
   const size_t smem = sizeof(float) * ((size_t)s->H * E * s->T + (((size_t)s->H * C + 3) & ~(size_t)3) +
                                        2 * 32 * ((size_t)s->H * D + 4));
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.needed()) {
     cudaError_t e = cudaFuncSetAttribute(hash_project_kernel<D, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "hash_project: %s", cudaGetErrorString(e));
-    configured = true;
+    configured.mark();
   }
   HEPT_REQUIRE(smem <= 100 * 1024, HEPT_EUNSUPPORTED, "hash_project: H*D=%d too wide for the staging buffer", s->H * D);
   dim3 grid((s->N + 31) / 32);

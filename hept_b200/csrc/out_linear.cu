@@ -471,35 +471,25 @@ __global__ void __launch_bounds__(32 * kOlParts) out_linear_reduce_kernel(const 
   }
 }
 
-static int sm_count() {
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0, n = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) sms = n;
-  }
-  return sms;
-}
-
 template <int OUT, int OUTS, int HT>
 static int launch_ol_fwd(const hept_shape* s, const float* x, const float* w, const float* b, float* out, cudaStream_t st) {
   const int IN = s->H * s->D;
   const size_t smem = sizeof(float) * (size_t)OUT * IN;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.needed()) {
     cudaError_t e = cudaFuncSetAttribute(out_linear_fwd_kernel<OUT, OUTS, HT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "out_linear_fwd: %s", cudaGetErrorString(e));
-    configured = true;
+    configured.mark();
   }
   HEPT_REQUIRE(smem <= 96 * 1024 && IN % 4 == 0, HEPT_EUNSUPPORTED, "out_linear_fwd: H*D=%d not supported", IN);
   if constexpr (OUT == 24) if (IN == OUT * 8) {    // the shipped H = 8, D = 24 shape: staged, register-tiled
     constexpr int TIN = OUT * 8;
     const size_t tsmem = sizeof(float) * ((size_t)OUT * (TIN + 4) + (size_t)kTlHits * (48 + 4));
-    static bool tconfigured = false;
-    if (!tconfigured) {
+    static DeviceOnce tconfigured;
+    if (tconfigured.needed()) {
       cudaError_t e = cudaFuncSetAttribute(out_linear_fwd_tiled_kernel<OUT, TIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem);
       HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "out_linear_fwd: %s", cudaGetErrorString(e));
-      tconfigured = true;
+      tconfigured.mark();
     }
     out_linear_fwd_tiled_kernel<OUT, TIN><<<(s->N + kTlHits - 1) / kTlHits, kTlThreads, tsmem, st>>>(x, w, b, s->N, out);
     HEPT_CHECK_LAUNCH("out_linear_fwd");
@@ -521,11 +511,11 @@ static int launch_ol_bwd(const hept_shape* s, const float* g, const float* w, co
                "out_linear_bwd: H*D=%d too wide", IN);
   if (dx) {
     const size_t smem = sizeof(float) * (size_t)OUT * IN;
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (configured.needed()) {
       cudaError_t e = cudaFuncSetAttribute(out_linear_bwd_input_kernel<OUT, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
       HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "out_linear_bwd: %s", cudaGetErrorString(e));
-      configured = true;
+      configured.mark();
     }
     HEPT_REQUIRE(smem <= 96 * 1024, HEPT_EUNSUPPORTED, "out_linear_bwd: H*D=%d too wide", IN);
     bool tiled = false;
@@ -533,11 +523,11 @@ static int launch_ol_bwd(const hept_shape* s, const float* g, const float* w, co
       tiled = true;
       constexpr int TIN = OUT * 8;
       const size_t tsmem = sizeof(float) * ((size_t)OUT * TIN + (size_t)kTlHits * (OUT + 4));
-      static bool tconfigured = false;
-      if (!tconfigured) {
+      static DeviceOnce tconfigured;
+      if (tconfigured.needed()) {
         cudaError_t e = cudaFuncSetAttribute(out_linear_bwd_input_tiled_kernel<OUT, TIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem);
         HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "out_linear_bwd: %s", cudaGetErrorString(e));
-        tconfigured = true;
+        tconfigured.mark();
       }
       out_linear_bwd_input_tiled_kernel<OUT, TIN><<<(s->N + kTlHits - 1) / kTlHits, kTlThreads, tsmem, st>>>(g, w, s->N, dx);
     }
@@ -557,11 +547,11 @@ static int launch_ol_bwd(const hept_shape* s, const float* g, const float* w, co
     ptiled = true;
     constexpr int TIN = OUT * 8, THREADS = kPgGroups * (OUT / 8) * (TIN / 8);
     const size_t tsmem = sizeof(float) * 2 * (size_t)kPgRows * (TIN + 4 + OUT + 4);
-    static bool tconfigured = false;
-    if (!tconfigured) {
+    static DeviceOnce tconfigured;
+    if (tconfigured.needed()) {
       cudaError_t e = cudaFuncSetAttribute(out_linear_bwd_params_tiled_kernel<OUT, TIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem);
       HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "out_linear_bwd: %s", cudaGetErrorString(e));
-      tconfigured = true;
+      tconfigured.mark();
     }
     const int tslabs = (s->N + kPgRows - 1) / kPgRows;
     ctas = sms * 2 < tslabs ? sms * 2 : tslabs;

@@ -379,11 +379,11 @@ extern "C" int hept_segmented_argsort(const float* keys, int32_t num_segments, i
   if (const int cs = cluster_size_for(num_segments, n)) {
     const int cap = (n + cs - 1) / cs;
     const size_t smem = cluster_sort_smem(cap);
-    static std::atomic<size_t> opted{0};
-    if (opted.load() < smem) {
+    static DeviceOnce opted;
+    if (opted.needed()) {
       HEPT_REQUIRE(cudaFuncSetAttribute(cluster_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cluster_sort_smem(kCsMaxCap)) == cudaSuccess,
                    HEPT_ECUDA, "segmented_argsort: cannot opt in to %zu bytes of shared memory", cluster_sort_smem(kCsMaxCap));
-      opted.store(cluster_sort_smem(kCsMaxCap));
+      opted.mark();
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)num_segments * cs);

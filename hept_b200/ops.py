@@ -9,6 +9,7 @@ The stage-wise entry points exist so parity tests can inject the oracle's interm
 from __future__ import annotations
 
 import ctypes as C
+import functools
 from dataclasses import dataclass
 from typing import Optional, Sequence, Tuple
 
@@ -41,6 +42,41 @@ def _stream(t: torch.Tensor) -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
 
 
+def _tensors(args):
+    for a in args:
+        if isinstance(a, torch.Tensor):
+            yield a
+        elif isinstance(a, (list, tuple)):
+            yield from _tensors(a)
+
+
+def _on_device(fn):
+    """Run a native stage with the tensors' device current.
+
+    The library launches on the CURRENT CUDA device and keeps per-device state (include/hept_b200.h): every tensor
+    argument must live on one CUDA device, and that device is made current for the call, so a module placed on
+    ``cuda:1`` with ``.to()`` works without the caller ever calling ``torch.cuda.set_device``.
+    """
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        dev = None
+        for t in _tensors(list(args) + list(kwargs.values())):
+            if not t.is_cuda:
+                raise RuntimeError(f"{fn.__name__}: tensor on {t.device}: hept_b200 runs on CUDA (sm_100a) only, "
+                                   "there is no CPU path")
+            if dev is None:
+                dev = t.device
+            elif t.device != dev:
+                raise RuntimeError(f"{fn.__name__}: tensors on different devices ({dev} and {t.device})")
+        if dev is None:
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+
+    return wrapper
+
+
 def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
     return C.c_void_p(0 if t is None else t.data_ptr())
 
@@ -70,6 +106,7 @@ def launch_count(reset: bool = False) -> int:
 
 
 # ------------------------------------------------------------------------------------------ stages
+@_on_device
 def coord_scale(w_rpe_weight: torch.Tensor, H: int, D: int, K: int) -> torch.Tensor:
     lib = _lib.load()
     w = _need(w_rpe_weight, "w_rpe.weight", torch.float32)
@@ -81,6 +118,7 @@ def coord_scale(w_rpe_weight: torch.Tensor, H: int, D: int, K: int) -> torch.Ten
     return scale
 
 
+@_on_device
 def coord_scale_backward(w_rpe_weight: torch.Tensor, scale: torch.Tensor, dscale: torch.Tensor, H: int, D: int,
                          K: int) -> torch.Tensor:
     lib = _lib.load()
@@ -94,6 +132,7 @@ def coord_scale_backward(w_rpe_weight: torch.Tensor, scale: torch.Tensor, dscale
     return dw
 
 
+@_on_device
 def hash_project(d: Dims, q, k, coords, scale, alpha) -> Tuple[torch.Tensor, torch.Tensor]:
     """-> proj (2, T, H, N), span (T, H)."""
     lib = _lib.load()
@@ -111,6 +150,7 @@ def hash_project(d: Dims, q, k, coords, scale, alpha) -> Tuple[torch.Tensor, tor
     return proj, span
 
 
+@_on_device
 def keys_from_packed_shifts(d: Dims, proj, span, combined_shifts) -> torch.Tensor:
     lib = _lib.load()
     proj = _need(proj, "proj", torch.float32, (2, d.T, d.H, d.N))
@@ -123,6 +163,7 @@ def keys_from_packed_shifts(d: Dims, proj, span, combined_shifts) -> torch.Tenso
     return keys
 
 
+@_on_device
 def keys_from_region_indices(d: Dims, proj, span, region_eta, region_phi, regions_h) -> torch.Tensor:
     lib = _lib.load()
     proj = _need(proj, "proj", torch.float32, (2, d.T, d.H, d.N))
@@ -137,6 +178,7 @@ def keys_from_region_indices(d: Dims, proj, span, region_eta, region_phi, region
     return keys
 
 
+@_on_device
 def segmented_argsort(keys: torch.Tensor) -> torch.Tensor:
     """Stable ascending argsort along the last dim of a float32 tensor -> int32 positions, same shape."""
     lib = _lib.load()
@@ -151,6 +193,7 @@ def segmented_argsort(keys: torch.Tensor) -> torch.Tensor:
     return pos
 
 
+@_on_device
 def hat_coords(d: Dims, coords, scale) -> torch.Tensor:
     """-> (N, H, 8): scale[h,c] * coords[n,c], zero padded (the coordinate part of q_hat / k_hat)."""
     lib = _lib.load()
@@ -162,6 +205,7 @@ def hat_coords(d: Dims, coords, scale) -> torch.Tensor:
     return hat
 
 
+@_on_device
 def block_attention_fwd(d: Dims, q, k, v, coords, scale, positions) -> torch.Tensor:
     """-> stage (H, N, T, 32): numerator [0:D) and normaliser [D] per (head, hit, table), original hit order."""
     lib = _lib.load()
@@ -179,6 +223,7 @@ def block_attention_fwd(d: Dims, q, k, v, coords, scale, positions) -> torch.Ten
     return stage
 
 
+@_on_device
 def or_combine(d: Dims, stage) -> Tuple[torch.Tensor, torch.Tensor]:
     lib = _lib.load()
     stage = _need(stage, "stage", torch.float32, (d.H, d.N, d.T, STAGE_ROW))
@@ -189,6 +234,7 @@ def or_combine(d: Dims, stage) -> Tuple[torch.Tensor, torch.Tensor]:
     return out_pre, den
 
 
+@_on_device
 def out_linear_fwd(d: Dims, out_pre, weight, bias) -> torch.Tensor:
     """out (N, D) = out_pre (N, H*D) weight^T + bias   (example/hept.py:80)."""
     lib = _lib.load()
@@ -201,6 +247,7 @@ def out_linear_fwd(d: Dims, out_pre, weight, bias) -> torch.Tensor:
     return out
 
 
+@_on_device
 def out_linear_bwd(d: Dims, d_out, weight, out_pre, need_input_grad: bool = True):
     """-> d_out_pre (N, H*D) or None, d_weight (D, H*D), d_bias (D)."""
     lib = _lib.load()
@@ -218,6 +265,7 @@ def out_linear_bwd(d: Dims, d_out, weight, out_pre, need_input_grad: bool = True
 
 
 # --------------------------------------------------------------------------------------- whole path
+@_on_device
 def attention_fwd(d: Dims, q, k, v, coords, w_rpe_weight, K: int, alpha, combined_shifts=None, region_indices=None,
                   regions_h=None):
     """a3..a12 in one native call -> (out_pre (N,H*D), den_sum (N,H), scale (H,C), positions (2,T,H,N) int32)."""
@@ -248,6 +296,7 @@ def attention_fwd(d: Dims, q, k, v, coords, w_rpe_weight, K: int, alpha, combine
     return out_pre, den, scale, pos
 
 
+@_on_device
 def attention_bwd(d: Dims, q, k, v, coords, scale, positions, out_pre, den_sum, d_out_pre):
     """-> dq, dk, dv (N, H*D), dscale (H, C)."""
     lib = _lib.load()

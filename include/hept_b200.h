@@ -19,6 +19,8 @@
  *
  * Supported compile-time shapes (D, C, B): (24,6,100) tracking, (24,4,100) pileup, (8,6,10) test.
  * Anything else returns HEPT_EUNSUPPORTED (no slow fallback, no CPU path).
+ * Devices: kernels run on the CURRENT CUDA device; the caller makes the device that owns the pointers current
+ * (hept_b200/ops.py does so around every call).  Per-device state (shared-memory opt-ins, SM counts) is kept per device.
  */
 #ifndef HEPT_B200_H
 #define HEPT_B200_H
@@ -154,30 +156,13 @@ int hept_get_engine(void);
 void hept_set_sort_variant(int variant);
 int hept_get_sort_variant(void);
 
-/* backward tile kernels: 1 = one lane per row (attn_bwd.cu), 2 = lane pairs + packed FFMA2 (attn_bwd2.cu),
- * 3 = tcgen05 tiles (attn_bwd_tc.cu; default).  The tcgen05 tiles either add the T tables' rows straight into dq / dk / dv in
- * table order (no staging rows, no summing kernel; needs an even number of heads) or stage them per table: 3 picks the
+/* backward tile kernels: 1 = fp32 CUDA-core tiles, one lane per row (attn_bwd.cu), 3 = tcgen05 tiles (attn_bwd_tc.cu;
+ * default).  The tcgen05 tiles either add the T tables' rows straight into dq / dk / dv in table order (no staging rows,
+ * no summing kernel; launched cooperatively, because its CTAs wait for each other) or stage them per table: 3 picks the
  * direct form when a (head, table) group is at least two waves of tiles, 4 = direct whenever possible, 5 = staged always.
- * Same bits either way. */
+ * Same bits either way.  Process-wide test / profiling aid (atomic). */
 void hept_set_bwd_variant(int variant);
 int hept_get_bwd_variant(void);
-
-/* self-test of the tcgen05 / TMEM building blocks (hept_b200/csrc/umma.cuh): S = A B^T with A (128,32),
- * Bm (112,32) both K-major, then O = S V with S read back from TMEM and V (112,32) MN-major.
- * Outputs S_out (128,112), O_out (128,32).  kmajor_base32 != 0 stores the K-major operands with the MN-major
- * operand's swizzle (SWIZZLE_128B_BASE32B), the single-image layout the backward tiles rely on.
- * Used by tests/test_gpu_umma.py only. */
-int hept_debug_umma_selftest(const float* A, const float* Bm, const float* V, float* S_out, float* O_out,
-                             int kmajor_base32, void* stream);
-
-/* S_xy = X Y^T and S_yx = Y X^T (X, Y (112,32) fp32; outputs (128,112), rows >= 112 zero) on the tensor core: probes
- * whether the tf32 MMA is bitwise symmetric under an exchange of its operands (tests/test_gpu_umma.py). */
-int hept_debug_umma_symmetry(const float* X, const float* Y, float* S_xy, float* S_yx, void* stream);
-
-/* cycles (clock64 of the issuing thread) from the first tcgen05.mma of a burst of `count` tf32 M = 128 MMAs to the
- * completion of its commit.  mode 0 / 1 / 4: TS MMAs with N = 32 into 1 / 2 / 4 accumulators; mode 2 / 3: SS MMAs with
- * N = 112 into 1 / 2 accumulators.  cycles is a device pointer to one int64.  Used by tools/umma_timing.py. */
-int hept_debug_umma_timing(int mode, int count, long long* cycles, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,12 +1,27 @@
 // Self-test of the tcgen05 building blocks (umma.cuh) on exactly representable data: an SS MMA with both
 // operands K-major (S = A B^T, 128 x 112 x 32) followed by a TS MMA whose A operand is read back from
 // TMEM and whose B operand is MN-major (O = S V, 128 x 32 x 112).  Used by tests/test_gpu_umma.py.
+//
+// TEST CODE: built into its own library (tests/native/libhept_umma_test.so, `make -C tests/native`), never linked into
+// the product library libhept_sm100.so; it shares only the header-only helpers of hept_b200/csrc (umma.cuh, common.cuh).
+#include <stdarg.h>
+
 #include <type_traits>
 
-#include "common.cuh"
-#include "umma.cuh"
+#include "../../hept_b200/csrc/common.cuh"
+#include "../../hept_b200/csrc/umma.cuh"
 
 namespace hept {
+
+// the two hooks of common.cuh's macros that the product library defines in abi.cu
+static thread_local char g_test_error[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_test_error, sizeof(g_test_error), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int) {}
 
 constexpr int kTM = 128, kTN = 112, kTK = 32, kTV = 32;
 
@@ -156,14 +171,16 @@ __global__ void __launch_bounds__(128, 1) umma_symmetry_kernel(const float* __re
 
 using namespace hept;
 
+extern "C" const char* hept_debug_last_error(void) { return hept::g_test_error; }
+
 extern "C" int hept_debug_umma_symmetry(const float* X, const float* Y, float* S_xy, float* S_yx, void* stream) {
   HEPT_REQUIRE(X && Y && S_xy && S_yx, HEPT_EINVAL, "umma_symmetry: null pointer");
   const size_t smem = (size_t)2 * kTM * 128 + 1024;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.needed()) {
     cudaError_t e = cudaFuncSetAttribute(umma_symmetry_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "umma_symmetry: %s", cudaGetErrorString(e));
-    configured = true;
+    configured.mark();
   }
   umma_symmetry_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(X, Y, S_xy, S_yx);
   HEPT_CHECK_LAUNCH("umma_symmetry");
@@ -174,13 +191,13 @@ extern "C" int hept_debug_umma_selftest(const float* A, const float* Bm, const f
                                         int kmajor_base32, void* stream) {
   HEPT_REQUIRE(A && Bm && V && S_out && O_out, HEPT_EINVAL, "umma_selftest: null pointer");
   const size_t smem = (size_t)(kTM + 3 * kTN) * 128 + 1024;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.needed()) {
     cudaError_t e = cudaFuncSetAttribute(umma_selftest_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(umma_selftest_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "umma_selftest: %s", cudaGetErrorString(e));
-    configured = true;
+    configured.mark();
   }
   if (kmajor_base32) umma_selftest_kernel<true><<<1, 128, smem, (cudaStream_t)stream>>>(A, Bm, V, S_out, O_out);
   else umma_selftest_kernel<false><<<1, 128, smem, (cudaStream_t)stream>>>(A, Bm, V, S_out, O_out);
@@ -288,11 +305,11 @@ __global__ void __launch_bounds__(128, 1) umma_timing_kernel(int mode, int count
 extern "C" int hept_debug_umma_timing(int mode, int count, long long* cycles, void* stream) {
   HEPT_REQUIRE(cycles && count > 0, HEPT_EINVAL, "umma_timing: bad argument");
   const size_t smem = (size_t)5 * 128 * 128 + 1024;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.needed()) {
     cudaError_t e = cudaFuncSetAttribute(hept::umma_timing_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "umma_timing: %s", cudaGetErrorString(e));
-    configured = true;
+    configured.mark();
   }
   hept::umma_timing_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(mode, count, cycles);
   HEPT_CHECK_LAUNCH("umma_timing");

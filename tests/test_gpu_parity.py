@@ -6,15 +6,22 @@ Tolerances (stated once, used everywhere):
   * projections: |ours - oracle_fp32| <= 4e-6 * sum_e |x_e alpha_e|  (a 30-term fp32 dot product whose
     accumulation order differs between MKL, cuBLAS and a sequential FMA chain, SURVEY.md 7.3-1);
   * attention outputs and gradients, permutations held fixed, relative Frobenius norms against the
-    float64 oracle:  err(ours) <= 3 * err(reference fp32) + FLOOR, FLOOR = 3e-6 (outputs) / 1e-5 (gradients).
-    Both are fp32 evaluations of the same formula with different summation orders, so their distances to the
-    float64 truth are two draws of the same rounding noise (the reference's own noise is 3e-7..7e-3 depending
-    on weight magnitudes); the factor 3 is the envelope on that noise, not slack in the math.
-    With the tcgen05 tile engine the operands are 3xTF32 splits (2^-22 relative instead of 2^-24) and the
-    tensor-core accumulator truncates, so FLOOR is 5x larger there (1.5e-5 / 5e-5);
-  * end to end against the reference's golden outputs: permutations may differ from the reference's
-    only at near-ties of the keys, and at most 0.2 % of positions; outputs of unaffected rows agree to
-    the tolerance above.
+    float64 oracle:  err(ours) <= 2.5 * err(reference fp32) + FLOOR, FLOOR = 3e-6 (outputs) / 1e-5 (gradients),
+    the same for every tile engine (fp32 CUDA-core tiles and tcgen05 3xTF32 tiles).
+    Both are fp32-grade evaluations of the same formula with different summation orders, so their distances to
+    the float64 truth are two draws of the same rounding noise (the reference's own noise is 3e-7 with default-init
+    weights up to 7e-2 (out) / 2e-1 (dq, dk) with the trained checkpoint's layer-0 weights); the
+    factor 2.5 is the envelope on that noise, not slack in the math;
+  * two weight regimes: A = default-init (six fixtures), B = the trained weights of the
+    reference's checkpoint, layers 0 and 2 (fixtures ckpt_l0 / ckpt_l2, tests/golden/make_ckpt_fixture.py), where
+    sqrt(2w) reaches 5 800 and the reference's score formula cancels.  In regime B the kernels (which centre every
+    block) must additionally be at least as close to float64 as the reference is;
+  * the headline sizes (60 000 and 61 237 hits, the 60 187-hit imbalanced batch) are compared with the oracle in
+    float32 and float64 like the small cases, in both regimes;
+  * end to end against the reference's golden outputs: permutations may differ from the reference's only where the
+    reference's own keys are exactly tied (its argsort is unstable) or within rounding of each other (near-ties: at
+    most 1e-4 of the positions, each within 1e-5 of the projection span); outputs of unaffected rows agree to the
+    tolerance above.
 """
 import json
 import os
@@ -23,7 +30,7 @@ import pytest
 import torch
 
 from oracle import hept_oracle as O
-from tests.helpers import CASES, load_case, rel_err
+from tests.helpers import ALL_CASES, CASES, CKPT_CASES, ckpt_params, ckpt_qkv, load_case, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -109,7 +116,7 @@ def oracle_trace(cfg, inputs, params, dtype=torch.float32, positions=None):
 
 
 # ------------------------------------------------------------------------------------------ stages
-@pytest.mark.parametrize("name", ["tiny_example", "small_batched", "pileup_small"])
+@pytest.mark.parametrize("name", ["tiny_example", "small_batched", "pileup_small", "ckpt_l0", "ckpt_l2"])
 def test_coord_scale_forward_backward(name):
     from hept_b200 import ops
 
@@ -153,7 +160,7 @@ def test_out_linear_forward_backward(shape):
     assert none is None and torch.equal(dw, dw3)
 
 
-@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("name", ALL_CASES)
 def test_projection_span_keys(name):
     from hept_b200 import ops
 
@@ -245,7 +252,7 @@ def _check_segmented_argsort(ops, segs, n):
     assert torch.equal(pos.cpu().long(), want)
 
 
-@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("name", ALL_CASES)
 def test_sort_matches_reference_up_to_key_ties(name):
     """Our permutation of OUR keys is the stable argsort (bit-exact); against the reference's permutation it
     may differ only where the reference's own keys are (nearly) tied."""
@@ -265,30 +272,34 @@ def test_sort_matches_reference_up_to_key_ties(name):
     ref_keys = torch.stack([gold["q_keys"], gold["k_keys"]])
     diff = pos != ref_pos
     a_all, b_all = ref_keys.gather(-1, pos), ref_keys.gather(-1, ref_pos)
-    # src/ padding rows all carry key +inf: any order among them is "the" reference order
-    both_inf = torch.isinf(a_all) & torch.isinf(b_all)
-    frac = float((diff & ~both_inf).float().mean())
-    REPORT[rkey(f"perm_mismatch_frac_{name}")] = frac
-    assert frac <= 2e-3
-    if diff.any():
-        a = a_all[diff]
-        b = b_all[diff]
-        fin = torch.isfinite(a) & torch.isfinite(b)
-        span = (ref_keys[torch.isfinite(ref_keys)].max() - ref_keys[torch.isfinite(ref_keys)].min()).abs()
-        assert torch.equal(torch.isfinite(a), torch.isfinite(b))
-        assert float((a[fin] - b[fin]).abs().max()) <= 1e-5 * float(span)
+    # (1) exact ties of the REFERENCE's keys (incl. the src/ padding rows, all +inf): its argsort is unstable, any order
+    #     among them is "the" reference order;  (2) near-ties: keys that differ, but by less than the rounding of a
+    #     30-term fp32 dot product summed in another order
+    exact = diff & (a_all == b_all)
+    near = diff & ~exact
+    REPORT[rkey(f"perm_exact_tie_frac_{name}")] = float(exact.float().mean())
+    REPORT[rkey(f"perm_near_tie_frac_{name}")] = float(near.float().mean())
+    REPORT[rkey(f"perm_mismatch_frac_{name}")] = float(diff.float().mean())
+    assert float(near.float().mean()) <= 1e-4
+    if near.any():
+        tr = oracle_trace(cfg, inputs, params)
+        span = torch.stack([tr["span"], tr["span"]]).expand(2, d.T, d.H, n)       # (2,T,H,N): projection range per (t,h)
+        assert bool(torch.isfinite(a_all[near]).all() and torch.isfinite(b_all[near]).all())
+        # a key is fl(proj + shift * span): two keys that differ are at least one ulp of the KEY apart (the shift term is
+        # up to ~1e3..1e7 spans), and a projection that moved by rounding moves its key by at most one or two such ulps
+        ulp = torch.maximum(a_all[near].abs(), b_all[near].abs()) * 2.0 ** -23
+        gap = (a_all[near] - b_all[near]).abs() / (4 * ulp + 1e-5 * span[near])
+        REPORT[rkey(f"perm_near_tie_max_gap_{name}")] = float(gap.max())
+        assert float(gap.max()) <= 1.0
 
 
 def _err_budget(ours, ref32, ref64, floor):
-    from hept_b200 import _lib
-
-    if _lib.load().hept_get_engine():
-        floor = floor * 5      # tcgen05 tiles: 3xTF32 operands carry 2^-22, not 2^-24, relative precision
+    """err(ours vs fp64) <= 2.5 * err(reference fp32 vs fp64) + floor, every engine alike."""
     e_ours, e_ref = rel_err(ours, ref64), rel_err(ref32, ref64)
-    return e_ours, e_ref, e_ours <= 3 * e_ref + floor
+    return e_ours, e_ref, e_ours <= 2.5 * e_ref + floor
 
 
-@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("name", ALL_CASES)
 def test_block_attention_forward_with_reference_permutations(name):
     """Stage a8-a12 fed the REFERENCE's permutations: numerators, normalisers and combined output."""
     from hept_b200 import ops
@@ -317,7 +328,7 @@ def test_block_attention_forward_with_reference_permutations(name):
     assert ok, (e_o, e_r)
 
 
-@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("name", ALL_CASES)
 def test_module_forward_backward_against_oracle(name):
     """HEPTAttention (drop-in module) forward + every gradient, against the float64 oracle evaluated with the
     permutations the module itself computed, with the reference's own fp32 noise as the yardstick."""
@@ -355,6 +366,8 @@ def test_module_forward_backward_against_oracle(name):
         floor = OUT_FLOOR if key == "out" else GRAD_FLOOR
         e_o, e_r, ok = _err_budget(val, r32[key], r64[key], floor)
         REPORT[rkey(f"module_{key}_{name}")] = [e_o, e_r]
+        if name in CKPT_CASES:       # regime B: the reference cancels, the centred tiles must not
+            ok = ok and e_o <= e_r + floor
         if not ok:
             bad.append((key, e_o, e_r))
     assert not bad, bad
@@ -384,18 +397,122 @@ def test_end_to_end_against_golden_reference_output(name):
     assert float(row_err.median()) < 5e-5
 
 
-# ------------------------------------------------------------------------- full-size property tests
-def _full_size_problem(n_raw=60000, seed=1):
+
+
+# ------------------------------------------------------------------------- the headline sizes
+def _full_size_problem(n_raw=60000, seed=1, regime="A", sizes=None):
+    """One synthetic tracking event of ``n_raw`` hits (or a batch of ``sizes``), prepared by the ORACLE's prepare_input.
+    regime A: default-init weights, q/k/v ~ N(0, 0.5^2); regime B: checkpoint layer-0 weights, q/k/v through its layers."""
     from hept_b200 import synthetic
 
     cfg = dict(synthetic.TRACKING)
-    coords_raw, batch = synthetic.batched_cloud([n_raw], cfg["coords_dim"], seed)
-    params = synthetic.module_params(cfg, seed)
-    x = torch.zeros(n_raw, 1)
+    sizes = [n_raw] if sizes is None else list(sizes)
+    coords_raw, batch = synthetic.batched_cloud(sizes, cfg["coords_dim"], seed)
+    params = synthetic.module_params(cfg, seed) if regime == "A" else ckpt_params(0)
+    x = torch.zeros(sum(sizes), 1)
     _, kw, _ = O.prepare_batched(x, coords_raw, batch, params["regions"], cfg["block_size"], cfg["num_heads"])
     n = kw["coords"].shape[0]
-    q, k, v = synthetic.qkv(n, cfg, seed)
+    q, k, v = synthetic.qkv(n, cfg, seed) if regime == "A" else ckpt_qkv(0, n, seed)
     return cfg, params, kw, q, k, v
+
+
+@pytest.mark.parametrize("regime", ["A", "B"])
+@pytest.mark.parametrize("workload", ["60000", "61237", "imbalanced-60187"])
+def test_headline_sizes_against_oracle(workload, regime, engine):
+    """BASELINE.json configs[1] (60 000 hits, and 61 237 which forces padding) and configs[3] (eight imbalanced events,
+    60 187 hits, two of them shorter than a block), UNSCALED: module forward + every gradient against the oracle in
+    float32 and float64, evaluated with the permutations the module itself computed — the same budget as the fixtures.
+    At this size the direct form of the tcgen05 backward is what runs (>= 2 waves of tiles per (head, table) group)."""
+    if engine == "simt" and regime == "B":
+        pytest.skip("regime B at full size runs on the tcgen05 engines (the fp32 tiles are covered by the ckpt fixtures)")
+    from hept_b200 import HEPTAttention, ops, synthetic
+
+    sizes = synthetic.event_sizes("batched-imbalanced") if workload.startswith("imbalanced") else [int(workload)]
+    cfg, params, kw, q, k, v = _full_size_problem(seed=3, regime=regime, sizes=sizes)
+    n = q.shape[0]
+    assert n == {"60000": 60000, "61237": 61300, "imbalanced-60187": 60500}[workload]
+    g = torch.randn(n, cfg["h_dim"], generator=torch.Generator().manual_seed(8))
+    inputs = {"query": q, "key": k, "value": v, "coords": kw["coords"], "combined_shifts": kw["combined_shifts"]}
+    mod = HEPTAttention(cfg["h_dim"] + cfg["coords_dim"], **cfg)
+    mod.load_state_dict({kk: params[kk] for kk in ("out_linear.weight", "out_linear.bias", "e2lsh.alpha")}, strict=True)
+    mod = mod.to(dev())
+    w_rpe = torch.nn.Linear(params["w_rpe.weight"].shape[1], params["w_rpe.weight"].shape[0])
+    w_rpe.load_state_dict({"weight": params["w_rpe.weight"], "bias": params["w_rpe.bias"]})
+    w_rpe = w_rpe.to(dev())
+    di = to_dev(inputs)
+    qd, kd, vd = (di[x].clone().requires_grad_(True) for x in ("query", "key", "value"))
+    out = mod(qd, kd, vd, w_rpe=w_rpe, coords=di["coords"], combined_shifts=di["combined_shifts"])
+    out.backward(g.to(dev()))
+    d = dims_of(cfg, n)
+    _, _, _, pos = ops.attention_fwd(d, qd.detach(), kd.detach(), vd.detach(), di["coords"], w_rpe.weight.detach(),
+                                     cfg["num_w_per_dist"], mod.e2lsh.alpha, combined_shifts=di["combined_shifts"])
+    positions = (pos[0].cpu().long(), pos[1].cpu().long())
+    # our permutation against the oracle's own stable argsort of ITS keys: exact ties cannot differ (both are stable),
+    # so every mismatch is a near-tie of keys that moved by rounding
+    r32 = O.forward_backward(inputs, params, cfg, g, torch.float32)
+    own = torch.stack([r32["q_pos"], r32["k_pos"]])
+    near = float((own != torch.stack(positions)).float().mean())
+    REPORT[rkey(f"headline_{workload}_{regime}_perm_near_tie_frac")] = near
+    assert near <= 1e-4
+    r32 = O.forward_backward(inputs, params, cfg, g, torch.float32, positions)
+    r64 = O.forward_backward(inputs, params, cfg, g, torch.float64, positions)
+    mine = {"out": out.detach().cpu(), "dq": qd.grad.cpu(), "dk": kd.grad.cpu(), "dv": vd.grad.cpu(),
+            "dw_rpe": w_rpe.weight.grad.cpu(), "dout_w": mod.out_linear.weight.grad.cpu(),
+            "dout_b": mod.out_linear.bias.grad.cpu()}
+    bad = []
+    for key, val in mine.items():
+        floor = OUT_FLOOR if key == "out" else GRAD_FLOOR
+        e_o, e_r, ok = _err_budget(val, r32[key], r64[key], floor)
+        REPORT[rkey(f"headline_{workload}_{regime}_{key}")] = [e_o, e_r]
+        if regime == "B":
+            ok = ok and e_o <= e_r + floor
+        if not ok:
+            bad.append((key, e_o, e_r))
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("name", CKPT_CASES)
+def test_clamp_mask_in_the_trained_weight_regime(name, engine):
+    """The reference's clamp(max=0) stops the gradient where its OWN fp32 score rounds positive (example/hept.py:12).  With
+    trained weights its scores carry errors of O(0.1 .. 10), so it masks (and clamps to P = 1) pairs that are not coincident
+    at all: an artefact of the cancellation, absent from the float64 evaluation.  Every engine here applies the mask to the
+    score it computes itself (centred rows: positive only for coincident points).  Recorded: how many pairs the reference
+    masks in fp32 and in fp64; asserted: the fp32 and tcgen05 engines agree with each other (the module tests assert that
+    both sit closer to float64 than the reference does)."""
+    from hept_b200 import _lib, ops
+
+    cfg, inputs, params, grad_out, gold, meta = load_case(name)
+    n = inputs["query"].shape[0]
+    d = dims_of(cfg, n)
+    di = to_dev(inputs)
+    positions = (gold["q_pos"].long(), gold["k_pos"].long())
+    for dt, tag in ((torch.float32, "ref_fp32"), (torch.float64, "fp64")):
+        tr = oracle_trace(cfg, inputs, params, dt, positions)
+        sq = O.gather_blocks(tr["q_hat"], positions[0], d.B)
+        sk = O.gather_blocks(tr["k_hat"], positions[1], d.B)
+        s_pre = (torch.matmul(sq, sk.transpose(-1, -2)) - 0.5 * (sq * sq).sum(-1, keepdim=True)
+                 - 0.5 * (sk * sk).sum(-1, keepdim=True).transpose(-1, -2))
+        REPORT[rkey(f"clamp_{tag}_positive_score_frac_{name}")] = float((s_pre > 0).double().mean())
+    if engine != "tcgen05":
+        return
+    w = params["w_rpe.weight"].to(dev())
+    scale = ops.coord_scale(w, d.H, d.D, cfg["num_w_per_dist"])
+    pos = torch.stack(positions).to(torch.int32).to(dev())
+    stage = ops.block_attention_fwd(d, di["query"], di["key"], di["value"], di["coords"], scale, pos)
+    out_pre, den = ops.or_combine(d, stage)
+    g = torch.randn(n, d.H * d.D, generator=torch.Generator().manual_seed(4)).to(dev())
+    lib = _lib.load()
+    res = {}
+    try:
+        for variant in (1, 5):
+            lib.hept_set_bwd_variant(variant)
+            res[variant] = ops.attention_bwd(d, di["query"], di["key"], di["value"], di["coords"], scale, pos, out_pre, den, g)
+    finally:
+        lib.hept_set_bwd_variant(3)
+    for nm, a, b in zip(("dq", "dk", "dv", "dscale"), res[5], res[1]):
+        e = rel_err(a.cpu(), b.cpu())
+        REPORT[rkey(f"clamp_engines_{nm}_{name}")] = e
+        assert e < 2e-4, (nm, e)
 
 
 def test_full_size_invariants_tracking60k():

@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 
 @pytest.mark.parametrize("kmajor_base32", [0])   # 1 (K-major operands in the MN-major operand's SWIZZLE_128B_BASE32B
 def test_umma_selftest_exact_on_small_integers(kmajor_base32):   # image) faults on sm_100a: the layouts cannot be shared
-    from hept_b200 import _lib
+    from tests import native as _lib
 
     lib = _lib.load()
     dev = torch.device("cuda:0")
@@ -41,7 +41,7 @@ def test_tf32_mma_is_symmetric_under_operand_exchange():
     import json
     import os
 
-    from hept_b200 import _lib
+    from tests import native as _lib
 
     lib = _lib.load()
     dev = torch.device("cuda:0")

@@ -11,10 +11,10 @@ import pytest
 import torch
 
 from oracle import hept_oracle as O
-from tests.helpers import CASES, load_case, rel_err
+from tests.helpers import ALL_CASES, CASES, load_case, rel_err
 
 
-@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("name", ALL_CASES)
 def test_keys_and_permutations_match_reference(name):
     cfg, inputs, params, grad_out, gold, meta = load_case(name)
     res = O.forward_backward(inputs, params, cfg, grad_out)
@@ -30,15 +30,18 @@ def test_keys_and_permutations_match_reference(name):
         assert torch.equal(mine.sort(-1).values, torch.arange(mine.shape[-1]).expand_as(mine))
 
 
-@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("name", ALL_CASES)
 def test_outputs_and_gradients_match_reference(name):
     """Oracle run with the REFERENCE's permutations injected reproduces its outputs and gradients."""
     cfg, inputs, params, grad_out, gold, meta = load_case(name)
     pos = (gold["q_pos"].long(), gold["k_pos"].long())
     res = O.forward_backward(inputs, params, cfg, grad_out, positions=pos)
     assert torch.equal(res["out"], gold["out"])
+    # reductions over N: summation order in autograd.  With the trained weights (ckpt cases) d w_rpe is a sum of terms
+    # ~1e5 times larger than the result (SURVEY.md 7.3-2), and the order of that sum is not fixed between two runs
+    red_tol = 1e-4 if name.startswith("ckpt") else 2e-6
     for g in ("dw_rpe", "dout_w", "dout_b"):
-        assert rel_err(res[g], gold[g]) < 2e-6, g          # reductions over N: summation order in autograd
+        assert rel_err(res[g], gold[g]) < red_tol, g
     for g in ("dq", "dk", "dv"):
         if g in gold:
             assert rel_err(res[g], gold[g]) < 1e-6, g
@@ -48,7 +51,7 @@ def test_outputs_and_gradients_match_reference(name):
             assert rel_err(res[g].double().sum(0), gold[g + "_colsum"]) < 1e-5, g
 
 
-@pytest.mark.parametrize("name", ["tiny_example", "small_batched", "tracking6k_seed42"])
+@pytest.mark.parametrize("name", ["tiny_example", "small_batched", "tracking6k_seed42", "ckpt_l0", "ckpt_l2"])
 def test_prepare_batched_matches_reference(name):
     """prepare_input / bit_shift / pad_and_unpad restatement vs the reference's outputs."""
     from hept_b200 import synthetic

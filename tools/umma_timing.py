@@ -10,7 +10,7 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
-from hept_b200 import _lib
+from tests import native as _lib
 
 lib = _lib.load()
 out = torch.zeros(1, dtype=torch.int64, device="cuda:0")
