@@ -48,6 +48,10 @@ SIGNATURES = {
     "hept_block_attention_bwd": (C.c_int, [_SP] + [_p] * 14 + [_sz, _p]),
     "hept_attention_fwd_workspace_bytes": (_sz, [_SP]),
     "hept_attention_fwd": (C.c_int, [_SP, _p, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "hept_prepare_batched_workspace_bytes": (_sz, [_i32, _i32, _i32]),
+    "hept_prepare_batched": (C.c_int, [_p, _i32, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _i32, _i32, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "hept_prepare_single_workspace_bytes": (_sz, [_i32]),
+    "hept_prepare_single": (C.c_int, [_p, _i32, _i32, _i32, _p, _i32, _p, _p, _p, _p, _sz, _p]),
     "hept_launch_count": (C.c_int, [C.c_int]),
     "hept_set_bwd_stage_mask": (None, [C.c_int]),
     "hept_set_engine": (None, [C.c_int]),

@@ -264,13 +264,12 @@ extern "C" int hept_prepare_batched(const float* coords, int32_t C, const int64_
                n_pad, max_event, block_size);
   HEPT_REQUIRE(TH > 0 && TH <= kPrepMaxTH, HEPT_EUNSUPPORTED, "prepare_batched: T*H=%d outside [1, %d]", TH, kPrepMaxTH);
   HEPT_REQUIRE(n_raw < (1 << 24), HEPT_EUNSUPPORTED, "prepare_batched: %d points: ranks are no longer exact in float32", n_raw);
-  // codes stay exact in the float32 sort key of the padding order: batch index and region bits together below 2^24
+  // the (table 0, head 0) code is the float32 sort key of the padding order: it must stay below 2^24 to be exact.  Region
+  // codes need <= 16 bits (two region indices of <= 8 bits: up to 255 regions per axis), the batch index the rest.
   {
-    long long regs = 1;
     int bits = 0;
     while ((1ll << bits) < num_events) ++bits;
-    HEPT_REQUIRE(bits + 14 <= 24, HEPT_EUNSUPPORTED, "prepare_batched: %d events: the (table 0, head 0) code may exceed 2^24", num_events);
-    (void)regs;
+    HEPT_REQUIRE(bits + 16 <= 24, HEPT_EUNSUPPORTED, "prepare_batched: %d events: the (table 0, head 0) code may exceed 2^24", num_events);
   }
   PrepPlan p = plan_prepare(n_raw, num_events, max_event);
   HEPT_REQUIRE(workspace_bytes >= p.total, HEPT_EWORKSPACE, "prepare_batched: workspace needs %zu bytes, got %zu", p.total,

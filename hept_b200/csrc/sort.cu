@@ -335,7 +335,9 @@ static int cluster_size_for(int segments, int n) {
   if (g_sort_variant.load(std::memory_order_relaxed) == 1 || forced < 0) return 0;
   const int need = (n + kCsMaxCap - 1) / kCsMaxCap;
   if (forced > 0) return need > 8 ? 0 : max(min(forced, 8), need);
-  if (n > 16384) return 0;
+  // a few long segments (the per-event rank sorts of prepare.cu: 2 .. 16 segments of up to 98 304 keys): one cluster each
+  // still fits a single wave, and one launch beats the eight of the global passes
+  if (n > 16384) return (need <= 8 && (long long)segments * need <= 64) ? need : 0;
   const int cs = n <= 2048 ? 1 : 2;
   return (long long)segments * cs <= 2 * 148 ? cs : 0;
 }
@@ -344,6 +346,9 @@ struct SortPlan {
   int tiles;
   size_t hist_bytes, keys_bytes, idx_bytes, total;
 };
+
+int segmented_argsort_launch(const float* keys, int32_t num_segments, int32_t n, int32_t* positions, void* workspace,
+                             size_t workspace_bytes, cudaStream_t st);
 
 static SortPlan plan_sort(int segments, int n) {
   SortPlan p;
@@ -369,6 +374,11 @@ extern "C" size_t hept_argsort_workspace_bytes(int32_t num_segments, int32_t n) 
 
 extern "C" int hept_segmented_argsort(const float* keys, int32_t num_segments, int32_t n, int32_t* positions,
                                       void* workspace, size_t workspace_bytes, void* stream) {
+  return segmented_argsort_launch(keys, num_segments, n, positions, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int hept::segmented_argsort_launch(const float* keys, int32_t num_segments, int32_t n, int32_t* positions, void* workspace,
+                                   size_t workspace_bytes, cudaStream_t stream) {
   HEPT_REQUIRE(keys && positions && workspace && num_segments > 0 && n > 0, HEPT_EINVAL,
                "segmented_argsort: bad argument");
   SortPlan p = plan_sort(num_segments, n);

@@ -82,10 +82,11 @@ class Transformer(nn.Module):
     ``forward(x, coords)`` (``task="pileup"`` adds the particle-id embedding, ``out_proj`` and the sigmoid)."""
 
     def __init__(self, in_dim: int, coords_dim: int, num_classes: int = 0, dropout: float = 0.1, flavour: str = "example",
-                 task: Optional[str] = None, attn_cls=HEPTAttention, **kwargs):
+                 task: Optional[str] = None, attn_cls=HEPTAttention, prepare_impl=prepare, **kwargs):
         super().__init__()
         assert flavour in ("example", "src")
         self.flavour, self.task = flavour, task
+        self._prepare = prepare_impl          # tests swap in an oracle-backed twin (attn_cls + prepare_impl) on CPU
         self.n_layers, self.h_dim = kwargs["n_layers"], kwargs["h_dim"]
         self.num_classes = num_classes
         if task == "pileup":                      # src/models/baselines/transformer.py:76-78
@@ -112,9 +113,9 @@ class Transformer(nn.Module):
         if self.flavour == "example":
             if batch is None:
                 batch = torch.zeros(x.shape[0], dtype=torch.long, device=x.device)
-            x, kwargs, keep = prepare.prepare_input(x, coords, batch, helper)
+            x, kwargs, keep = self._prepare.prepare_input(x, coords, batch, helper)
         else:
-            x, kwargs = prepare.prepare_input_single(x, coords, helper)
+            x, kwargs = self._prepare.prepare_input_single(x, coords, helper)
             keep = slice(0, kwargs["raw_size"])
         enc = self.feat_encoder(x)
         stack = [enc]

@@ -264,6 +264,52 @@ def out_linear_bwd(d: Dims, d_out, weight, out_pre, need_input_grad: bool = True
     return dx, dw, db
 
 
+# ------------------------------------------------------------------------------- a13..a17 preparation
+@_on_device
+def prepare_batched(coords, batch, offsets, num_events: int, n_raw: int, n_pad: int, max_event: int, regions_h, block_size: int,
+                    want_int32: bool = True):
+    """example/ flavour of prepare_input on the library's kernels.  ``offsets`` = int32 device tensor
+    [event_start (E+1) | pad_start (E+1)].  -> combined_shifts (TH, n_pad) int64, the same as int32 (or None),
+    take (n_pad) int64, is_real (n_pad) bool, coords_pad (n_pad, C)."""
+    lib = _lib.load()
+    coords = _need(coords, "coords", torch.float32, (n_raw, coords.shape[-1]))
+    batch = _need(batch, "batch", torch.int64, (n_raw,))
+    offsets = _need(offsets, "offsets", torch.int32, (2 * (num_events + 1),))
+    th = regions_h.shape[1]
+    regions_h = _need(regions_h, "regions_h", torch.float32, (2, th))
+    dev, c = coords.device, coords.shape[1]
+    shifts = torch.empty(th, n_pad, dtype=torch.int64, device=dev)
+    shifts32 = torch.empty(th, n_pad, dtype=torch.int32, device=dev) if want_int32 else None
+    take = torch.empty(n_pad, dtype=torch.int64, device=dev)
+    real = torch.empty(n_pad, dtype=torch.uint8, device=dev)
+    coords_pad = torch.empty(n_pad, c, dtype=torch.float32, device=dev)
+    ws = _workspace(lib.hept_prepare_batched_workspace_bytes(n_raw, num_events, max_event), coords)
+    ev_start = C.c_void_p(offsets.data_ptr())
+    pad_start = C.c_void_p(offsets.data_ptr() + 4 * (num_events + 1))
+    _lib.check(lib.hept_prepare_batched(_ptr(coords), c, _ptr(batch), ev_start, pad_start, num_events, n_raw, n_pad, max_event,
+                                        _ptr(regions_h), th, block_size, _ptr(shifts), _ptr(shifts32), _ptr(take), _ptr(real),
+                                        _ptr(coords_pad), _ptr(ws), ws.numel(), _stream(coords)), "hept_prepare_batched")
+    return shifts, shifts32, take, real.view(torch.bool), coords_pad
+
+
+@_on_device
+def prepare_single(coords, n_pad: int, regions_h):
+    """src/ flavour of prepare_input.  -> coords_pad (n_pad, C), region_eta, region_phi (TH, n_pad) float32."""
+    lib = _lib.load()
+    coords = _need(coords, "coords", torch.float32)
+    n_raw, c = coords.shape
+    th = regions_h.shape[1]
+    regions_h = _need(regions_h, "regions_h", torch.float32, (2, th))
+    dev = coords.device
+    coords_pad = torch.empty(n_pad, c, dtype=torch.float32, device=dev)
+    eta = torch.empty(th, n_pad, dtype=torch.float32, device=dev)
+    phi = torch.empty(th, n_pad, dtype=torch.float32, device=dev)
+    ws = _workspace(lib.hept_prepare_single_workspace_bytes(n_pad), coords)
+    _lib.check(lib.hept_prepare_single(_ptr(coords), c, n_raw, n_pad, _ptr(regions_h), th, _ptr(coords_pad), _ptr(eta),
+                                       _ptr(phi), _ptr(ws), ws.numel(), _stream(coords)), "hept_prepare_single")
+    return coords_pad, eta, phi
+
+
 # --------------------------------------------------------------------------------------- whole path
 @_on_device
 def attention_fwd(d: Dims, q, k, v, coords, w_rpe_weight, K: int, alpha, combined_shifts=None, region_indices=None,

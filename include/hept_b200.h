@@ -137,6 +137,31 @@ int hept_attention_fwd(const hept_shape* s, const float* q, const float* k, cons
                        const float* regions_h, float* scale, int32_t* positions, float* out_pre,
                        float* den_sum, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- a13..a17  per-forward preparation of the AND-hash inputs -----------------------------------------------------
+ * example/ flavour: prepare_input of example/transformer.py:35-63 (quantile_partition example/hept_utils.py:6-14, bit_shift
+ * example/transformer.py:10-13, pad_and_unpad :16-32) for a batch of events, without the reference's per-event host loop.
+ *   coords (n_raw, C) fp32 (columns 0 / 1 = eta / phi); batch (n_raw) int64, ascending; event_start, pad_start: DEVICE
+ *   arrays of num_events + 1 int32 offsets of the events in raw / padded order (the caller knows the event sizes: they
+ *   decide n_pad, the size of every output); max_event = the longest event; regions_h (2, TH) fp32 = the model's `regions`
+ *   parameter rearranged "c a h -> a (c h)"; block_size B.
+ * Outputs, all in padded order: combined_shifts (TH, n_pad) int64 (+ the same values as int32 when combined_shifts32 is
+ * non-null), take (n_pad) int64 = index of the raw point every padded row shows (the reference's pad_seq: x[take]),
+ * is_real (n_pad) uint8 (the reference's unpad_seq), coords_pad (n_pad, C).
+ * Sort tie-break: stable (the reference's argsort is not; only points with EQUAL eta, phi or code can differ). */
+size_t hept_prepare_batched_workspace_bytes(int32_t n_raw, int32_t num_events, int32_t max_event);
+int hept_prepare_batched(const float* coords, int32_t C, const int64_t* batch, const int32_t* event_start,
+                         const int32_t* pad_start, int32_t num_events, int32_t n_raw, int32_t n_pad, int32_t max_event,
+                         const float* regions_h, int32_t TH, int32_t block_size, int64_t* combined_shifts,
+                         int32_t* combined_shifts32, int64_t* take, uint8_t* is_real, float* coords_pad, void* workspace,
+                         size_t workspace_bytes, void* stream);
+/* src/ flavour: HEPT branch of prepare_input, src/models/baselines/transformer.py:43-57 (one event): coords padded with +inf
+ * to n_pad rows for the ranking, region_eta / region_phi (TH, n_pad) fp32 = quantile regions of the eta / phi ranks, then
+ * the padding rows of coords_pad (n_pad, C) set to zero. */
+size_t hept_prepare_single_workspace_bytes(int32_t n_pad);
+int hept_prepare_single(const float* coords, int32_t C, int32_t n_raw, int32_t n_pad, const float* regions_h, int32_t TH,
+                        float* coords_pad, float* region_eta, float* region_phi, void* workspace, size_t workspace_bytes,
+                        void* stream);
+
 /* kernel launches this library enqueued (any thread of the process) since the counter was last reset
  * (bench.py's gpu_launches); reset != 0 zeroes the counter after reading it. */
 int hept_launch_count(int reset);

@@ -690,22 +690,6 @@ def test_direct_backward_head_groups(heads, engine):
 
 
 # ------------------------------------------------------- BASELINE.json configs[2..3] and the prepare step on device
-def test_prepare_input_on_device_matches_cpu():
-    from hept_b200 import prepare, synthetic
-
-    cfg = dict(synthetic.TRACKING)
-    sizes = [2100, 1500, 1130, 900, 300, 70, 130, 57]
-    coords, batch = synthetic.batched_cloud(sizes, cfg["coords_dim"], 9)
-    params = synthetic.module_params(cfg, 9)
-    helper = {"block_size": 100, "regions": params["regions"], "num_heads": 8}
-    x = torch.arange(coords.shape[0], dtype=torch.float32)[:, None]
-    xc, kc, rc = prepare.prepare_input(x, coords, batch, helper)
-    helper_d = dict(helper, regions=params["regions"].to(dev()))
-    xd, kd, rd = prepare.prepare_input(x.to(dev()), coords.to(dev()), batch.to(dev()), helper_d)
-    assert torch.equal(rd.cpu(), rc) and torch.equal(xd.cpu(), xc)
-    assert torch.equal(kd["combined_shifts"].cpu(), kc["combined_shifts"]) and torch.equal(kd["coords"].cpu(), kc["coords"])
-
-
 def test_batched_imbalanced_events_against_oracle():
     """configs[3]: eight events of very different sizes (two shorter than a block) through prepare_input and the
     module, forward + backward, against the float64 oracle (sizes scaled by 1/10 so the oracle runs in seconds)."""
@@ -715,8 +699,10 @@ def test_batched_imbalanced_events_against_oracle():
     sizes = [2100, 1500, 1130, 900, 300, 70, 130, 57]
     coords, batch = synthetic.batched_cloud(sizes, cfg["coords_dim"], 21)
     params = synthetic.module_params(cfg, 21)
-    helper = {"block_size": 100, "regions": params["regions"], "num_heads": 8}
-    _, kw, real = prepare.prepare_input(torch.zeros(coords.shape[0], 1), coords, batch, helper)
+    helper = {"block_size": 100, "regions": params["regions"].to(dev()), "num_heads": 8}
+    _, kw, real = prepare.prepare_input(torch.zeros(coords.shape[0], 1, device=dev()), coords.to(dev()), batch.to(dev()), helper)
+    kw = {kk: vv.cpu() for kk, vv in kw.items()}
+    real = real.cpu()
     n = kw["coords"].shape[0]
     q, k, v = synthetic.qkv(n, cfg, 21)
     g = torch.randn(n, cfg["h_dim"], generator=torch.Generator().manual_seed(2))
@@ -761,7 +747,8 @@ def test_pileup_shape_forward_inference():
     coords_raw = synthetic.point_cloud(n_raw, 4, 31)
     params = synthetic.module_params(cfg, 31)
     x = torch.zeros(n_raw, 3)
-    _, kw = prepare.prepare_input_single(x, coords_raw, {"block_size": 100, "regions": params["regions"]})
+    _, kw = prepare.prepare_input_single(x.to(dev()), coords_raw.to(dev()), {"block_size": 100, "regions": params["regions"].to(dev())})
+    kw = {kk: ([t.cpu() for t in vv] if isinstance(vv, list) else vv.cpu() if isinstance(vv, torch.Tensor) else vv) for kk, vv in kw.items()}
     n = kw["coords"].shape[0]
     assert n == 10000 and kw["raw_size"] == n_raw
     q, k, v = synthetic.qkv(n, cfg, 31)

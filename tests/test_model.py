@@ -58,11 +58,28 @@ class OracleAttention(torch.nn.Module):
     def forward(self, q, k, v, **kwargs):
         from oracle import hept_oracle as O
 
+        flavour = ({"combined_shifts": kwargs["combined_shifts"]} if "combined_shifts" in kwargs else
+                   {"raw_size": kwargs["raw_size"], "regions_h": kwargs["regions_h"], "region_indices": kwargs["region_indices"]})
         return O.attention_forward(q, k, v, out_weight=self.out_linear.weight, out_bias=self.out_linear.bias,
                                    w_rpe_weight=kwargs["w_rpe"].weight, alpha=self.e2lsh.alpha, coords=kwargs["coords"],
                                    block_size=self.cfg["block_size"], num_heads=self.cfg["num_heads"],
-                                   dim_per_head=self.cfg["h_dim"], num_w_per_dist=self.cfg["num_w_per_dist"],
-                                   combined_shifts=kwargs["combined_shifts"])
+                                   dim_per_head=self.cfg["h_dim"], num_w_per_dist=self.cfg["num_w_per_dist"], **flavour)
+
+
+class OraclePrepare:
+    """prepare_input / prepare_input_single of the oracle behind the product module's call surface (tests only)."""
+
+    @staticmethod
+    def prepare_input(x, coords, batch, helper):
+        from oracle import hept_oracle as O
+
+        return O.prepare_batched(x, coords, batch, helper["regions"], helper["block_size"], helper["num_heads"])
+
+    @staticmethod
+    def prepare_input_single(x, coords, helper):
+        from oracle import hept_oracle as O
+
+        return O.prepare_single_event(x, coords, helper["regions"], helper["block_size"])
 
 
 @pytest.mark.gpu
@@ -70,7 +87,7 @@ def test_whole_model_forward_backward_against_oracle_backed_model():
     cfg = dict(TRACKING)
     torch.manual_seed(5)
     ours = Transformer(in_dim=15, coords_dim=6, **cfg).eval()
-    ref = Transformer(in_dim=15, coords_dim=6, attn_cls=OracleAttention, **cfg).eval()
+    ref = Transformer(in_dim=15, coords_dim=6, attn_cls=OracleAttention, prepare_impl=OraclePrepare, **cfg).eval()
     ref.load_state_dict(ours.state_dict(), strict=True)
     sizes = [830, 411, 57]
     coords, batch = synthetic.batched_cloud(sizes, 6, 3)
@@ -100,6 +117,14 @@ def test_pileup_model_inference_src_flavour():
     n = 4321
     coords = synthetic.point_cloud(n, 4, 8)
     x = torch.cat([torch.randn(n, 7) * 0.5, torch.randint(0, 7, (n, 1)).float()], dim=1)
+    ref = Transformer(in_dim=8, coords_dim=4, task="pileup", flavour="src", attn_cls=OracleAttention, prepare_impl=OraclePrepare,
+                      **cfg).eval()
+    ref.load_state_dict(m.state_dict(), strict=True)
     with torch.no_grad():
         y = m(x.cuda(), coords.cuda())
-    assert y.shape == (n, 1) and bool(((y > 0) & (y < 1)).all())
+        want = ref(x, coords)
+    assert y.shape == want.shape == (n, 1) and bool(((y > 0) & (y < 1)).all())
+    # BASELINE.json configs[2]: forward-only inference of the pileup model against the oracle-backed twin (same weights):
+    # four attention layers deep, a handful of rows sit in blocks whose tie order differs
+    err = (y.cpu() - want).abs().squeeze(1)
+    assert float(err.median()) < 2e-5 and float((err > 1e-3).float().mean()) < 0.05
