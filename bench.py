@@ -45,15 +45,29 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def make_event(seed: int, n_raw: int = N_RAW):
-    """Synthetic tracking-shaped event, prepared with the product-side prepare_input -> CPU tensors."""
-    from hept_b200 import prepare, synthetic
+WORKLOAD = "tracking-60k fwd+bwd (HEPTAttention, H=8 D=24 C=6 T=3 B=100), one 60000-hit event per step per GPU"
+
+
+def make_event(seed: int, n_raw: int = N_RAW, device=None):
+    """Synthetic tracking-shaped event -> CPU tensors.  ``device`` given: the product's prepare_input (CUDA kernels behind
+    the C ABI) builds the hash codes; ``device=None`` (the CPU reference arm only): the oracle's restatement does."""
+    from hept_b200 import synthetic
 
     cfg = dict(synthetic.TRACKING)
     coords_raw, batch = synthetic.batched_cloud([n_raw], cfg["coords_dim"], seed)
     params = synthetic.module_params(cfg, 0)
-    helper = {"block_size": cfg["block_size"], "regions": params["regions"], "num_heads": cfg["num_heads"]}
-    _, kw, _ = prepare.prepare_input(torch.zeros(n_raw, 1), coords_raw, batch, helper)
+    if device is not None:
+        from hept_b200 import prepare
+
+        helper = {"block_size": cfg["block_size"], "regions": params["regions"].to(device), "num_heads": cfg["num_heads"]}
+        _, kw, _ = prepare.prepare_input(torch.zeros(n_raw, 1, device=device), coords_raw.to(device), batch.to(device), helper,
+                                         sizes=[n_raw])
+        kw = {k: v.cpu() for k, v in kw.items()}
+    else:
+        from oracle import hept_oracle as O
+
+        _, kw, _ = O.prepare_batched(torch.zeros(n_raw, 1), coords_raw, batch, params["regions"], cfg["block_size"],
+                                     cfg["num_heads"])
     n = kw["coords"].shape[0]
     q, k, v = synthetic.qkv(n, cfg, seed)
     g = torch.randn(n, cfg["h_dim"], generator=torch.Generator().manual_seed(seed + 5))
@@ -145,8 +159,8 @@ def run_reference(args):
         "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "impl": "reference",
-        "config": {"workload": "tracking-60k fwd+bwd (HEPTAttention, H=8 D=24 C=6 T=3 B=100)",
-                   "sample": f"{n}-hit events, cost linear in hits"},
+        "config": {"workload": WORKLOAD},
+        "sample": f"{n}-hit events, cost linear in hits",
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{args.steps} fwd+bwd steps on {n}-hit synthetic tracking events, torch CPU eager fp32"},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -185,7 +199,7 @@ def run_ours(args):
     engine_name = ("tcgen05" if _lib.load().hept_get_engine() else "simt") + f"+bwd{_lib.load().hept_get_bwd_variant()}"
 
     n_sets = 4                                  # rotate over 4 events: ~0.75 GB of inputs, far beyond the 126 MB L2
-    events = [make_event(100 * rank + i) for i in range(n_sets)]
+    events = [make_event(100 * rank + i, device=dev) for i in range(n_sets)]
     cfg, params = events[0][0], events[0][1]
     mod = HEPTAttention(cfg["h_dim"] + cfg["coords_dim"], **cfg)
     mod.load_state_dict({k: params[k] for k in ("out_linear.weight", "out_linear.bias", "e2lsh.alpha")}, strict=True)
@@ -290,10 +304,10 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "tracking-60k fwd+bwd (HEPTAttention, H=8 D=24 C=6 T=3 B=100), one 60000-hit event per step per GPU",
-                   "l2": f"inputs rotate over {n_sets} events (~190 MB each) so no step re-reads L2-resident inputs",
-                   "collective": "NCCL all-reduce of parameter gradients per step" if world > 1 else "none",
-                   "tile_engine": engine_name},
+        "config": {"workload": WORKLOAD},
+        "details": {"l2": f"inputs rotate over {n_sets} events (~190 MB each) so no step re-reads L2-resident inputs",
+                    "collective": "NCCL all-reduce of parameter gradients per step" if world > 1 else "none",
+                    "tile_engine": engine_name},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / e2e_steps},
         "gpu_launches": launches,
@@ -305,7 +319,10 @@ def run_ours(args):
         line["path_roofline"] = {"bytes_per_hit": FWD_BWD_BYTES_PER_HIT,
                                  "achieved_gbs": FWD_BWD_BYTES_PER_HIT * value / world / 1e9,
                                  "frac": FWD_BWD_BYTES_PER_HIT * value / world / 1e9 / peak}
-        line["roofline"] = kernel_roofline(resident, gouts, cfg, mod, w_rpe, peak, peak_src, n_sets)
+        line["roofline"] = kernel_roofline(resident, gouts, cfg, mod, w_rpe, peak, peak_src, n_sets, value / world)
+        inc, ipath = _committed(PROFILE_TAG + "_incumbent.json")
+        if inc:      # the reference's formulation on the same GPU (library kernels), measured by tests/test_gpu_incumbent.py
+            line["incumbent_gpu"] = dict(inc, source=ipath)
         if world == 1:
             rate, dt, threads = cpu_port_rate(N_RAW, 2, 1)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
@@ -316,11 +333,22 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def kernel_roofline(resident, gouts, cfg, mod, w_rpe, peak, peak_src, n_sets):
-    """Time each native stage alone with CUDA events (same inputs, rotating) and report the dominant kernel.
+FWD_BYTES_PER_HIT, BWD_BYTES_PER_HIT = 2616, 5720      # compulsory bytes of the forward / backward call
+FLOP_PER_HIT = 952128                                    # algorithmic fp32 FLOPs, fwd + bwd
+PROFILE_TAG = "r2"                                       # profiles/<tag>_traffic.json, <tag>_ncu_*.csv, <tag>_incumbent.json
 
-    Algorithmic bytes per launch = that kernel's compulsory traffic (fp32 rows in, fp32 rows out, int32
-    permutations), per hit x 60 000 hits — DESIGN.md "Kernels" lists the per-hit figures."""
+
+def _committed(name):
+    path = os.path.join(ROOT, "profiles", name)
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "profiles/" + name
+    return None, None
+
+
+def kernel_roofline(resident, gouts, cfg, mod, w_rpe, peak, peak_src, n_sets, path_hits_per_s):
+    """The dominant kernel (the tcgen05 backward tile kernel) against the HBM roofline with SURVEY.md 8(d)'s bytes, timed live
+    with CUDA events, next to what bounds it according to the committed ncu captures."""
     from hept_b200 import ops, _lib
 
     lib = _lib.load()
@@ -347,55 +375,59 @@ def kernel_roofline(resident, gouts, cfg, mod, w_rpe, peak, peak_src, n_sets):
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / reps * 1e-3
 
-    qkv_b, perm_b, stage_b = 3 * H * D * 4, 2 * T * H * 4, T * H * 128
     variant = lib.hept_get_bwd_variant()
-    per_hit = {   # algorithmic bytes per hit of each tile kernel (reads + writes at its own boundary)
-        "block_attn_fwd": qkv_b + 4 * C + perm_b + stage_b,
-        "block_attn_bwd_dq": qkv_b + 4 * C + perm_b + 2 * H * D * 4 + 4 * H + stage_b,
-        "block_attn_bwd_dkv": qkv_b + 4 * C + perm_b + 2 * H * D * 4 + 4 * H + stage_b + T * H * D * 4,
-        # fused tcgen05 backward: q, k, v, scaled coordinates (N,H,8), gradient rows (N,H,32), permutations in;
-        # dq^, dk^, dv rows of D floats per (head, hit, table) out
-        "block_attn_bwd_tc": qkv_b + H * 32 + H * 128 + perm_b + 3 * T * H * D * 4,
-    }
-    flops = {"block_attn_fwd": 2 * T * H * B * (D + C + D), "block_attn_bwd_dq": 2 * T * H * B * (2 * (D + C) + D),
-             "block_attn_bwd_dkv": 2 * T * H * B * (2 * (D + C) + 2 * D),
-             "block_attn_bwd_tc": 2 * T * H * B * (2 * (D + C) + 2 * D + 2 * (D + C) + D)}   # both sides recompute S and dP
-    times = {}
-    times["block_attn_fwd"] = ev_time(lambda i: ops.block_attention_fwd(d, *saved[i % n_sets][:6]))
-    if variant >= 3:
-        lib.hept_set_bwd_stage_mask(3)
-        t_all = ev_time(lambda i: ops.attention_bwd(d, *saved[i % n_sets]))
-        lib.hept_set_bwd_stage_mask(7)
-        times["block_attn_bwd_tc"] = t_all
-    else:
-        for name, mask in (("block_attn_bwd_dq", 1), ("block_attn_bwd_dkv", 2)):
-            lib.hept_set_bwd_stage_mask(mask)
-            times[name] = ev_time(lambda i: ops.attention_bwd(d, *saved[i % n_sets]))
-        lib.hept_set_bwd_stage_mask(7)
-    top = max(times, key=times.get)
-    achieved = per_hit[top] * N_RAW / times[top] / 1e9
-    # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (tools/ncu_summary.py)
+    tc = bool(lib.hept_get_engine()) and variant >= 3
+    t_fwd = ev_time(lambda i: ops.block_attention_fwd(d, *saved[i % n_sets][:6]))
+    lib.hept_set_bwd_stage_mask(0)            # the streaming pre-pass alone (gradient rows, scaled coordinates)
+    t_pre = ev_time(lambda i: ops.attention_bwd(d, *saved[i % n_sets]))
+    lib.hept_set_bwd_stage_mask(3)            # pre-pass + tile kernel(s), without the final reductions
+    t_tiles = ev_time(lambda i: ops.attention_bwd(d, *saved[i % n_sets]))
+    lib.hept_set_bwd_stage_mask(7)
+    t_bwd = max(t_tiles - t_pre, 1e-9)
+    kernel = "block_attn_bwd_tc_kernel" if tc else "block_attn_bwd_dq_kernel + block_attn_bwd_dkv_kernel"
+    bytes_per_launch = BWD_BYTES_PER_HIT * N_RAW
+    achieved = bytes_per_launch / t_bwd / 1e9
     traffic, tsrc = None, None
-    tpath = os.path.join(ROOT, "profiles", "r1e_traffic.json")
-    if os.path.exists(tpath):
-        with open(tpath) as f:
-            tj = json.load(f)
-        names = {"block_attn_fwd": "block_attn_fwd_tc_kernel" if lib.hept_get_engine() else "block_attn_fwd_kernel",
-                 "block_attn_bwd_dq": "block_attn_bwd_dq_kernel" if variant == 1 else "block_attn_bwd_pair_kernel",
-                 "block_attn_bwd_dkv": "block_attn_bwd_dkv_kernel" if variant == 1 else "block_attn_bwd_pair_kernel",
-                 "block_attn_bwd_tc": "block_attn_bwd_tc_kernel"}
-        if names[top] in tj:
-            traffic, tsrc = tj[names[top]]["dram_bytes_per_launch"], "profiles/r1e_traffic.json (" + tj[names[top]]["source"] + ")"
-    tensor = variant >= 3 or lib.hept_get_engine()
-    return {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": traffic, "traffic_source": tsrc, "peak_source": peak_src, "bytes_per_launch": per_hit[top] * N_RAW,
-            "kernel_ms": {k: v * 1e3 for k, v in times.items()},
-            "tile_tflops": {k: flops[k] * N_RAW / times[k] / 1e12 for k in times},
-            "note": ("kernel_ms of block_attn_bwd_tc includes its two streaming pre-passes (scaled coordinates, gradient rows; "
-                     "~40 us) and, in its default direct form, the sum over the T tables (rows added into dq/dk/dv by the tile kernel: "
-                     "the 81 us bwd_table_sum launch of the staged form is gone, this kernel is ~35 us longer); the tile kernels are bounded by the thread-side TMEM port and by contention between the warp roles "
-                     "(DESIGN.md 4), not by HBM: tile_tflops counts algorithmic fp32 FLOPs (each is three tf32 MMA passes)") if tensor else
-                    "tile kernels are fp32-FMA bound, not HBM bound (SURVEY.md 7.3-3); tile_tflops is against ~74 TF/s SIMT peak"}
+    tj, tpath = _committed(PROFILE_TAG + "_traffic.json")
+    if tj is None:
+        tj, tpath = _committed("r1e_traffic.json")
+    if tj and tc and "block_attn_bwd_tc_kernel" in tj:
+        traffic = tj["block_attn_bwd_tc_kernel"]["dram_bytes_per_launch"]
+        tsrc = f"{tpath} ({tj['block_attn_bwd_tc_kernel']['source']})"
+    # tensor side.  No TF32 GEMM peak is in MEASURED_PEAKS.json: half the measured sustained bf16 rate is used and said so.
+    peaks, _ = None, None
+    ppath = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    bf16 = 1400.0
+    if os.path.exists(ppath):
+        with open(ppath) as f:
+            bf16 = float(json.load(f).get("bf16_tflops_sustained", bf16))
+    tf32_peak = bf16 / 2
+    bwd_flop_per_hit = 2 * T * H * B * (2 * (D + C) + 2 * D + 2 * (D + C) + D)       # S, dP on both sides, dV, dQ, dK
+    alg_tflops = 2 * T * H * B * (2 * (D + C) + 3 * D) * N_RAW / t_bwd / 1e12          # without the second evaluation of S, dP
+    issued_tflops = 3 * bwd_flop_per_hit * N_RAW / t_bwd / 1e12                        # 3xTF32: three tensor-core passes each
+    pad = (B * B) / (128.0 * ((B + 15) // 16 * 16))                                   # 100 x 100 tiles run as M = 128, N = 112
+    ceil_hits = tf32_peak * 1e12 / 3 * pad / FLOP_PER_HIT
+    return {
+        "bound": "tensor" if tc else "fp32",
+        "bound_evidence": ("ncu --set full of this kernel (profiles/): DRAM throughput ~15 % of peak, tensor pipe ~35 % active, issue slots "
+                           "~39 %: no unit is saturated; the tensor pipe (3xTF32, M = 128 padding, 52-cycle floor of the N = 32 / 64 "
+                           "products) is the nearest ceiling, the thread-side TMEM port what keeps it from it (DESIGN.md 4)"),
+        "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "bytes_per_launch": bytes_per_launch, "bytes_per_hit": BWD_BYTES_PER_HIT,
+        "bytes_model": "SURVEY.md 8(d) backward: dout, q, k, v, coords, permutations, saved (O, L), dq, dk, dv",
+        "traffic": traffic, "traffic_source": tsrc, "peak_source": peak_src,
+        "kernel_ms": {"block_attn_fwd": t_fwd * 1e3, "block_attn_bwd": t_bwd * 1e3, "bwd_pre_pass": t_pre * 1e3},
+        "fwd_kernel": {"bytes_per_hit": FWD_BYTES_PER_HIT, "achieved": FWD_BYTES_PER_HIT * N_RAW / t_fwd / 1e9,
+                       "frac": FWD_BYTES_PER_HIT * N_RAW / t_fwd / 1e9 / peak},
+        "tensor_frac": issued_tflops / tf32_peak, "issued_tf32_tflops": issued_tflops, "algorithmic_tflops": alg_tflops,
+        "tf32_peak_tflops": tf32_peak,
+        "tf32_peak_source": "half of bf16_tflops_sustained in MEASURED_PEAKS.json (no TF32 GEMM was measured)",
+        "ceiling": {"hits_per_s": ceil_hits, "frac_of_hbm_roofline": FWD_BWD_BYTES_PER_HIT * ceil_hits / 1e9 / peak,
+                    "achieved_frac_of_ceiling": path_hits_per_s / ceil_hits,
+                    "why": ("952 128 algorithmic FLOP per hit, each three TF32 tensor-core passes (3xTF32 keeps fp32-grade scores), "
+                            "100 x 100 tiles issued as M = 128 x N = 112: the whole path cannot exceed this fraction of the HBM "
+                            "roofline whatever the kernels do; the 60 % target assumes one pass per FLOP")},
+    }
 
 
 def main():
@@ -404,7 +436,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--bwd", default=None, type=int, choices=[1, 2, 3], help="backward tile variant (default: library default)")
+    ap.add_argument("--bwd", default=None, type=int, choices=[1, 3, 4, 5], help="backward tile variant (default: library default)")
     ap.add_argument("--engine", default=None, choices=["simt", "tcgen05"], help="tile engine (default: library default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -270,7 +270,7 @@ def pack_bits(low: Tensor, high: Tensor) -> Tensor:
     return (high << width) | low
 
 
-def pad_plan(block_size: int, order_key: Tensor, sizes: Tensor) -> Tuple[Tensor, Tensor]:
+def pad_plan(block_size: int, order_key: Tensor, sizes: Tensor, stable: bool = False) -> Tuple[Tensor, Tensor]:
     """example/transformer.py:16-32 (``pad_and_unpad``), restated without in-place index shuffling.
 
     Every event is padded to a multiple of ``block_size`` by repeating real
@@ -280,13 +280,15 @@ def pad_plan(block_size: int, order_key: Tensor, sizes: Tensor) -> Tuple[Tensor,
     event shorter than ``block_size`` that index reaches into the previous
     event; for event 0 it is negative and wraps like any
     Python index.  Reproduced as is.
+    ``stable``: break ties of ``order_key`` by ascending index (the convention the product pins, like for the hash sort)
+    instead of whatever torch's default argsort does (what the reference calls).
     Returns (gather index into the raw points (N_pad,), bool mask of real rows).
     """
     sizes = sizes.long()
     padded = (sizes + block_size - 1) // block_size * block_size
     pads = padded - sizes
     total = int(padded.sum())
-    order = order_key.argsort()
+    order = order_key.argsort(stable=True) if stable else order_key.argsort()
     n_raw = int(sizes.sum())
     take = torch.empty(total, dtype=torch.long)
     real = torch.ones(total, dtype=torch.bool)
@@ -304,7 +306,8 @@ def pad_plan(block_size: int, order_key: Tensor, sizes: Tensor) -> Tuple[Tensor,
     return take, real
 
 
-def prepare_batched(x: Tensor, coords: Tensor, batch: Tensor, regions: Tensor, block_size: int, num_heads: int):
+def prepare_batched(x: Tensor, coords: Tensor, batch: Tensor, regions: Tensor, block_size: int, num_heads: int,
+                    stable: bool = False):
     """example/transformer.py:35-63.  regions (T,2,H) -> kwargs {combined_shifts (T,H,Np) int64, coords (Np,C)}."""
     t, two, h = regions.shape
     reg = regions.permute(1, 0, 2).reshape(two, t * h)             # "c a h -> a (c h)"
@@ -313,15 +316,15 @@ def prepare_batched(x: Tensor, coords: Tensor, batch: Tensor, regions: Tensor, b
     start = 0
     for s in sizes.tolist():
         c = coords[start : start + s]
-        eta_parts.append(quantile_regions(torch.argsort(c[:, 0], dim=-1), reg[0][:, None]))
-        phi_parts.append(quantile_regions(torch.argsort(c[:, 1], dim=-1), reg[1][:, None]))
+        eta_parts.append(quantile_regions(torch.argsort(c[:, 0], dim=-1, stable=stable), reg[0][:, None]))
+        phi_parts.append(quantile_regions(torch.argsort(c[:, 1], dim=-1, stable=stable), reg[1][:, None]))
         start += s
     eta = torch.cat(eta_parts, dim=-1).long()
     phi = torch.cat(phi_parts, dim=-1).long()
     code = pack_bits(eta, phi)
     code = pack_bits(code, batch[None])
     code = code.view(t, h, -1)
-    take, real = pad_plan(block_size, code[0, 0], sizes)
+    take, real = pad_plan(block_size, code[0, 0], sizes, stable)
     return x[take], {"combined_shifts": code[..., take], "coords": coords[take]}, real
 
 

@@ -73,7 +73,7 @@ class OraclePrepare:
     def prepare_input(x, coords, batch, helper):
         from oracle import hept_oracle as O
 
-        return O.prepare_batched(x, coords, batch, helper["regions"], helper["block_size"], helper["num_heads"])
+        return O.prepare_batched(x, coords, batch, helper["regions"], helper["block_size"], helper["num_heads"], stable=True)
 
     @staticmethod
     def prepare_input_single(x, coords, helper):

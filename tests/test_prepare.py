@@ -64,6 +64,9 @@ def test_batched_prepare_against_the_oracle(sizes):
         assert xp.shape[0] == 200 + 100 + 400
         ev1_pad = xp[:, 0].long()[200 + 57: 300]
         assert bool((batch[ev1_pad] == 0).all())          # event 1's 43 padding rows are copies of event-0 points
+    # with the oracle's sorts pinned to the stable tie-break everything is equal, padding rows included
+    xs, kw_s, real_s = O.prepare_batched(x, coords_raw, batch, params["regions"], 100, 8, stable=True)
+    assert torch.equal(xp, xs) and torch.equal(shifts, kw_s["combined_shifts"]) and torch.equal(kw["coords"].cpu(), kw_s["coords"])
     # passing the sizes avoids the read-back of bincount and changes nothing
     xp2, kw2, real2 = prepare.prepare_input(x.to(DEV), coords_raw.to(DEV), batch.to(DEV), _helper(cfg, params), sizes=sizes)
     assert torch.equal(kw2["combined_shifts"].cpu(), shifts) and torch.equal(xp2.cpu(), xp)

@@ -27,7 +27,7 @@ TILES, EVENTS = 64, 32
 lib = _lib.load()
 lib.hept_set_engine(1)
 lib.hept_set_bwd_variant(3)
-cfg, params, inp, g = bench.make_event(7, 60000)
+cfg, params, inp, g = bench.make_event(7, 60000, device="cuda:0")
 dev = torch.device("cuda:0")
 inp = {k: v.to(dev) for k, v in inp.items()}
 n = inp["query"].shape[0]

@@ -17,7 +17,7 @@ _lib.load().hept_set_engine(1 if os.environ.get("HEPT_ENGINE", "tcgen05") == "tc
 _lib.load().hept_set_bwd_variant(int(os.environ.get("HEPT_BWD", "3")))
 n_raw = int(sys.argv[1]) if len(sys.argv) > 1 else 60000
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
-cfg, params, inp, g = bench.make_event(7, n_raw)
+cfg, params, inp, g = bench.make_event(7, n_raw, device="cuda:0")
 dev = torch.device("cuda:0")
 inp = {k: v.to(dev) for k, v in inp.items()}
 n = inp["query"].shape[0]

@@ -18,7 +18,7 @@ lib = _lib.load()
 dev = torch.device("cuda:0")
 sets = []
 for i in range(4):
-    cfg, params, inp, g = bench.make_event(7 + i, n_raw)
+    cfg, params, inp, g = bench.make_event(7 + i, n_raw, device="cuda:0")
     inp = {k: v.to(dev) for k, v in inp.items()}
     sets.append(inp)
 n = sets[0]["query"].shape[0]
