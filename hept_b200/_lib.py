@@ -52,6 +52,12 @@ SIGNATURES = {
     "hept_prepare_batched": (C.c_int, [_p, _i32, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _i32, _i32, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "hept_prepare_single_workspace_bytes": (_sz, [_i32]),
     "hept_prepare_single": (C.c_int, [_p, _i32, _i32, _i32, _p, _i32, _p, _p, _p, _p, _sz, _p]),
+    "hept_keys_from_packed_shifts32": (C.c_int, [_SP, _p, _p, _p, _p, _p]),
+    "hept_attention_fwd_shifts32": (C.c_int, [_SP, _p, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "hept_attn_qkv_supported": (C.c_int, [_i32, _i32]),
+    "hept_attn_qkv_fwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _i32, _i32, C.c_float, _p, _p, _p, _p, _p, _p]),
+    "hept_attn_qkv_bwd_workspace_bytes": (_sz, [_i32, _i32, _i32]),
+    "hept_attn_qkv_bwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _i32, _i32, _i32, C.c_float, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "hept_launch_count": (C.c_int, [C.c_int]),
     "hept_set_bwd_stage_mask": (None, [C.c_int]),
     "hept_set_engine": (None, [C.c_int]),

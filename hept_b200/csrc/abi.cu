@@ -67,15 +67,40 @@ extern "C" size_t hept_attention_fwd_workspace_bytes(const hept_shape* s) {
   return plan_fwd(s).total;
 }
 
+static int attention_fwd_impl(const hept_shape* s, const float* q, const float* k, const float* v, const float* coords,
+                              const float* w_rpe_weight, int32_t K, const float* alpha, const int64_t* combined_shifts,
+                              const int32_t* combined_shifts32, const float* region_eta, const float* region_phi,
+                              const float* regions_h, float* scale, int32_t* positions, float* out_pre, float* den_sum,
+                              void* workspace, size_t workspace_bytes, void* stream);
+
 extern "C" int hept_attention_fwd(const hept_shape* s, const float* q, const float* k, const float* v,
                                   const float* coords, const float* w_rpe_weight, int32_t K, const float* alpha,
                                   const int64_t* combined_shifts, const float* region_eta, const float* region_phi,
                                   const float* regions_h, float* scale, int32_t* positions, float* out_pre,
                                   float* den_sum, void* workspace, size_t workspace_bytes, void* stream) {
+  return attention_fwd_impl(s, q, k, v, coords, w_rpe_weight, K, alpha, combined_shifts, nullptr, region_eta, region_phi, regions_h,
+                            scale, positions, out_pre, den_sum, workspace, workspace_bytes, stream);
+}
+
+extern "C" int hept_attention_fwd_shifts32(const hept_shape* s, const float* q, const float* k, const float* v,
+                                           const float* coords, const float* w_rpe_weight, int32_t K, const float* alpha,
+                                           const int32_t* combined_shifts32, float* scale, int32_t* positions,
+                                           float* out_pre, float* den_sum, void* workspace, size_t workspace_bytes,
+                                           void* stream) {
+  HEPT_REQUIRE(combined_shifts32, HEPT_EINVAL, "attention_fwd_shifts32: null pointer");
+  return attention_fwd_impl(s, q, k, v, coords, w_rpe_weight, K, alpha, nullptr, combined_shifts32, nullptr, nullptr, nullptr, scale,
+                            positions, out_pre, den_sum, workspace, workspace_bytes, stream);
+}
+
+static int attention_fwd_impl(const hept_shape* s, const float* q, const float* k, const float* v, const float* coords,
+                              const float* w_rpe_weight, int32_t K, const float* alpha, const int64_t* combined_shifts,
+                              const int32_t* combined_shifts32, const float* region_eta, const float* region_phi,
+                              const float* regions_h, float* scale, int32_t* positions, float* out_pre, float* den_sum,
+                              void* workspace, size_t workspace_bytes, void* stream) {
   if (int rc = validate_shape(s)) return rc;
   HEPT_REQUIRE(q && k && v && coords && w_rpe_weight && alpha && scale && positions && out_pre && den_sum && workspace,
                HEPT_EINVAL, "attention_fwd: null pointer");
-  const bool packed = combined_shifts != nullptr;
+  const bool packed = combined_shifts != nullptr || combined_shifts32 != nullptr;
   const bool regions = region_eta && region_phi && regions_h;
   HEPT_REQUIRE(packed != regions, HEPT_EINVAL,
                "attention_fwd: pass either combined_shifts or (region_eta, region_phi, regions_h)");
@@ -96,7 +121,8 @@ extern "C" int hept_attention_fwd(const hept_shape* s, const float* q, const flo
   if ((rc = hept_coord_scale_fwd(w_rpe_weight, s->H, s->D, s->C - 1, K, scale, stream))) return rc;
   bool hat_done = false;   // the fused projection kernel emits the scaled coordinates as a by-product
   if ((rc = hash_project_impl(s, q, k, coords, scale, alpha, proj, span, ext, p.ext_bytes, hat, &hat_done, stream))) return rc;
-  if (packed) rc = hept_keys_from_packed_shifts(s, proj, span, combined_shifts, keys, stream);
+  if (combined_shifts32) rc = hept_keys_from_packed_shifts32(s, proj, span, combined_shifts32, keys, stream);
+  else if (packed) rc = hept_keys_from_packed_shifts(s, proj, span, combined_shifts, keys, stream);
   else rc = hept_keys_from_region_indices(s, proj, span, region_eta, region_phi, regions_h, keys, stream);
   if (rc) return rc;
   if ((rc = hept_segmented_argsort(keys, 2 * s->T * s->H, s->N, positions, sort_ws, p.sort_bytes, stream))) return rc;

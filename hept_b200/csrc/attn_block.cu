@@ -1,0 +1,356 @@
+// The caller's side of the boundary: the front of the reference's Attn block,
+//     x_normed = norm1(x);  q, k, v = w_q(x_normed), w_k(x_normed), w_v(x_normed)        example/transformer.py:157-158
+// (src/models/baselines/transformer.py:209-212), forward and backward, as streaming fp32 kernels, so that a hit enters the
+// library as its 96-byte activation row instead of three 768-byte q / k / v rows: with host-resident inputs the call is
+// no longer a PCIe benchmark (2 520 -> 312 bytes per hit over the link), and on the device the three projections stop
+// being library GEMM launches.  q, k, v are still materialised in HBM (they are what the hash and tile kernels gather).
+//
+//   qkv_weights_t        Wt (3, DM, OW) = the three (OW, DM) weights transposed once per call (the row-wise products below
+//                        want the DM rows of a matrix contiguous over its OW columns)
+//   ln_qkv_fwd           128 hits per CTA: LayerNorm of the rows (two-pass variance, eps inside the square root like
+//                        torch.nn.functional.layer_norm), xn kept for the backward, then q / k / v = xn Wt with 4-hit x 8-column
+//                        register tiles (packed fp32 FMAs), weights and xn rows in shared memory
+//   ln_qkv_bwd_input     dxn = dq Wq + dk Wk + dv Wv with 4-hit x 6-output register tiles over cp.async-staged gradient rows,
+//                        then the LayerNorm backward of the row (4 adjacent lanes share a hit) -> dx, and the CTA's partial
+//                        sums of d gamma / d beta (fixed order: deterministic)
+//   ln_params_reduce     fixed-order sum of those partials
+//   weight gradients     dW_m = dq_m^T xn: the out_linear parameter-gradient kernels (out_linear.cu) with the roles of the
+//                        operands exchanged, result written transposed
+#include "common.cuh"
+
+namespace hept {
+
+int qkv_weight_grads(const float* xn, const float* dq, const float* dk, const float* dv, int N, int H, int D, float* dwq,
+                     float* dwk, float* dwv, float* partial, size_t partial_floats, cudaStream_t st);
+size_t qkv_weight_grads_partial_floats(int H, int D);
+
+constexpr int kAbHits = 128, kAbThreads = 128;
+
+// Wt[m][j][c] = W_m[c][j]
+__global__ void __launch_bounds__(256) qkv_weights_t_kernel(const float* __restrict__ wq, const float* __restrict__ wk,
+                                                            const float* __restrict__ wv, int DM, int OW, float* __restrict__ wt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int per = DM * OW;
+  if (i >= 3 * per) return;
+  const int m = i / per, r = i - m * per;
+  const int j = r / OW, c = r - j * OW;
+  const float* w = m == 0 ? wq : (m == 1 ? wk : wv);
+  wt[i] = __ldg(w + (size_t)c * DM + j);
+}
+
+template <int DM, int OW>
+__global__ void __launch_bounds__(kAbThreads, 3) ln_qkv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                                   const float* __restrict__ beta, const float* __restrict__ wt,
+                                                                   int N, float eps, float* __restrict__ xn_out,
+                                                                   float* __restrict__ q, float* __restrict__ k, float* __restrict__ v) {
+  constexpr int XS = DM + 4;
+  static_assert(DM % 4 == 0 && OW % 32 == 0, "tile shape");
+  extern __shared__ __align__(16) float s_dyn[];
+  float* s_w = s_dyn;                        // (3, DM, OW)
+  float* s_x = s_w + 3 * DM * OW;            // (kAbHits, XS) normalised rows
+  const int tid = threadIdx.x;
+  const int n0 = blockIdx.x * kAbHits;
+  const int rows = min(kAbHits, N - n0);
+  for (int i = tid; i < 3 * DM * OW / 4; i += kAbThreads) reinterpret_cast<float4*>(s_w)[i] = __ldg(reinterpret_cast<const float4*>(wt) + i);
+  {  // LayerNorm: one hit per thread
+    const int r = tid;
+    float xv[DM];
+    if (r < rows) {
+#pragma unroll
+      for (int c4 = 0; c4 < DM / 4; ++c4) {
+        const float4 t = ldg4(x + (size_t)(n0 + r) * DM + 4 * c4);
+        xv[4 * c4] = t.x; xv[4 * c4 + 1] = t.y; xv[4 * c4 + 2] = t.z; xv[4 * c4 + 3] = t.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < DM; ++j) xv[j] = 0.f;
+    }
+    float mean = 0.f;
+#pragma unroll
+    for (int j = 0; j < DM; ++j) mean += xv[j];
+    mean *= 1.f / DM;
+    float var = 0.f;
+#pragma unroll
+    for (int j = 0; j < DM; ++j) { const float dlt = xv[j] - mean; var = fmaf(dlt, dlt, var); }
+    const float rstd = 1.f / sqrtf(var * (1.f / DM) + eps);
+#pragma unroll
+    for (int j = 0; j < DM; ++j) xv[j] = fmaf((xv[j] - mean) * rstd, __ldg(gamma + j), __ldg(beta + j));
+#pragma unroll
+    for (int c4 = 0; c4 < DM / 4; ++c4) {
+      const float4 t = make_float4(xv[4 * c4], xv[4 * c4 + 1], xv[4 * c4 + 2], xv[4 * c4 + 3]);
+      *reinterpret_cast<float4*>(s_x + r * XS + 4 * c4) = t;
+      if (r < rows) *reinterpret_cast<float4*>(xn_out + (size_t)(n0 + r) * DM + 4 * c4) = t;
+    }
+  }
+  __syncthreads();
+  // thread = (hq = tid / 4, c0 = tid % 4): hits hq + 32 t x columns [8 cg, 8 cg + 8), cg = c0 + 4 i
+  const int hq = tid >> 2, c0 = tid & 3;
+#pragma unroll 1
+  for (int m = 0; m < 3; ++m) {
+    float* __restrict__ out = m == 0 ? q : (m == 1 ? k : v);
+    const float* wm = s_w + m * DM * OW;
+#pragma unroll 1
+    for (int i = 0; i < OW / 32; ++i) {
+      asm volatile("" ::: "memory");           // keep the xn rows in shared memory (hoisting them costs 96 registers)
+      const int cg = c0 + 4 * i;
+      float4 a0[4], a1[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) { a0[t] = make_float4(0.f, 0.f, 0.f, 0.f); a1[t] = a0[t]; }
+#pragma unroll
+      for (int j4 = 0; j4 < DM / 4; ++j4) {
+        float4 gv[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) gv[t] = *reinterpret_cast<const float4*>(s_x + (hq + 32 * t) * XS + 4 * j4);
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const float4 w0 = *reinterpret_cast<const float4*>(wm + (4 * j4 + jj) * OW + 8 * cg);
+          const float4 w1 = *reinterpret_cast<const float4*>(wm + (4 * j4 + jj) * OW + 8 * cg + 4);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float gj = jj == 0 ? gv[t].x : (jj == 1 ? gv[t].y : (jj == 2 ? gv[t].z : gv[t].w));
+            const float2 g2 = make_float2(gj, gj);
+            float2 r;
+            r = __ffma2_rn(g2, make_float2(w0.x, w0.y), make_float2(a0[t].x, a0[t].y)); a0[t].x = r.x; a0[t].y = r.y;
+            r = __ffma2_rn(g2, make_float2(w0.z, w0.w), make_float2(a0[t].z, a0[t].w)); a0[t].z = r.x; a0[t].w = r.y;
+            r = __ffma2_rn(g2, make_float2(w1.x, w1.y), make_float2(a1[t].x, a1[t].y)); a1[t].x = r.x; a1[t].y = r.y;
+            r = __ffma2_rn(g2, make_float2(w1.z, w1.w), make_float2(a1[t].z, a1[t].w)); a1[t].z = r.x; a1[t].w = r.y;
+          }
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int r = hq + 32 * t;
+        if (r < rows) {
+          float4* dst = reinterpret_cast<float4*>(out + (size_t)(n0 + r) * OW + 8 * cg);
+          dst[0] = a0[t];
+          dst[1] = a1[t];
+        }
+      }
+    }
+  }
+}
+
+// dxn = dq Wq + dk Wk + dv Wv, then the LayerNorm backward.  thread = (hq = tid / 4, og = tid % 4): hits hq + 32 t x outputs
+// [PER og, PER og + PER), PER = DM / 4; the four threads of a hit are adjacent lanes.
+template <int DM, int OW>
+__global__ void __launch_bounds__(kAbThreads, 2) ln_qkv_bwd_input_kernel(const float* __restrict__ dq, const float* __restrict__ dk,
+                                                                         const float* __restrict__ dv, const float* __restrict__ wt,
+                                                                         const float* __restrict__ x, const float* __restrict__ gamma,
+                                                                         int N, float eps, float* __restrict__ dx,
+                                                                         float* __restrict__ partial) {
+  constexpr int KC = 48, NCH = OW / KC, XS = KC + 4, WS = OW + 4, PER = DM / 4;
+  static_assert(OW % KC == 0 && DM % 4 == 0 && PER % 2 == 0, "tile shape");
+  extern __shared__ __align__(16) float s_dyn[];
+  float* s_w = s_dyn;                              // (3, DM, WS)
+  float* s_x = s_w + 3 * DM * WS;                  // (kAbHits, XS) one chunk of gradient rows
+  float* s_red = s_x;                              // reused at the end: (32, 2 DM) per-hit-group sums of d gamma / d beta
+  const int tid = threadIdx.x, hq = tid >> 2, og = tid & 3;
+  const int n0 = blockIdx.x * kAbHits;
+  const int rows = min(kAbHits, N - n0);
+  auto load_chunk = [&](int ch) {
+    const int m = ch / NCH, kc = ch - m * NCH;
+    const float* src = m == 0 ? dq : (m == 1 ? dk : dv);
+    for (int i = tid; i < kAbHits * (KC / 4); i += kAbThreads) {
+      const int r = i / (KC / 4), c4 = i - r * (KC / 4);
+      if (r < rows) cp_async16_cg(s_x + r * XS + 4 * c4, src + (size_t)(n0 + r) * OW + kc * KC + 4 * c4);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  load_chunk(0);
+  for (int i = tid; i < 3 * DM * (OW / 4); i += kAbThreads) {
+    const int mj = i / (OW / 4), c4 = i - mj * (OW / 4);
+    *reinterpret_cast<float4*>(s_w + mj * WS + 4 * c4) = ldg4(wt + (size_t)mj * OW + 4 * c4);
+  }
+  float2 acc[4][PER];
+#pragma unroll
+  for (int u = 0; u < PER; ++u)
+#pragma unroll
+    for (int t = 0; t < 4; ++t) acc[t][u] = make_float2(0.f, 0.f);
+#pragma unroll 1
+  for (int ch = 0; ch < 3 * NCH; ++ch) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    const int m = ch / NCH, kc = ch - m * NCH;
+    const float* xs = s_x + hq * XS;
+    const float* ws = s_w + (m * DM + og * PER) * WS + kc * KC;
+#pragma unroll 4
+    for (int c4 = 0; c4 < KC / 4; ++c4) {
+      float4 xv[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) xv[t] = *reinterpret_cast<const float4*>(xs + 32 * t * XS + 4 * c4);
+#pragma unroll
+      for (int u = 0; u < PER; ++u) {
+        const float4 wv = *reinterpret_cast<const float4*>(ws + u * WS + 4 * c4);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          acc[t][u] = __ffma2_rn(make_float2(xv[t].x, xv[t].y), make_float2(wv.x, wv.y), acc[t][u]);
+          acc[t][u] = __ffma2_rn(make_float2(xv[t].z, xv[t].w), make_float2(wv.z, wv.w), acc[t][u]);
+        }
+      }
+    }
+    __syncthreads();
+    if (ch + 1 < 3 * NCH) load_chunk(ch + 1);
+  }
+  // LayerNorm backward of each hit: y = xhat gamma + beta, xhat = (x - mean) rstd
+  //   dx = rstd (g - mean(g) - xhat mean(g xhat)), g = dxn gamma;  d gamma += dxn xhat;  d beta += dxn
+  float gam[PER], dgam[PER], dbet[PER];
+#pragma unroll
+  for (int u = 0; u < PER; ++u) { gam[u] = __ldg(gamma + og * PER + u); dgam[u] = 0.f; dbet[u] = 0.f; }
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int r = hq + 32 * t;
+    const bool live = r < rows;
+    float xv[PER], dxn[PER];
+#pragma unroll
+    for (int u2 = 0; u2 < PER / 2; ++u2) {
+      const float2 tt = live ? ldg2(x + (size_t)(n0 + r) * DM + og * PER + 2 * u2) : make_float2(0.f, 0.f);
+      xv[2 * u2] = tt.x; xv[2 * u2 + 1] = tt.y;
+    }
+#pragma unroll
+    for (int u = 0; u < PER; ++u) dxn[u] = acc[t][u].x + acc[t][u].y;
+    float s = 0.f;
+#pragma unroll
+    for (int u = 0; u < PER; ++u) s += xv[u];
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    const float mean = s * (1.f / DM);
+    float vs = 0.f;
+#pragma unroll
+    for (int u = 0; u < PER; ++u) { const float dlt = xv[u] - mean; vs = fmaf(dlt, dlt, vs); }
+    vs += __shfl_xor_sync(0xffffffffu, vs, 1);
+    vs += __shfl_xor_sync(0xffffffffu, vs, 2);
+    const float rstd = 1.f / sqrtf(vs * (1.f / DM) + eps);
+    float xh[PER], g[PER], m1 = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+      xh[u] = (xv[u] - mean) * rstd;
+      g[u] = dxn[u] * gam[u];
+      m1 += g[u];
+      m2 = fmaf(g[u], xh[u], m2);
+    }
+    m1 += __shfl_xor_sync(0xffffffffu, m1, 1);
+    m1 += __shfl_xor_sync(0xffffffffu, m1, 2);
+    m2 += __shfl_xor_sync(0xffffffffu, m2, 1);
+    m2 += __shfl_xor_sync(0xffffffffu, m2, 2);
+    m1 *= 1.f / DM;
+    m2 *= 1.f / DM;
+    if (live) {
+      float o[PER];
+#pragma unroll
+      for (int u = 0; u < PER; ++u) {
+        o[u] = rstd * (g[u] - m1 - xh[u] * m2);
+        dgam[u] = fmaf(dxn[u], xh[u], dgam[u]);
+        dbet[u] += dxn[u];
+      }
+#pragma unroll
+      for (int u2 = 0; u2 < PER / 2; ++u2)
+        *reinterpret_cast<float2*>(dx + (size_t)(n0 + r) * DM + og * PER + 2 * u2) = make_float2(o[2 * u2], o[2 * u2 + 1]);
+    }
+  }
+  // the CTA's sums: hit groups in order 0 .. 31 (fixed order)
+  __syncthreads();
+#pragma unroll
+  for (int u = 0; u < PER; ++u) {
+    s_red[hq * 2 * DM + og * PER + u] = dgam[u];
+    s_red[hq * 2 * DM + DM + og * PER + u] = dbet[u];
+  }
+  __syncthreads();
+  if (tid < 2 * DM) {
+    float s = 0.f;
+#pragma unroll 8
+    for (int g2 = 0; g2 < 32; ++g2) s += s_red[g2 * 2 * DM + tid];
+    partial[(size_t)blockIdx.x * 2 * DM + tid] = s;
+  }
+}
+
+// d gamma / d beta = fixed-order sum over the CTAs' partials (ctas, 2 DM): one CTA, tree over 256 strided sums
+__global__ void __launch_bounds__(256) ln_params_reduce_kernel(const float* __restrict__ partial, int ctas, int DM,
+                                                               float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ float red[256];
+  const int e = blockIdx.x;                  // entry in [0, 2 DM)
+  float s = 0.f;
+  for (int b = threadIdx.x; b < ctas; b += 256) s += partial[(size_t)b * 2 * DM + e];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    if (e < DM) dgamma[e] = red[0];
+    else dbeta[e - DM] = red[0];
+  }
+}
+
+template <int DM, int OW>
+static int launch_qkv_fwd(const float* x, const float* gamma, const float* beta, const float* wq, const float* wk, const float* wv,
+                          int N, float eps, float* wt, float* xn, float* q, float* k, float* v, cudaStream_t st) {
+  const size_t smem = sizeof(float) * (3 * (size_t)DM * OW + (size_t)kAbHits * (DM + 4));
+  static DeviceOnce configured;
+  if (configured.needed()) {
+    cudaError_t e = cudaFuncSetAttribute(ln_qkv_fwd_kernel<DM, OW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "attn_qkv_fwd: cannot reserve %zu B of shared memory: %s", smem, cudaGetErrorString(e));
+    configured.mark();
+  }
+  qkv_weights_t_kernel<<<(3 * DM * OW + 255) / 256, 256, 0, st>>>(wq, wk, wv, DM, OW, wt);
+  HEPT_CHECK_LAUNCH("qkv_weights_t");
+  ln_qkv_fwd_kernel<DM, OW><<<(N + kAbHits - 1) / kAbHits, kAbThreads, smem, st>>>(x, gamma, beta, wt, N, eps, xn, q, k, v);
+  HEPT_CHECK_LAUNCH("ln_qkv_fwd");
+  return HEPT_OK;
+}
+
+template <int DM, int OW>
+static int launch_qkv_bwd(const float* x, const float* xn, const float* gamma, const float* wt, const float* dq, const float* dk,
+                          const float* dv, int N, int H, int D, float eps, float* dx, float* dgamma, float* dbeta, float* dwq,
+                          float* dwk, float* dwv, float* ws, size_t ws_floats, cudaStream_t st) {
+  const size_t smem = sizeof(float) * (3 * (size_t)DM * (OW + 4) + (size_t)kAbHits * (48 + 4));
+  static_assert(kAbHits * (48 + 4) >= 32 * 2 * DM, "the staging buffer doubles as the reduction buffer");
+  static DeviceOnce configured;
+  if (configured.needed()) {
+    cudaError_t e = cudaFuncSetAttribute(ln_qkv_bwd_input_kernel<DM, OW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "attn_qkv_bwd: cannot reserve %zu B of shared memory: %s", smem, cudaGetErrorString(e));
+    configured.mark();
+  }
+  const int ctas = (N + kAbHits - 1) / kAbHits;
+  const size_t ln_floats = (size_t)ctas * 2 * DM;
+  HEPT_REQUIRE(ws_floats >= ln_floats + qkv_weight_grads_partial_floats(H, D), HEPT_EWORKSPACE, "attn_qkv_bwd: workspace too small");
+  ln_qkv_bwd_input_kernel<DM, OW><<<ctas, kAbThreads, smem, st>>>(dq, dk, dv, wt, x, gamma, N, eps, dx, ws);
+  HEPT_CHECK_LAUNCH("ln_qkv_bwd_input");
+  ln_params_reduce_kernel<<<2 * DM, 256, 0, st>>>(ws, ctas, DM, dgamma, dbeta);
+  HEPT_CHECK_LAUNCH("ln_params_reduce");
+  return qkv_weight_grads(xn, dq, dk, dv, N, H, D, dwq, dwk, dwv, ws + ln_floats, ws_floats - ln_floats, st);
+}
+
+}  // namespace hept
+
+using namespace hept;
+
+extern "C" int hept_attn_qkv_supported(int32_t H, int32_t D) { return H == 8 && D == 24; }
+
+extern "C" size_t hept_attn_qkv_bwd_workspace_bytes(int32_t N, int32_t H, int32_t D) {
+  if (N <= 0 || H <= 0 || D <= 0) return 0;
+  return sizeof(float) * ((size_t)((N + kAbHits - 1) / kAbHits) * 2 * D + qkv_weight_grads_partial_floats(H, D));
+}
+
+extern "C" int hept_attn_qkv_fwd(const float* x, const float* norm_weight, const float* norm_bias, const float* w_q,
+                                 const float* w_k, const float* w_v, int32_t N, int32_t H, int32_t D, float eps, float* wt,
+                                 float* x_normed, float* q, float* k, float* v, void* stream) {
+  HEPT_REQUIRE(x && norm_weight && norm_bias && w_q && w_k && w_v && wt && x_normed && q && k && v && N > 0, HEPT_EINVAL,
+               "attn_qkv_fwd: bad argument");
+  HEPT_REQUIRE(hept_attn_qkv_supported(H, D), HEPT_EUNSUPPORTED, "attn_qkv_fwd: (H=%d, D=%d) not compiled in", H, D);
+  return launch_qkv_fwd<24, 192>(x, norm_weight, norm_bias, w_q, w_k, w_v, N, eps, wt, x_normed, q, k, v, (cudaStream_t)stream);
+}
+
+extern "C" int hept_attn_qkv_bwd(const float* x, const float* x_normed, const float* norm_weight, const float* wt,
+                                 const float* dq, const float* dk, const float* dv, int32_t N, int32_t H, int32_t D, float eps,
+                                 float* dx, float* d_norm_weight, float* d_norm_bias, float* d_w_q, float* d_w_k, float* d_w_v,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
+  HEPT_REQUIRE(x && x_normed && norm_weight && wt && dq && dk && dv && dx && d_norm_weight && d_norm_bias && d_w_q && d_w_k &&
+                   d_w_v && workspace && N > 0,
+               HEPT_EINVAL, "attn_qkv_bwd: bad argument");
+  HEPT_REQUIRE(hept_attn_qkv_supported(H, D), HEPT_EUNSUPPORTED, "attn_qkv_bwd: (H=%d, D=%d) not compiled in", H, D);
+  HEPT_REQUIRE(workspace_bytes >= hept_attn_qkv_bwd_workspace_bytes(N, H, D), HEPT_EWORKSPACE, "attn_qkv_bwd: workspace needs %zu bytes",
+               hept_attn_qkv_bwd_workspace_bytes(N, H, D));
+  return launch_qkv_bwd<24, 192>(x, x_normed, norm_weight, wt, dq, dk, dv, N, H, D, eps, dx, d_norm_weight, d_norm_bias, d_w_q,
+                                 d_w_k, d_w_v, (float*)workspace, workspace_bytes / sizeof(float), (cudaStream_t)stream);
+}

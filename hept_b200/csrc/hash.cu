@@ -161,12 +161,13 @@ __global__ void hat_coords_kernel(const float* __restrict__ coords, const float*
 // ---------------------------------------------------------------------------------------------------
 // keys.  Explicit round-to-nearest multiply and add: an FMA contraction would not match eager torch.
 // ---------------------------------------------------------------------------------------------------
+template <typename ShiftT>     // int64 as the reference's prepare_input delivers them, or the same values as int32
 __global__ void keys_packed_kernel(const float* __restrict__ proj, const float* __restrict__ span,
-                                   const int64_t* __restrict__ shifts, int N, size_t thn, float* __restrict__ keys) {
+                                   const ShiftT* __restrict__ shifts, int N, size_t thn, float* __restrict__ keys) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= thn) return;
   float sp = span[i / N];
-  float sh = __fmul_rn((float)shifts[i], sp);  // int64 -> f32 (rne), then one rounding for the product
+  float sh = __fmul_rn((float)shifts[i], sp);  // integer -> f32 (rne), then one rounding for the product
   keys[i] = __fadd_rn(proj[i], sh);
   keys[thn + i] = __fadd_rn(proj[thn + i], sh);
 }
@@ -495,8 +496,19 @@ extern "C" int hept_keys_from_packed_shifts(const hept_shape* s, const float* pr
   if (int rc = validate_shape(s)) return rc;
   HEPT_REQUIRE(proj && span && combined_shifts && keys, HEPT_EINVAL, "keys_from_packed_shifts: null pointer");
   size_t thn = (size_t)s->T * s->H * s->N;
-  keys_packed_kernel<<<(unsigned)((thn + 255) / 256), 256, 0, (cudaStream_t)stream>>>(proj, span, combined_shifts,
-                                                                                     s->N, thn, keys);
+  keys_packed_kernel<int64_t><<<(unsigned)((thn + 255) / 256), 256, 0, (cudaStream_t)stream>>>(proj, span, combined_shifts,
+                                                                                              s->N, thn, keys);
+  HEPT_CHECK_LAUNCH("keys_packed");
+  return HEPT_OK;
+}
+
+extern "C" int hept_keys_from_packed_shifts32(const hept_shape* s, const float* proj, const float* span,
+                                              const int32_t* combined_shifts32, float* keys, void* stream) {
+  if (int rc = validate_shape(s)) return rc;
+  HEPT_REQUIRE(proj && span && combined_shifts32 && keys, HEPT_EINVAL, "keys_from_packed_shifts32: null pointer");
+  size_t thn = (size_t)s->T * s->H * s->N;
+  keys_packed_kernel<int32_t><<<(unsigned)((thn + 255) / 256), 256, 0, (cudaStream_t)stream>>>(proj, span, combined_shifts32,
+                                                                                              s->N, thn, keys);
   HEPT_CHECK_LAUNCH("keys_packed");
   return HEPT_OK;
 }

@@ -441,7 +441,8 @@ __global__ void __launch_bounds__(kPgGroups * (OUT / 8) * (IN / 8), 2) out_linea
 // Entries [OUT][OUT..IN) are unused.
 constexpr int kOlParts = 16;
 __global__ void __launch_bounds__(32 * kOlParts) out_linear_reduce_kernel(const float* __restrict__ partial, int ctas, int OUT,
-                                                                          int IN, float* __restrict__ dw, float* __restrict__ db) {
+                                                                          int IN, float* __restrict__ dw, float* __restrict__ db,
+                                                                          bool transposed = false) {
   __shared__ float red[kOlParts][32];
   const int e = threadIdx.x & 31, part = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + e;
@@ -466,8 +467,8 @@ __global__ void __launch_bounds__(32 * kOlParts) out_linear_reduce_kernel(const 
 #pragma unroll
     for (int p = 1; p < kOlParts; ++p) t += red[p][e];
     const int j = i / IN, c = i - j * IN;
-    if (j < OUT) dw[i] = t;
-    else if (c < OUT) db[c] = t;
+    if (j < OUT) dw[transposed ? c * OUT + j : i] = t;     // transposed: dw is (IN, OUT)
+    else if (c < OUT && db) db[c] = t;
   }
 }
 
@@ -566,6 +567,39 @@ static int launch_ol_bwd(const hept_shape* s, const float* g, const float* w, co
   const int entries = (OUT + 1) * IN;
   out_linear_reduce_kernel<<<(entries + 31) / 32, 32 * kOlParts, 0, st>>>(partial, ctas, OUT, IN, dw, db);
   HEPT_CHECK_LAUNCH("out_linear_reduce");
+  return HEPT_OK;
+}
+
+// The three weight gradients of the attention block's projections (attn_block.cu): dW_m (H*D, D) = dq_m^T xn is the
+// parameter-gradient product above with the operands' roles exchanged (g := xn (N, D), x := dq_m (N, H*D)), written transposed.
+size_t qkv_weight_grads_partial_floats(int H, int D) { return (size_t)kOlMaxCtas * (D + 1) * H * D; }
+
+int qkv_weight_grads(const float* xn, const float* dq, const float* dk, const float* dv, int N, int H, int D, float* dwq,
+                     float* dwk, float* dwv, float* partial, size_t partial_floats, cudaStream_t st) {
+  HEPT_REQUIRE(D == 24 && H == 8, HEPT_EUNSUPPORTED, "qkv_weight_grads: (H=%d, D=%d) not compiled in", H, D);
+  HEPT_REQUIRE(partial_floats >= qkv_weight_grads_partial_floats(H, D), HEPT_EWORKSPACE, "qkv_weight_grads: workspace too small");
+  constexpr int OUT = 24, TIN = 192, THREADS = kPgGroups * (OUT / 8) * (TIN / 8);
+  const size_t tsmem = sizeof(float) * 2 * (size_t)kPgRows * (TIN + 4 + OUT + 4);
+  static DeviceOnce configured;
+  if (configured.needed()) {
+    cudaError_t e = cudaFuncSetAttribute(out_linear_bwd_params_tiled_kernel<OUT, TIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem);
+    HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "qkv_weight_grads: %s", cudaGetErrorString(e));
+    configured.mark();
+  }
+  const int sms = sm_count();
+  HEPT_REQUIRE(sms > 0, HEPT_ECUDA, "qkv_weight_grads: cannot read the SM count");
+  const int tslabs = (N + kPgRows - 1) / kPgRows;
+  int ctas = sms * 2 < tslabs ? sms * 2 : tslabs;
+  if (ctas > kOlMaxCtas) ctas = kOlMaxCtas;
+  const int entries = (OUT + 1) * TIN;
+  const float* src[3] = {dq, dk, dv};
+  float* dst[3] = {dwq, dwk, dwv};
+  for (int m = 0; m < 3; ++m) {     // one partial buffer, reused: the launches are ordered on the stream
+    out_linear_bwd_params_tiled_kernel<OUT, TIN><<<ctas, THREADS, tsmem, st>>>(xn, src[m], N, partial);
+    HEPT_CHECK_LAUNCH("qkv_weight_grads");
+    out_linear_reduce_kernel<<<(entries + 31) / 32, 32 * kOlParts, 0, st>>>(partial, ctas, OUT, TIN, dst[m], nullptr, true);
+    HEPT_CHECK_LAUNCH("qkv_weight_reduce");
+  }
   return HEPT_OK;
 }
 

@@ -78,6 +78,9 @@ int hept_hat_coords(const hept_shape* s, const float* coords, const float* scale
  * keys[s,t,h,n] = proj[s,t,h,n] + float(combined_shifts[t,h,n]) * span[t,h]   (convert, mul, add). */
 int hept_keys_from_packed_shifts(const hept_shape* s, const float* proj, const float* span,
                                  const int64_t* combined_shifts, float* keys, void* stream);
+/* the same with the codes as int32 (hept_prepare_batched emits both; the values are identical, 96 bytes per hit fewer) */
+int hept_keys_from_packed_shifts32(const hept_shape* s, const float* proj, const float* span,
+                                   const int32_t* combined_shifts32, float* keys, void* stream);
 /* ---- a6' AND-construction, src/ flavour (src/models/attention/hept.py:46-56, 93-101) ----------
  * region_eta/phi (T*H, N) float, regions_h (2, T*H); rows >= raw_size get +inf. */
 int hept_keys_from_region_indices(const hept_shape* s, const float* proj, const float* span,
@@ -161,6 +164,31 @@ size_t hept_prepare_single_workspace_bytes(int32_t n_pad);
 int hept_prepare_single(const float* coords, int32_t C, int32_t n_raw, int32_t n_pad, const float* regions_h, int32_t TH,
                         float* coords_pad, float* region_eta, float* region_phi, void* workspace, size_t workspace_bytes,
                         void* stream);
+
+/* hept_attention_fwd for the example/ flavour with int32 codes */
+int hept_attention_fwd_shifts32(const hept_shape* s, const float* q, const float* k, const float* v, const float* coords,
+                                const float* w_rpe_weight, int32_t K, const float* alpha, const int32_t* combined_shifts32,
+                                float* scale, int32_t* positions, float* out_pre, float* den_sum, void* workspace,
+                                size_t workspace_bytes, void* stream);
+
+/* ---- the front of the caller's Attn block ------------------------------------------------------
+ * x_normed = norm1(x); q, k, v = w_q(x_normed), w_k(x_normed), w_v(x_normed)   (example/transformer.py:157-158,
+ * src/models/baselines/transformer.py:209-212): LayerNorm over D (eps inside the square root) and three bias-free
+ * Linear(D, H*D).  With it a hit crosses the boundary as its D-float activation row instead of three H*D-float rows.
+ *   x (N, D); norm_weight, norm_bias (D); w_q, w_k, w_v (H*D, D) as nn.Linear stores them.
+ *   forward outputs: wt (3, D, H*D) the transposed weights, x_normed (N, D) (both kept for the backward), q, k, v (N, H*D).
+ *   backward: dq, dk, dv (N, H*D) -> dx (N, D) (the gradient through norm1 only: the block's residual path is the caller's),
+ *   d_norm_weight, d_norm_bias (D), d_w_q, d_w_k, d_w_v (H*D, D); deterministic (fixed-order reductions).
+ * Compiled for (H, D) = (8, 24): hept_attn_qkv_supported says so; other shapes return HEPT_EUNSUPPORTED. */
+int hept_attn_qkv_supported(int32_t H, int32_t D);
+int hept_attn_qkv_fwd(const float* x, const float* norm_weight, const float* norm_bias, const float* w_q, const float* w_k,
+                      const float* w_v, int32_t N, int32_t H, int32_t D, float eps, float* wt, float* x_normed, float* q,
+                      float* k, float* v, void* stream);
+size_t hept_attn_qkv_bwd_workspace_bytes(int32_t N, int32_t H, int32_t D);
+int hept_attn_qkv_bwd(const float* x, const float* x_normed, const float* norm_weight, const float* wt, const float* dq,
+                      const float* dk, const float* dv, int32_t N, int32_t H, int32_t D, float eps, float* dx,
+                      float* d_norm_weight, float* d_norm_bias, float* d_w_q, float* d_w_k, float* d_w_v, void* workspace,
+                      size_t workspace_bytes, void* stream);
 
 /* kernel launches this library enqueued (any thread of the process) since the counter was last reset
  * (bench.py's gpu_launches); reset != 0 zeroes the counter after reading it. */
