@@ -74,6 +74,35 @@ class _HeptCore(torch.autograd.Function):
         return dq, dk, dv, dw, None, None, None, None, None, None, None, None
 
 
+class _AttnFront(torch.autograd.Function):
+    """x (N, D) -> q, k, v (N, H*D): ``norm1`` then ``w_q / w_k / w_v`` of the reference's Attn block
+    (example/transformer.py:157-158; src/models/baselines/transformer.py:209-212) on the library's kernels
+    (csrc/attn_block.cu).  The gradient w.r.t. x is the one through norm1; the block's residual path stays with autograd."""
+
+    @staticmethod
+    def forward(ctx, x, norm_weight, norm_bias, w_q, w_k, w_v, H: int, D: int, eps: float):
+        x = x.contiguous()
+        q, k, v, xn, wt = ops.attn_qkv_fwd(x, norm_weight, norm_bias, w_q, w_k, w_v, H, D, eps)
+        ctx.save_for_backward(x, xn, norm_weight, wt)
+        ctx.shape = (H, D, eps)
+        return q, k, v
+
+    @staticmethod
+    def backward(ctx, dq, dk, dv):
+        x, xn, gamma, wt = ctx.saved_tensors
+        H, D, eps = ctx.shape
+        dx, dgam, dbet, dwq, dwk, dwv = ops.attn_qkv_bwd(x, xn, gamma, wt, dq.contiguous(), dk.contiguous(), dv.contiguous(), H, D, eps)
+        return dx, dgam, dbet, dwq, dwk, dwv, None, None, None
+
+
+def attn_front(x: torch.Tensor, norm1: nn.LayerNorm, w_q: nn.Linear, w_k: nn.Linear, w_v: nn.Linear, num_heads: int):
+    """``norm1(x)`` followed by the three bias-free projections -> q, k, v, in one native forward (and one native backward)."""
+    d = x.shape[-1]
+    if not ops.attn_qkv_supported(num_heads, d):
+        raise NotImplementedError(f"attn_front: (H={num_heads}, D={d}) not compiled in (hept_attn_qkv_supported)")
+    return _AttnFront.apply(x.float(), norm1.weight, norm1.bias, w_q.weight, w_k.weight, w_v.weight, num_heads, d, norm1.eps)
+
+
 class _OutLinear(torch.autograd.Function):
     """out_pre (N, H*D), weight (D, H*D), bias (D) -> out (N, D): ``out_linear`` of example/hept.py:80 on the library's own
     streaming kernels (csrc/out_linear.cu) instead of three library GEMMs."""
@@ -125,7 +154,10 @@ class HEPTAttention(nn.Module):
         if n % self.block_size != 0:
             raise ValueError(f"N={n} is not a multiple of block_size={self.block_size} (pad with prepare_input first)")
         w = kwargs["w_rpe"].weight
-        shifts = kwargs.get("combined_shifts")
+        # the same codes as int32 when the caller's prepare_input provides them (hept_b200.prepare does): 96 bytes per hit less
+        shifts = kwargs.get("combined_shifts32")
+        if shifts is None:
+            shifts = kwargs.get("combined_shifts")
         eta = phi = regions_h = None
         raw = n
         if shifts is None:

@@ -155,11 +155,12 @@ def keys_from_packed_shifts(d: Dims, proj, span, combined_shifts) -> torch.Tenso
     lib = _lib.load()
     proj = _need(proj, "proj", torch.float32, (2, d.T, d.H, d.N))
     span = _need(span, "span", torch.float32, (d.T, d.H))
-    sh = _need(combined_shifts, "combined_shifts", torch.int64, (d.T, d.H, d.N))
+    sh32 = combined_shifts.dtype == torch.int32
+    sh = _need(combined_shifts, "combined_shifts", torch.int32 if sh32 else torch.int64, (d.T, d.H, d.N))
     keys = torch.empty_like(proj)
     s = d.struct()
-    _lib.check(lib.hept_keys_from_packed_shifts(C.byref(s), _ptr(proj), _ptr(span), _ptr(sh), _ptr(keys), _stream(proj)),
-               "hept_keys_from_packed_shifts")
+    fn = lib.hept_keys_from_packed_shifts32 if sh32 else lib.hept_keys_from_packed_shifts
+    _lib.check(fn(C.byref(s), _ptr(proj), _ptr(span), _ptr(sh), _ptr(keys), _stream(proj)), "hept_keys_from_packed_shifts")
     return keys
 
 
@@ -264,6 +265,50 @@ def out_linear_bwd(d: Dims, d_out, weight, out_pre, need_input_grad: bool = True
     return dx, dw, db
 
 
+# ---------------------------------------------------------------- norm1 + w_q / w_k / w_v
+def attn_qkv_supported(H: int, D: int) -> bool:
+    return bool(_lib.load().hept_attn_qkv_supported(H, D))
+
+
+@_on_device
+def attn_qkv_fwd(x, norm_weight, norm_bias, w_q, w_k, w_v, H: int, D: int, eps: float):
+    """x (N, D) -> q, k, v (N, H*D) = w(norm1(x)); also returns x_normed (N, D) and the transposed weights wt (3, D, H*D)."""
+    lib = _lib.load()
+    n = x.shape[0]
+    x = _need(x, "x", torch.float32, (n, D))
+    g = _need(norm_weight, "norm1.weight", torch.float32, (D,))
+    b = _need(norm_bias, "norm1.bias", torch.float32, (D,))
+    ws_ = [_need(w, nm, torch.float32, (H * D, D)) for w, nm in ((w_q, "w_q.weight"), (w_k, "w_k.weight"), (w_v, "w_v.weight"))]
+    dev = x.device
+    wt = torch.empty(3, D, H * D, dtype=torch.float32, device=dev)
+    xn = torch.empty(n, D, dtype=torch.float32, device=dev)
+    q, k, v = (torch.empty(n, H * D, dtype=torch.float32, device=dev) for _ in range(3))
+    _lib.check(lib.hept_attn_qkv_fwd(_ptr(x), _ptr(g), _ptr(b), _ptr(ws_[0]), _ptr(ws_[1]), _ptr(ws_[2]), n, H, D, float(eps),
+                                     _ptr(wt), _ptr(xn), _ptr(q), _ptr(k), _ptr(v), _stream(x)), "hept_attn_qkv_fwd")
+    return q, k, v, xn, wt
+
+
+@_on_device
+def attn_qkv_bwd(x, xn, norm_weight, wt, dq, dk, dv, H: int, D: int, eps: float):
+    """-> dx (N, D), d norm1.weight, d norm1.bias (D), d w_q, d w_k, d w_v (H*D, D)."""
+    lib = _lib.load()
+    n = x.shape[0]
+    x = _need(x, "x", torch.float32, (n, D))
+    xn = _need(xn, "x_normed", torch.float32, (n, D))
+    g = _need(norm_weight, "norm1.weight", torch.float32, (D,))
+    wt = _need(wt, "wt", torch.float32, (3, D, H * D))
+    dq, dk, dv = (_need(t, nm, torch.float32, (n, H * D)) for t, nm in ((dq, "dq"), (dk, "dk"), (dv, "dv")))
+    dev = x.device
+    dx = torch.empty(n, D, dtype=torch.float32, device=dev)
+    dgam, dbet = torch.empty(D, dtype=torch.float32, device=dev), torch.empty(D, dtype=torch.float32, device=dev)
+    dwq, dwk, dwv = (torch.empty(H * D, D, dtype=torch.float32, device=dev) for _ in range(3))
+    ws = _workspace(lib.hept_attn_qkv_bwd_workspace_bytes(n, H, D), x)
+    _lib.check(lib.hept_attn_qkv_bwd(_ptr(x), _ptr(xn), _ptr(g), _ptr(wt), _ptr(dq), _ptr(dk), _ptr(dv), n, H, D, float(eps),
+                                     _ptr(dx), _ptr(dgam), _ptr(dbet), _ptr(dwq), _ptr(dwk), _ptr(dwv), _ptr(ws), ws.numel(),
+                                     _stream(x)), "hept_attn_qkv_bwd")
+    return dx, dgam, dbet, dwq, dwk, dwv
+
+
 # ------------------------------------------------------------------------------- a13..a17 preparation
 @_on_device
 def prepare_batched(coords, batch, offsets, num_events: int, n_raw: int, n_pad: int, max_event: int, regions_h, block_size: int,
@@ -323,8 +368,9 @@ def attention_fwd(d: Dims, q, k, v, coords, w_rpe_weight, K: int, alpha, combine
     w = _need(w_rpe_weight, "w_rpe.weight", torch.float32, (d.H * d.D, (d.C - 1) * K))
     alpha = _need(alpha, "e2lsh.alpha", torch.float32, (d.H, d.E, d.T))
     sh = eta = phi = rh = None
+    sh32 = combined_shifts is not None and combined_shifts.dtype == torch.int32
     if combined_shifts is not None:
-        sh = _need(combined_shifts, "combined_shifts", torch.int64, (d.T, d.H, d.N))
+        sh = _need(combined_shifts, "combined_shifts", torch.int32 if sh32 else torch.int64, (d.T, d.H, d.N))
     else:
         eta = _need(region_indices[0], "region_indices[0]", torch.float32, (d.T * d.H, d.N))
         phi = _need(region_indices[1], "region_indices[1]", torch.float32, (d.T * d.H, d.N))
@@ -336,6 +382,11 @@ def attention_fwd(d: Dims, q, k, v, coords, w_rpe_weight, K: int, alpha, combine
     den = torch.empty(d.N, d.H, dtype=torch.float32, device=dev)
     s = d.struct()
     ws = _workspace(lib.hept_attention_fwd_workspace_bytes(C.byref(s)), q)
+    if sh32:
+        _lib.check(lib.hept_attention_fwd_shifts32(C.byref(s), _ptr(q), _ptr(k), _ptr(v), _ptr(coords), _ptr(w), K, _ptr(alpha),
+                                                   _ptr(sh), _ptr(scale), _ptr(pos), _ptr(out_pre), _ptr(den), _ptr(ws),
+                                                   ws.numel(), _stream(q)), "hept_attention_fwd_shifts32")
+        return out_pre, den, scale, pos
     _lib.check(lib.hept_attention_fwd(C.byref(s), _ptr(q), _ptr(k), _ptr(v), _ptr(coords), _ptr(w), K, _ptr(alpha),
                                       _ptr(sh), _ptr(eta), _ptr(phi), _ptr(rh), _ptr(scale), _ptr(pos), _ptr(out_pre),
                                       _ptr(den), _ptr(ws), ws.numel(), _stream(q)), "hept_attention_fwd")
