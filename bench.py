@@ -8,8 +8,10 @@ q, k, v, w_rpe.weight and out_linear.* (BASELINE.json configs[1]: ~60k hits, blo
 tables, 8 heads x 24 dims, coords_dim 6).  Prints ONE JSON line (rank 0).
 
   value      hits/s, whole job, inputs already resident in HBM, CUDA-event timed, max over ranks
-  e2e        the same metric through the module call with HOST (pinned) inputs: H2D of q, k, v, coords,
-             combined_shifts and D2H of the output + parameter gradients inside the timed region
+  e2e        the same metric with HOST (pinned) inputs, H2D of the inputs and D2H of the output + parameter gradients
+             inside the timed region, at the Attn-block boundary: the 96-byte activation row of a hit
+             crosses the link and norm1 + w_q / w_k / w_v run in the library in front of the same HEPTAttention
+  e2e_module_boundary   the same at the reference module's own boundary (q, k, v cross the link: PCIe-bound)
   roofline   dominant kernel, algorithmic bytes per launch / its CUDA-event duration, vs the measured HBM peak
   cpu_baseline  the oracle (a torch-CPU restatement of the reference, kind "port") timed on this box's cores
 
@@ -208,6 +210,8 @@ def run_ours(args):
     w_rpe.load_state_dict({"weight": params["w_rpe.weight"], "bias": params["w_rpe.bias"]})
     w_rpe = w_rpe.to(dev)
     trainable = [w_rpe.weight, mod.out_linear.weight, mod.out_linear.bias]
+    # gradients live in one persistent flat buffer (hept_b200/sharding.py): ONE NCCL launch per step for the collective
+    bucket = sharding.GradBucket(trainable)
 
     host = [{k: v.pin_memory() for k, v in e[2].items()} for e in events]
     gouts = [e[3].to(dev) for e in events]
@@ -218,15 +222,14 @@ def run_ours(args):
     n_hits = resident[0]["query"].shape[0]
 
     def step(inp, g):
-        for p in trainable:
-            p.grad = None
+        bucket.zero()
         for k in ("query", "key", "value"):
             inp[k].grad = None
         out = mod(inp["query"], inp["key"], inp["value"], w_rpe=w_rpe, coords=inp["coords"],
                   combined_shifts=inp["combined_shifts"])
         out.backward(g)
         if world > 1:
-            sharding.allreduce_gradients(trainable)
+            bucket.allreduce()
         return out
 
     def timed(fn, steps, warmup):
@@ -258,47 +261,91 @@ def run_ours(args):
         ms, launches = timed(lambda i: step(resident[i % n_sets], gouts[i % n_sets]), args.steps, args.warmup)
     value = world * args.steps * N_RAW / (ms * 1e-3)
 
-    # ---- end to end through the module with host buffers -------------------------------------------
+    # ---- end to end with HOST buffers --------------------------------------------------------------
     # Double-buffered: the H2D copy of step i+1 runs on a copy stream while step i computes; every step still
     # copies its own inputs from pinned host memory and reads its results back inside the timed region.
-    staging = [{k: torch.empty_like(v, device=dev) for k, v in host[0].items()} for _ in range(2)]
-    out_host = torch.empty(n_hits, cfg["h_dim"]).pin_memory()
-    grad_host = [torch.empty_like(p, device="cpu").pin_memory() for p in trainable]
-    h2d = sum(v.numel() * v.element_size() for v in host[0].values())
-    d2h = out_host.numel() * 4 + sum(g.numel() * 4 for g in grad_host)
-    copy_stream = torch.cuda.Stream(device=dev)
-    ready = [torch.cuda.Event() for _ in range(2)]
-    consumed = [torch.cuda.Event() for _ in range(2)]
-    issued = set()
+    def e2e_leg(host_sets, grad_keys, run, result_params, out_width):
+        staging = [{k: torch.empty_like(v, device=dev) for k, v in host_sets[0].items()} for _ in range(2)]
+        out_host = torch.empty(n_hits, out_width).pin_memory()
+        grad_host = [torch.empty_like(p, device="cpu").pin_memory() for p in result_params]
+        h2d = sum(v.numel() * v.element_size() for v in host_sets[0].values())
+        d2h = out_host.numel() * 4 + sum(g.numel() * 4 for g in grad_host)
+        copy_stream = torch.cuda.Stream(device=dev)
+        ready = [torch.cuda.Event() for _ in range(2)]
+        consumed = [torch.cuda.Event() for _ in range(2)]
+        issued = set()
 
-    def prefetch(i):
-        if i in issued:
-            return
-        issued.add(i)
-        b = i % 2
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(consumed[b])          # buffer b was last read by step i-2
-            for k, v in host[i % n_sets].items():
-                staging[b][k].copy_(v, non_blocking=True)
-            ready[b].record(copy_stream)
+        def prefetch(i):
+            if i in issued:
+                return
+            issued.add(i)
+            b = i % 2
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[b])          # buffer b was last read by step i-2
+                for k, v in host_sets[i % n_sets].items():
+                    staging[b][k].copy_(v, non_blocking=True)
+                ready[b].record(copy_stream)
 
-    def e2e_step(i):
-        prefetch(i)
-        prefetch(i + 1)
-        b = i % 2
-        torch.cuda.current_stream().wait_event(ready[b])
-        inp = dict(staging[b])
-        for k in ("query", "key", "value"):
-            inp[k] = inp[k].detach().requires_grad_(True)
-        out = step(inp, gouts[i % n_sets])
-        consumed[b].record(torch.cuda.current_stream())
-        out_host.copy_(out.detach(), non_blocking=True)
-        for gh, p in zip(grad_host, trainable):
-            gh.copy_(p.grad, non_blocking=True)
+        def e2e_step(i):
+            prefetch(i)
+            prefetch(i + 1)
+            b = i % 2
+            torch.cuda.current_stream().wait_event(ready[b])
+            inp = dict(staging[b])
+            for k in grad_keys:
+                inp[k] = inp[k].detach().requires_grad_(True)
+            out = run(inp, gouts[i % n_sets])
+            consumed[b].record(torch.cuda.current_stream())
+            out_host.copy_(out.detach(), non_blocking=True)
+            for gh, p in zip(grad_host, result_params):
+                gh.copy_(p.grad, non_blocking=True)
 
-    e2e_steps = max(3, min(args.steps, 10))
-    ms_e2e, _ = timed(e2e_step, e2e_steps, 3)
-    e2e_value = world * e2e_steps * N_RAW / (ms_e2e * 1e-3)
+        steps = max(3, min(args.steps, 10))
+        ms_leg, _ = timed(e2e_step, steps, 3)
+        return {"value": world * steps * N_RAW / (ms_leg * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": ms_leg / steps}
+
+    # (1) the module boundary of the reference, HEPTAttention.forward(query, key, value, ...): q, k, v cross the link
+    e2e_module = e2e_leg(host, ("query", "key", "value"), step, trainable, cfg["h_dim"])
+    e2e_module["boundary"] = ("HEPTAttention.forward: q, k, v (N,192) fp32, coords, int64 codes from pinned host memory; "
+                              "output (N,24) + parameter gradients read back")
+
+    # (2) the Attn-block boundary: the activation row x (N,24) crosses the link, norm1 + w_q / w_k / w_v run
+    # in the library (csrc/attn_block.cu) in front of the same HEPTAttention; MORE work per hit than (1), 12x fewer bytes
+    from hept_b200.attention import attn_front
+
+    g0 = torch.Generator().manual_seed(4242 + rank)
+    norm1 = torch.nn.LayerNorm(cfg["h_dim"]).to(dev)
+    w_qkv = [torch.nn.Linear(cfg["h_dim"], cfg["num_heads"] * cfg["h_dim"], bias=False).to(dev) for _ in range(3)]
+    front_params = [norm1.weight, norm1.bias] + [w.weight for w in w_qkv]
+    bucket_blk = sharding.GradBucket(trainable + front_params)      # re-homes the three attention parameters' .grad too
+    host_x = [{"x": (torch.randn(n_hits, cfg["h_dim"], generator=g0) * 0.7).pin_memory(), "coords": h["coords"],
+               "combined_shifts32": h["combined_shifts"].to(torch.int32).pin_memory()} for h in host]
+
+    def block_step(inp, g):
+        bucket_blk.zero()
+        q, k, v = attn_front(inp["x"], norm1, w_qkv[0], w_qkv[1], w_qkv[2], cfg["num_heads"])
+        out = mod(q, k, v, w_rpe=w_rpe, coords=inp["coords"], combined_shifts32=inp["combined_shifts32"])
+        out.backward(g)
+        if world > 1:
+            bucket_blk.allreduce()
+        return out
+
+    resident_x = [{k: v.to(dev) for k, v in h.items()} for h in host_x]
+    for r in resident_x:
+        r["x"].requires_grad_(True)
+
+    def block_resident(i):
+        r = resident_x[i % n_sets]
+        r["x"].grad = None
+        block_step(r, gouts[i % n_sets])
+
+    ms_blk, launches_blk = timed(block_resident, args.steps, args.warmup)
+    e2e_block = e2e_leg(host_x, ("x",), block_step, trainable + front_params, cfg["h_dim"])
+    e2e_block["boundary"] = ("Attn block front + HEPTAttention: x (N,24) fp32, coords, int32 codes from pinned host memory; norm1 and "
+                             "w_q / w_k / w_v computed on the device; output (N,24) + parameter gradients read back")
+    e2e_block["device_resident_same_boundary"] = {"value": world * args.steps * N_RAW / (ms_blk * 1e-3),
+                                                  "ms_per_step": ms_blk / args.steps, "gpu_launches": launches_blk}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -308,11 +355,43 @@ def run_ours(args):
         "details": {"l2": f"inputs rotate over {n_sets} events (~190 MB each) so no step re-reads L2-resident inputs",
                     "collective": "NCCL all-reduce of parameter gradients per step" if world > 1 else "none",
                     "tile_engine": engine_name},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": ms_e2e / e2e_steps},
+        "e2e": e2e_block,
+        "e2e_module_boundary": e2e_module,
         "gpu_launches": launches,
         "clocks": clocks.summary(),
     }
+
+    # ---- BASELINE.json configs[4]: the tracking training step sharded by event -----------------------------------
+    # 4-layer HEPT Transformer (329 364 parameters) forward + backward + Adam, one 60 000-hit event per rank per step, the
+    # gradients of all parameters in ONE flat bucket all-reduced (averaged) with one NCCL launch.  The loss is a stand-in
+    # (mean square of the embedding): the reference's InfoNCE needs pair lists from the dataset (out of scope).
+    if not args.no_train:
+        from hept_b200 import synthetic
+        from hept_b200.model import Transformer
+
+        tcfg = {k: v for k, v in synthetic.TRACKING.items() if k != "coords_dim"}
+        torch.manual_seed(1234)                         # the same initial weights on every rank
+        model = Transformer(in_dim=15, coords_dim=6, **tcfg).to(dev)
+        tbucket = sharding.GradBucket(model.parameters())
+        opt = torch.optim.Adam(tbucket.params, lr=1e-3, fused=True)
+        tcoords = [synthetic.point_cloud(N_RAW, 6, 1000 + 10 * rank + i).to(dev) for i in range(2)]
+        tx = [(torch.randn(N_RAW, 15, generator=torch.Generator().manual_seed(rank + 7 * i)) * 0.5).to(dev) for i in range(2)]
+        tbatch = torch.zeros(N_RAW, dtype=torch.long, device=dev)
+
+        def train_step(i):
+            tbucket.zero()
+            out = model(tx[i % 2], tcoords[i % 2], tbatch)
+            (out ** 2).mean().backward()
+            if world > 1:
+                tbucket.allreduce()
+            opt.step()
+
+        t_steps = max(3, min(args.steps, 6))
+        ms_t, launches_t = timed(train_step, t_steps, 3)
+        line["train_step"] = {"workload": "tracking Transformer (4 HEPT layers) fwd + bwd + Adam, one 60000-hit event per rank per step",
+                              "value": world * t_steps * N_RAW / (ms_t * 1e-3), "unit": UNIT, "ms_per_step": ms_t / t_steps,
+                              "allreduce_bytes": tbucket.nbytes if world > 1 else 0, "collective": "one NCCL all-reduce (AVG) of the flat gradient bucket",
+                              "native_launches_per_step": launches_t / t_steps, "loss": "stand-in (mean square of the embedding)"}
 
     if rank == 0:
         peak, peak_src = load_peaks()
@@ -436,6 +515,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step leg (BASELINE.json configs[4])")
     ap.add_argument("--bwd", default=None, type=int, choices=[1, 3, 4, 5], help="backward tile variant (default: library default)")
     ap.add_argument("--engine", default=None, choices=["simt", "tcgen05"], help="tile engine (default: library default)")
     args = ap.parse_args()

@@ -160,6 +160,55 @@ def test_gradient_allreduce_two_ranks_gloo():
         assert nbytes == (15 + 3) * 4
 
 
+def _bucket_worker(rank, world, port, out):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(5, 3)
+    unused = torch.nn.Parameter(torch.ones(4))                           # like w_rpe.bias: trainable, never used
+    bucket = sharding.GradBucket([lin.weight, lin.bias, unused])
+    res = []
+    for step in range(2):                                                # two steps: zero() must really reset the views
+        bucket.zero()
+        events = sharding.events_of_rank(6, rank, world)
+        x = torch.stack([torch.full((5,), float(e + 1 + step)) for e in events])
+        lin(x).sum().backward()
+        assert bucket.attached()
+        bucket.allreduce(average=True)
+        res.append((lin.weight.grad.clone(), lin.bias.grad.clone(), unused.grad.clone()))
+    out.put((rank, res, bucket.nbytes))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_flat_gradient_bucket_two_ranks_gloo():
+    """GradBucket: .grad tensors are views of one flat buffer, all-reduced in place (world_size 2 over gloo); the average
+    over the ranks equals the single-process gradient over all events divided by the world size."""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_bucket_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted((out.get(timeout=120) for _ in range(2)), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for step in range(2):
+        torch.manual_seed(0)
+        lin = torch.nn.Linear(5, 3)
+        x = torch.stack([torch.full((5,), float(e + 1 + step)) for e in range(6)])
+        lin(x).sum().backward()
+        for rank, res, nbytes in got:
+            gw, gb, gu = res[step]
+            assert torch.allclose(gw, lin.weight.grad / 2) and torch.allclose(gb, lin.bias.grad / 2)
+            assert bool((gu == 0).all()) and nbytes == (15 + 3 + 4) * 4
+
+
 def test_trace_variant_of_the_library_builds():
     """The pipeline timeline probe (csrc/trace.cuh, `make TRACE=1`) is compiled out of the product library; this keeps the
     instrumented variant building (it exports the two setters tools/pipeline_trace.py binds)."""
