@@ -264,15 +264,18 @@ def run_ours(args):
     # ---- end to end with HOST buffers --------------------------------------------------------------
     # Double-buffered: the H2D copy of step i+1 runs on a copy stream while step i computes; every step still
     # copies its own inputs from pinned host memory and reads its results back inside the timed region.
-    def e2e_leg(host_sets, grad_keys, run, result_params, out_width):
+    def e2e_leg(host_sets, grad_keys, run, grads, out_width):       # grads: the GradBucket whose flat buffer is read back
         staging = [{k: torch.empty_like(v, device=dev) for k, v in host_sets[0].items()} for _ in range(2)]
         out_host = torch.empty(n_hits, out_width).pin_memory()
-        grad_host = [torch.empty_like(p, device="cpu").pin_memory() for p in result_params]
+        grad_host = torch.empty_like(grads.flat, device="cpu").pin_memory()
+        grad_stage = torch.empty_like(grads.flat)                       # device copy the read-back stream reads from
         h2d = sum(v.numel() * v.element_size() for v in host_sets[0].values())
-        d2h = out_host.numel() * 4 + sum(g.numel() * 4 for g in grad_host)
+        d2h = out_host.numel() * 4 + grad_host.numel() * 4
         copy_stream = torch.cuda.Stream(device=dev)
+        back_stream = torch.cuda.Stream(device=dev)      # read-back of step i overlaps the compute of step i + 1
         ready = [torch.cuda.Event() for _ in range(2)]
         consumed = [torch.cuda.Event() for _ in range(2)]
+        computed, read_back = torch.cuda.Event(), torch.cuda.Event()
         issued = set()
 
         def prefetch(i):
@@ -290,15 +293,23 @@ def run_ours(args):
             prefetch(i)
             prefetch(i + 1)
             b = i % 2
-            torch.cuda.current_stream().wait_event(ready[b])
+            cur = torch.cuda.current_stream()
+            cur.wait_event(ready[b])
             inp = dict(staging[b])
             for k in grad_keys:
                 inp[k] = inp[k].detach().requires_grad_(True)
             out = run(inp, gouts[i % n_sets])
-            consumed[b].record(torch.cuda.current_stream())
-            out_host.copy_(out.detach(), non_blocking=True)
-            for gh, p in zip(grad_host, result_params):
-                gh.copy_(p.grad, non_blocking=True)
+            consumed[b].record(cur)
+            cur.wait_event(read_back)                        # the previous step's gradients have left their staging copies
+            grad_stage.copy_(grads.flat)
+            computed.record(cur)
+            out = out.detach()
+            out.record_stream(back_stream)
+            with torch.cuda.stream(back_stream):
+                back_stream.wait_event(computed)
+                out_host.copy_(out, non_blocking=True)
+                grad_host.copy_(grad_stage, non_blocking=True)
+                read_back.record(back_stream)
 
         steps = max(3, min(args.steps, 10))
         ms_leg, _ = timed(e2e_step, steps, 3)
@@ -306,7 +317,7 @@ def run_ours(args):
                 "d2h_bytes_per_step": d2h, "ms_per_step": ms_leg / steps}
 
     # (1) the module boundary of the reference, HEPTAttention.forward(query, key, value, ...): q, k, v cross the link
-    e2e_module = e2e_leg(host, ("query", "key", "value"), step, trainable, cfg["h_dim"])
+    e2e_module = e2e_leg(host, ("query", "key", "value"), step, bucket, cfg["h_dim"])
     e2e_module["boundary"] = ("HEPTAttention.forward: q, k, v (N,192) fp32, coords, int64 codes from pinned host memory; "
                               "output (N,24) + parameter gradients read back")
 
@@ -341,7 +352,7 @@ def run_ours(args):
         block_step(r, gouts[i % n_sets])
 
     ms_blk, launches_blk = timed(block_resident, args.steps, args.warmup)
-    e2e_block = e2e_leg(host_x, ("x",), block_step, trainable + front_params, cfg["h_dim"])
+    e2e_block = e2e_leg(host_x, ("x",), block_step, bucket_blk, cfg["h_dim"])
     e2e_block["boundary"] = ("Attn block front + HEPTAttention: x (N,24) fp32, coords, int32 codes from pinned host memory; norm1 and "
                              "w_q / w_k / w_v computed on the device; output (N,24) + parameter gradients read back")
     e2e_block["device_resident_same_boundary"] = {"value": world * args.steps * N_RAW / (ms_blk * 1e-3),
