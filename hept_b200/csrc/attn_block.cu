@@ -39,19 +39,24 @@ __global__ void __launch_bounds__(256) qkv_weights_t_kernel(const float* __restr
 }
 
 template <int DM, int OW>
-__global__ void __launch_bounds__(kAbThreads, 3) ln_qkv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+__global__ void __launch_bounds__(kAbThreads, 4) ln_qkv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                                    const float* __restrict__ beta, const float* __restrict__ wt,
                                                                    int N, float eps, float* __restrict__ xn_out,
                                                                    float* __restrict__ q, float* __restrict__ k, float* __restrict__ v) {
   constexpr int XS = DM + 4;
   static_assert(DM % 4 == 0 && OW % 32 == 0, "tile shape");
   extern __shared__ __align__(16) float s_dyn[];
-  float* s_w = s_dyn;                        // (3, DM, OW)
-  float* s_x = s_w + 3 * DM * OW;            // (kAbHits, XS) normalised rows
+  // one CTA = 128 hits x ONE of the three matrices (blockIdx.y): 32 KB of shared memory instead of 70, so four CTAs fit an
+  // SM and the 3 x 469 small CTAs of a 60k-hit event leave no half-empty last wave (the normalisation is repeated per
+  // matrix: 24 floats per hit)
+  float* s_w = s_dyn;                        // (DM, OW) of matrix m
+  float* s_x = s_w + DM * OW;                // (kAbHits, XS) normalised rows
   const int tid = threadIdx.x;
+  const int m = blockIdx.y;
   const int n0 = blockIdx.x * kAbHits;
   const int rows = min(kAbHits, N - n0);
-  for (int i = tid; i < 3 * DM * OW / 4; i += kAbThreads) reinterpret_cast<float4*>(s_w)[i] = __ldg(reinterpret_cast<const float4*>(wt) + i);
+  for (int i = tid; i < DM * OW / 4; i += kAbThreads)
+    reinterpret_cast<float4*>(s_w)[i] = __ldg(reinterpret_cast<const float4*>(wt + (size_t)m * DM * OW) + i);
   {  // LayerNorm: one hit per thread
     const int r = tid;
     float xv[DM];
@@ -79,16 +84,15 @@ __global__ void __launch_bounds__(kAbThreads, 3) ln_qkv_fwd_kernel(const float* 
     for (int c4 = 0; c4 < DM / 4; ++c4) {
       const float4 t = make_float4(xv[4 * c4], xv[4 * c4 + 1], xv[4 * c4 + 2], xv[4 * c4 + 3]);
       *reinterpret_cast<float4*>(s_x + r * XS + 4 * c4) = t;
-      if (r < rows) *reinterpret_cast<float4*>(xn_out + (size_t)(n0 + r) * DM + 4 * c4) = t;
+      if (r < rows && m == 0) *reinterpret_cast<float4*>(xn_out + (size_t)(n0 + r) * DM + 4 * c4) = t;
     }
   }
   __syncthreads();
   // thread = (hq = tid / 4, c0 = tid % 4): hits hq + 32 t x columns [8 cg, 8 cg + 8), cg = c0 + 4 i
   const int hq = tid >> 2, c0 = tid & 3;
-#pragma unroll 1
-  for (int m = 0; m < 3; ++m) {
+  {
     float* __restrict__ out = m == 0 ? q : (m == 1 ? k : v);
-    const float* wm = s_w + m * DM * OW;
+    const float* wm = s_w;
 #pragma unroll 1
     for (int i = 0; i < OW / 32; ++i) {
       asm volatile("" ::: "memory");           // keep the xn rows in shared memory (hoisting them costs 96 registers)
@@ -130,10 +134,11 @@ __global__ void __launch_bounds__(kAbThreads, 3) ln_qkv_fwd_kernel(const float* 
   }
 }
 
-// dxn = dq Wq + dk Wk + dv Wv, then the LayerNorm backward.  thread = (hq = tid / 4, og = tid % 4): hits hq + 32 t x outputs
+// dxn = dq Wq + dk Wk + dv Wv, then the LayerNorm backward.  thread = (hq = tid / 4, og = tid % 4): hits hq + 64 t x outputs
 // [PER og, PER og + PER), PER = DM / 4; the four threads of a hit are adjacent lanes.
+constexpr int kAbBwdHits = 256, kAbBwdThreads = 256;   // two CTAs of 8 warps per SM: a 60k-hit event is ONE wave of 235 CTAs
 template <int DM, int OW>
-__global__ void __launch_bounds__(kAbThreads, 2) ln_qkv_bwd_input_kernel(const float* __restrict__ dq, const float* __restrict__ dk,
+__global__ void __launch_bounds__(kAbBwdThreads, 2) ln_qkv_bwd_input_kernel(const float* __restrict__ dq, const float* __restrict__ dk,
                                                                          const float* __restrict__ dv, const float* __restrict__ wt,
                                                                          const float* __restrict__ x, const float* __restrict__ gamma,
                                                                          int N, float eps, float* __restrict__ dx,
@@ -142,22 +147,22 @@ __global__ void __launch_bounds__(kAbThreads, 2) ln_qkv_bwd_input_kernel(const f
   static_assert(OW % KC == 0 && DM % 4 == 0 && PER % 2 == 0, "tile shape");
   extern __shared__ __align__(16) float s_dyn[];
   float* s_w = s_dyn;                              // (3, DM, WS)
-  float* s_x = s_w + 3 * DM * WS;                  // (kAbHits, XS) one chunk of gradient rows
-  float* s_red = s_x;                              // reused at the end: (32, 2 DM) per-hit-group sums of d gamma / d beta
+  float* s_x = s_w + 3 * DM * WS;                  // (kAbBwdHits, XS) one chunk of gradient rows
+  float* s_red = s_x;                              // reused at the end: (64, 2 DM) per-hit-group sums of d gamma / d beta
   const int tid = threadIdx.x, hq = tid >> 2, og = tid & 3;
-  const int n0 = blockIdx.x * kAbHits;
-  const int rows = min(kAbHits, N - n0);
+  const int n0 = blockIdx.x * kAbBwdHits;
+  const int rows = min(kAbBwdHits, N - n0);
   auto load_chunk = [&](int ch) {
     const int m = ch / NCH, kc = ch - m * NCH;
     const float* src = m == 0 ? dq : (m == 1 ? dk : dv);
-    for (int i = tid; i < kAbHits * (KC / 4); i += kAbThreads) {
+    for (int i = tid; i < kAbBwdHits * (KC / 4); i += kAbBwdThreads) {
       const int r = i / (KC / 4), c4 = i - r * (KC / 4);
       if (r < rows) cp_async16_cg(s_x + r * XS + 4 * c4, src + (size_t)(n0 + r) * OW + kc * KC + 4 * c4);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
   load_chunk(0);
-  for (int i = tid; i < 3 * DM * (OW / 4); i += kAbThreads) {
+  for (int i = tid; i < 3 * DM * (OW / 4); i += kAbBwdThreads) {
     const int mj = i / (OW / 4), c4 = i - mj * (OW / 4);
     *reinterpret_cast<float4*>(s_w + mj * WS + 4 * c4) = ldg4(wt + (size_t)mj * OW + 4 * c4);
   }
@@ -177,7 +182,7 @@ __global__ void __launch_bounds__(kAbThreads, 2) ln_qkv_bwd_input_kernel(const f
     for (int c4 = 0; c4 < KC / 4; ++c4) {
       float4 xv[4];
 #pragma unroll
-      for (int t = 0; t < 4; ++t) xv[t] = *reinterpret_cast<const float4*>(xs + 32 * t * XS + 4 * c4);
+      for (int t = 0; t < 4; ++t) xv[t] = *reinterpret_cast<const float4*>(xs + 64 * t * XS + 4 * c4);
 #pragma unroll
       for (int u = 0; u < PER; ++u) {
         const float4 wv = *reinterpret_cast<const float4*>(ws + u * WS + 4 * c4);
@@ -198,7 +203,7 @@ __global__ void __launch_bounds__(kAbThreads, 2) ln_qkv_bwd_input_kernel(const f
   for (int u = 0; u < PER; ++u) { gam[u] = __ldg(gamma + og * PER + u); dgam[u] = 0.f; dbet[u] = 0.f; }
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
-    const int r = hq + 32 * t;
+    const int r = hq + 64 * t;
     const bool live = r < rows;
     float xv[PER], dxn[PER];
 #pragma unroll
@@ -247,7 +252,7 @@ __global__ void __launch_bounds__(kAbThreads, 2) ln_qkv_bwd_input_kernel(const f
         *reinterpret_cast<float2*>(dx + (size_t)(n0 + r) * DM + og * PER + 2 * u2) = make_float2(o[2 * u2], o[2 * u2 + 1]);
     }
   }
-  // the CTA's sums: hit groups in order 0 .. 31 (fixed order)
+  // the CTA's sums: hit groups in order 0 .. 63 (fixed order)
   __syncthreads();
 #pragma unroll
   for (int u = 0; u < PER; ++u) {
@@ -258,7 +263,7 @@ __global__ void __launch_bounds__(kAbThreads, 2) ln_qkv_bwd_input_kernel(const f
   if (tid < 2 * DM) {
     float s = 0.f;
 #pragma unroll 8
-    for (int g2 = 0; g2 < 32; ++g2) s += s_red[g2 * 2 * DM + tid];
+    for (int g2 = 0; g2 < 64; ++g2) s += s_red[g2 * 2 * DM + tid];
     partial[(size_t)blockIdx.x * 2 * DM + tid] = s;
   }
 }
@@ -285,7 +290,7 @@ __global__ void __launch_bounds__(256) ln_params_reduce_kernel(const float* __re
 template <int DM, int OW>
 static int launch_qkv_fwd(const float* x, const float* gamma, const float* beta, const float* wq, const float* wk, const float* wv,
                           int N, float eps, float* wt, float* xn, float* q, float* k, float* v, cudaStream_t st) {
-  const size_t smem = sizeof(float) * (3 * (size_t)DM * OW + (size_t)kAbHits * (DM + 4));
+  const size_t smem = sizeof(float) * ((size_t)DM * OW + (size_t)kAbHits * (DM + 4));
   static DeviceOnce configured;
   if (configured.needed()) {
     cudaError_t e = cudaFuncSetAttribute(ln_qkv_fwd_kernel<DM, OW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -294,7 +299,7 @@ static int launch_qkv_fwd(const float* x, const float* gamma, const float* beta,
   }
   qkv_weights_t_kernel<<<(3 * DM * OW + 255) / 256, 256, 0, st>>>(wq, wk, wv, DM, OW, wt);
   HEPT_CHECK_LAUNCH("qkv_weights_t");
-  ln_qkv_fwd_kernel<DM, OW><<<(N + kAbHits - 1) / kAbHits, kAbThreads, smem, st>>>(x, gamma, beta, wt, N, eps, xn, q, k, v);
+  ln_qkv_fwd_kernel<DM, OW><<<dim3((N + kAbHits - 1) / kAbHits, 3), kAbThreads, smem, st>>>(x, gamma, beta, wt, N, eps, xn, q, k, v);
   HEPT_CHECK_LAUNCH("ln_qkv_fwd");
   return HEPT_OK;
 }
@@ -303,18 +308,18 @@ template <int DM, int OW>
 static int launch_qkv_bwd(const float* x, const float* xn, const float* gamma, const float* wt, const float* dq, const float* dk,
                           const float* dv, int N, int H, int D, float eps, float* dx, float* dgamma, float* dbeta, float* dwq,
                           float* dwk, float* dwv, float* ws, size_t ws_floats, cudaStream_t st) {
-  const size_t smem = sizeof(float) * (3 * (size_t)DM * (OW + 4) + (size_t)kAbHits * (48 + 4));
-  static_assert(kAbHits * (48 + 4) >= 32 * 2 * DM, "the staging buffer doubles as the reduction buffer");
+  const size_t smem = sizeof(float) * (3 * (size_t)DM * (OW + 4) + (size_t)kAbBwdHits * (48 + 4));
+  static_assert(kAbBwdHits * (48 + 4) >= 64 * 2 * DM, "the staging buffer doubles as the reduction buffer");
   static DeviceOnce configured;
   if (configured.needed()) {
     cudaError_t e = cudaFuncSetAttribute(ln_qkv_bwd_input_kernel<DM, OW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "attn_qkv_bwd: cannot reserve %zu B of shared memory: %s", smem, cudaGetErrorString(e));
     configured.mark();
   }
-  const int ctas = (N + kAbHits - 1) / kAbHits;
+  const int ctas = (N + kAbBwdHits - 1) / kAbBwdHits;
   const size_t ln_floats = (size_t)ctas * 2 * DM;
   HEPT_REQUIRE(ws_floats >= ln_floats + qkv_weight_grads_partial_floats(H, D), HEPT_EWORKSPACE, "attn_qkv_bwd: workspace too small");
-  ln_qkv_bwd_input_kernel<DM, OW><<<ctas, kAbThreads, smem, st>>>(dq, dk, dv, wt, x, gamma, N, eps, dx, ws);
+  ln_qkv_bwd_input_kernel<DM, OW><<<ctas, kAbBwdThreads, smem, st>>>(dq, dk, dv, wt, x, gamma, N, eps, dx, ws);
   HEPT_CHECK_LAUNCH("ln_qkv_bwd_input");
   ln_params_reduce_kernel<<<2 * DM, 256, 0, st>>>(ws, ctas, DM, dgamma, dbeta);
   HEPT_CHECK_LAUNCH("ln_params_reduce");
@@ -329,7 +334,7 @@ extern "C" int hept_attn_qkv_supported(int32_t H, int32_t D) { return H == 8 && 
 
 extern "C" size_t hept_attn_qkv_bwd_workspace_bytes(int32_t N, int32_t H, int32_t D) {
   if (N <= 0 || H <= 0 || D <= 0) return 0;
-  return sizeof(float) * ((size_t)((N + kAbHits - 1) / kAbHits) * 2 * D + qkv_weight_grads_partial_floats(H, D));
+  return sizeof(float) * ((size_t)((N + kAbBwdHits - 1) / kAbBwdHits) * 2 * D + qkv_weight_grads_partial_floats(H, D));
 }
 
 extern "C" int hept_attn_qkv_fwd(const float* x, const float* norm_weight, const float* norm_bias, const float* w_q,
