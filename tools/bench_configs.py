@@ -65,23 +65,42 @@ def attention_problem(sizes, seed):
             t.grad = None
         mod(q, k, v, w_rpe=w_rpe, **kw).backward(g)
 
-    return step, n
+    def graphed():
+        from hept_b200.graphed import graphed_attention
+
+        gs = graphed_attention(mod, w_rpe, q, k, v, kw["coords"], kw["combined_shifts32"])
+
+        def gstep():
+            for t in (q, k, v):
+                t.grad = None
+            gs(q, k, v, kw["coords"], kw["combined_shifts32"]).backward(g)
+
+        return gstep
+
+    return step, n, graphed
 
 
 results = []
 if world == 1:
     for name, sizes in (("attention fwd+bwd, 6037 hits (tracking-6k)", [6037]), ("attention fwd+bwd, 60000 hits", [60000]), ("attention fwd+bwd, 61237 hits (padded to 61300)", [61237]),
                         ("attention fwd+bwd, 8 imbalanced events, 60187 hits", synthetic.event_sizes("batched-imbalanced"))):
-        step, n = attention_problem(sizes, 3)
+        step, n, graphed = attention_problem(sizes, 3)
         ms = timeit(step)
-        results.append({"config": name, "ms_per_step": ms, "hits_per_s": sum(sizes) / ms * 1e3, "padded_hits": n})
+        ms_g = timeit(graphed())
+        results.append({"config": name, "ms_per_step": ms, "hits_per_s": sum(sizes) / ms * 1e3, "padded_hits": n,
+                        "ms_per_step_cuda_graph": ms_g, "hits_per_s_cuda_graph": sum(sizes) / ms_g * 1e3})
     m = Transformer(in_dim=8, coords_dim=4, task="pileup", flavour="src", **PILEUP).eval().to(dev)
     for n in (5000, 10000, 20000):
         coords = synthetic.point_cloud(n, 4, 8).to(dev)
         x = torch.cat([torch.randn(n, 7) * 0.5, torch.randint(0, 7, (n, 1)).float()], dim=1).to(dev)
         with torch.no_grad():
             ms = timeit(lambda: m(x, coords))
-        results.append({"config": f"pileup Transformer forward-only, {n} hits", "ms_per_step": ms, "hits_per_s": n / ms * 1e3})
+        from hept_b200.graphed import GraphedInference
+
+        gi = GraphedInference(m, (x, coords))
+        ms_g = timeit(lambda: gi.run(x, coords))
+        results.append({"config": f"pileup Transformer forward-only, {n} hits", "ms_per_step": ms, "hits_per_s": n / ms * 1e3,
+                        "ms_per_step_cuda_graph": ms_g, "hits_per_s_cuda_graph": n / ms_g * 1e3})
 
 # configs[4]: training step of the tracking model, one 60k event per rank per step
 model = Transformer(in_dim=15, coords_dim=6, **TRACKING).to(dev)
