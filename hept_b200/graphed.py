@@ -39,7 +39,8 @@ def graphed_attention(attn: HEPTAttention, w_rpe: nn.Module, query, key, value, 
     sample = tuple(t.detach().clone().requires_grad_(t.requires_grad) for t in (query, key, value)) + \
         (coords.detach().clone(), combined_shifts.detach().clone())
     with torch.cuda.device(query.device):
-        return torch.cuda.make_graphed_callables(step, sample, num_warmup_iters=num_warmup_iters)
+        return torch.cuda.make_graphed_callables(step, sample, num_warmup_iters=num_warmup_iters,
+                                                 allow_unused_input=True)   # w_rpe.bias, e2lsh.alpha never get a gradient
 
 
 class GraphedInference:
