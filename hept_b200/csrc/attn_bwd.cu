@@ -357,12 +357,20 @@ extern "C" int hept_block_attention_bwd(const hept_shape* s, const float* q, con
                "block_attention_bwd: workspace needs %zu bytes", hept_attention_bwd_workspace_bytes(s));
   cudaStream_t st = (cudaStream_t)stream;
   char* ws = (char*)workspace;
-  if (bwd_variant() >= 3)
+  if (bwd_variant() >= 3 && tc_tiles_supported(s->D, s->C, s->B))
     return block_attention_bwd_tc(s, q, k, v, coords, scale, positions, out_pre, den_sum, d_out_pre, dq, dk, dv, dscale, ws, st);
   if (s->D == 24 && s->C == 6 && s->B == 100)
     return launch_bwd<24, 6, 100, 5, 1, 3, 1>(s, q, k, v, coords, scale, positions, out_pre, den_sum, d_out_pre, dq, dk, dv, dscale, ws, st);
   if (s->D == 24 && s->C == 4 && s->B == 100)
     return launch_bwd<24, 4, 100, 5, 1, 3, 1>(s, q, k, v, coords, scale, positions, out_pre, den_sum, d_out_pre, dq, dk, dv, dscale, ws, st);
+  if (s->D == 24 && s->C == 6 && s->B == 64)
+    return launch_bwd<24, 6, 64, 8, 1, 5, 1>(s, q, k, v, coords, scale, positions, out_pre, den_sum, d_out_pre, dq, dk, dv, dscale, ws, st);
+  if (s->D == 24 && s->C == 4 && s->B == 64)
+    return launch_bwd<24, 4, 64, 8, 1, 5, 1>(s, q, k, v, coords, scale, positions, out_pre, den_sum, d_out_pre, dq, dk, dv, dscale, ws, st);
+  if (s->D == 24 && s->C == 6 && s->B == 128)
+    return launch_bwd<24, 6, 128, 4, 1, 2, 1>(s, q, k, v, coords, scale, positions, out_pre, den_sum, d_out_pre, dq, dk, dv, dscale, ws, st);
+  if (s->D == 24 && s->C == 4 && s->B == 128)
+    return launch_bwd<24, 4, 128, 4, 1, 2, 1>(s, q, k, v, coords, scale, positions, out_pre, den_sum, d_out_pre, dq, dk, dv, dscale, ws, st);
   if (s->D == 8 && s->C == 6 && s->B == 10)
     return launch_bwd<8, 6, 10, 4, 1, 4, 1>(s, q, k, v, coords, scale, positions, out_pre, den_sum, d_out_pre, dq, dk, dv, dscale, ws, st);
   set_error("block_attention_bwd: (D=%d, C=%d, B=%d) not compiled in", s->D, s->C, s->B);

@@ -996,6 +996,10 @@ int block_attention_bwd_tc(const hept_shape* s, const float* q, const float* k, 
     return launch_bwd_tc<24, 6, 100>(s, q, k, v, coords, scale, positions, out_pre, den_sum, d_out_pre, dq, dk, dv, dscale, ws, st);
   if (s->D == 24 && s->C == 4 && s->B == 100)
     return launch_bwd_tc<24, 4, 100>(s, q, k, v, coords, scale, positions, out_pre, den_sum, d_out_pre, dq, dk, dv, dscale, ws, st);
+  if (s->D == 24 && s->C == 6 && s->B == 64)
+    return launch_bwd_tc<24, 6, 64>(s, q, k, v, coords, scale, positions, out_pre, den_sum, d_out_pre, dq, dk, dv, dscale, ws, st);
+  if (s->D == 24 && s->C == 4 && s->B == 64)
+    return launch_bwd_tc<24, 4, 64>(s, q, k, v, coords, scale, positions, out_pre, den_sum, d_out_pre, dq, dk, dv, dscale, ws, st);
   if (s->D == 8 && s->C == 6 && s->B == 10)
     return launch_bwd_tc<8, 6, 10>(s, q, k, v, coords, scale, positions, out_pre, den_sum, d_out_pre, dq, dk, dv, dscale, ws, st);
   set_error("block_attention_bwd (tensor-core engine): (D=%d, C=%d, B=%d) not compiled in", s->D, s->C, s->B);

@@ -159,7 +159,12 @@ int block_attention_fwd_tc(const hept_shape* s, const float* q, const float* k, 
 using namespace hept;
 
 extern "C" int hept_shape_supported(int32_t D, int32_t C, int32_t B) {
-  return (D == 24 && C == 6 && B == 100) || (D == 24 && C == 4 && B == 100) || (D == 8 && C == 6 && B == 10);
+  return (D == 24 && (C == 6 || C == 4) && (B == 100 || B == 64 || B == 128)) || (D == 8 && C == 6 && B == 10);
+}
+namespace hept {
+// the tcgen05 tiles keep two (forward) or four (backward) score accumulators of B columns in the 512 TMEM columns:
+// blocks of up to 112 hits; larger blocks run on the fp32 CUDA-core tiles whatever engine is selected
+bool tc_tiles_supported(int D, int C, int B) { return hept_shape_supported(D, C, B) && B <= 112; }
 }
 
 extern "C" int hept_block_attention_fwd(const hept_shape* s, const float* q, const float* k, const float* v,
@@ -169,12 +174,16 @@ extern "C" int hept_block_attention_fwd(const hept_shape* s, const float* q, con
   HEPT_REQUIRE(q && k && v && coords && scale && positions && stage, HEPT_EINVAL, "block_attention_fwd: null pointer");
   HEPT_REQUIRE((long long)s->T * s->H <= 65535, HEPT_EINVAL, "block_attention_fwd: T*H too large");
   cudaStream_t st = (cudaStream_t)stream;
-  if (engine() == 1) {
+  if (engine() == 1 && tc_tiles_supported(s->D, s->C, s->B)) {
     HEPT_REQUIRE(hat_coords, HEPT_EINVAL, "block_attention_fwd: the tcgen05 engine needs hat_coords (hept_hat_coords)");
     return block_attention_fwd_tc(s, q, k, v, hat_coords, positions, stage, st);
   }
   if (s->D == 24 && s->C == 6 && s->B == 100) return launch_fwd<24, 6, 100, 5, 2, 2>(s, q, k, v, coords, scale, positions, stage, st);
   if (s->D == 24 && s->C == 4 && s->B == 100) return launch_fwd<24, 4, 100, 5, 2, 2>(s, q, k, v, coords, scale, positions, stage, st);
+  if (s->D == 24 && s->C == 6 && s->B == 64) return launch_fwd<24, 6, 64, 8, 2, 2>(s, q, k, v, coords, scale, positions, stage, st);
+  if (s->D == 24 && s->C == 4 && s->B == 64) return launch_fwd<24, 4, 64, 8, 2, 2>(s, q, k, v, coords, scale, positions, stage, st);
+  if (s->D == 24 && s->C == 6 && s->B == 128) return launch_fwd<24, 6, 128, 4, 2, 2>(s, q, k, v, coords, scale, positions, stage, st);
+  if (s->D == 24 && s->C == 4 && s->B == 128) return launch_fwd<24, 4, 128, 4, 2, 2>(s, q, k, v, coords, scale, positions, stage, st);
   if (s->D == 8 && s->C == 6 && s->B == 10) return launch_fwd<8, 6, 10, 4, 2, 1>(s, q, k, v, coords, scale, positions, stage, st);
   set_error("block_attention_fwd: (D=%d, C=%d, B=%d) not compiled in", s->D, s->C, s->B);
   return HEPT_EUNSUPPORTED;

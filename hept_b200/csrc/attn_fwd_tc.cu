@@ -538,6 +538,8 @@ int block_attention_fwd_tc(const hept_shape* s, const float* q, const float* k, 
                            const int32_t* positions, float* stage, cudaStream_t st) {
   if (s->D == 24 && s->C == 6 && s->B == 100) return launch_fwd_tc<24, 6, 100>(s, q, k, v, hatc, positions, stage, st);
   if (s->D == 24 && s->C == 4 && s->B == 100) return launch_fwd_tc<24, 4, 100>(s, q, k, v, hatc, positions, stage, st);
+  if (s->D == 24 && s->C == 6 && s->B == 64) return launch_fwd_tc<24, 6, 64>(s, q, k, v, hatc, positions, stage, st);
+  if (s->D == 24 && s->C == 4 && s->B == 64) return launch_fwd_tc<24, 4, 64>(s, q, k, v, hatc, positions, stage, st);
   if (s->D == 8 && s->C == 6 && s->B == 10) return launch_fwd_tc<8, 6, 10>(s, q, k, v, hatc, positions, stage, st);
   set_error("block_attention_fwd (tensor-core engine): (D=%d, C=%d, B=%d) not compiled in", s->D, s->C, s->B);
   return HEPT_EUNSUPPORTED;

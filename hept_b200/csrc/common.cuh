@@ -17,6 +17,7 @@ void count_launch(int n = 1);
 int bwd_stage_mask();
 int engine();  // 0 = fp32 SIMT tiles, 1 = tcgen05 tiles
 int bwd_variant();
+bool tc_tiles_supported(int D, int C, int B);   // blocks of up to 112 hits fit the TMEM layout of the tcgen05 tiles
 int hash_project_impl(const hept_shape* s, const float* q, const float* k, const float* coords, const float* scale,
                       const float* alpha, float* proj, float* span, void* workspace, size_t workspace_bytes, float* hat,
                       bool* hat_done, void* stream);

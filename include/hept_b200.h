@@ -17,8 +17,9 @@
  *   - symbols: N hits (multiple of B), H heads, D dims/head, C coords_dim, E = D + C,
  *     T n_hashes, B block_size, R = C - 1, K num_w_per_dist.
  *
- * Supported compile-time shapes (D, C, B): (24,6,100) tracking, (24,4,100) pileup, (8,6,10) test.
- * Anything else returns HEPT_EUNSUPPORTED (no slow fallback, no CPU path).
+ * Supported compile-time shapes: D = 24 with C in {6 (tracking), 4 (pileup)} and B in {64, 100, 128}, and (D, C, B) =
+ * (8, 6, 10) for tests.  Anything else returns HEPT_EUNSUPPORTED (no slow fallback, no CPU path); T <= 4, H <= 32.
+ * Blocks of 128 hits do not fit the TMEM layout of the tcgen05 tiles and run on the fp32 CUDA-core tiles.
  * Devices: kernels run on the CURRENT CUDA device; the caller makes the device that owns the pointers current
  * (hept_b200/ops.py does so around every call).  Per-device state (shared-memory opt-ins, SM counts) is kept per device.
  */

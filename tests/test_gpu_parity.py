@@ -695,6 +695,48 @@ def test_direct_backward_head_groups(heads, engine):
 
 
 # ------------------------------------------------------- BASELINE.json configs[2..3] and the prepare step on device
+@pytest.mark.parametrize("coords_dim", [6, 4])
+@pytest.mark.parametrize("block", [64, 128])
+def test_other_block_sizes_against_oracle(block, coords_dim):
+    """block_size 64 and 128 (the reference takes any block_size, example/hept.py:37): module forward + gradients against
+    the oracle.  128-hit blocks do not fit the TMEM layout of the tcgen05 tiles and run on the fp32 tiles under every engine
+    setting."""
+    from hept_b200 import HEPTAttention, ops, synthetic
+
+    cfg = dict(synthetic.TRACKING if coords_dim == 6 else synthetic.PILEUP, block_size=block)
+    n_raw = 2937
+    coords_raw, batch = synthetic.batched_cloud([n_raw], coords_dim, block)
+    params = synthetic.module_params(cfg, block)
+    _, kw, _ = O.prepare_batched(torch.zeros(n_raw, 1), coords_raw, batch, params["regions"], block, cfg["num_heads"])
+    n = kw["coords"].shape[0]
+    assert n % block == 0
+    q, k, v = synthetic.qkv(n, cfg, block)
+    g = torch.randn(n, cfg["h_dim"], generator=torch.Generator().manual_seed(2))
+    inputs = {"query": q, "key": k, "value": v, "coords": kw["coords"], "combined_shifts": kw["combined_shifts"]}
+    mod = HEPTAttention(cfg["h_dim"] + coords_dim, **cfg)
+    mod.load_state_dict({kk: params[kk] for kk in ("out_linear.weight", "out_linear.bias", "e2lsh.alpha")}, strict=True)
+    mod = mod.to(dev())
+    w_rpe = torch.nn.Linear(params["w_rpe.weight"].shape[1], params["w_rpe.weight"].shape[0])
+    w_rpe.load_state_dict({"weight": params["w_rpe.weight"], "bias": params["w_rpe.bias"]})
+    w_rpe = w_rpe.to(dev())
+    di = to_dev(inputs)
+    qd, kd, vd = (di[x].clone().requires_grad_(True) for x in ("query", "key", "value"))
+    out = mod(qd, kd, vd, w_rpe=w_rpe, coords=di["coords"], combined_shifts=di["combined_shifts"])
+    out.backward(g.to(dev()))
+    d = dims_of(cfg, n)
+    _, _, _, pos = ops.attention_fwd(d, qd.detach(), kd.detach(), vd.detach(), di["coords"], w_rpe.weight.detach(),
+                                     cfg["num_w_per_dist"], mod.e2lsh.alpha, combined_shifts=di["combined_shifts"])
+    positions = (pos[0].cpu().long(), pos[1].cpu().long())
+    r32 = O.forward_backward(inputs, params, cfg, g, torch.float32, positions)
+    r64 = O.forward_backward(inputs, params, cfg, g, torch.float64, positions)
+    mine = {"out": out.detach().cpu(), "dq": qd.grad.cpu(), "dk": kd.grad.cpu(), "dv": vd.grad.cpu(),
+            "dw_rpe": w_rpe.weight.grad.cpu()}
+    for key, val in mine.items():
+        e_o, e_r, ok = _err_budget(val, r32[key], r64[key], OUT_FLOOR if key == "out" else GRAD_FLOOR)
+        REPORT[rkey(f"block{block}_c{coords_dim}_{key}")] = [e_o, e_r]
+        assert ok, (key, e_o, e_r)
+
+
 def test_batched_imbalanced_events_against_oracle():
     """configs[3]: eight events of very different sizes (two shorter than a block) through prepare_input and the
     module, forward + backward, against the float64 oracle (sizes scaled by 1/10 so the oracle runs in seconds)."""
