@@ -70,6 +70,23 @@ lib.hept_set_bwd_stage_mask(3)
 t["bwd_pre+tiles"] = ev(lambda i: ops.attention_bwd(d, S(i)["query"], S(i)["key"], S(i)["value"], S(i)["coords"], scale,
                                                     M(i)["pos"], M(i)["out"], M(i)["den"], M(i)["g"]))
 lib.hept_set_bwd_stage_mask(7)
+# the rows either side of the attention call: prepare_input (a13-a17) and the Attn front
+from hept_b200 import prepare, synthetic
+
+craw, batch = synthetic.batched_cloud([n_raw], cfg["coords_dim"], 7)
+craw, batch = craw.to(dev), batch.to(dev)
+helper = {"block_size": cfg["block_size"], "regions": params["regions"].to(dev), "num_heads": cfg["num_heads"]}
+xin = torch.zeros(n_raw, 1, device=dev)
+t["prepare_input_batched"] = ev(lambda i: prepare.prepare_input(xin, craw, batch, helper, sizes=[n_raw]))
+t["prepare_input_single"] = ev(lambda i: prepare.prepare_input_single(xin, craw, helper))
+if ops.attn_qkv_supported(d.H, d.D):
+    gen = torch.Generator().manual_seed(3)
+    x = (torch.randn(n, d.D, generator=gen) * 0.7).to(dev)
+    gam, bet = torch.ones(d.D, device=dev), torch.zeros(d.D, device=dev)
+    wq, wk, wv = ((torch.randn(d.H * d.D, d.D, generator=gen) / d.D ** 0.5).to(dev) for _ in range(3))
+    q_, k_, v_, xn, wt = ops.attn_qkv_fwd(x, gam, bet, wq, wk, wv, d.H, d.D, 1e-5)
+    t["attn_qkv_fwd"] = ev(lambda i: ops.attn_qkv_fwd(x, gam, bet, wq, wk, wv, d.H, d.D, 1e-5))
+    t["attn_qkv_bwd"] = ev(lambda i: ops.attn_qkv_bwd(x, xn, gam, wt, S(i)["query"], S(i)["key"], S(i)["value"], d.H, d.D, 1e-5))
 t = {k: round(v, 1) for k, v in t.items()}
 print(json.dumps(t))
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
