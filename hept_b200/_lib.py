@@ -49,7 +49,7 @@ SIGNATURES = {
     "hept_attention_fwd_workspace_bytes": (_sz, [_SP]),
     "hept_attention_fwd": (C.c_int, [_SP, _p, _p, _p, _p, _p, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "hept_prepare_batched_workspace_bytes": (_sz, [_i32, _i32, _i32]),
-    "hept_prepare_batched": (C.c_int, [_p, _i32, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _i32, _i32, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "hept_prepare_batched": (C.c_int, [_p, _i32, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "hept_prepare_single_workspace_bytes": (_sz, [_i32]),
     "hept_prepare_single": (C.c_int, [_p, _i32, _i32, _i32, _p, _i32, _p, _p, _p, _p, _sz, _p]),
     "hept_keys_from_packed_shifts32": (C.c_int, [_SP, _p, _p, _p, _p, _p]),

@@ -125,9 +125,7 @@ __global__ void __launch_bounds__(kAbThreads, 4) ln_qkv_fwd_kernel(const float* 
       for (int t = 0; t < 4; ++t) {
         const int r = hq + 32 * t;
         if (r < rows) {
-          float4* dst = reinterpret_cast<float4*>(out + (size_t)(n0 + r) * OW + 8 * cg);
-          dst[0] = a0[t];
-          dst[1] = a1[t];
+          st_global_v8(out + (size_t)(n0 + r) * OW + 8 * cg, a0[t], a1[t]);
         }
       }
     }

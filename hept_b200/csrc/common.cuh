@@ -102,6 +102,12 @@ __device__ __forceinline__ void cp_async16_ca(void* smem_dst, const void* gsrc) 
 __device__ __forceinline__ void cp_async16_cg(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
+// one 256-bit store (STG.E.256, sm_100): a thread's 32 contiguous bytes leave as ONE full sector instead of two half-sector
+// writes that the L2 has to merge; dst must be 32-byte aligned
+__device__ __forceinline__ void st_global_v8(float* dst, const float4 a, const float4 b) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               :: "l"(dst), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
+}
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float2 ldg2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
 

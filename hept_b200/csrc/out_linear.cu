@@ -339,9 +339,7 @@ __global__ void __launch_bounds__(kTlThreads, 4) out_linear_bwd_input_tiled_kern
     for (int t = 0; t < 4; ++t) {
       const int r = q + 32 * t;
       if (r < rows) {
-        float4* dst = reinterpret_cast<float4*>(dx + (size_t)(n0 + r) * IN + 8 * cg);
-        dst[0] = a0[t];
-        dst[1] = a1[t];
+        st_global_v8(dx + (size_t)(n0 + r) * IN + 8 * cg, a0[t], a1[t]);
       }
     }
   }
@@ -350,14 +348,15 @@ __global__ void __launch_bounds__(kTlThreads, 4) out_linear_bwd_input_tiled_kern
 // weight / bias gradient, stage 1: a CTA = kPgGroups hit groups x (OUT / 8) x (IN / 8) threads; a thread owns an 8 x 8 tile
 // of dW; slabs of kPgRows hits are staged in shared memory (double-buffered cp.async); group p takes the hits p, p + G, ...
 // of a slab.  The groups' tiles are added through shared memory in group order (deterministic), db by the ct == 0 threads.
-constexpr int kPgGroups = 4, kPgRows = 32;
+constexpr int kPgGroups = 4, kPgRows = 32, kPgStages = 3;
 template <int OUT, int IN>
 __global__ void __launch_bounds__(kPgGroups * (OUT / 8) * (IN / 8), 2) out_linear_bwd_params_tiled_kernel(
     const float* __restrict__ g, const float* __restrict__ x, int N, float* __restrict__ partial) {
   constexpr int JT = OUT / 8, CT = IN / 8, PER = JT * CT, THREADS = kPgGroups * PER;
   constexpr int XS = IN + 4, GS = OUT + 4, SLAB = kPgRows * (XS + GS);
   static_assert(2 * SLAB >= (OUT + 1) * IN, "the staging buffers double as the reduction buffer");
-  extern __shared__ __align__(16) float s_dyn[];   // 2 x [ (kPgRows, XS) | (kPgRows, GS) ]
+  extern __shared__ __align__(16) float s_dyn[];   // kPgStages x [ (kPgRows, XS) | (kPgRows, GS) ]: the loads of two slabs are in
+                                                   // flight while one is consumed (a slab's compute is shorter than its load latency)
   const int tid = threadIdx.x, p = tid / PER, u = tid % PER;
   const int jt = u / CT, ct = u % CT;
   float2 acc[8][4];                                // 8 x 8 tile as column pairs: packed fp32 FMAs, two columns per issue slot
@@ -384,18 +383,19 @@ __global__ void __launch_bounds__(kPgGroups * (OUT / 8) * (IN / 8), 2) out_linea
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
   int slab = blockIdx.x, it = 0;
-  if (slab < slabs) load_slab(slab, 0);
+#pragma unroll
+  for (int pre = 0; pre < kPgStages - 1; ++pre) {      // one commit group per stage, empty ones included: the waits count groups
+    if (slab + pre * (int)gridDim.x < slabs) load_slab(slab + pre * gridDim.x, pre);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
+  }
 #pragma unroll 1
   for (; slab < slabs; slab += gridDim.x, ++it) {
-    const int next = slab + gridDim.x;
-    if (next < slabs) {
-      load_slab(next, (it + 1) & 1);
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
-    } else {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-    }
+    const int next = slab + (kPgStages - 1) * (int)gridDim.x;
+    if (next < slabs) load_slab(next, (it + kPgStages - 1) % kPgStages);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group %0;" :: "n"(kPgStages - 1) : "memory");
     __syncthreads();
-    const float* xs = s_dyn + (it & 1) * SLAB;
+    const float* xs = s_dyn + (it % kPgStages) * SLAB;
     const float* gs = xs + kPgRows * XS;
     const int rows = min(kPgRows, N - slab * kPgRows);
 #pragma unroll 2
@@ -547,7 +547,7 @@ static int launch_ol_bwd(const hept_shape* s, const float* g, const float* w, co
   if constexpr (OUT == 24) if (IN == OUT * 8) {
     ptiled = true;
     constexpr int TIN = OUT * 8, THREADS = kPgGroups * (OUT / 8) * (TIN / 8);
-    const size_t tsmem = sizeof(float) * 2 * (size_t)kPgRows * (TIN + 4 + OUT + 4);
+    const size_t tsmem = sizeof(float) * kPgStages * (size_t)kPgRows * (TIN + 4 + OUT + 4);
     static DeviceOnce tconfigured;
     if (tconfigured.needed()) {
       cudaError_t e = cudaFuncSetAttribute(out_linear_bwd_params_tiled_kernel<OUT, TIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem);
@@ -579,7 +579,7 @@ int qkv_weight_grads(const float* xn, const float* dq, const float* dk, const fl
   HEPT_REQUIRE(D == 24 && H == 8, HEPT_EUNSUPPORTED, "qkv_weight_grads: (H=%d, D=%d) not compiled in", H, D);
   HEPT_REQUIRE(partial_floats >= qkv_weight_grads_partial_floats(H, D), HEPT_EWORKSPACE, "qkv_weight_grads: workspace too small");
   constexpr int OUT = 24, TIN = 192, THREADS = kPgGroups * (OUT / 8) * (TIN / 8);
-  const size_t tsmem = sizeof(float) * 2 * (size_t)kPgRows * (TIN + 4 + OUT + 4);
+  const size_t tsmem = sizeof(float) * kPgStages * (size_t)kPgRows * (TIN + 4 + OUT + 4);
   static DeviceOnce configured;
   if (configured.needed()) {
     cudaError_t e = cudaFuncSetAttribute(out_linear_bwd_params_tiled_kernel<OUT, TIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem);

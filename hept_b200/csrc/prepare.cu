@@ -16,14 +16,16 @@
 //   region = floor(rank / width) + 1                      exact in float32 for rank < 2^24 (both are integers)
 //   bits   = ceil(log2(max + 1))                          (example/transformer.py:11-12) computed in integers; equal to
 //                                                         the float32 formula for max < 2^21 (region codes are < 2^16)
+// The padding order (argsort of the (table 0, head 0) code) sorts the integer codes themselves: ceil(code_bits / 8) radix
+// passes instead of the four a float key needs.
 // Sort tie-break: stable (lowest index first); the reference's argsort is unstable, so among points with EQUAL eta (or phi,
 // or packed code) it may pick another order — the documented deviation of DESIGN.md section 1.
 #include "common.cuh"
 
 namespace hept {
 
-int segmented_argsort_launch(const float* keys, int32_t num_segments, int32_t n, int32_t* positions, void* workspace,
-                             size_t workspace_bytes, cudaStream_t st);
+int segmented_argsort_launch(const void* keys, int32_t num_segments, int32_t n, int32_t* positions, void* workspace,
+                             size_t workspace_bytes, cudaStream_t st, int key_bits = 0);
 
 constexpr int kPrepThreads = 256;
 constexpr int kPrepMaxTH = 64;
@@ -49,10 +51,24 @@ __device__ __forceinline__ int event_of(const int32_t* __restrict__ start, int E
 }
 
 // keys (2 * E, L): segment (a, e) holds coords[start_e .. start_e + n_e, a], padded with +inf up to L
+// The first TH threads also start the per-(table, head) bookkeeping: meta[2 th] = bits1 = ceil(log2(max eta region + 1)),
+// known from the event sizes alone (the largest region of an event is that of its last rank); meta[2 th + 1] = 0, the running
+// maximum of code1 = (phi << bits1) | eta that prep_code_max_kernel raises.
 __global__ void __launch_bounds__(kPrepThreads) prep_keys_kernel(const float* __restrict__ coords, int C,
                                                                  const int32_t* __restrict__ ev_start, int E, int L,
-                                                                 float* __restrict__ keys) {
+                                                                 float* __restrict__ keys, const float* __restrict__ regions_h,
+                                                                 int TH, int32_t* __restrict__ meta) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < (size_t)TH) {
+    const float r_eta = __ldg(regions_h + idx);
+    long long mx = 0;
+    for (int e = 0; e < E; ++e) {
+      const int n = __ldg(ev_start + e + 1) - __ldg(ev_start + e);
+      if (n > 0) mx = max(mx, (long long)region_of(n - 1, region_width(r_eta, n)));
+    }
+    meta[2 * idx] = ceil_log2(mx + 1);
+    meta[2 * idx + 1] = 0;
+  }
   if (idx >= (size_t)2 * E * L) return;
   const int i = (int)(idx % L);
   const int seg = (int)(idx / L);
@@ -73,54 +89,31 @@ __global__ void __launch_bounds__(kPrepThreads) prep_rank_kernel(const int32_t* 
   if (r < n) rank[(size_t)a * n_raw + s + __ldg(pos + idx)] = r;
 }
 
-// Per (table, head) th: bits1 = ceil(log2(max eta region + 1)) from the event sizes alone (the largest region of an event
-// is that of its last rank), then max over all points of code1 = (phi << bits1) | eta -> bits2.  One CTA per th.
-// meta[th] = {bits1, bits2}.
-__global__ void __launch_bounds__(kPrepThreads) prep_bits_kernel(const int32_t* __restrict__ rank, const int32_t* __restrict__ ev_start,
-                                                                 int E, int n_raw, const float* __restrict__ regions_h, int TH,
-                                                                 int32_t* __restrict__ meta) {
-  __shared__ long long red[kPrepThreads];
-  __shared__ int s_bits1;
-  const int th = blockIdx.x;
-  const float r_eta = __ldg(regions_h + th), r_phi = __ldg(regions_h + TH + th);
-  long long mx = 0;
-  for (int e = threadIdx.x; e < E; e += kPrepThreads) {
+// meta[2 th + 1] = max over all points of code1 = (phi << bits1) | eta for (table, head) th = blockIdx.y (integer atomicMax:
+// order-independent, deterministic); bits2 = ceil(log2(that + 1)) is taken where it is used.
+__global__ void __launch_bounds__(kPrepThreads) prep_code_max_kernel(const int32_t* __restrict__ rank, const int32_t* __restrict__ ev_start,
+                                                                     int E, int n_raw, const float* __restrict__ regions_h, int TH,
+                                                                     int32_t* __restrict__ meta) {
+  __shared__ int red[kPrepThreads / 32];
+  const int th = blockIdx.y;
+  const int p = blockIdx.x * kPrepThreads + threadIdx.x;
+  int code = 0;
+  if (p < n_raw) {
+    const int e = event_of(ev_start, E, p);
     const int n = __ldg(ev_start + e + 1) - __ldg(ev_start + e);
-    if (n > 0) mx = max(mx, (long long)region_of(n - 1, region_width(r_eta, n)));
+    const int eta = region_of(__ldg(rank + p), region_width(__ldg(regions_h + th), n));
+    const int phi = region_of(__ldg(rank + n_raw + p), region_width(__ldg(regions_h + TH + th), n));
+    code = (phi << __ldg(meta + 2 * th)) | eta;
   }
-  red[threadIdx.x] = mx;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) code = max(code, __shfl_xor_sync(0xffffffffu, code, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = code;
   __syncthreads();
-  for (int o = kPrepThreads / 2; o > 0; o >>= 1) {
-    if (threadIdx.x < o) red[threadIdx.x] = max(red[threadIdx.x], red[threadIdx.x + o]);
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) s_bits1 = ceil_log2(red[0] + 1);
-  __syncthreads();
-  const int bits1 = s_bits1;
-  mx = 0;
-  int e = 0, e_end = 0;
-  float w_eta = 1.f, w_phi = 1.f;
-  for (int p = threadIdx.x; p < n_raw; p += kPrepThreads) {
-    if (p >= e_end) {   // points are visited in ascending order by each thread: the event only moves forward
-      e = event_of(ev_start, E, p);
-      e_end = __ldg(ev_start + e + 1);
-      const int n = e_end - __ldg(ev_start + e);
-      w_eta = region_width(r_eta, n);
-      w_phi = region_width(r_phi, n);
-    }
-    const long long eta = region_of(__ldg(rank + p), w_eta), phi = region_of(__ldg(rank + n_raw + p), w_phi);
-    mx = max(mx, (phi << bits1) | eta);
-  }
-  __syncthreads();
-  red[threadIdx.x] = mx;
-  __syncthreads();
-  for (int o = kPrepThreads / 2; o > 0; o >>= 1) {
-    if (threadIdx.x < o) red[threadIdx.x] = max(red[threadIdx.x], red[threadIdx.x + o]);
-    __syncthreads();
-  }
   if (threadIdx.x == 0) {
-    meta[2 * th] = bits1;
-    meta[2 * th + 1] = ceil_log2(red[0] + 1);
+    int m = red[0];
+#pragma unroll
+    for (int w = 1; w < kPrepThreads / 32; ++w) m = max(m, red[w]);
+    atomicMax(meta + 2 * th + 1, m);
   }
 }
 
@@ -132,18 +125,19 @@ __device__ __forceinline__ long long packed_code(int rank_eta, int rank_phi, int
   return (batch_id << bits2) | ((phi << bits1) | eta);
 }
 
-// key00[p] = float(code of (table 0, head 0)): the order the padding rows are drawn from (example/transformer.py:59,23)
+// key00[p] = code of (table 0, head 0) as an integer sort key: the order the padding rows are drawn from
+// (example/transformer.py:59,23)
 __global__ void __launch_bounds__(kPrepThreads) prep_key00_kernel(const int32_t* __restrict__ rank, const int64_t* __restrict__ batch,
                                                                   const int32_t* __restrict__ ev_start, int E, int n_raw,
                                                                   const float* __restrict__ regions_h, int TH,
-                                                                  const int32_t* __restrict__ meta, float* __restrict__ key00) {
+                                                                  const int32_t* __restrict__ meta, uint32_t* __restrict__ key00) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n_raw) return;
   const int e = event_of(ev_start, E, p);
   const int n = __ldg(ev_start + e + 1) - __ldg(ev_start + e);
   const long long code = packed_code(__ldg(rank + p), __ldg(rank + n_raw + p), n, __ldg(batch + p), __ldg(regions_h),
-                                     __ldg(regions_h + TH), __ldg(meta), __ldg(meta + 1));
-  key00[p] = (float)code;     // exact below 2^24 (checked on the host side of the call)
+                                     __ldg(regions_h + TH), __ldg(meta), ceil_log2((long long)__ldg(meta + 1) + 1));
+  key00[p] = (uint32_t)code;   // below 2^code_bits (the caller's bound, checked on the host side of the call)
 }
 
 // Padded row i: which raw point it shows (take), whether it is real, its coordinates and its codes for every (table, head).
@@ -162,7 +156,7 @@ __global__ void __launch_bounds__(THREADS) prep_emit_kernel(const float* __restr
   __shared__ int s_meta[2 * kPrepMaxTH];
   for (int j = threadIdx.x; j < 2 * TH; j += THREADS) {
     s_reg[j] = __ldg(regions_h + j);
-    s_meta[j] = __ldg(meta + j);
+    s_meta[j] = (j & 1) ? ceil_log2((long long)__ldg(meta + j) + 1) : __ldg(meta + j);    // (bits1, bits2) per (table, head)
   }
   __syncthreads();
   const int i = blockIdx.x * THREADS + threadIdx.x;
@@ -254,7 +248,7 @@ extern "C" size_t hept_prepare_batched_workspace_bytes(int32_t n_raw, int32_t nu
 extern "C" int hept_prepare_batched(const float* coords, int32_t C, const int64_t* batch, const int32_t* event_start,
                                     const int32_t* pad_start, int32_t num_events, int32_t n_raw, int32_t n_pad,
                                     int32_t max_event, const float* regions_h, int32_t TH, int32_t block_size,
-                                    int64_t* combined_shifts, int32_t* combined_shifts32, int64_t* take, uint8_t* is_real,
+                                    int32_t code_bits, int64_t* combined_shifts, int32_t* combined_shifts32, int64_t* take, uint8_t* is_real,
                                     float* coords_pad, void* workspace, size_t workspace_bytes, void* stream) {
   HEPT_REQUIRE(coords && batch && event_start && pad_start && regions_h && combined_shifts && take && is_real && coords_pad &&
                    workspace,
@@ -264,13 +258,10 @@ extern "C" int hept_prepare_batched(const float* coords, int32_t C, const int64_
                n_pad, max_event, block_size);
   HEPT_REQUIRE(TH > 0 && TH <= kPrepMaxTH, HEPT_EUNSUPPORTED, "prepare_batched: T*H=%d outside [1, %d]", TH, kPrepMaxTH);
   HEPT_REQUIRE(n_raw < (1 << 24), HEPT_EUNSUPPORTED, "prepare_batched: %d points: ranks are no longer exact in float32", n_raw);
-  // the (table 0, head 0) code is the float32 sort key of the padding order: it must stay below 2^24 to be exact.  Region
-  // codes need <= 16 bits (two region indices of <= 8 bits: up to 255 regions per axis), the batch index the rest.
-  {
-    int bits = 0;
-    while ((1ll << bits) < num_events) ++bits;
-    HEPT_REQUIRE(bits + 16 <= 24, HEPT_EUNSUPPORTED, "prepare_batched: %d events: the (table 0, head 0) code may exceed 2^24", num_events);
-  }
+  // code_bits: the caller's upper bound on the bits of the (table 0, head 0) code (batch index over both region indices);
+  // it decides how many 8-bit passes the padding-order sort runs.  0 = unknown: all 32.
+  HEPT_REQUIRE(code_bits >= 0 && code_bits <= 32, HEPT_EINVAL, "prepare_batched: code_bits=%d outside [0, 32]", code_bits);
+  if (code_bits == 0) code_bits = 32;
   PrepPlan p = plan_prepare(n_raw, num_events, max_event);
   HEPT_REQUIRE(workspace_bytes >= p.total, HEPT_EWORKSPACE, "prepare_batched: workspace needs %zu bytes, got %zu", p.total,
                workspace_bytes);
@@ -280,23 +271,24 @@ extern "C" int hept_prepare_batched(const float* coords, int32_t C, const int64_
   int32_t* pos = (int32_t*)w;         w += p.pos_bytes;
   int32_t* rank = (int32_t*)w;        w += p.rank_bytes;
   int32_t* meta = (int32_t*)w;        w += p.meta_bytes;
-  float* key00 = (float*)w;           w += p.key00_bytes;
+  uint32_t* key00 = (uint32_t*)w;     w += p.key00_bytes;
   int32_t* order = (int32_t*)w;       w += p.order_bytes;
   void* sort_ws = w;
   const int E = num_events, L = max_event;
   const size_t seg_items = (size_t)2 * E * L;
   const unsigned seg_grid = (unsigned)((seg_items + kPrepThreads - 1) / kPrepThreads);
-  prep_keys_kernel<<<seg_grid, kPrepThreads, 0, st>>>(coords, C, event_start, E, L, keys);
+  prep_keys_kernel<<<seg_grid, kPrepThreads, 0, st>>>(coords, C, event_start, E, L, keys, regions_h, TH, meta);
   HEPT_CHECK_LAUNCH("prep_keys");
   if (int rc = segmented_argsort_launch(keys, 2 * E, L, pos, sort_ws, p.sort_bytes, st)) return rc;
   prep_rank_kernel<<<seg_grid, kPrepThreads, 0, st>>>(pos, event_start, E, L, n_raw, rank);
   HEPT_CHECK_LAUNCH("prep_rank");
-  prep_bits_kernel<<<TH, kPrepThreads, 0, st>>>(rank, event_start, E, n_raw, regions_h, TH, meta);
-  HEPT_CHECK_LAUNCH("prep_bits");
+  prep_code_max_kernel<<<dim3((n_raw + kPrepThreads - 1) / kPrepThreads, TH), kPrepThreads, 0, st>>>(rank, event_start, E, n_raw,
+                                                                                                     regions_h, TH, meta);
+  HEPT_CHECK_LAUNCH("prep_code_max");
   prep_key00_kernel<<<(n_raw + kPrepThreads - 1) / kPrepThreads, kPrepThreads, 0, st>>>(rank, batch, event_start, E, n_raw, regions_h,
                                                                                          TH, meta, key00);
   HEPT_CHECK_LAUNCH("prep_key00");
-  if (int rc = segmented_argsort_launch(key00, 1, n_raw, order, sort_ws, p.sort_bytes, st)) return rc;
+  if (int rc = segmented_argsort_launch(key00, 1, n_raw, order, sort_ws, p.sort_bytes, st, code_bits)) return rc;
   prep_emit_kernel<128><<<(n_pad + 127) / 128, 128, 0, st>>>(coords, C, batch, rank, order, event_start, pad_start, E, n_raw, n_pad,
                                                              block_size, regions_h, TH, meta, combined_shifts, combined_shifts32, take,
                                                              is_real, coords_pad);

@@ -335,9 +335,8 @@ static int cluster_size_for(int segments, int n) {
   if (g_sort_variant.load(std::memory_order_relaxed) == 1 || forced < 0) return 0;
   const int need = (n + kCsMaxCap - 1) / kCsMaxCap;
   if (forced > 0) return need > 8 ? 0 : max(min(forced, 8), need);
-  // a few long segments (the per-event rank sorts of prepare.cu: 2 .. 16 segments of up to 98 304 keys): one cluster each
-  // still fits a single wave, and one launch beats the eight of the global passes
-  if (n > 16384) return (need <= 8 && (long long)segments * need <= 64) ? need : 0;
+  if (n > 16384) return 0;    // measured again with 2 segments of 60 000 keys (prepare.cu): 99 us in 5-CTA clusters (the remote
+                              // stores of the ranking serialise) against ~50 us for the eight small launches of the global passes
   const int cs = n <= 2048 ? 1 : 2;
   return (long long)segments * cs <= 2 * 148 ? cs : 0;
 }
@@ -347,8 +346,8 @@ struct SortPlan {
   size_t hist_bytes, keys_bytes, idx_bytes, total;
 };
 
-int segmented_argsort_launch(const float* keys, int32_t num_segments, int32_t n, int32_t* positions, void* workspace,
-                             size_t workspace_bytes, cudaStream_t st);
+int segmented_argsort_launch(const void* keys, int32_t num_segments, int32_t n, int32_t* positions, void* workspace,
+                             size_t workspace_bytes, cudaStream_t st, int key_bits = 0);
 
 static SortPlan plan_sort(int segments, int n) {
   SortPlan p;
@@ -377,8 +376,11 @@ extern "C" int hept_segmented_argsort(const float* keys, int32_t num_segments, i
   return segmented_argsort_launch(keys, num_segments, n, positions, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
-int hept::segmented_argsort_launch(const float* keys, int32_t num_segments, int32_t n, int32_t* positions, void* workspace,
-                                   size_t workspace_bytes, cudaStream_t stream) {
+// key_bits == 0: float32 keys (four 8-bit passes over their order-preserving bits).  key_bits > 0: the keys are uint32 whose
+// bits above key_bits are zero (the packed region codes of prepare.cu): ceil(key_bits / 8) passes, global path only.
+int hept::segmented_argsort_launch(const void* keys_v, int32_t num_segments, int32_t n, int32_t* positions, void* workspace,
+                                   size_t workspace_bytes, cudaStream_t stream, int key_bits) {
+  const float* keys = (const float*)keys_v;
   HEPT_REQUIRE(keys && positions && workspace && num_segments > 0 && n > 0, HEPT_EINVAL,
                "segmented_argsort: bad argument");
   SortPlan p = plan_sort(num_segments, n);
@@ -386,7 +388,7 @@ int hept::segmented_argsort_launch(const float* keys, int32_t num_segments, int3
                p.total, workspace_bytes);
   HEPT_REQUIRE(num_segments <= 65535, HEPT_EINVAL, "segmented_argsort: too many segments (%d)", num_segments);
   cudaStream_t st = (cudaStream_t)stream;
-  if (const int cs = cluster_size_for(num_segments, n)) {
+  if (const int cs = key_bits > 0 ? 0 : cluster_size_for(num_segments, n)) {
     const int cap = (n + cs - 1) / cs;
     const size_t smem = cluster_sort_smem(cap);
     static DeviceOnce opted;
@@ -419,16 +421,17 @@ int hept::segmented_argsort_launch(const float* keys, int32_t num_segments, int3
   uint32_t* kbuf[2] = {(uint32_t*)w, (uint32_t*)(w + p.keys_bytes)};  w += 2 * p.keys_bytes;
   int32_t* ibuf[2] = {(int32_t*)w, (int32_t*)(w + p.idx_bytes)};
   dim3 grid(p.tiles, num_segments);
-  const int passes = 32 / kRadixBits;
+  const int passes = key_bits > 0 ? (key_bits + kRadixBits - 1) / kRadixBits : 32 / kRadixBits;
   const void* kin = keys;
   const int32_t* iin = nullptr;
   for (int pass = 0; pass < passes; ++pass) {
     const bool first = pass == 0, last = pass == passes - 1;
-    radix_hist_kernel<<<grid, kSortThreads, 0, st>>>(kin, first, n, p.tiles, pass * kRadixBits, hist);
+    const bool as_float = first && key_bits == 0;
+    radix_hist_kernel<<<grid, kSortThreads, 0, st>>>(kin, as_float, n, p.tiles, pass * kRadixBits, hist);
     HEPT_CHECK_LAUNCH("radix_hist");
     uint32_t* kout = last ? nullptr : kbuf[pass & 1];
     int32_t* iout = last ? positions : ibuf[pass & 1];
-    radix_scatter_kernel<<<grid, kSortThreads, 0, st>>>(kin, first, iin, n, p.tiles, pass * kRadixBits, hist, kout,
+    radix_scatter_kernel<<<grid, kSortThreads, 0, st>>>(kin, as_float, iin, n, p.tiles, pass * kRadixBits, hist, kout,
                                                         iout);
     HEPT_CHECK_LAUNCH("radix_scatter");
     kin = kout;

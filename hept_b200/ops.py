@@ -312,7 +312,7 @@ def attn_qkv_bwd(x, xn, norm_weight, wt, dq, dk, dv, H: int, D: int, eps: float)
 # ------------------------------------------------------------------------------- a13..a17 preparation
 @_on_device
 def prepare_batched(coords, batch, offsets, num_events: int, n_raw: int, n_pad: int, max_event: int, regions_h, block_size: int,
-                    want_int32: bool = True):
+                    want_int32: bool = True, code_bits: int = 0):
     """example/ flavour of prepare_input on the library's kernels.  ``offsets`` = int32 device tensor
     [event_start (E+1) | pad_start (E+1)].  -> combined_shifts (TH, n_pad) int64, the same as int32 (or None),
     take (n_pad) int64, is_real (n_pad) bool, coords_pad (n_pad, C)."""
@@ -332,7 +332,7 @@ def prepare_batched(coords, batch, offsets, num_events: int, n_raw: int, n_pad: 
     ev_start = C.c_void_p(offsets.data_ptr())
     pad_start = C.c_void_p(offsets.data_ptr() + 4 * (num_events + 1))
     _lib.check(lib.hept_prepare_batched(_ptr(coords), c, _ptr(batch), ev_start, pad_start, num_events, n_raw, n_pad, max_event,
-                                        _ptr(regions_h), th, block_size, _ptr(shifts), _ptr(shifts32), _ptr(take), _ptr(real),
+                                        _ptr(regions_h), th, block_size, int(code_bits), _ptr(shifts), _ptr(shifts32), _ptr(take), _ptr(real),
                                         _ptr(coords_pad), _ptr(ws), ws.numel(), _stream(coords)), "hept_prepare_batched")
     return shifts, shifts32, take, real.view(torch.bool), coords_pad
 

@@ -17,6 +17,7 @@ argsort breaks ties between EQUAL eta / phi / code values differently (tests/tes
 """
 from __future__ import annotations
 
+import math
 from typing import Dict, Optional, Sequence
 
 import torch
@@ -24,10 +25,38 @@ import torch
 from . import ops
 
 
-def _regions_h(regions: torch.Tensor) -> torch.Tensor:
-    """(T, 2, H) -> (2, T*H): the reference's rearrange "c a h -> a (c h)" (example/transformer.py:37)."""
-    t, two, heads = regions.shape
-    return regions.permute(1, 0, 2).reshape(two, t * heads).contiguous().float()
+_REGION_CACHE: Dict = {}
+_OFFSET_CACHE: Dict = {}
+
+
+def _regions_h(regions: torch.Tensor):
+    """(T, 2, H) -> ((2, T*H) device tensor: the reference's rearrange "c a h -> a (c h)" (example/transformer.py:37), and
+    the bits one region index needs).  ``regions`` is a frozen parameter: both are computed once per tensor version."""
+    key = (regions.data_ptr(), regions._version, regions.device)
+    hit = _REGION_CACHE.get(key)
+    if hit is None:
+        t, two, heads = regions.shape
+        rh = regions.detach().permute(1, 0, 2).reshape(two, t * heads).contiguous().float()
+        top = int(math.ceil(float(rh.max()))) + 2           # region = floor(rank / ceil(n / r)) + 1 <= ceil(r) + 1
+        if len(_REGION_CACHE) > 64:
+            _REGION_CACHE.clear()
+        hit = _REGION_CACHE[key] = (rh, max(1, (top - 1).bit_length()))
+    return hit
+
+
+def _offsets(sizes, block: int, dev):
+    """int32 device tensor [event_start (E+1) | pad_start (E+1)] + (n_raw, n_pad); cached per (sizes, block, device)."""
+    key = (tuple(sizes), block, dev)
+    hit = _OFFSET_CACHE.get(key)
+    if hit is None:
+        ev_start, pad_start = [0], [0]
+        for s in sizes:
+            ev_start.append(ev_start[-1] + s)
+            pad_start.append(pad_start[-1] + (s + block - 1) // block * block)
+        if len(_OFFSET_CACHE) > 256:
+            _OFFSET_CACHE.clear()
+        hit = _OFFSET_CACHE[key] = (torch.tensor(ev_start + pad_start, dtype=torch.int32, device=dev), ev_start[-1], pad_start[-1])
+    return hit
 
 
 def prepare_input(x: torch.Tensor, coords: torch.Tensor, batch: torch.Tensor, helper_params: Dict,
@@ -46,16 +75,14 @@ def prepare_input(x: torch.Tensor, coords: torch.Tensor, batch: torch.Tensor, he
         if sizes is None:
             sizes = torch.bincount(batch).tolist()          # the one host read-back: it decides the output sizes
         sizes = [int(s) for s in sizes]
-        ev_start, pad_start = [0], [0]
-        for s in sizes:
-            ev_start.append(ev_start[-1] + s)
-            pad_start.append(pad_start[-1] + (s + block - 1) // block * block)
-        n_raw, n_pad = ev_start[-1], pad_start[-1]
+        offsets, n_raw, n_pad = _offsets(sizes, block, dev)
         if n_raw != coords.shape[0]:
             raise ValueError(f"event sizes sum to {n_raw} but there are {coords.shape[0]} points")
-        offsets = torch.tensor(ev_start + pad_start, dtype=torch.int32).to(dev, non_blocking=True)
+        regions_h, region_bits = _regions_h(regions if regions.device == dev else regions.to(dev))
+        code_bits = max(1, (len(sizes) - 1).bit_length()) + 2 * region_bits      # batch index over phi over eta
         shifts, shifts32, take, real, coords_pad = ops.prepare_batched(
-            coords.float(), batch, offsets, len(sizes), n_raw, n_pad, max(sizes), _regions_h(regions.to(dev)), block)
+            coords.float(), batch, offsets, len(sizes), n_raw, n_pad, max(sizes), regions_h, block,
+            code_bits=code_bits if code_bits <= 32 else 0)
         kwargs = {"combined_shifts": shifts.view(t, heads, n_pad), "combined_shifts32": shifts32.view(t, heads, n_pad),
                   "coords": coords_pad}
     return x[take], kwargs, real
@@ -70,7 +97,7 @@ def prepare_input_single(x: torch.Tensor, coords: torch.Tensor, helper_funcs: Di
     with torch.no_grad():
         n = x.shape[0]
         pad = (-n) % block
-        regions_h = _regions_h(regions.to(coords.device))
+        regions_h, _ = _regions_h(regions if regions.device == coords.device else regions.to(coords.device))
         if pad:
             x = torch.cat([x, x.new_zeros((pad,) + tuple(x.shape[1:]))])
         coords_pad, eta, phi = ops.prepare_single(coords.float(), n + pad, regions_h)

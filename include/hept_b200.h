@@ -147,7 +147,9 @@ int hept_attention_fwd(const hept_shape* s, const float* q, const float* k, cons
  *   coords (n_raw, C) fp32 (columns 0 / 1 = eta / phi); batch (n_raw) int64, ascending; event_start, pad_start: DEVICE
  *   arrays of num_events + 1 int32 offsets of the events in raw / padded order (the caller knows the event sizes: they
  *   decide n_pad, the size of every output); max_event = the longest event; regions_h (2, TH) fp32 = the model's `regions`
- *   parameter rearranged "c a h -> a (c h)"; block_size B.
+ *   parameter rearranged "c a h -> a (c h)"; block_size B; code_bits = an upper bound on the number of bits of the
+ *   (table 0, head 0) code, ceil(log2(num_events)) + 2 ceil(log2(max regions per axis + 2)) (0 = unknown, 32): the padding
+ *   order is a radix sort of those integer codes, one pass per 8 bits.
  * Outputs, all in padded order: combined_shifts (TH, n_pad) int64 (+ the same values as int32 when combined_shifts32 is
  * non-null), take (n_pad) int64 = index of the raw point every padded row shows (the reference's pad_seq: x[take]),
  * is_real (n_pad) uint8 (the reference's unpad_seq), coords_pad (n_pad, C).
@@ -155,7 +157,7 @@ int hept_attention_fwd(const hept_shape* s, const float* q, const float* k, cons
 size_t hept_prepare_batched_workspace_bytes(int32_t n_raw, int32_t num_events, int32_t max_event);
 int hept_prepare_batched(const float* coords, int32_t C, const int64_t* batch, const int32_t* event_start,
                          const int32_t* pad_start, int32_t num_events, int32_t n_raw, int32_t n_pad, int32_t max_event,
-                         const float* regions_h, int32_t TH, int32_t block_size, int64_t* combined_shifts,
+                         const float* regions_h, int32_t TH, int32_t block_size, int32_t code_bits, int64_t* combined_shifts,
                          int32_t* combined_shifts32, int64_t* take, uint8_t* is_real, float* coords_pad, void* workspace,
                          size_t workspace_bytes, void* stream);
 /* src/ flavour: HEPT branch of prepare_input, src/models/baselines/transformer.py:43-57 (one event): coords padded with +inf
