@@ -25,23 +25,24 @@ import torch
 from . import ops
 
 
-_REGION_CACHE: Dict = {}
 _OFFSET_CACHE: Dict = {}
 
 
 def _regions_h(regions: torch.Tensor):
     """(T, 2, H) -> ((2, T*H) device tensor: the reference's rearrange "c a h -> a (c h)" (example/transformer.py:37), and
-    the bits one region index needs).  ``regions`` is a frozen parameter: both are computed once per tensor version."""
-    key = (regions.data_ptr(), regions._version, regions.device)
-    hit = _REGION_CACHE.get(key)
-    if hit is None:
+    the bits one region index needs).  ``regions`` is a frozen parameter: both are computed once per tensor version and kept
+    ON the tensor object (a cache keyed by address would outlive the tensor and hit a stranger at the same address)."""
+    hit = getattr(regions, "_hept_regions_h", None)
+    if hit is None or hit[0] != regions._version:
         t, two, heads = regions.shape
         rh = regions.detach().permute(1, 0, 2).reshape(two, t * heads).contiguous().float()
         top = int(math.ceil(float(rh.max()))) + 2           # region = floor(rank / ceil(n / r)) + 1 <= ceil(r) + 1
-        if len(_REGION_CACHE) > 64:
-            _REGION_CACHE.clear()
-        hit = _REGION_CACHE[key] = (rh, max(1, (top - 1).bit_length()))
-    return hit
+        hit = (regions._version, rh, max(1, (top - 1).bit_length()))
+        try:
+            regions._hept_regions_h = hit
+        except AttributeError:
+            pass
+    return hit[1], hit[2]
 
 
 def _offsets(sizes, block: int, dev):
