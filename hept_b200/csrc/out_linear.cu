@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(kTlThreads, 4) out_linear_bwd_input_tiled_kern
 // weight / bias gradient, stage 1: a CTA = kPgGroups hit groups x (OUT / 8) x (IN / 8) threads; a thread owns an 8 x 8 tile
 // of dW; slabs of kPgRows hits are staged in shared memory (double-buffered cp.async); group p takes the hits p, p + G, ...
 // of a slab.  The groups' tiles are added through shared memory in group order (deterministic), db by the ct == 0 threads.
-constexpr int kPgGroups = 4, kPgRows = 32, kPgStages = 3;
+constexpr int kPgGroups = 4, kPgRows = 32, kPgStages = 2;   // (three stages measured: no gain, the loop is barrier-bound)
 template <int OUT, int IN>
 __global__ void __launch_bounds__(kPgGroups * (OUT / 8) * (IN / 8), 2) out_linear_bwd_params_tiled_kernel(
     const float* __restrict__ g, const float* __restrict__ x, int N, float* __restrict__ partial) {
