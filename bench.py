@@ -264,7 +264,7 @@ def run_ours(args):
     # ---- end to end with HOST buffers --------------------------------------------------------------
     # Double-buffered: the H2D copy of step i+1 runs on a copy stream while step i computes; every step still
     # copies its own inputs from pinned host memory and reads its results back inside the timed region.
-    def e2e_leg(host_sets, grad_keys, run, grads, out_width):       # grads: the GradBucket whose flat buffer is read back
+    def e2e_leg(host_sets, grad_keys, run, grads, out_width, do_h2d=True, do_d2h=True):   # grads: the GradBucket that is read back
         staging = [{k: torch.empty_like(v, device=dev) for k, v in host_sets[0].items()} for _ in range(2)]
         out_host = torch.empty(n_hits, out_width).pin_memory()
         grad_host = torch.empty_like(grads.flat, device="cpu").pin_memory()
@@ -285,8 +285,9 @@ def run_ours(args):
             b = i % 2
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(consumed[b])          # buffer b was last read by step i-2
-                for k, v in host_sets[i % n_sets].items():
-                    staging[b][k].copy_(v, non_blocking=True)
+                if do_h2d or i < 2:
+                    for k, v in host_sets[i % n_sets].items():
+                        staging[b][k].copy_(v, non_blocking=True)
                 ready[b].record(copy_stream)
 
         def e2e_step(i):
@@ -307,8 +308,9 @@ def run_ours(args):
             out.record_stream(back_stream)
             with torch.cuda.stream(back_stream):
                 back_stream.wait_event(computed)
-                out_host.copy_(out, non_blocking=True)
-                grad_host.copy_(grad_stage, non_blocking=True)
+                if do_d2h:
+                    out_host.copy_(out, non_blocking=True)
+                    grad_host.copy_(grad_stage, non_blocking=True)
                 read_back.record(back_stream)
 
         steps = max(3, min(args.steps, 10))
@@ -355,6 +357,28 @@ def run_ours(args):
     e2e_block = e2e_leg(host_x, ("x",), block_step, bucket_blk, cfg["h_dim"])
     e2e_block["boundary"] = ("Attn block front + HEPTAttention: x (N,24) fp32, coords, int32 codes from pinned host memory; norm1 and "
                              "w_q / w_k / w_v computed on the device; output (N,24) + parameter gradients read back")
+    # the same leg with the compute captured in CUDA graphs (hept_b200/graphed.py): two graph launches per step instead of ~45
+    # kernel launches — on a box where eight ranks share the host's PCIe / launch path, the launches, not the 13 MB of copies,
+    # are what the concurrent DMA traffic delays
+    from hept_b200.graphed import graphed_attn_block
+
+    gstep = graphed_attn_block(mod, w_rpe, norm1, w_qkv[0], w_qkv[1], w_qkv[2], resident_x[0]["x"].detach().requires_grad_(True),
+                               resident_x[0]["coords"], resident_x[0]["combined_shifts32"])
+
+    def block_step_graphed(inp, g):
+        bucket_blk.zero()
+        out = gstep(inp["x"], inp["coords"], inp["combined_shifts32"])
+        out.backward(g)
+        if world > 1:
+            bucket_blk.allreduce()
+        return out
+
+    e2e_graph = e2e_leg(host_x, ("x",), block_step_graphed, bucket_blk, cfg["h_dim"])
+    e2e_block["cuda_graph_replay"] = {"value": e2e_graph["value"], "ms_per_step": e2e_graph["ms_per_step"]}
+    if args.e2e_diag:      # where does the end-to-end leg lose time (multi-GPU boxes): the same leg without one copy direction
+        e2e_block["diag_no_d2h_ms"] = e2e_leg(host_x, ("x",), block_step, bucket_blk, cfg["h_dim"], do_d2h=False)["ms_per_step"]
+        e2e_block["diag_no_h2d_ms"] = e2e_leg(host_x, ("x",), block_step, bucket_blk, cfg["h_dim"], do_h2d=False)["ms_per_step"]
+        e2e_block["diag_no_copies_ms"] = e2e_leg(host_x, ("x",), block_step, bucket_blk, cfg["h_dim"], do_h2d=False, do_d2h=False)["ms_per_step"]
     e2e_block["device_resident_same_boundary"] = {"value": world * args.steps * N_RAW / (ms_blk * 1e-3),
                                                   "ms_per_step": ms_blk / args.steps, "gpu_launches": launches_blk}
 
@@ -544,6 +568,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--e2e-diag", action="store_true", help="extra end-to-end legs without H2D / D2H (diagnostic)")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step leg (BASELINE.json configs[4])")
     ap.add_argument("--bwd", default=None, type=int, choices=[1, 3, 4, 5], help="backward tile variant (default: library default)")
     ap.add_argument("--engine", default=None, choices=["simt", "tcgen05"], help="tile engine (default: library default)")

@@ -43,6 +43,32 @@ def graphed_attention(attn: HEPTAttention, w_rpe: nn.Module, query, key, value, 
                                                  allow_unused_input=True)   # w_rpe.bias, e2lsh.alpha never get a gradient
 
 
+class _BlockStep(nn.Module):
+    """(x, coords, combined_shifts) -> attention output of an Attn block: norm1 -> w_q / w_k / w_v -> HEPTAttention."""
+
+    def __init__(self, attn: HEPTAttention, w_rpe: nn.Module, norm1: nn.LayerNorm, w_q: nn.Linear, w_k: nn.Linear, w_v: nn.Linear):
+        super().__init__()
+        self.attn, self.w_rpe, self.norm1, self.w_q, self.w_k, self.w_v = attn, w_rpe, norm1, w_q, w_k, w_v
+
+    def forward(self, x, coords, combined_shifts):
+        from .attention import attn_front
+
+        q, k, v = attn_front(x, self.norm1, self.w_q, self.w_k, self.w_v, self.attn.num_heads)
+        return self.attn(q, k, v, w_rpe=self.w_rpe, coords=coords, combined_shifts=combined_shifts)
+
+
+def graphed_attn_block(attn: HEPTAttention, w_rpe: nn.Module, norm1: nn.LayerNorm, w_q: nn.Linear, w_k: nn.Linear, w_v: nn.Linear,
+                       x, coords, combined_shifts, num_warmup_iters: int = 3):
+    """-> callable(x, coords, combined_shifts) replaying captured forward / backward graphs of the front of the reference's
+    Attn block (example/transformer.py:157-159) followed by the attention module: two graph launches per step."""
+    if not x.is_cuda:
+        raise RuntimeError("graphed_attn_block needs CUDA tensors (there is no CPU path)")
+    step = _BlockStep(attn, w_rpe, norm1, w_q, w_k, w_v)
+    sample = (x.detach().clone().requires_grad_(x.requires_grad), coords.detach().clone(), combined_shifts.detach().clone())
+    with torch.cuda.device(x.device):
+        return torch.cuda.make_graphed_callables(step, sample, num_warmup_iters=num_warmup_iters, allow_unused_input=True)
+
+
 class GraphedInference:
     """Forward-only replay of a whole model call (e.g. the pileup Transformer, src/ flavour: BASELINE.json configs[2]) for one
     input shape: ``run(*inputs)`` copies the inputs into the captured buffers, replays, and returns the static output."""
