@@ -309,6 +309,47 @@ def attn_qkv_bwd(x, xn, norm_weight, wt, dq, dk, dv, H: int, D: int, eps: float)
     return dx, dgam, dbet, dwq, dwk, dwv
 
 
+# ------------------------------------------------------------------ InfoNCE loss
+METRICS = {"l2_rbf": 0, "l2_inverse": 1, "cosine": 2}
+
+
+@_on_device
+def infonce_fwd(x, point_pairs, cluster_ids, recons, pts, metric: str, tau: float, pt_thres: float = 0.9):
+    """-> loss (0-dim tensor), saved state (uint8 tensor) for infonce_bwd."""
+    lib = _lib.load()
+    x = _need(x, "x", torch.float32)
+    n, d = x.shape
+    pairs = _need(point_pairs, "point_pairs", torch.int64)
+    if pairs.dim() != 2 or pairs.shape[0] != 2:
+        raise ValueError(f"point_pairs must be (2, P), got {tuple(pairs.shape)}")
+    p = pairs.shape[1]
+    cid = _need(cluster_ids, "cluster_ids", torch.int64, (n,))
+    recons = _need(recons, "recons", torch.float32, (n,))
+    pts = _need(pts, "pts", torch.float32, (n,))
+    loss = torch.empty((), dtype=torch.float32, device=x.device)
+    saved = _workspace(lib.hept_infonce_saved_bytes(n, p), x)
+    ws = _workspace(lib.hept_infonce_workspace_bytes(n, p, 0), x)
+    _lib.check(lib.hept_infonce_fwd(_ptr(x), n, d, _ptr(pairs), p, _ptr(cid), _ptr(recons), _ptr(pts), float(pt_thres),
+                                    METRICS[metric], float(tau), _ptr(loss), _ptr(saved), saved.numel(), _ptr(ws), ws.numel(),
+                                    _stream(x)), "hept_infonce_fwd")
+    return loss, saved
+
+
+@_on_device
+def infonce_bwd(x, point_pairs, saved, grad_loss, metric: str, tau: float):
+    lib = _lib.load()
+    x = _need(x, "x", torch.float32)
+    n, d = x.shape
+    pairs = _need(point_pairs, "point_pairs", torch.int64)
+    p = pairs.shape[1]
+    g = _need(grad_loss.reshape(1), "grad_loss", torch.float32, (1,))
+    dx = torch.empty_like(x)
+    ws = _workspace(lib.hept_infonce_workspace_bytes(n, p, 1), x)
+    _lib.check(lib.hept_infonce_bwd(_ptr(x), n, d, _ptr(pairs), p, METRICS[metric], float(tau), _ptr(g), _ptr(saved), saved.numel(),
+                                    _ptr(dx), _ptr(ws), ws.numel(), _stream(x)), "hept_infonce_bwd")
+    return dx
+
+
 # ------------------------------------------------------------------------------- a13..a17 preparation
 @_on_device
 def prepare_batched(coords, batch, offsets, num_events: int, n_raw: int, n_pad: int, max_event: int, regions_h, block_size: int,

@@ -193,6 +193,21 @@ int hept_attn_qkv_bwd(const float* x, const float* x_normed, const float* norm_w
                       float* d_norm_weight, float* d_norm_bias, float* d_w_q, float* d_w_k, float* d_w_v, void* workspace,
                       size_t workspace_bytes, void* stream);
 
+/* ---- SURVEY.md 8(f)-4, first half: InfoNCE loss of the tracking task (src/utils/losses.py:8-74) ---------------------------
+ * x (N, d <= 16) embeddings; point_pairs (2, P) int64; cluster_ids (N) int64; recons, pts (N) fp32; metric 0 = l2_rbf,
+ * 1 = l2_inverse, 2 = cosine (losses.py:20-30); pt_thres 0.9 in the reference (losses.py:17).  loss: one device float.
+ * `saved` (hept_infonce_saved_bytes) carries the forward's state to the backward (scores, pair flags, the CSR index of the
+ * pairs by first point, per-point denominators, label sizes); `workspace` is scratch (hept_infonce_workspace_bytes).
+ * Deterministic: every floating-point sum runs in a fixed order (no floating-point atomics).  grad_loss: one device float. */
+size_t hept_infonce_saved_bytes(int32_t N, int64_t P);
+size_t hept_infonce_workspace_bytes(int32_t N, int64_t P, int32_t backward);
+int hept_infonce_fwd(const float* x, int32_t N, int32_t d, const int64_t* point_pairs, int64_t P, const int64_t* cluster_ids,
+                     const float* recons, const float* pts, float pt_thres, int32_t metric, float tau, float* loss, void* saved,
+                     size_t saved_bytes, void* workspace, size_t workspace_bytes, void* stream);
+int hept_infonce_bwd(const float* x, int32_t N, int32_t d, const int64_t* point_pairs, int64_t P, int32_t metric, float tau,
+                     const float* grad_loss, const void* saved, size_t saved_bytes, float* dx, void* workspace,
+                     size_t workspace_bytes, void* stream);
+
 /* kernel launches this library enqueued (any thread of the process) since the counter was last reset
  * (bench.py's gpu_launches); reset != 0 zeroes the counter after reading it. */
 int hept_launch_count(int reset);

@@ -346,6 +346,58 @@ def prepare_single_event(x: Tensor, coords: Tensor, regions: Tensor, block_size:
 
 
 # --------------------------------------------------------------------------
+# SURVEY.md 8(f)-4  InfoNCE loss of the tracking task      src/utils/losses.py:8-74, src/utils/metrics.py:8-16
+# --------------------------------------------------------------------------
+def segment_reduce_sorted(src: Tensor, index: Tensor, reduce: str) -> Tensor:
+    """``deterministic_scatter`` (losses.py:66-74): sort by index, then torch_scatter.segment_csr over the runs of equal
+    indices — restated with a sequential index_add_ over the sorted values (torch_scatter is not installed here;
+    segment_csr(src, indptr, "sum" | "mean") is the sum / mean of src[indptr[g]:indptr[g+1]]).  Returns one entry per DISTINCT
+    index, in ascending index order."""
+    sorted_arg = torch.argsort(index)
+    sorted_index = index[sorted_arg]
+    sorted_src = src[sorted_arg]
+    _, inverse, counts = torch.unique_consecutive(sorted_index, return_inverse=True, return_counts=True)
+    out = sorted_src.new_zeros(counts.numel()).index_add_(0, inverse, sorted_src)
+    return out / counts.to(src.dtype) if reduce == "mean" else out
+
+
+def pair_mask(cluster_ids: Tensor, point_pairs: Tensor, recons: Tensor, pts: Tensor, pt_thres: float = 0.9) -> Tensor:
+    """Positive pairs: same cluster (losses.py:15) and both points reconstructable with pt above the threshold
+    (``pair_filter``, metrics.py:8-16)."""
+    a, b = point_pairs[0], point_pairs[1]
+    return (cluster_ids[a] == cluster_ids[b]) & (recons[a] != 0) & (recons[b] != 0) & (pts[a] > pt_thres) & (pts[b] > pt_thres)
+
+
+def infonce_loss(x: Tensor, point_pairs: Tensor, cluster_ids: Tensor, recons: Tensor, pts: Tensor, tau: float,
+                 dist_metric: str, compact_like_reference: bool = True) -> Tensor:
+    """InfoNCELoss.forward (losses.py:14-39) + calc_info_nce (losses.py:41-53).
+
+    ``compact_like_reference``: the reference indexes the compacted per-point sums (one entry per point owning a negative
+    pair) with raw point numbers (losses.py:48-51); False scatters them to point numbers first (what the product does).  The
+    two agree whenever every point up to the largest first index owns a negative pair."""
+    a, b = point_pairs[0], point_pairs[1]
+    pos = pair_mask(cluster_ids, point_pairs, recons, pts)
+    neg = ~pos
+    if dist_metric == "cosine":
+        sim = torch.nn.functional.cosine_similarity(x[a], x[b], dim=-1)
+    else:
+        dist = torch.linalg.norm(x[a] - x[b], ord=2, dim=-1)
+        sim = torch.exp(-dist / (2 * 0.75 ** 2)) if dist_metric == "l2_rbf" else 1.0 / (dist + 1.0)
+    scaled = sim / tau
+    e = torch.exp(scaled - scaled.max())
+    group = a[neg]
+    den = segment_reduce_sorted(e[neg], group, "sum").clamp(min=0)
+    if not compact_like_reference:
+        full = den.new_zeros(x.shape[0])
+        full[torch.unique(group)] = den
+        den = full
+    den = den[a[pos]]
+    per_pair = -torch.log(e[pos] / (e[pos] + den))
+    labels = torch.unique(cluster_ids[a[pos]], return_inverse=True)[1]
+    return segment_reduce_sorted(per_pair, labels, "mean").mean()
+
+
+# --------------------------------------------------------------------------
 # convenience: run fwd+bwd and hand back everything a parity test compares
 # --------------------------------------------------------------------------
 def forward_backward(inputs: Dict[str, Tensor], params: Dict[str, Tensor], cfg: Dict[str, int], grad_out: Tensor,
