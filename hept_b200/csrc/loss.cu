@@ -363,6 +363,22 @@ __global__ void __launch_bounds__(kLossThreads) nce_grad_x_kernel(const float* _
   for (int j = 0; j < d; ++j) dx[(size_t)i * d + j] = acc[j];
 }
 
+// points in ascending cluster-id order (64-bit ids): stable radix sort by the low word, then by the high word.
+// scratch: keys, pos1, pos2 (N words each) + sort workspace.  Shared with metrics.cu.
+int order_by_cluster_id(const int64_t* cid, int N, uint32_t* keys, int32_t* pos1, int32_t* pos2, int32_t* order, void* sort_ws,
+                        size_t sort_bytes, cudaStream_t st) {
+  const unsigned ng = (unsigned)((N + kLossThreads - 1) / kLossThreads);
+  nce_cid_words_kernel<<<ng, kLossThreads, 0, st>>>(cid, nullptr, N, 0, keys);
+  HEPT_CHECK_LAUNCH("cid_words");
+  if (int rc = segmented_argsort_launch(keys, 1, N, pos1, sort_ws, sort_bytes, st, 32)) return rc;
+  nce_cid_words_kernel<<<ng, kLossThreads, 0, st>>>(cid, pos1, N, 1, keys);
+  HEPT_CHECK_LAUNCH("cid_words");
+  if (int rc = segmented_argsort_launch(keys, 1, N, pos2, sort_ws, sort_bytes, st, 32)) return rc;
+  nce_compose_kernel<<<ng, kLossThreads, 0, st>>>(pos1, pos2, N, order);
+  HEPT_CHECK_LAUNCH("cid_compose");
+  return HEPT_OK;
+}
+
 static size_t nce_scratch_bytes(int N, long long P, bool backward) {
   const size_t blocks = (size_t)((P + kLossThreads - 1) / kLossThreads);
   size_t b = align_up(sizeof(int32_t) * (size_t)N, 256) * 2 + align_up(sizeof(uint32_t) * blocks, 256);   // count, cursor, block maxima
@@ -445,15 +461,7 @@ extern "C" int hept_infonce_fwd(const float* x, int32_t N, int32_t d, const int6
   if (int rc = build_csr(point_pairs, Pi, N, 0, count, cursor, row_ptr, csr, true, st)) return rc;
   nce_point_fwd_kernel<<<ng, kLossThreads, 0, st>>>(row_ptr, csr, s, flag, scal, N, D, lsum, npos);
   HEPT_CHECK_LAUNCH("nce_point_fwd");
-  // points in cluster-id order: stable sort by the low word, then by the high word of the 64-bit id
-  nce_cid_words_kernel<<<ng, kLossThreads, 0, st>>>(cluster_ids, nullptr, N, 0, keys);
-  HEPT_CHECK_LAUNCH("nce_cid_words");
-  if (int rc = segmented_argsort_launch(keys, 1, N, pos1, sort_ws, sort_bytes, st, 32)) return rc;
-  nce_cid_words_kernel<<<ng, kLossThreads, 0, st>>>(cluster_ids, pos1, N, 1, keys);
-  HEPT_CHECK_LAUNCH("nce_cid_words");
-  if (int rc = segmented_argsort_launch(keys, 1, N, pos2, sort_ws, sort_bytes, st, 32)) return rc;
-  nce_compose_kernel<<<ng, kLossThreads, 0, st>>>(pos1, pos2, N, order);
-  HEPT_CHECK_LAUNCH("nce_compose");
+  if (int rc = order_by_cluster_id(cluster_ids, N, keys, pos1, pos2, order, sort_ws, sort_bytes, st)) return rc;
   nce_label_kernel<<<ng, kLossThreads, 0, st>>>(order, cluster_ids, lsum, npos, N, n_label, part_sum, part_cnt);
   HEPT_CHECK_LAUNCH("nce_label");
   nce_final_kernel<<<1, kLossThreads, 0, st>>>(part_sum, part_cnt, (int)ng, scal, loss);

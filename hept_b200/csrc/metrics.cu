@@ -1,0 +1,186 @@
+// SURVEY.md 8(f)-4, second half: the kNN metrics of the tracking task, `acc_and_pr_at_k` + `calc_scores`
+// (src/utils/metrics.py:23-93), on the device.  The reference builds the dense (queries x N) distance matrix with cdist,
+// takes topk(K + 1) per row, copies the indices to the host and scores them in a numba loop; at 60 000 hits that matrix is
+// 14 GB.  Here a CTA of 128 queries streams the candidates through shared memory in tiles; every thread keeps the K + 1
+// nearest of its query (ties: lower index first) and scores them in place:
+//   neighbours = the K nearest after dropping the first (the query itself)               metrics.py:76
+//   k = cluster size - 1 (points with k == 0 are skipped)                               metrics.py:51,72-73
+//   accuracy = matches among the first k / k;  precision = matches / K;  recall = matches / k      metrics.py:84-86
+// and the means over the scored queries come from a fixed-order reduction (deterministic).
+#include "common.cuh"
+
+namespace hept {
+
+int order_by_cluster_id(const int64_t* cid, int N, uint32_t* keys, int32_t* pos1, int32_t* pos2, int32_t* order, void* sort_ws,
+                        size_t sort_bytes, cudaStream_t st);
+
+constexpr int kKnnThreads = 128, kKnnTile = 256, kKnnDim = 16, kKnnMaxK = 32;
+
+// size_of[point] = number of points with the same cluster id (points in cluster-id order)
+__global__ void __launch_bounds__(256) cluster_size_kernel(const int32_t* __restrict__ order, const int64_t* __restrict__ cid, int N,
+                                                           int32_t* __restrict__ size_of) {
+  const int r = blockIdx.x * 256 + threadIdx.x;
+  if (r >= N) return;
+  const int64_t c = cid[order[r]];
+  if (r == 0 || cid[order[r - 1]] != c) {
+    int e = r;
+    while (e < N && cid[order[e]] == c) ++e;
+    for (int u = r; u < e; ++u) size_of[order[u]] = e - r;
+  }
+}
+
+__global__ void __launch_bounds__(256) inv_norm_kernel(const float* __restrict__ x, int d, int N, float* __restrict__ inv) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= N) return;
+  float s = 0.f;
+  for (int j = 0; j < d; ++j) { const float v = x[(size_t)i * d + j]; s = fmaf(v, v, s); }
+  inv[i] = 1.f / fmaxf(sqrtf(s), 1e-8f);
+}
+
+// res (M, 4): accuracy, precision, recall, scored (1 / 0) per query; res_k (M): k of the query (for the reference's K check)
+__global__ void __launch_bounds__(kKnnThreads) knn_scores_kernel(const float* __restrict__ x, int d, int N, const int64_t* __restrict__ queries,
+                                                                 int M, const int64_t* __restrict__ cid, const int32_t* __restrict__ size_of,
+                                                                 const float* __restrict__ inv_norm, int cosine, int K,
+                                                                 float* __restrict__ res, int32_t* __restrict__ res_k) {
+  __shared__ float tile[kKnnTile * kKnnDim];
+  __shared__ float tile_inv[kKnnTile];
+  const int qi = blockIdx.x * kKnnThreads + threadIdx.x;
+  const bool live = qi < M;
+  const int q = live ? (int)queries[qi] : 0;
+  float xq[kKnnDim];
+#pragma unroll
+  for (int j = 0; j < kKnnDim; ++j) xq[j] = (live && j < d) ? __ldg(x + (size_t)q * d + j) : 0.f;
+  const float inv_q = cosine ? __ldg(inv_norm + q) : 0.f;
+  float bd[kKnnMaxK];
+  int bi[kKnnMaxK];
+  const int keep = K + 1;
+  for (int u = 0; u < keep; ++u) { bd[u] = __int_as_float(0x7f800000); bi[u] = -1; }
+  for (int c0 = 0; c0 < N; c0 += kKnnTile) {
+    const int cnt = min(kKnnTile, N - c0);
+    __syncthreads();
+    for (int u = threadIdx.x; u < cnt * d; u += kKnnThreads) {
+      const int c = u / d, j = u - c * d;
+      tile[c * kKnnDim + j] = __ldg(x + (size_t)(c0 + c) * d + j);
+    }
+    if (cosine) for (int u = threadIdx.x; u < cnt; u += kKnnThreads) tile_inv[u] = __ldg(inv_norm + c0 + u);
+    __syncthreads();
+    if (!live) continue;
+    for (int c = 0; c < cnt; ++c) {
+      float acc = 0.f;
+      if (cosine) {
+#pragma unroll
+        for (int j = 0; j < kKnnDim; ++j) acc = fmaf(xq[j], tile[c * kKnnDim + j], acc);     // columns >= d of xq are zero
+        acc = 1.f - acc * inv_q * tile_inv[c];
+      } else {
+#pragma unroll
+        for (int j = 0; j < kKnnDim; ++j) { const float df = j < d ? xq[j] - tile[c * kKnnDim + j] : 0.f; acc = fmaf(df, df, acc); }
+      }
+      if (acc < bd[keep - 1]) {                     // strict: among equal distances the lower index stays in front
+        int u = keep - 1;
+        while (u > 0 && bd[u - 1] > acc) { bd[u] = bd[u - 1]; bi[u] = bi[u - 1]; --u; }
+        bd[u] = acc;
+        bi[u] = c0 + c;
+      }
+    }
+  }
+  if (!live) return;
+  const int k = __ldg(size_of + q) - 1;
+  res_k[qi] = k;
+  float a = 0.f, p = 0.f, r = 0.f, scored = 0.f;
+  if (k > 0) {
+    const int64_t mine = __ldg(cid + q);
+    int m_all = 0, m_k = 0;
+    for (int u = 1; u <= K; ++u) {
+      const bool match = bi[u] >= 0 && __ldg(cid + bi[u]) == mine;
+      m_all += match;
+      if (u <= k) m_k += match;
+    }
+    a = (float)m_k / (float)k;
+    p = (float)m_all / (float)K;
+    r = (float)m_all / (float)k;
+    scored = 1.f;
+  }
+  res[(size_t)qi * 4 + 0] = a;
+  res[(size_t)qi * 4 + 1] = p;
+  res[(size_t)qi * 4 + 2] = r;
+  res[(size_t)qi * 4 + 3] = scored;
+}
+
+// out[0..2] = means of accuracy / precision / recall over the scored queries, out[3] = their number, out[4] = max k
+__global__ void __launch_bounds__(256) knn_reduce_kernel(const float* __restrict__ res, const int32_t* __restrict__ res_k, int M,
+                                                         float* __restrict__ out) {
+  __shared__ double red[4][256];
+  __shared__ int redk[256];
+  double s[4] = {0, 0, 0, 0};
+  int mk = 0;
+  for (int i = threadIdx.x; i < M; i += 256) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) s[c] += (double)res[(size_t)i * 4 + c];
+    mk = max(mk, res_k[i]);
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) red[c][threadIdx.x] = s[c];
+  redk[threadIdx.x] = mk;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) red[c][threadIdx.x] += red[c][threadIdx.x + o];
+      redk[threadIdx.x] = max(redk[threadIdx.x], redk[threadIdx.x + o]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double n = red[3][0];
+    out[0] = (float)(red[0][0] / n);
+    out[1] = (float)(red[1][0] / n);
+    out[2] = (float)(red[2][0] / n);
+    out[3] = (float)n;
+    out[4] = (float)redk[0];
+  }
+}
+
+}  // namespace hept
+
+using namespace hept;
+
+extern "C" size_t hept_knn_metrics_workspace_bytes(int32_t N, int32_t M) {
+  if (N <= 0 || M <= 0) return 0;
+  const size_t nb = align_up(sizeof(int32_t) * (size_t)N, 256);
+  return 6 * nb + align_up(hept_argsort_workspace_bytes(1, N), 256) + align_up(sizeof(float) * 4 * (size_t)M, 256) +
+         align_up(sizeof(int32_t) * (size_t)M, 256);
+}
+
+extern "C" int hept_knn_metrics(const float* x, int32_t N, int32_t d, const int64_t* cluster_ids, const int64_t* queries, int32_t M,
+                                int32_t cosine, int32_t K, float* out, void* workspace, size_t workspace_bytes, void* stream) {
+  HEPT_REQUIRE(x && cluster_ids && queries && out && workspace, HEPT_EINVAL, "knn_metrics: null pointer");
+  HEPT_REQUIRE(N > 0 && M > 0 && d > 0 && d <= kKnnDim && K > 0 && K + 1 <= kKnnMaxK && K + 1 <= N, HEPT_EINVAL,
+               "knn_metrics: bad argument (N=%d M=%d d=%d K=%d)", N, M, d, K);
+  HEPT_REQUIRE(workspace_bytes >= hept_knn_metrics_workspace_bytes(N, M), HEPT_EWORKSPACE, "knn_metrics: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t nb = align_up(sizeof(int32_t) * (size_t)N, 256);
+  char* w = (char*)workspace;
+  uint32_t* keys = (uint32_t*)w;     w += nb;
+  int32_t* pos1 = (int32_t*)w;       w += nb;
+  int32_t* pos2 = (int32_t*)w;       w += nb;
+  int32_t* order = (int32_t*)w;      w += nb;
+  int32_t* size_of = (int32_t*)w;    w += nb;
+  float* inv = (float*)w;            w += nb;
+  void* sort_ws = w;                 const size_t sort_bytes = align_up(hept_argsort_workspace_bytes(1, N), 256);
+  w += sort_bytes;
+  float* res = (float*)w;            w += align_up(sizeof(float) * 4 * (size_t)M, 256);
+  int32_t* res_k = (int32_t*)w;
+  if (int rc = order_by_cluster_id(cluster_ids, N, keys, pos1, pos2, order, sort_ws, sort_bytes, st)) return rc;
+  cluster_size_kernel<<<(N + 255) / 256, 256, 0, st>>>(order, cluster_ids, N, size_of);
+  HEPT_CHECK_LAUNCH("cluster_size");
+  if (cosine) {
+    inv_norm_kernel<<<(N + 255) / 256, 256, 0, st>>>(x, d, N, inv);
+    HEPT_CHECK_LAUNCH("inv_norm");
+  }
+  knn_scores_kernel<<<(M + kKnnThreads - 1) / kKnnThreads, kKnnThreads, 0, st>>>(x, d, N, queries, M, cluster_ids, size_of, inv, cosine, K,
+                                                                                 res, res_k);
+  HEPT_CHECK_LAUNCH("knn_scores");
+  knn_reduce_kernel<<<1, 256, 0, st>>>(res, res_k, M, out);
+  HEPT_CHECK_LAUNCH("knn_reduce");
+  return HEPT_OK;
+}

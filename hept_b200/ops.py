@@ -350,6 +350,21 @@ def infonce_bwd(x, point_pairs, saved, grad_loss, metric: str, tau: float):
     return dx
 
 
+@_on_device
+def knn_metrics(x, cluster_ids, queries, cosine: bool, K: int):
+    """-> 5 floats on the device: mean accuracy, precision, recall, number of scored queries, largest k seen."""
+    lib = _lib.load()
+    x = _need(x, "embeddings", torch.float32)
+    n, d = x.shape
+    cid = _need(cluster_ids, "cluster_ids", torch.int64, (n,))
+    qs = _need(queries, "queries", torch.int64)
+    out = torch.empty(5, dtype=torch.float32, device=x.device)
+    ws = _workspace(lib.hept_knn_metrics_workspace_bytes(n, qs.numel()), x)
+    _lib.check(lib.hept_knn_metrics(_ptr(x), n, d, _ptr(cid), _ptr(qs), qs.numel(), 1 if cosine else 0, K, _ptr(out), _ptr(ws),
+                                    ws.numel(), _stream(x)), "hept_knn_metrics")
+    return out
+
+
 # ------------------------------------------------------------------------------- a13..a17 preparation
 @_on_device
 def prepare_batched(coords, batch, offsets, num_events: int, n_raw: int, n_pad: int, max_event: int, regions_h, block_size: int,

@@ -208,6 +208,15 @@ int hept_infonce_bwd(const float* x, int32_t N, int32_t d, const int64_t* point_
                      const float* grad_loss, const void* saved, size_t saved_bytes, float* dx, void* workspace,
                      size_t workspace_bytes, void* stream);
 
+/* ---- SURVEY.md 8(f)-4, second half: kNN metrics (acc_and_pr_at_k + calc_scores, src/utils/metrics.py:23-93) --------------
+ * x (N, d <= 16) embeddings, cluster_ids (N) int64, queries (M) int64 = the points that pass the reference's mask, in order;
+ * cosine != 0: distance 1 - cos instead of Euclidean; K neighbours after dropping the nearest (the query itself).
+ * out (5 floats, device): mean accuracy, precision, recall over the queries whose cluster has more than one point, their
+ * number, and the largest k = cluster size - 1 seen (the reference asserts it is <= K).  Deterministic. */
+size_t hept_knn_metrics_workspace_bytes(int32_t N, int32_t M);
+int hept_knn_metrics(const float* x, int32_t N, int32_t d, const int64_t* cluster_ids, const int64_t* queries, int32_t M,
+                     int32_t cosine, int32_t K, float* out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* kernel launches this library enqueued (any thread of the process) since the counter was last reset
  * (bench.py's gpu_launches); reset != 0 zeroes the counter after reading it. */
 int hept_launch_count(int reset);

@@ -397,6 +397,29 @@ def infonce_loss(x: Tensor, point_pairs: Tensor, cluster_ids: Tensor, recons: Te
     return segment_reduce_sorted(per_pair, labels, "mean").mean()
 
 
+def knn_metrics(embeddings: Tensor, cluster_ids: Tensor, mask: Tensor, dist_metric: str, K: int = 19):
+    """``acc_and_pr_at_k`` + ``calc_scores`` (src/utils/metrics.py:23-93): for every masked point the K nearest neighbours
+    (after dropping the nearest, the point itself) among ALL points; k = cluster size - 1; accuracy = matches in the first k /
+    k, precision = matches / K, recall = matches / k; points with k == 0 are skipped; means over the rest."""
+    if "l2" in dist_metric:
+        dist = torch.cdist(embeddings[mask], embeddings, p=2.0)
+    else:
+        dist = 1 - torch.nn.functional.cosine_similarity(embeddings[mask].unsqueeze(1), embeddings.unsqueeze(0), dim=-1)
+    uniq, counts = torch.unique(cluster_ids, return_counts=True)
+    size_of = counts[torch.searchsorted(uniq, cluster_ids)]
+    k_list = size_of[mask] - 1
+    assert int(k_list.max()) <= K, f"K is too small, max k is {int(k_list.max())}"
+    idx = dist.topk(K + 1, dim=1, largest=False, sorted=True)[1][:, 1:]
+    matches = cluster_ids[idx] == cluster_ids[mask][:, None]
+    keep = k_list > 0
+    k = k_list[keep].double()
+    in_first_k = (torch.arange(K)[None, :] < k_list[keep][:, None]) & matches[keep]
+    acc = (in_first_k.sum(1).double() / k).mean()
+    prec = (matches[keep].sum(1).double() / K).mean()
+    rec = (matches[keep].sum(1).double() / k).mean()
+    return float(acc), float(prec), float(rec)
+
+
 # --------------------------------------------------------------------------
 # convenience: run fwd+bwd and hand back everything a parity test compares
 # --------------------------------------------------------------------------

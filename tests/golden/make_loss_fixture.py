@@ -52,7 +52,7 @@ def load_reference_losses():
         sys.modules[f"refutils.{name}"] = mod
         spec.loader.exec_module(mod)
         mods[name] = mod
-    return mods["losses"]
+    return mods["losses"], mods["metrics"]
 
 
 def problem(n=1500, dim=12, seed=0, per_point=24):
@@ -76,9 +76,26 @@ def problem(n=1500, dim=12, seed=0, per_point=24):
     return x, pairs, cid, recons, pts
 
 
+def metric_problem(n=1800, dim=12, seed=1):
+    """Embeddings clustered by particle (clusters of 2 .. 14 points, some singletons), cluster ids, and a point mask."""
+    g = torch.Generator().manual_seed(seed)
+    sizes = torch.randint(1, 15, (n,), generator=g)
+    owner = torch.repeat_interleave(torch.arange(n), sizes)[:n]
+    owner = owner[torch.randperm(n, generator=g)]
+    centre = torch.randn(int(owner.max()) + 1, dim, generator=g) * 2.0
+    x = (centre[owner] + 0.3 * torch.randn(n, dim, generator=g)).float().contiguous()
+    cid = (owner.long() + 1) * 4503599627370497 % (1 << 62)
+    mask = torch.rand(n, generator=g) < 0.6
+    return x, cid, mask
+
+
 def main():
-    L = load_reference_losses()
+    L, M = load_reference_losses()
     out = {}
+    x, cid, mask = metric_problem()
+    for metric in ("l2_rbf", "cosine"):
+        out[f"knn_{metric}"] = np.asarray(M.acc_and_pr_at_k(x, cid, mask, metric, K=19), dtype=np.float64)
+    out["meta_chk_knn_x"] = np.asarray(float(x.double().sum()))
     for metric in ("l2_rbf", "l2_inverse", "cosine"):
         x, pairs, cid, recons, pts = problem()
         xr = x.clone().requires_grad_(True)

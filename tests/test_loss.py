@@ -78,3 +78,40 @@ def test_infonce_against_reference_fixture_on_gpu():
         loss.backward()
         assert abs(float(loss) - float(z[f"loss_{metric}"])) <= 1e-5 * abs(float(z[f"loss_{metric}"]))
         assert rel_err(xd.grad.cpu(), torch.from_numpy(z[f"dx_{metric}"])) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------ kNN metrics
+@pytest.mark.parametrize("metric", ["l2_rbf", "cosine"])
+def test_oracle_knn_metrics_match_reference_fixture(metric):
+    z = np.load(os.path.join(GOLDEN, "infonce_small.npz"))
+    x, cid, mask = MLF.metric_problem()
+    assert abs(float(x.double().sum()) - float(z["meta_chk_knn_x"])) < 1e-9 * abs(float(z["meta_chk_knn_x"]))
+    got = O.knn_metrics(x, cid, mask, metric, K=19)
+    assert np.allclose(np.asarray(got), z[f"knn_{metric}"], rtol=0, atol=1e-9)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("metric", ["l2_rbf", "cosine"])
+@pytest.mark.parametrize("n", [1800, 20000])
+def test_knn_metrics_kernel_against_oracle(metric, n):
+    """hept_knn_metrics against the oracle (dense cdist + topk): the neighbour SETS can differ only where two candidates are
+    equally far to rounding (cdist takes the matmul form of the distance), so the three means agree to 1e-4."""
+    from hept_b200 import metrics
+
+    x, cid, mask = MLF.metric_problem(n=n, seed=n)
+    want = O.knn_metrics(x, cid, mask, metric, K=19)
+    got = metrics.acc_and_pr_at_k(x.cuda(), cid.cuda(), mask.cuda(), metric, K=19)
+    assert np.allclose(np.asarray(got), np.asarray(want), rtol=0, atol=1e-4), (got, want)
+    again = metrics.acc_and_pr_at_k(x.cuda(), cid.cuda(), mask.cuda(), metric, K=19)
+    assert got == again
+
+
+@pytest.mark.gpu
+def test_knn_metrics_against_reference_fixture_on_gpu():
+    from hept_b200 import metrics
+
+    z = np.load(os.path.join(GOLDEN, "infonce_small.npz"))
+    x, cid, mask = MLF.metric_problem()
+    for metric in ("l2_rbf", "cosine"):
+        got = metrics.acc_and_pr_at_k(x.cuda(), cid.cuda(), mask.cuda(), metric, K=19)
+        assert np.allclose(np.asarray(got), z[f"knn_{metric}"], rtol=0, atol=1e-4)
