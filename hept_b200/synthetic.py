@@ -92,6 +92,34 @@ def qkv(n: int, cfg: Dict[str, int], seed: int = 0, std: float = 0.5):
     return tuple((torch.randn(n, width, generator=g) * std).contiguous() for _ in range(3))
 
 
+def tracking_truth(n_hits: int, seed: int = 0, random_pairs_per_hit: int = 32):
+    """Synthetic truth of one tracking event for the loss / metrics (src/tracking_trainer.py:26, src/utils/losses.py):
+    ``cluster_ids`` (64-bit particle ids, ~12 hits each, 3 % noise hits with id 0), ``recons`` (0 / 1), ``pts``, and
+    ``point_pairs`` (2, P): every hit paired with its particle mates and with ``random_pairs_per_hit`` other hits (the
+    dataset ships radius-graph pairs capped at 256 per hit, src/datasets/tracking.py:153), shuffled."""
+    g = torch.Generator().manual_seed(seed + 31337)
+    n_part = max(1, n_hits // 12)
+    owner = torch.randint(0, n_part, (n_hits,), generator=g)
+    cid = (owner.long() + 1) * 4503599627370497 % (1 << 62)
+    cid[torch.rand(n_hits, generator=g) < 0.03] = 0
+    recons = (torch.rand(n_hits, generator=g) < 0.9).float()
+    pts = torch.rand(n_hits, generator=g) * 3.0
+    src = torch.arange(n_hits).repeat_interleave(random_pairs_per_hit)
+    dst = torch.randint(0, n_hits, (n_hits * random_pairs_per_hit,), generator=g)
+    order = torch.argsort(owner, stable=True)
+    so = owner[order]
+    mates = []
+    for shift in range(1, 12):                       # hits of one particle are adjacent in `order`
+        same = so[shift:] == so[:-shift]
+        a, b = order[shift:][same], order[:-shift][same]
+        mates.append(torch.stack([a, b]))
+        mates.append(torch.stack([b, a]))
+    pairs = torch.cat([torch.stack([src, dst])] + mates, dim=1)
+    pairs = pairs[:, pairs[0] != pairs[1]]
+    pairs = pairs[:, torch.randperm(pairs.shape[1], generator=g)].contiguous()
+    return cid, recons, pts, pairs
+
+
 def event_sizes(kind: str) -> List[int]:
     """Raw hit counts of the BASELINE.json configs."""
     return {

@@ -87,6 +87,26 @@ if ops.attn_qkv_supported(d.H, d.D):
     q_, k_, v_, xn, wt = ops.attn_qkv_fwd(x, gam, bet, wq, wk, wv, d.H, d.D, 1e-5)
     t["attn_qkv_fwd"] = ev(lambda i: ops.attn_qkv_fwd(x, gam, bet, wq, wk, wv, d.H, d.D, 1e-5))
     t["attn_qkv_bwd"] = ev(lambda i: ops.attn_qkv_bwd(x, xn, gam, wt, S(i)["query"], S(i)["key"], S(i)["value"], d.H, d.D, 1e-5))
+# loss and metrics at this size
+from hept_b200 import metrics as hmetrics
+from hept_b200.losses import InfoNCELoss
+
+cidt, recons, pts, pairs = (a.to(dev) for a in synthetic.tracking_truth(n_raw, 5))
+emb = (torch.randn(n_raw, 12, generator=torch.Generator().manual_seed(9)) * 0.5).to(dev).requires_grad_(True)
+crit = InfoNCELoss(0.05, "l2_rbf")
+t["infonce_fwd"] = ev(lambda i: crit(emb, pairs, cidt, recons, pts))
+
+
+def _fb(i):
+    emb.grad = None
+    crit(emb, pairs, cidt, recons, pts).backward()
+
+
+t["infonce_fwd_bwd"] = ev(_fb)
+t["infonce_pairs"] = float(pairs.shape[1])
+mask = hmetrics.point_filter(cidt, recons, pts, 0.9)
+t["knn_metrics"] = ev(lambda i: hmetrics.acc_and_pr_at_k(emb.detach(), cidt, mask, "l2_rbf"), reps=3)
+t["knn_queries"] = float(mask.sum())
 t = {k: round(v, 1) for k, v in t.items()}
 print(json.dumps(t))
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
