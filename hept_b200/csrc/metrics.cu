@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(kKnnThreads) knn_scores_kernel(const float* __
       float acc = 0.f;
       if (cosine) {
 #pragma unroll
-        for (int j = 0; j < kKnnDim; ++j) acc = fmaf(xq[j], tile[c * kKnnDim + j], acc);     // columns >= d of xq are zero
+        for (int j = 0; j < kKnnDim; ++j) acc = j < d ? fmaf(xq[j], tile[c * kKnnDim + j], acc) : acc;   // (columns >= d of the tile are stale)
         acc = 1.f - acc * inv_q * tile_inv[c];
       } else {
 #pragma unroll
