@@ -55,32 +55,48 @@ __global__ void __launch_bounds__(kKnnThreads) knn_scores_kernel(const float* __
   int bi[kKnnMaxK];
   const int keep = K + 1;
   for (int u = 0; u < keep; ++u) { bd[u] = __int_as_float(0x7f800000); bi[u] = -1; }
+  float worst = __int_as_float(0x7f800000);          // bd[keep - 1], kept in a register
+  auto offer = [&](float dist, int idx) {
+    if (dist < worst) {                               // strict: among equal distances the lower index stays in front
+      int u = keep - 1;
+      while (u > 0 && bd[u - 1] > dist) { bd[u] = bd[u - 1]; bi[u] = bi[u - 1]; --u; }
+      bd[u] = dist;
+      bi[u] = idx;
+      worst = bd[keep - 1];
+    }
+  };
   for (int c0 = 0; c0 < N; c0 += kKnnTile) {
     const int cnt = min(kKnnTile, N - c0);
     __syncthreads();
-    for (int u = threadIdx.x; u < cnt * d; u += kKnnThreads) {
-      const int c = u / d, j = u - c * d;
-      tile[c * kKnnDim + j] = __ldg(x + (size_t)(c0 + c) * d + j);
+    for (int u = threadIdx.x; u < kKnnTile * kKnnDim; u += kKnnThreads) {       // columns >= d and rows >= cnt are zero
+      const int c = u / kKnnDim, j = u - c * kKnnDim;
+      tile[u] = (c < cnt && j < d) ? __ldg(x + (size_t)(c0 + c) * d + j) : 0.f;
     }
-    if (cosine) for (int u = threadIdx.x; u < cnt; u += kKnnThreads) tile_inv[u] = __ldg(inv_norm + c0 + u);
+    if (cosine) for (int u = threadIdx.x; u < kKnnTile; u += kKnnThreads) tile_inv[u] = u < cnt ? __ldg(inv_norm + c0 + u) : 0.f;
     __syncthreads();
     if (!live) continue;
-    for (int c = 0; c < cnt; ++c) {
-      float acc = 0.f;
-      if (cosine) {
+    // four candidates at a time: independent accumulators, 16-byte broadcast reads of the tile
+    for (int c = 0; c < cnt; c += 4) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int j = 0; j < kKnnDim; ++j) acc = j < d ? fmaf(xq[j], tile[c * kKnnDim + j], acc) : acc;   // (columns >= d of the tile are stale)
-        acc = 1.f - acc * inv_q * tile_inv[c];
-      } else {
+      for (int j4 = 0; j4 < kKnnDim / 4; ++j4) {
 #pragma unroll
-        for (int j = 0; j < kKnnDim; ++j) { const float df = j < d ? xq[j] - tile[c * kKnnDim + j] : 0.f; acc = fmaf(df, df, acc); }
+        for (int t = 0; t < 4; ++t) {
+          const float4 v = *reinterpret_cast<const float4*>(tile + (c + t) * kKnnDim + 4 * j4);
+          if (cosine) {
+            acc[t] = fmaf(xq[4 * j4], v.x, acc[t]); acc[t] = fmaf(xq[4 * j4 + 1], v.y, acc[t]);
+            acc[t] = fmaf(xq[4 * j4 + 2], v.z, acc[t]); acc[t] = fmaf(xq[4 * j4 + 3], v.w, acc[t]);
+          } else {
+            float df = xq[4 * j4] - v.x;      acc[t] = fmaf(df, df, acc[t]);
+            df = xq[4 * j4 + 1] - v.y;        acc[t] = fmaf(df, df, acc[t]);
+            df = xq[4 * j4 + 2] - v.z;        acc[t] = fmaf(df, df, acc[t]);
+            df = xq[4 * j4 + 3] - v.w;        acc[t] = fmaf(df, df, acc[t]);
+          }
+        }
       }
-      if (acc < bd[keep - 1]) {                     // strict: among equal distances the lower index stays in front
-        int u = keep - 1;
-        while (u > 0 && bd[u - 1] > acc) { bd[u] = bd[u - 1]; bi[u] = bi[u - 1]; --u; }
-        bd[u] = acc;
-        bi[u] = c0 + c;
-      }
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        if (c + t < cnt) offer(cosine ? 1.f - acc[t] * inv_q * tile_inv[c + t] : acc[t], c0 + c + t);
     }
   }
   if (!live) return;
