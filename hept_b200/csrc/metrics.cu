@@ -37,14 +37,22 @@ __global__ void __launch_bounds__(256) inv_norm_kernel(const float* __restrict__
   inv[i] = 1.f / fmaxf(sqrtf(s), 1e-8f);
 }
 
-// res (M, 4): accuracy, precision, recall, scored (1 / 0) per query; res_k (M): k of the query (for the reference's K check)
-__global__ void __launch_bounds__(kKnnThreads) knn_scores_kernel(const float* __restrict__ x, int d, int N, const int64_t* __restrict__ queries,
+// res (M, 4): accuracy, precision, recall, scored (1 / 0) per query; res_k (M): k of the query (for the reference's K check).
+// A query is scanned by kKnnSlices adjacent lanes (lane s takes the candidates c = s mod kKnnSlices of every tile): one thread
+// per query would leave the GPU with eight warps per SM.  The slices' sorted lists are merged through shared memory by
+// (distance, index), so ties still resolve to the lower index.
+constexpr int kKnnSlices = 8;
+__global__ void __launch_bounds__(kKnnThreads, 6) knn_scores_kernel(const float* __restrict__ x, int d, int N, const int64_t* __restrict__ queries,
                                                                  int M, const int64_t* __restrict__ cid, const int32_t* __restrict__ size_of,
                                                                  const float* __restrict__ inv_norm, int cosine, int K,
                                                                  float* __restrict__ res, int32_t* __restrict__ res_k) {
-  __shared__ float tile[kKnnTile * kKnnDim];
+  __shared__ __align__(16) float sbuf[2 * kKnnThreads * kKnnMaxK];        // the candidate tile, later the merge lists
+  static_assert(2 * kKnnThreads * kKnnMaxK >= kKnnTile * kKnnDim, "the merge lists cover the tile");
   __shared__ float tile_inv[kKnnTile];
-  const int qi = blockIdx.x * kKnnThreads + threadIdx.x;
+  float* tile = sbuf;
+  constexpr int QPC = kKnnThreads / kKnnSlices;          // queries per CTA
+  const int slice = threadIdx.x % kKnnSlices;
+  const int qi = blockIdx.x * QPC + threadIdx.x / kKnnSlices;
   const bool live = qi < M;
   const int q = live ? (int)queries[qi] : 0;
   float xq[kKnnDim];
@@ -54,7 +62,7 @@ __global__ void __launch_bounds__(kKnnThreads) knn_scores_kernel(const float* __
   float bd[kKnnMaxK];
   int bi[kKnnMaxK];
   const int keep = K + 1;
-  for (int u = 0; u < keep; ++u) { bd[u] = __int_as_float(0x7f800000); bi[u] = -1; }
+  for (int u = 0; u < kKnnMaxK; ++u) { bd[u] = __int_as_float(0x7f800000); bi[u] = 0x7fffffff; }
   float worst = __int_as_float(0x7f800000);          // bd[keep - 1], kept in a register
   auto offer = [&](float dist, int idx) {
     if (dist < worst) {                               // strict: among equal distances the lower index stays in front
@@ -75,14 +83,15 @@ __global__ void __launch_bounds__(kKnnThreads) knn_scores_kernel(const float* __
     if (cosine) for (int u = threadIdx.x; u < kKnnTile; u += kKnnThreads) tile_inv[u] = u < cnt ? __ldg(inv_norm + c0 + u) : 0.f;
     __syncthreads();
     if (!live) continue;
-    // four candidates at a time: independent accumulators, 16-byte broadcast reads of the tile
-    for (int c = 0; c < cnt; c += 4) {
+    // four candidates of this lane's slice at a time: independent accumulators, 16-byte reads of the tile
+    for (int c = slice; c < cnt; c += 4 * kKnnSlices) {
       float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int j4 = 0; j4 < kKnnDim / 4; ++j4) {
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
-          const float4 v = *reinterpret_cast<const float4*>(tile + (c + t) * kKnnDim + 4 * j4);
+          const int ct = min(c + t * kKnnSlices, kKnnTile - 1);
+          const float4 v = *reinterpret_cast<const float4*>(tile + ct * kKnnDim + 4 * j4);
           if (cosine) {
             acc[t] = fmaf(xq[4 * j4], v.x, acc[t]); acc[t] = fmaf(xq[4 * j4 + 1], v.y, acc[t]);
             acc[t] = fmaf(xq[4 * j4 + 2], v.z, acc[t]); acc[t] = fmaf(xq[4 * j4 + 3], v.w, acc[t]);
@@ -95,11 +104,38 @@ __global__ void __launch_bounds__(kKnnThreads) knn_scores_kernel(const float* __
         }
       }
 #pragma unroll
-      for (int t = 0; t < 4; ++t)
-        if (c + t < cnt) offer(cosine ? 1.f - acc[t] * inv_q * tile_inv[c + t] : acc[t], c0 + c + t);
+      for (int t = 0; t < 4; ++t) {
+        const int ct = c + t * kKnnSlices;
+        if (ct < cnt) offer(cosine ? 1.f - acc[t] * inv_q * tile_inv[ct] : acc[t], c0 + ct);
+      }
     }
   }
-  if (!live) return;
+  // merge the slices' lists of a query through shared memory: slice 0 picks the K + 1 smallest by (distance, index)
+  __syncthreads();
+  float* md2 = sbuf;
+  int* mi2 = reinterpret_cast<int*>(sbuf + kKnnThreads * kKnnMaxK);
+  for (int u = 0; u < kKnnMaxK; ++u) { md2[threadIdx.x * kKnnMaxK + u] = bd[u]; mi2[threadIdx.x * kKnnMaxK + u] = bi[u]; }
+  __syncthreads();
+  if (!live || slice != 0) return;
+  int head[kKnnSlices];
+#pragma unroll
+  for (int s2 = 0; s2 < kKnnSlices; ++s2) head[s2] = 0;
+  const int base = threadIdx.x * kKnnMaxK;                                 // this query's slices are threads tid .. tid + 7
+  for (int u = 0; u < keep; ++u) {
+    int best = 0;
+    float bdist = md2[base + head[0]];
+    int bidx = mi2[base + head[0]];
+#pragma unroll
+    for (int s2 = 1; s2 < kKnnSlices; ++s2) {
+      const float dd = md2[base + s2 * kKnnMaxK + head[s2]];
+      const int ii = mi2[base + s2 * kKnnMaxK + head[s2]];
+      if (dd < bdist || (dd == bdist && ii < bidx)) { best = s2; bdist = dd; bidx = ii; }
+    }
+#pragma unroll
+    for (int s2 = 0; s2 < kKnnSlices; ++s2) head[s2] += (s2 == best);
+    bd[u] = bdist;
+    bi[u] = bidx;
+  }
   const int k = __ldg(size_of + q) - 1;
   res_k[qi] = k;
   float a = 0.f, p = 0.f, r = 0.f, scored = 0.f;
@@ -107,7 +143,7 @@ __global__ void __launch_bounds__(kKnnThreads) knn_scores_kernel(const float* __
     const int64_t mine = __ldg(cid + q);
     int m_all = 0, m_k = 0;
     for (int u = 1; u <= K; ++u) {
-      const bool match = bi[u] >= 0 && __ldg(cid + bi[u]) == mine;
+      const bool match = bi[u] != 0x7fffffff && __ldg(cid + bi[u]) == mine;
       m_all += match;
       if (u <= k) m_k += match;
     }
@@ -193,7 +229,7 @@ extern "C" int hept_knn_metrics(const float* x, int32_t N, int32_t d, const int6
     inv_norm_kernel<<<(N + 255) / 256, 256, 0, st>>>(x, d, N, inv);
     HEPT_CHECK_LAUNCH("inv_norm");
   }
-  knn_scores_kernel<<<(M + kKnnThreads - 1) / kKnnThreads, kKnnThreads, 0, st>>>(x, d, N, queries, M, cluster_ids, size_of, inv, cosine, K,
+  knn_scores_kernel<<<(M + (kKnnThreads / kKnnSlices) - 1) / (kKnnThreads / kKnnSlices), kKnnThreads, 0, st>>>(x, d, N, queries, M, cluster_ids, size_of, inv, cosine, K,
                                                                                  res, res_k);
   HEPT_CHECK_LAUNCH("knn_scores");
   knn_reduce_kernel<<<1, 256, 0, st>>>(res, res_k, M, out);
