@@ -1,8 +1,8 @@
 // SURVEY.md 8(f)-4, second half: the kNN metrics of the tracking task, `acc_and_pr_at_k` + `calc_scores`
 // (src/utils/metrics.py:23-93), on the device.  The reference builds the dense (queries x N) distance matrix with cdist,
 // takes topk(K + 1) per row, copies the indices to the host and scores them in a numba loop; at 60 000 hits that matrix is
-// 14 GB.  Here a CTA of 128 queries streams the candidates through shared memory in tiles; every thread keeps the K + 1
-// nearest of its query (ties: lower index first) and scores them in place:
+// 14 GB.  Here a CTA of 128 queries streams one slice of the candidates through shared memory in tiles; every thread keeps the
+// K + 1 nearest of its query in that slice (ties: lower index first), a second kernel merges the slices and scores:
 //   neighbours = the K nearest after dropping the first (the query itself)               metrics.py:76
 //   k = cluster size - 1 (points with k == 0 are skipped)                               metrics.py:51,72-73
 //   accuracy = matches among the first k / k;  precision = matches / K;  recall = matches / k      metrics.py:84-86
@@ -37,24 +37,21 @@ __global__ void __launch_bounds__(256) inv_norm_kernel(const float* __restrict__
   inv[i] = 1.f / fmaxf(sqrtf(s), 1e-8f);
 }
 
-// res (M, 4): accuracy, precision, recall, scored (1 / 0) per query; res_k (M): k of the query (for the reference's K check).
-// A query is scanned by kKnnSlices adjacent lanes (lane s takes the candidates c = s mod kKnnSlices of every tile): one thread
-// per query would leave the GPU with eight warps per SM.  The slices' sorted lists are merged through shared memory by
-// (distance, index), so ties still resolve to the lower index.
+// Scan: a CTA = 128 queries (one per thread) x one of kKnnSlices slices of the candidate range (blockIdx.y); the candidates
+// stream through shared memory in tiles shared by the 128 queries.  One slice per query would leave the GPU with eight warps
+// per SM: the slices multiply the CTAs, not the tile loads.  Every (query, slice) leaves its K + 1 nearest, sorted by
+// (distance, index), in `lists`; knn_merge_kernel merges the slices and scores.
 constexpr int kKnnSlices = 8;
-__global__ void __launch_bounds__(kKnnThreads, 6) knn_scores_kernel(const float* __restrict__ x, int d, int N, const int64_t* __restrict__ queries,
-                                                                 int M, const int64_t* __restrict__ cid, const int32_t* __restrict__ size_of,
-                                                                 const float* __restrict__ inv_norm, int cosine, int K,
-                                                                 float* __restrict__ res, int32_t* __restrict__ res_k) {
-  __shared__ __align__(16) float sbuf[2 * kKnnThreads * kKnnMaxK];        // the candidate tile, later the merge lists
-  static_assert(2 * kKnnThreads * kKnnMaxK >= kKnnTile * kKnnDim, "the merge lists cover the tile");
+__global__ void __launch_bounds__(kKnnThreads, 6) knn_scan_kernel(const float* __restrict__ x, int d, int N, const int64_t* __restrict__ queries,
+                                                                  int M, const float* __restrict__ inv_norm, int cosine, int K,
+                                                                  float* __restrict__ list_d, int32_t* __restrict__ list_i) {
+  __shared__ __align__(16) float tile[kKnnTile * kKnnDim];
   __shared__ float tile_inv[kKnnTile];
-  float* tile = sbuf;
-  constexpr int QPC = kKnnThreads / kKnnSlices;          // queries per CTA
-  const int slice = threadIdx.x % kKnnSlices;
-  const int qi = blockIdx.x * QPC + threadIdx.x / kKnnSlices;
+  const int qi = blockIdx.x * kKnnThreads + threadIdx.x;
   const bool live = qi < M;
   const int q = live ? (int)queries[qi] : 0;
+  const int tiles = (N + kKnnTile - 1) / kKnnTile, per = (tiles + kKnnSlices - 1) / kKnnSlices;
+  const int lo = blockIdx.y * per * kKnnTile, hi = min(N, lo + per * kKnnTile);
   float xq[kKnnDim];
 #pragma unroll
   for (int j = 0; j < kKnnDim; ++j) xq[j] = (live && j < d) ? __ldg(x + (size_t)q * d + j) : 0.f;
@@ -73,8 +70,8 @@ __global__ void __launch_bounds__(kKnnThreads, 6) knn_scores_kernel(const float*
       worst = bd[keep - 1];
     }
   };
-  for (int c0 = 0; c0 < N; c0 += kKnnTile) {
-    const int cnt = min(kKnnTile, N - c0);
+  for (int c0 = lo; c0 < hi; c0 += kKnnTile) {
+    const int cnt = min(kKnnTile, hi - c0);
     __syncthreads();
     for (int u = threadIdx.x; u < kKnnTile * kKnnDim; u += kKnnThreads) {       // columns >= d and rows >= cnt are zero
       const int c = u / kKnnDim, j = u - c * kKnnDim;
@@ -83,15 +80,14 @@ __global__ void __launch_bounds__(kKnnThreads, 6) knn_scores_kernel(const float*
     if (cosine) for (int u = threadIdx.x; u < kKnnTile; u += kKnnThreads) tile_inv[u] = u < cnt ? __ldg(inv_norm + c0 + u) : 0.f;
     __syncthreads();
     if (!live) continue;
-    // four candidates of this lane's slice at a time: independent accumulators, 16-byte reads of the tile
-    for (int c = slice; c < cnt; c += 4 * kKnnSlices) {
+    // four candidates at a time: independent accumulators, 16-byte broadcast reads of the tile
+    for (int c = 0; c < cnt; c += 4) {
       float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int j4 = 0; j4 < kKnnDim / 4; ++j4) {
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
-          const int ct = min(c + t * kKnnSlices, kKnnTile - 1);
-          const float4 v = *reinterpret_cast<const float4*>(tile + ct * kKnnDim + 4 * j4);
+          const float4 v = *reinterpret_cast<const float4*>(tile + (c + t) * kKnnDim + 4 * j4);
           if (cosine) {
             acc[t] = fmaf(xq[4 * j4], v.x, acc[t]); acc[t] = fmaf(xq[4 * j4 + 1], v.y, acc[t]);
             acc[t] = fmaf(xq[4 * j4 + 2], v.z, acc[t]); acc[t] = fmaf(xq[4 * j4 + 3], v.w, acc[t]);
@@ -104,36 +100,41 @@ __global__ void __launch_bounds__(kKnnThreads, 6) knn_scores_kernel(const float*
         }
       }
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const int ct = c + t * kKnnSlices;
-        if (ct < cnt) offer(cosine ? 1.f - acc[t] * inv_q * tile_inv[ct] : acc[t], c0 + ct);
-      }
+      for (int t = 0; t < 4; ++t)
+        if (c + t < cnt) offer(cosine ? 1.f - acc[t] * inv_q * tile_inv[c + t] : acc[t], c0 + c + t);
     }
   }
-  // merge the slices' lists of a query through shared memory: slice 0 picks the K + 1 smallest by (distance, index)
-  __syncthreads();
-  float* md2 = sbuf;
-  int* mi2 = reinterpret_cast<int*>(sbuf + kKnnThreads * kKnnMaxK);
-  for (int u = 0; u < kKnnMaxK; ++u) { md2[threadIdx.x * kKnnMaxK + u] = bd[u]; mi2[threadIdx.x * kKnnMaxK + u] = bi[u]; }
-  __syncthreads();
-  if (!live || slice != 0) return;
+  if (!live) return;
+  const size_t base = ((size_t)qi * kKnnSlices + blockIdx.y) * kKnnMaxK;
+  for (int u = 0; u < kKnnMaxK; ++u) { list_d[base + u] = bd[u]; list_i[base + u] = bi[u]; }
+}
+
+// res (M, 4): accuracy, precision, recall, scored (1 / 0) per query; res_k (M): k of the query (for the reference's K check)
+__global__ void __launch_bounds__(kKnnThreads) knn_merge_kernel(const float* __restrict__ list_d, const int32_t* __restrict__ list_i,
+                                                                const int64_t* __restrict__ queries, int M, const int64_t* __restrict__ cid,
+                                                                const int32_t* __restrict__ size_of, int K, float* __restrict__ res,
+                                                                int32_t* __restrict__ res_k) {
+  const int qi = blockIdx.x * kKnnThreads + threadIdx.x;
+  if (qi >= M) return;
+  const int q = (int)queries[qi];
+  const int keep = K + 1;
+  int bi[kKnnMaxK];
   int head[kKnnSlices];
 #pragma unroll
   for (int s2 = 0; s2 < kKnnSlices; ++s2) head[s2] = 0;
-  const int base = threadIdx.x * kKnnMaxK;                                 // this query's slices are threads tid .. tid + 7
-  for (int u = 0; u < keep; ++u) {
+  const size_t base = (size_t)qi * kKnnSlices * kKnnMaxK;
+  for (int u = 0; u < keep; ++u) {                     // slices cover ascending index ranges: ties resolve to the lower slice
     int best = 0;
-    float bdist = md2[base + head[0]];
-    int bidx = mi2[base + head[0]];
+    float bdist = list_d[base + head[0]];
+    int bidx = list_i[base + head[0]];
 #pragma unroll
     for (int s2 = 1; s2 < kKnnSlices; ++s2) {
-      const float dd = md2[base + s2 * kKnnMaxK + head[s2]];
-      const int ii = mi2[base + s2 * kKnnMaxK + head[s2]];
+      const float dd = list_d[base + s2 * kKnnMaxK + head[s2]];
+      const int ii = list_i[base + s2 * kKnnMaxK + head[s2]];
       if (dd < bdist || (dd == bdist && ii < bidx)) { best = s2; bdist = dd; bidx = ii; }
     }
 #pragma unroll
     for (int s2 = 0; s2 < kKnnSlices; ++s2) head[s2] += (s2 == best);
-    bd[u] = bdist;
     bi[u] = bidx;
   }
   const int k = __ldg(size_of + q) - 1;
@@ -200,7 +201,7 @@ extern "C" size_t hept_knn_metrics_workspace_bytes(int32_t N, int32_t M) {
   if (N <= 0 || M <= 0) return 0;
   const size_t nb = align_up(sizeof(int32_t) * (size_t)N, 256);
   return 6 * nb + align_up(hept_argsort_workspace_bytes(1, N), 256) + align_up(sizeof(float) * 4 * (size_t)M, 256) +
-         align_up(sizeof(int32_t) * (size_t)M, 256);
+         align_up(sizeof(int32_t) * (size_t)M, 256) + 2 * align_up(sizeof(float) * (size_t)M * kKnnSlices * kKnnMaxK, 256);
 }
 
 extern "C" int hept_knn_metrics(const float* x, int32_t N, int32_t d, const int64_t* cluster_ids, const int64_t* queries, int32_t M,
@@ -221,7 +222,9 @@ extern "C" int hept_knn_metrics(const float* x, int32_t N, int32_t d, const int6
   void* sort_ws = w;                 const size_t sort_bytes = align_up(hept_argsort_workspace_bytes(1, N), 256);
   w += sort_bytes;
   float* res = (float*)w;            w += align_up(sizeof(float) * 4 * (size_t)M, 256);
-  int32_t* res_k = (int32_t*)w;
+  int32_t* res_k = (int32_t*)w;      w += align_up(sizeof(int32_t) * (size_t)M, 256);
+  float* list_d = (float*)w;         w += align_up(sizeof(float) * (size_t)M * kKnnSlices * kKnnMaxK, 256);
+  int32_t* list_i = (int32_t*)w;
   if (int rc = order_by_cluster_id(cluster_ids, N, keys, pos1, pos2, order, sort_ws, sort_bytes, st)) return rc;
   cluster_size_kernel<<<(N + 255) / 256, 256, 0, st>>>(order, cluster_ids, N, size_of);
   HEPT_CHECK_LAUNCH("cluster_size");
@@ -229,9 +232,11 @@ extern "C" int hept_knn_metrics(const float* x, int32_t N, int32_t d, const int6
     inv_norm_kernel<<<(N + 255) / 256, 256, 0, st>>>(x, d, N, inv);
     HEPT_CHECK_LAUNCH("inv_norm");
   }
-  knn_scores_kernel<<<(M + (kKnnThreads / kKnnSlices) - 1) / (kKnnThreads / kKnnSlices), kKnnThreads, 0, st>>>(x, d, N, queries, M, cluster_ids, size_of, inv, cosine, K,
-                                                                                 res, res_k);
-  HEPT_CHECK_LAUNCH("knn_scores");
+  const unsigned qg = (unsigned)((M + kKnnThreads - 1) / kKnnThreads);
+  knn_scan_kernel<<<dim3(qg, kKnnSlices), kKnnThreads, 0, st>>>(x, d, N, queries, M, inv, cosine, K, list_d, list_i);
+  HEPT_CHECK_LAUNCH("knn_scan");
+  knn_merge_kernel<<<qg, kKnnThreads, 0, st>>>(list_d, list_i, queries, M, cluster_ids, size_of, K, res, res_k);
+  HEPT_CHECK_LAUNCH("knn_merge");
   knn_reduce_kernel<<<1, 256, 0, st>>>(res, res_k, M, out);
   HEPT_CHECK_LAUNCH("knn_reduce");
   return HEPT_OK;
