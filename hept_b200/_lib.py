@@ -64,6 +64,8 @@ SIGNATURES = {
     "hept_infonce_bwd": (C.c_int, [_p, _i32, _i32, _p, C.c_int64, _i32, C.c_float, _p, _p, _sz, _p, _p, _sz, _p]),
     "hept_knn_metrics_workspace_bytes": (_sz, [_i32, _i32]),
     "hept_knn_metrics": (C.c_int, [_p, _i32, _i32, _p, _p, _i32, _i32, _i32, _p, _p, _sz, _p]),
+    "hept_p2p_flag_bytes": (_sz, []),
+    "hept_p2p_allreduce": (C.c_int, [_p, _i32, _i32, C.c_int64, C.c_uint32, C.c_float, _p, _p, _p]),
     "hept_launch_count": (C.c_int, [C.c_int]),
     "hept_set_bwd_stage_mask": (None, [C.c_int]),
     "hept_set_engine": (None, [C.c_int]),

@@ -217,6 +217,16 @@ size_t hept_knn_metrics_workspace_bytes(int32_t N, int32_t M);
 int hept_knn_metrics(const float* x, int32_t N, int32_t d, const int64_t* cluster_ids, const int64_t* queries, int32_t M,
                      int32_t cosine, int32_t K, float* out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- the gradient all-reduce of the data-parallel training step as ONE kernel over NVLink peer memory -----
+ * bufs_dev: device array of `world` base pointers of the ranks' symmetric buffers, each laid out [hept_p2p_flag_bytes() of
+ * flags, zero before the first call | n_floats of data]; n_floats % 4 == 0; seq: a call counter, the same on every rank,
+ * increasing by 1 per call, never 0.  Every rank's data becomes scale * (sum over ranks, in rank order: the same bits on every
+ * rank).  scratch: n_floats of local memory.  *err is set non-zero if a peer does not arrive within ~1 s (the kernel never
+ * hangs).  The mapping of the peers' buffers is the host's business (hept_b200/sharding.py uses torch symmetric memory). */
+size_t hept_p2p_flag_bytes(void);
+int hept_p2p_allreduce(void* const* bufs_dev, int32_t rank, int32_t world, int64_t n_floats, uint32_t seq, float scale,
+                       float* scratch, int32_t* err, void* stream);
+
 /* kernel launches this library enqueued (any thread of the process) since the counter was last reset
  * (bench.py's gpu_launches); reset != 0 zeroes the counter after reading it. */
 int hept_launch_count(int reset);
