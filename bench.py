@@ -211,7 +211,7 @@ def run_ours(args):
     w_rpe = w_rpe.to(dev)
     trainable = [w_rpe.weight, mod.out_linear.weight, mod.out_linear.bias]
     # gradients live in one persistent flat buffer (hept_b200/sharding.py): ONE NCCL launch per step for the collective
-    bucket = sharding.GradBucket(trainable)
+    bucket = sharding.GradBucket(trainable, p2p=not args.nccl)
 
     host = [{k: v.pin_memory() for k, v in e[2].items()} for e in events]
     gouts = [e[3].to(dev) for e in events]
@@ -331,7 +331,7 @@ def run_ours(args):
     norm1 = torch.nn.LayerNorm(cfg["h_dim"]).to(dev)
     w_qkv = [torch.nn.Linear(cfg["h_dim"], cfg["num_heads"] * cfg["h_dim"], bias=False).to(dev) for _ in range(3)]
     front_params = [norm1.weight, norm1.bias] + [w.weight for w in w_qkv]
-    bucket_blk = sharding.GradBucket(trainable + front_params)      # re-homes the three attention parameters' .grad too
+    bucket_blk = sharding.GradBucket(trainable + front_params, p2p=not args.nccl)   # re-homes the three attention parameters' .grad too
     host_x = [{"x": (torch.randn(n_hits, cfg["h_dim"], generator=g0) * 0.7).pin_memory(), "coords": h["coords"],
                "combined_shifts32": h["combined_shifts"].to(torch.int32).pin_memory()} for h in host]
 
@@ -388,7 +388,8 @@ def run_ours(args):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD},
         "details": {"l2": f"inputs rotate over {n_sets} events (~190 MB each) so no step re-reads L2-resident inputs",
-                    "collective": "NCCL all-reduce of parameter gradients per step" if world > 1 else "none",
+                    "collective": ("none" if world == 1 else "one-shot all-reduce of the flat gradient bucket over NVLink peer memory "
+                                   "(hept_p2p_allreduce)" if bucket.uses_p2p else f"NCCL all-reduce (AVG) of the flat gradient bucket ({bucket.p2p_error})"),
                     "tile_engine": engine_name},
         "e2e": e2e_block,
         "e2e_module_boundary": e2e_module,
@@ -407,7 +408,7 @@ def run_ours(args):
         tcfg = {k: v for k, v in synthetic.TRACKING.items() if k != "coords_dim"}
         torch.manual_seed(1234)                         # the same initial weights on every rank
         model = Transformer(in_dim=15, coords_dim=6, **tcfg).to(dev)
-        tbucket = sharding.GradBucket(model.parameters())
+        tbucket = sharding.GradBucket(model.parameters(), p2p=not args.nccl)
         opt = torch.optim.Adam(tbucket.params, lr=1e-3, fused=True)
         tcoords = [synthetic.point_cloud(N_RAW, 6, 1000 + 10 * rank + i).to(dev) for i in range(2)]
         tx = [(torch.randn(N_RAW, 15, generator=torch.Generator().manual_seed(rank + 7 * i)) * 0.5).to(dev) for i in range(2)]
@@ -430,7 +431,7 @@ def run_ours(args):
         ms_t, launches_t = timed(train_step, t_steps, 3)
         line["train_step"] = {"workload": "tracking Transformer (4 HEPT layers) fwd + bwd + Adam, one 60000-hit event per rank per step",
                               "value": world * t_steps * N_RAW / (ms_t * 1e-3), "unit": UNIT, "ms_per_step": ms_t / t_steps,
-                              "allreduce_bytes": tbucket.nbytes if world > 1 else 0, "collective": "one NCCL all-reduce (AVG) of the flat gradient bucket",
+                              "allreduce_bytes": tbucket.nbytes if world > 1 else 0, "collective": "hept_p2p_allreduce (one kernel over NVLink peer memory)" if tbucket.uses_p2p else "one NCCL all-reduce (AVG) of the flat gradient bucket",
                               "native_launches_per_step": launches_t / t_steps,
                               "loss": f"InfoNCE (l2_rbf, tau 0.05) over {truth[0][3].shape[1]} synthetic point pairs, on the library's kernels"}
 
@@ -574,6 +575,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nccl", action="store_true", help="all-reduce the gradient bucket with NCCL instead of the library's NVLink kernel")
     ap.add_argument("--e2e-diag", action="store_true", help="extra end-to-end legs without H2D / D2H (diagnostic)")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step leg (BASELINE.json configs[4])")
     ap.add_argument("--bwd", default=None, type=int, choices=[1, 3, 4, 5], help="backward tile variant (default: library default)")

@@ -13,8 +13,8 @@
 
 namespace hept {
 
-constexpr int kP2pThreads = 512, kP2pMaxCtas = 32, kP2pMaxWorld = 16;
-constexpr size_t kP2pFlagBytes = 2 * kP2pMaxCtas * kP2pMaxWorld * sizeof(uint32_t);      // 4 KB in front of the data
+constexpr int kP2pThreads = 512, kP2pMaxCtas = 64, kP2pMaxWorld = 16;
+constexpr size_t kP2pFlagBytes = 2 * kP2pMaxCtas * kP2pMaxWorld * sizeof(uint32_t);      // 8 KB in front of the data
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
@@ -26,7 +26,7 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 }
 __device__ __forceinline__ float4 ld_peer4(const float* p) {
   float4 v;
-  asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
   return v;
 }
 
@@ -56,11 +56,14 @@ __global__ void __launch_bounds__(kP2pThreads) p2p_allreduce_kernel(uint8_t* con
   const long long lo = blockIdx.x * per, hi = min(n4, lo + per);
   cross_gpu_barrier(bufs, rank, world, 0, ctas, seq, err);                  // every rank's slice is final and visible
   for (long long i = lo + threadIdx.x; i < hi; i += kP2pThreads) {
+    float4 v[kP2pMaxWorld];
+#pragma unroll
+    for (int p = 0; p < kP2pMaxWorld; ++p)                                   // every peer's load in flight before the first add
+      if (p < world) v[p] = ld_peer4(reinterpret_cast<const float*>(bufs[p] + kP2pFlagBytes) + 4 * i);
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int p = 0; p < world; ++p) {                                        // rank order: the same bits on every rank
-      const float4 v = ld_peer4(reinterpret_cast<const float*>(bufs[p] + kP2pFlagBytes) + 4 * i);
-      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-    }
+#pragma unroll
+    for (int p = 0; p < kP2pMaxWorld; ++p)                                   // rank order: the same bits on every rank
+      if (p < world) { s.x += v[p].x; s.y += v[p].y; s.z += v[p].z; s.w += v[p].w; }
     scratch[i] = make_float4(s.x * scale, s.y * scale, s.z * scale, s.w * scale);
   }
   cross_gpu_barrier(bufs, rank, world, 1, ctas, seq, err);                  // every peer has read my slice: it may change now
@@ -80,7 +83,7 @@ extern "C" int hept_p2p_allreduce(void* const* bufs_dev, int32_t rank, int32_t w
   HEPT_REQUIRE(world >= 1 && world <= kP2pMaxWorld && rank >= 0 && rank < world && n_floats > 0 && n_floats % 4 == 0 && seq != 0, HEPT_EINVAL,
                "p2p_allreduce: bad argument (rank=%d world=%d n=%lld seq=%u)", rank, world, (long long)n_floats, seq);
   const long long n4 = n_floats / 4;
-  int ctas = (int)((n4 + 4 * kP2pThreads - 1) / (4 * kP2pThreads));       // ~ four 16-byte elements per thread
+  int ctas = (int)((n4 + kP2pThreads - 1) / kP2pThreads);                 // one 16-byte element per thread up to 64 CTAs
   ctas = ctas < 1 ? 1 : (ctas > kP2pMaxCtas ? kP2pMaxCtas : ctas);
   p2p_allreduce_kernel<<<ctas, kP2pThreads, 0, (cudaStream_t)stream>>>((uint8_t* const*)bufs_dev, rank, world, n4, seq, scale,
                                                                        (float4*)scratch, err);
