@@ -120,6 +120,14 @@ def test_round_robin_event_assignment():
         sharding.events_of_rank(4, 4, 4)
 
 
+def _free_port():
+    import socket
+
+    with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as sock:
+        sock.bind(("127.0.0.1", 0))
+        return sock.getsockname()[1]
+
+
 def _gloo_worker(rank, world, port, out):
     import torch.distributed as dist
 
@@ -143,7 +151,7 @@ def test_gradient_allreduce_two_ranks_gloo():
 
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
-    port = 29500 + os.getpid() % 2000
+    port = _free_port()
     procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, out)) for r in range(2)]
     for p in procs:
         p.start()
@@ -190,7 +198,7 @@ def test_flat_gradient_bucket_two_ranks_gloo():
 
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
-    port = 31500 + os.getpid() % 2000
+    port = _free_port()
     procs = [ctx.Process(target=_bucket_worker, args=(r, 2, port, out)) for r in range(2)]
     for p in procs:
         p.start()
