@@ -98,7 +98,15 @@ HEPT_TRACE_SETTER(hept_debug_trace_bwd)
 #ifndef HEPT_BWD_PROD_WAIT
 #define HEPT_BWD_PROD_WAIT DVDONE
 #endif
-enum BtBar { KFULL, MFULL, MFREE, QREADY, KREADY, DSRDY, DQDONE, PTRDY, DVDONE, DSTRDY, DKDONE, STFREE, BT_NBAR };
+#ifndef HEPT_BWD_SPLIT
+#define HEPT_BWD_SPLIT 0
+#endif
+// HEPT_BWD_SPLIT=1 (experiment, `make VARIANT=split EXTRA=-DHEPT_BWD_SPLIT=1`, tools/ab_split.sh): the three TS products start
+// on the FIRST HALF of their A operand (k-steps [0, HK)) while the epilogue still writes the second half, and dS^T is written
+// back in two halves behind dQ's two halves.  Correct (same bits: the parity suite passes), but SLOWER: 834 us against 805 at
+// 60k hits.  The MMAs that now run under the epilogue's TMEM traffic are stretched by more than the overlap hides — the
+// thread-side TMEM port, not the dependency chain, is what bounds the tile.
+enum BtBar { KFULL, MFULL, MFREE, QREADY, KREADY, DSRDY, DQDONE, PTRDY, DVDONE, DSTRDY, DKDONE, STFREE, PTHALF, DSHALF, DQHALF, DSTHALF, BT_NBAR };
 
 using umma::split4;
 using umma::split_tf32;
@@ -206,6 +214,10 @@ __global__ void __launch_bounds__(kBtThreads, 1)
     umma::mbar_init(&mbar[DSTRDY], EW);
     umma::mbar_init(&mbar[DKDONE], 1);
     umma::mbar_init(&mbar[STFREE], EW);
+    umma::mbar_init(&mbar[PTHALF], EW);
+    umma::mbar_init(&mbar[DSHALF], EW);
+    umma::mbar_init(&mbar[DQHALF], 1);
+    umma::mbar_init(&mbar[DSTHALF], EW);
   }
   if (warp == EW + PW) umma::tmem_alloc<CF::TMEM_COLS>(&tmem_slot);
   if (warp >= EW && warp < EW + PW) {
@@ -247,6 +259,9 @@ __global__ void __launch_bounds__(kBtThreads, 1)
     const int part = warp >> 2;                            // column part of that lane
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     constexpr int MAXCH = (KSTEPS + kBtParts - 1) / kBtParts;   // 8-column chunks per thread
+    constexpr int HK = (KSTEPS + 1) / 2;                        // k-steps of the first half of a TS product
+    constexpr int HCI = (HK - 1) / kBtParts;                    // after chunk iteration HCI every chunk < HK of this thread is done
+    static_assert(HCI < MAXCH, "half split");
     // warp-level arrive: every lane's TMEM stores are complete and fenced before lane 0 signals
     auto arrive_tmem = [&](BtBar b) {
       umma::tmem_wait_st();
@@ -335,6 +350,7 @@ __global__ void __launch_bounds__(kBtThreads, 1)
             umma::tmem_st8(tST + lane_base + 8 * ch, phv);
             umma::tmem_st8(tDPT + lane_base + 8 * ch, plv);
           }
+          if (HEPT_BWD_SPLIT && ci == HCI) arrive_tmem(PTHALF);     // this warp's chunks of k-steps [0, HK) are in TMEM
         }
       }
       arrive_tmem(PTRDY);
@@ -364,6 +380,7 @@ __global__ void __launch_bounds__(kBtThreads, 1)
             umma::tmem_st8(tS + lane_base + 8 * ch, dh);
             umma::tmem_st8(tDP + lane_base + 8 * ch, dl);
           }
+          if (HEPT_BWD_SPLIT && ci == HCI) arrive_tmem(DSHALF);
         }
       }
       arrive_tmem(DSRDY);
@@ -454,13 +471,21 @@ __global__ void __launch_bounds__(kBtThreads, 1)
       if (warp == 0) HEPT_TRACE_EVENT(BE_DVOUT, it);
 
       // ---- dS^T goes where dS was, as soon as dQ has consumed dS; dK then accumulates into tO (dv rows are out) --------
-      umma::mbar_wait(&mbar[DQDONE], ph);
+      umma::mbar_wait(&mbar[HEPT_BWD_SPLIT ? DQHALF : DQDONE], ph);      // dQ has consumed k-steps [0, HK) of dS (or all of it)
       umma::fence_after_sync();
       if (warp == 0) HEPT_TRACE_EVENT(BE_DQDONE, it);
+      bool second_half = false;
+      auto open_second_half = [&]() {                    // the chunks of k-steps >= HK: dQ must be done with ALL of dS
+        arrive_tmem(DSTHALF);                            // (also: this warp has read dV out of tO)
+        umma::mbar_wait(&mbar[DQDONE], ph);
+        umma::fence_after_sync();
+        second_half = true;
+      };
 #pragma unroll
       for (int ci = 0; ci < MAXCH; ++ci) {
         const int ch = part + ci * kBtParts;
         if (ch < KSTEPS) {
+          if (HEPT_BWD_SPLIT && ch >= HK && !second_half) open_second_half();
           float dh[8], dl[8];
 #pragma unroll
           for (int u = 0; u < 8; ++u) trunc_tf32(dsr[ci * 8 + u], dh[u], dl[u]);
@@ -468,6 +493,7 @@ __global__ void __launch_bounds__(kBtThreads, 1)
           umma::tmem_st8(tDP + lane_base + 8 * ch, dl);
         }
       }
+      if (HEPT_BWD_SPLIT && !second_half) open_second_half();
       arrive_tmem(DSTRDY);                               // also: this warp has read dV out of tO
       if (warp == 0) HEPT_TRACE_EVENT(BE_DSTRDY, it);
 
@@ -731,12 +757,13 @@ __global__ void __launch_bounds__(kBtThreads, 1)
     // accumulates into the upper half; the epilogue adds the halves in fp32.  A third fewer MMAs and a third fewer reads
     // of A from TMEM, whose read bandwidth bounds this kernel.  `bh` = the hi tile; its lo tile follows it.
     // Called by the elected lane only.
-    auto ts_product = [&](uint32_t d, uint32_t a_hi, uint32_t a_lo, int bh) {
+    [[maybe_unused]] constexpr int HK = (KSTEPS + 1) / 2;
+    auto ts_product = [&](uint32_t d, uint32_t a_hi, uint32_t a_lo, int bh, int k0, int k1) {
       uint64_t base = mdesc0;
       asm volatile("" : "+l"(base));
       const uint64_t db = base + (uint64_t)((bh * CF::TILE) >> 4);
 #pragma unroll 1
-      for (int kk = 0; kk < KSTEPS; ++kk) {
+      for (int kk = k0; kk < k1; ++kk) {
         umma::mma_ts(d, a_hi + 8 * kk, db + 64 * kk, idesc_o64, kk != 0);
         umma::mma_ts(d + 32, a_lo + 8 * kk, db + 64 * kk, idesc_o, true);
       }
@@ -774,29 +801,67 @@ __global__ void __launch_bounds__(kBtThreads, 1)
     for (; tile < total_tiles; tile += gridDim.x, ++it) {
       const uint32_t ph = it & 1;
       const bool more = tile + (int)gridDim.x < total_tiles;
+#if HEPT_BWD_SPLIT
+      wait(PTHALF, ph);
+      wait(MFULL, ph);
+      HEPT_TRACE_EVENT(BM_DV_GO, it);
+      if (umma::elect_one()) ts_product(tO, tST, tDPT, CF::MGH, 0, HK);          // dV = P^T G', first half of P^T
+      __syncwarp();
+      wait(PTRDY, ph);
+      if (umma::elect_one()) {
+        ts_product(tO, tST, tDPT, CF::MGH, HK, KSTEPS);
+        umma::commit(&mbar[DVDONE]);
+      }
+      __syncwarp();
+      wait(DSHALF, ph);
+      HEPT_TRACE_EVENT(BM_DQ_GO, it);
+      if (umma::elect_one()) {
+        ts_product(tST, tS, tDP, CF::MKH, 0, HK);       // dQ = dS K^: accumulator over the P^T columns dV has consumed
+        umma::commit(&mbar[DQHALF]);                    // k-steps [0, HK) of dS are consumed: dS^T may go there
+      }
+      __syncwarp();
+      wait(DSRDY, ph);
+      if (umma::elect_one()) {
+        ts_product(tST, tS, tDP, CF::MKH, HK, KSTEPS);
+        umma::commit(&mbar[DQDONE]);
+      }
+      __syncwarp();
+      wait(DSTHALF, ph);
+      HEPT_TRACE_EVENT(BM_DK_GO, it);
+      if (umma::elect_one()) ts_product(tO, tS, tDP, CF::MQH, 0, HK);            // dK = dS^T Q^: A where dS was, accumulator where dV was
+      __syncwarp();
+      wait(DSTRDY, ph);
+      if (umma::elect_one()) {
+        ts_product(tO, tS, tDP, CF::MQH, HK, KSTEPS);
+        umma::commit(&mbar[DKDONE]);
+        umma::commit(&mbar[MFREE]);
+      }
+      __syncwarp();
+#else
       wait(PTRDY, ph);
       wait(MFULL, ph);
       HEPT_TRACE_EVENT(BM_DV_GO, it);
       if (umma::elect_one()) {
-        ts_product(tO, tST, tDPT, CF::MGH);             // dV = P^T G'
+        ts_product(tO, tST, tDPT, CF::MGH, 0, KSTEPS);  // dV = P^T G'
         umma::commit(&mbar[DVDONE]);
       }
       __syncwarp();
       wait(DSRDY, ph);
       HEPT_TRACE_EVENT(BM_DQ_GO, it);
       if (umma::elect_one()) {
-        ts_product(tST, tS, tDP, CF::MKH);              // dQ = dS K^: accumulator over the P^T columns dV has consumed
+        ts_product(tST, tS, tDP, CF::MKH, 0, KSTEPS);   // dQ = dS K^: accumulator over the P^T columns dV has consumed
         umma::commit(&mbar[DQDONE]);
       }
       __syncwarp();
       wait(DSTRDY, ph);
       HEPT_TRACE_EVENT(BM_DK_GO, it);
       if (umma::elect_one()) {
-        ts_product(tO, tS, tDP, CF::MQH);               // dK = dS^T Q^: A where dS was, accumulator where dV was (read out)
+        ts_product(tO, tS, tDP, CF::MQH, 0, KSTEPS);    // dK = dS^T Q^: A where dS was, accumulator where dV was (read out)
         umma::commit(&mbar[DKDONE]);
         umma::commit(&mbar[MFREE]);
       }
       __syncwarp();
+#endif
       // The next tile's key-side scores (the epilogue starts with them) overwrite tST / tDPT, where dQ accumulated: they
       // wait for the epilogue to read dq out; the query-side scores follow (tS / tDP: behind dK in pipe order).
       if (more) {
