@@ -32,11 +32,8 @@ constexpr int kSortWarps = kSortThreads / 32;
 #ifndef HEPT_SORT_BLOCKS
 #define HEPT_SORT_BLOCKS 3
 #endif
-constexpr int kItemsLarge = HEPT_SORT_ITEMS;                 // 4096 keys per CTA: the 2 T H segments of an attention call
-constexpr int kItemsSmall = 4;                               // 1024 keys per CTA: sorts of a few hundred thousand keys in all (the
-                                                             // rank sorts of prepare.cu) are bound by the serial ranking chain of
-                                                             // a CTA, not by throughput: shorter chains, four times the CTAs
-constexpr long long kSmallSortKeys = 400000;
+constexpr int kItemsPerThread = HEPT_SORT_ITEMS;
+constexpr int kTile = kSortThreads * kItemsPerThread;  // 4096 keys per CTA
 
 // lanes of the warp whose (valid, 8-bit digit) equals mine, from nine ballots.  __match_any_sync gives the same mask
 // but its cost grows with the number of distinct values in the warp (measured: the low-byte passes, where all 32
@@ -59,11 +56,9 @@ __device__ __forceinline__ uint32_t load_key(const void* keys, size_t i, bool as
 }
 
 // tile_hist (segments, tiles, 256)
-template <int kItemsPerThread>
 __global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const void* __restrict__ keys, bool as_float, int n,
                                                                    int tiles, int shift,
                                                                    uint32_t* __restrict__ tile_hist) {
-  constexpr int kTile = kSortThreads * kItemsPerThread;
   __shared__ uint32_t hist[kRadix];
   const int tile = blockIdx.x, seg = blockIdx.y;
   hist[threadIdx.x] = 0;
@@ -88,14 +83,12 @@ __global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const void* __
 
 // keys_in/idx_in -> keys_out/idx_out.  idx_in == nullptr means the identity (first pass);
 // keys_out == nullptr means the keys are no longer needed (last pass).
-template <int kItemsPerThread>
 __global__ void __launch_bounds__(kSortThreads, HEPT_SORT_BLOCKS) radix_scatter_kernel(const void* __restrict__ keys_in, bool as_float,
                                                                       const int32_t* __restrict__ idx_in, int n,
                                                                       int tiles, int shift,
                                                                       const uint32_t* __restrict__ tile_hist,
                                                                       uint32_t* __restrict__ keys_out,
                                                                       int32_t* __restrict__ idx_out) {
-  constexpr int kTile = kSortThreads * kItemsPerThread;
   __shared__ uint32_t warp_off[kSortWarps][kRadix];   // per-warp digit counts, then tile-local start offsets
   __shared__ uint32_t scan_tmp[kRadix];
   __shared__ uint32_t local_start[kRadix];            // first tile-local slot of each digit
@@ -356,12 +349,8 @@ struct SortPlan {
 int segmented_argsort_launch(const void* keys, int32_t num_segments, int32_t n, int32_t* positions, void* workspace,
                              size_t workspace_bytes, cudaStream_t st, int key_bits = 0);
 
-static int sort_tile(int segments, int n) {
-  return kSortThreads * ((long long)segments * n <= kSmallSortKeys ? kItemsSmall : kItemsLarge);
-}
 static SortPlan plan_sort(int segments, int n) {
   SortPlan p;
-  const int kTile = sort_tile(segments, n);
   p.tiles = (n + kTile - 1) / kTile;
   p.hist_bytes = align_up(sizeof(uint32_t) * (size_t)segments * p.tiles * kRadix, 256);
   p.keys_bytes = align_up(sizeof(uint32_t) * (size_t)segments * n, 256);
@@ -432,23 +421,18 @@ int hept::segmented_argsort_launch(const void* keys_v, int32_t num_segments, int
   uint32_t* kbuf[2] = {(uint32_t*)w, (uint32_t*)(w + p.keys_bytes)};  w += 2 * p.keys_bytes;
   int32_t* ibuf[2] = {(int32_t*)w, (int32_t*)(w + p.idx_bytes)};
   dim3 grid(p.tiles, num_segments);
-  const bool small = sort_tile(num_segments, n) == kSortThreads * kItemsSmall;
   const int passes = key_bits > 0 ? (key_bits + kRadixBits - 1) / kRadixBits : 32 / kRadixBits;
   const void* kin = keys;
   const int32_t* iin = nullptr;
   for (int pass = 0; pass < passes; ++pass) {
     const bool first = pass == 0, last = pass == passes - 1;
     const bool as_float = first && key_bits == 0;
+    radix_hist_kernel<<<grid, kSortThreads, 0, st>>>(kin, as_float, n, p.tiles, pass * kRadixBits, hist);
+    HEPT_CHECK_LAUNCH("radix_hist");
     uint32_t* kout = last ? nullptr : kbuf[pass & 1];
     int32_t* iout = last ? positions : ibuf[pass & 1];
-    if (small) {
-      radix_hist_kernel<kItemsSmall><<<grid, kSortThreads, 0, st>>>(kin, as_float, n, p.tiles, pass * kRadixBits, hist);
-      radix_scatter_kernel<kItemsSmall><<<grid, kSortThreads, 0, st>>>(kin, as_float, iin, n, p.tiles, pass * kRadixBits, hist, kout, iout);
-    } else {
-      radix_hist_kernel<kItemsLarge><<<grid, kSortThreads, 0, st>>>(kin, as_float, n, p.tiles, pass * kRadixBits, hist);
-      radix_scatter_kernel<kItemsLarge><<<grid, kSortThreads, 0, st>>>(kin, as_float, iin, n, p.tiles, pass * kRadixBits, hist, kout, iout);
-    }
-    HEPT_CHECK_LAUNCH("radix_hist");
+    radix_scatter_kernel<<<grid, kSortThreads, 0, st>>>(kin, as_float, iin, n, p.tiles, pass * kRadixBits, hist, kout,
+                                                        iout);
     HEPT_CHECK_LAUNCH("radix_scatter");
     kin = kout;
     iin = iout;
