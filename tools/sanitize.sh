@@ -6,12 +6,12 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_gpu_parity.py tests/test_gpu_umma.py tests/test_prepare.py \
-    tests/test_attn_front.py -x -q -m gpu \
-    -k "(tiny_example or tiny_src or small_batched or small_src or umma or 57 or 130 or 127 or 1300) and not headline and not cluster_sizes" \
+    tests/test_attn_front.py tests/test_loss.py -x -q -m gpu \
+    -k "(tiny_example or tiny_src or small_batched or small_src or umma or 57 or 130 or 127 or 1300 or 300-3 or 1800 or fixture_on_gpu) and not headline and not cluster_sizes" \
     > gpurun_out/sanitizer_memcheck.log 2>&1
 echo "memcheck exit $?" >> gpurun_out/sanitizer_memcheck.log
-compute-sanitizer --tool racecheck --error-exitcode 7 python -m pytest tests/test_gpu_parity.py tests/test_prepare.py tests/test_attn_front.py -x -q -m gpu \
-    -k "(out_linear and 1300) or (projection and small_batched) or coord_scale or (argsort and 4097) or 130 or (attn_front and 1300)" \
+compute-sanitizer --tool racecheck --error-exitcode 7 python -m pytest tests/test_gpu_parity.py tests/test_prepare.py tests/test_attn_front.py tests/test_loss.py -x -q -m gpu \
+    -k "(out_linear and 1300) or (projection and small_batched) or coord_scale or (argsort and 4097) or 130 or (attn_front and 1300) or 300-3 or (knn and 1800)" \
     > gpurun_out/sanitizer_racecheck.log 2>&1
 echo "racecheck exit $?" >> gpurun_out/sanitizer_racecheck.log
 tail -n 6 gpurun_out/sanitizer_memcheck.log gpurun_out/sanitizer_racecheck.log
