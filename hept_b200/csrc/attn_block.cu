@@ -17,6 +17,7 @@
 //   weight gradients     dW_m = dq_m^T xn: the out_linear parameter-gradient kernels (out_linear.cu) with the roles of the
 //                        operands exchanged, result written transposed
 #include "common.cuh"
+#include "mma_tf32.cuh"
 
 namespace hept {
 
@@ -135,34 +136,44 @@ __global__ void __launch_bounds__(kAbThreads, 4) ln_qkv_fwd_kernel(const float* 
 // dxn = dq Wq + dk Wk + dv Wv, then the LayerNorm backward.  thread = (hq = tid / 4, og = tid % 4): hits hq + 64 t x outputs
 // [PER og, PER og + PER), PER = DM / 4; the four threads of a hit are adjacent lanes.
 constexpr int kAbBwdHits = 256, kAbBwdThreads = 256;   // two CTAs of 8 warps per SM: a 60k-hit event is ONE wave of 235 CTAs
+constexpr int kAbBwdKc = 24, kAbBwdStages = 3;         // ring of three 24-column chunks: 94 KB per CTA
 template <int DM, int OW>
 __global__ void __launch_bounds__(kAbBwdThreads, 2) ln_qkv_bwd_input_kernel(const float* __restrict__ dq, const float* __restrict__ dk,
                                                                          const float* __restrict__ dv, const float* __restrict__ wt,
                                                                          const float* __restrict__ x, const float* __restrict__ gamma,
                                                                          int N, float eps, float* __restrict__ dx,
                                                                          float* __restrict__ partial) {
-  constexpr int KC = 48, NCH = OW / KC, XS = KC + 4, WS = OW + 4, PER = DM / 4;
-  static_assert(OW % KC == 0 && DM % 4 == 0 && PER % 2 == 0, "tile shape");
-  extern __shared__ __align__(16) float s_dyn[];
-  float* s_w = s_dyn;                              // (3, DM, WS)
-  float* s_x = s_w + 3 * DM * WS;                  // (kAbBwdHits, XS) one chunk of gradient rows
-  float* s_red = s_x;                              // reused at the end: (64, 2 DM) per-hit-group sums of d gamma / d beta
+  constexpr int KC = kAbBwdKc, NCH = OW / KC, XS = KC + 4, PER = DM / 4, STAGES = kAbBwdStages;
+  constexpr int STAGE = (kAbBwdHits + DM) * XS;    // floats per ring slot: the gradient rows' chunk | the weights' chunk
+  static_assert(OW % KC == 0 && DM % 4 == 0 && PER % 2 == 0 && KC % 4 == 0, "tile shape");
+  static_assert(STAGES * STAGE >= 64 * 2 * DM, "the ring doubles as the reduction buffer");
+  extern __shared__ __align__(16) float s_dyn[];   // STAGES x [ (kAbBwdHits, XS) | (DM, XS) ]: a ring over the 3 NCH chunks; the
+                                                   // loads of STAGES - 1 chunks are in flight while one is consumed
+  float* s_red = s_dyn;                            // reused at the end: (64, 2 DM) per-hit-group sums of d gamma / d beta
   const int tid = threadIdx.x, hq = tid >> 2, og = tid & 3;
   const int n0 = blockIdx.x * kAbBwdHits;
   const int rows = min(kAbBwdHits, N - n0);
   auto load_chunk = [&](int ch) {
     const int m = ch / NCH, kc = ch - m * NCH;
+    float* sx = s_dyn + (ch % STAGES) * STAGE;
+    float* sw = sx + kAbBwdHits * XS;
     const float* src = m == 0 ? dq : (m == 1 ? dk : dv);
     for (int i = tid; i < kAbBwdHits * (KC / 4); i += kAbBwdThreads) {
       const int r = i / (KC / 4), c4 = i - r * (KC / 4);
-      if (r < rows) cp_async16_cg(s_x + r * XS + 4 * c4, src + (size_t)(n0 + r) * OW + kc * KC + 4 * c4);
+      if (r < rows) cp_async16_cg(sx + r * XS + 4 * c4, src + (size_t)(n0 + r) * OW + kc * KC + 4 * c4);
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
+    for (int i = tid; i < DM * (KC / 4); i += kAbBwdThreads) {     // Wt[m][j][kc KC ..): L2-resident, 55 KB in all
+      const int j = i / (KC / 4), c4 = i - j * (KC / 4);
+      cp_async16_cg(sw + j * XS + 4 * c4, wt + ((size_t)m * DM + j) * OW + kc * KC + 4 * c4);
+    }
   };
-  load_chunk(0);
-  for (int i = tid; i < 3 * DM * (OW / 4); i += kAbBwdThreads) {
-    const int mj = i / (OW / 4), c4 = i - mj * (OW / 4);
-    *reinterpret_cast<float4*>(s_w + mj * WS + 4 * c4) = ldg4(wt + (size_t)mj * OW + 4 * c4);
+  if (rows < kAbBwdHits)                           // a short last tile: its dead rows are read by the FMAs below (and dropped)
+    for (int i = tid; i < STAGES * STAGE; i += kAbBwdThreads) s_dyn[i] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int pre = 0; pre < STAGES - 1; ++pre) {     // one commit group per chunk, empty ones included: the waits count groups
+    if (pre < 3 * NCH) load_chunk(pre);
+    asm volatile("cp.async.commit_group;" ::: "memory");
   }
   float2 acc[4][PER];
 #pragma unroll
@@ -171,19 +182,20 @@ __global__ void __launch_bounds__(kAbBwdThreads, 2) ln_qkv_bwd_input_kernel(cons
     for (int t = 0; t < 4; ++t) acc[t][u] = make_float2(0.f, 0.f);
 #pragma unroll 1
   for (int ch = 0; ch < 3 * NCH; ++ch) {
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
-    const int m = ch / NCH, kc = ch - m * NCH;
-    const float* xs = s_x + hq * XS;
-    const float* ws = s_w + (m * DM + og * PER) * WS + kc * KC;
-#pragma unroll 4
+    asm volatile("cp.async.wait_group %0;" :: "n"(STAGES - 2) : "memory");
+    __syncthreads();                               // chunk ch has landed for every thread; the slot of chunk ch - 1 is free
+    if (ch + STAGES - 1 < 3 * NCH) load_chunk(ch + STAGES - 1);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    const float* xs = s_dyn + (ch % STAGES) * STAGE + hq * XS;
+    const float* ws = s_dyn + (ch % STAGES) * STAGE + kAbBwdHits * XS + og * PER * XS;
+#pragma unroll
     for (int c4 = 0; c4 < KC / 4; ++c4) {
       float4 xv[4];
 #pragma unroll
       for (int t = 0; t < 4; ++t) xv[t] = *reinterpret_cast<const float4*>(xs + 64 * t * XS + 4 * c4);
 #pragma unroll
       for (int u = 0; u < PER; ++u) {
-        const float4 wv = *reinterpret_cast<const float4*>(ws + u * WS + 4 * c4);
+        const float4 wv = *reinterpret_cast<const float4*>(ws + u * XS + 4 * c4);
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           acc[t][u] = __ffma2_rn(make_float2(xv[t].x, xv[t].y), make_float2(wv.x, wv.y), acc[t][u]);
@@ -191,9 +203,8 @@ __global__ void __launch_bounds__(kAbBwdThreads, 2) ln_qkv_bwd_input_kernel(cons
         }
       }
     }
-    __syncthreads();
-    if (ch + 1 < 3 * NCH) load_chunk(ch + 1);
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   // LayerNorm backward of each hit: y = xhat gamma + beta, xhat = (x - mean) rstd
   //   dx = rstd (g - mean(g) - xhat mean(g xhat)), g = dxn gamma;  d gamma += dxn xhat;  d beta += dxn
   float gam[PER], dgam[PER], dbet[PER];
@@ -266,6 +277,185 @@ __global__ void __launch_bounds__(kAbBwdThreads, 2) ln_qkv_bwd_input_kernel(cons
   }
 }
 
+// The same on the legacy tensor path (mma_tf32.cuh): dxn (hits x DM) = [dq | dk | dv] (hits x 3 OW) * [Wq; Wk; Wv] (3 OW x DM).
+// One persistent CTA of 16 warps per SM; a warp owns 16-hit tiles (tile = blockIdx.x + gridDim.x (warp + 16 j): every SM gets
+// the same number of tiles to within one) and needs no CTA barrier inside the loop:
+//   B  the three weights, split into tf32 hi / lo ONCE per CTA and parked in shared memory in fragment order:
+//      s_b[k-step][n-tile][lane] = {b0 hi, b0 lo, b1 hi, b1 lo} -- one conflict-free 128-bit load per (k-step, n-tile)
+//   A  the gradient rows, read straight from global memory: within a block of 32 columns lane t of a row's quad holds the
+//      columns 4 t .. 4 t + 3 (k-slot t of k-steps 0 .. 3) and 16 + 4 t .. (k-slot t + 4) -- K is the contraction index, any
+//      bijection will do, and this one makes every load a full 16-byte vector, a row's quad cover whole sectors.  Three
+//      blocks (12 vectors per thread) are in flight ahead of the one being multiplied.
+//   C  a thread ends with 6 of the 24 dxn of two hits (the C fragment); the four lanes of a quad share a hit exactly as in
+//      the CUDA-core kernel above, and the LayerNorm backward / d gamma / d beta follow it line by line.
+constexpr int kAbMmaWarps = 16, kAbMmaThreads = 32 * kAbMmaWarps, kAbMmaTile = 16, kAbMmaAhead = 3;
+template <int DM, int OW>
+constexpr size_t ln_qkv_bwd_mma_smem_bytes() { return sizeof(uint4) * (3 * OW / 8) * (DM / 8) * 32; }
+
+template <int DM, int OW>
+__global__ void __launch_bounds__(kAbMmaThreads, 1) ln_qkv_bwd_input_mma_kernel(const float* __restrict__ dq, const float* __restrict__ dk,
+                                                                              const float* __restrict__ dv, const float* __restrict__ wt,
+                                                                              const float* __restrict__ x, const float* __restrict__ gamma,
+                                                                              int N, float eps, float* __restrict__ dx,
+                                                                              float* __restrict__ partial) {
+  constexpr int NT = DM / 8, KB = OW / 32, KS = 3 * OW / 8;       // n-tiles, 32-column blocks per matrix, k-steps in all
+  static_assert(DM % 8 == 0 && OW % 32 == 0, "tile shape");
+  static_assert(KS * NT * 32 * 4 >= kAbMmaWarps * 2 * DM, "the fragment store doubles as the reduction buffer");
+  extern __shared__ __align__(16) uint4 s_b[];                     // (KS, NT, 32)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gq = lane >> 2, t = lane & 3;
+  for (int i = tid; i < KS * NT * 32; i += kAbMmaThreads) {
+    const int l = i & 31, nt = (i >> 5) % NT, ks = i / (32 * NT);
+    const int m = ks / (OW / 8), kk = ks - m * (OW / 8);
+    const int k0 = 32 * (kk >> 2) + 4 * (l & 3) + (kk & 3), n = 8 * nt + (l >> 2);
+    const float* wrow = wt + ((size_t)m * DM + n) * OW;            // Wt[m][n][k] = W_m[k][n]
+    uint4 v;
+    split_tf32(__ldg(wrow + k0), v.x, v.y);
+    split_tf32(__ldg(wrow + k0 + 16), v.z, v.w);
+    s_b[i] = v;
+  }
+  __syncthreads();
+  float gam[NT][2], dgam[NT][2], dbet[NT][2];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) { gam[nt][e] = __ldg(gamma + 8 * nt + 2 * t + e); dgam[nt][e] = 0.f; dbet[nt][e] = 0.f; }
+  const int tiles = (N + kAbMmaTile - 1) / kAbMmaTile;
+#pragma unroll 1
+  for (int tile = blockIdx.x + gridDim.x * warp; tile < tiles; tile += gridDim.x * kAbMmaWarps) {
+    const int ra = tile * kAbMmaTile + gq, rb = ra + 8;
+    const bool la = ra < N, lb = rb < N;
+    const size_t oa = (size_t)(la ? ra : 0) * OW + 4 * t, ob = (size_t)(lb ? rb : 0) * OW + 4 * t;   // dead rows read row 0, dropped below
+    float acc[NT][4];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
+    float4 ring[kAbMmaAhead][4];                                    // [block in flight][row a slot t, row b slot t, row a slot t + 4, row b slot t + 4]
+    auto load_block = [&](int blk, float4 (&dst)[4]) {
+      const int m = blk / KB, kb = blk - m * KB;
+      const float* src = m == 0 ? dq : (m == 1 ? dk : dv);
+      dst[0] = ldg4(src + oa + 32 * kb);
+      dst[1] = ldg4(src + ob + 32 * kb);
+      dst[2] = ldg4(src + oa + 32 * kb + 16);
+      dst[3] = ldg4(src + ob + 32 * kb + 16);
+    };
+#pragma unroll
+    for (int pre = 0; pre < kAbMmaAhead; ++pre) load_block(pre, ring[pre]);
+#pragma unroll
+    for (int blk = 0; blk < 3 * KB; ++blk) {
+      float4 cur[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) cur[e] = ring[blk % kAbMmaAhead][e];
+      if (blk + kAbMmaAhead < 3 * KB) load_block(blk + kAbMmaAhead, ring[blk % kAbMmaAhead]);
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        uint32_t ah[4], al[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float v = s == 0 ? cur[e].x : (s == 1 ? cur[e].y : (s == 2 ? cur[e].z : cur[e].w));
+          split_tf32(v, ah[e], al[e]);
+        }
+        uint4 b[NT];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) b[nt] = s_b[((blk * 4 + s) * NT + nt) * 32 + lane];
+        // the small terms first; product kind outermost, so that consecutive mma write different accumulators
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) mma_tf32(acc[nt], al, b[nt].x, b[nt].z);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) mma_tf32(acc[nt], ah, b[nt].y, b[nt].w);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) mma_tf32(acc[nt], ah, b[nt].x, b[nt].z);
+      }
+    }
+    // LayerNorm backward of the two hits: y = xhat gamma + beta, xhat = (x - mean) rstd
+    //   dx = rstd (g - mean(g) - xhat mean(g xhat)), g = dxn gamma;  d gamma += dxn xhat;  d beta += dxn
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int r = h == 0 ? ra : rb;
+      const bool live = h == 0 ? la : lb;
+      float xv[NT][2], dxn[NT][2];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const float2 tt = live ? ldg2(x + (size_t)r * DM + 8 * nt + 2 * t) : make_float2(0.f, 0.f);
+        xv[nt][0] = tt.x; xv[nt][1] = tt.y;
+        dxn[nt][0] = acc[nt][2 * h]; dxn[nt][1] = acc[nt][2 * h + 1];
+      }
+      float sum = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) sum += xv[nt][0] + xv[nt][1];
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      const float mean = sum * (1.f / DM);
+      float vs = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) { const float dlt = xv[nt][e] - mean; vs = fmaf(dlt, dlt, vs); }
+      vs += __shfl_xor_sync(0xffffffffu, vs, 1);
+      vs += __shfl_xor_sync(0xffffffffu, vs, 2);
+      const float rstd = 1.f / sqrtf(vs * (1.f / DM) + eps);
+      float xh[NT][2], gg[NT][2], m1 = 0.f, m2 = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          xh[nt][e] = (xv[nt][e] - mean) * rstd;
+          gg[nt][e] = dxn[nt][e] * gam[nt][e];
+          m1 += gg[nt][e];
+          m2 = fmaf(gg[nt][e], xh[nt][e], m2);
+        }
+      m1 += __shfl_xor_sync(0xffffffffu, m1, 1);
+      m1 += __shfl_xor_sync(0xffffffffu, m1, 2);
+      m2 += __shfl_xor_sync(0xffffffffu, m2, 1);
+      m2 += __shfl_xor_sync(0xffffffffu, m2, 2);
+      m1 *= 1.f / DM;
+      m2 *= 1.f / DM;
+      if (live) {
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          float o[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            o[e] = rstd * (gg[nt][e] - m1 - xh[nt][e] * m2);
+            dgam[nt][e] = fmaf(dxn[nt][e], xh[nt][e], dgam[nt][e]);
+            dbet[nt][e] += dxn[nt][e];
+          }
+          *reinterpret_cast<float2*>(dx + (size_t)r * DM + 8 * nt + 2 * t) = make_float2(o[0], o[1]);
+        }
+      }
+    }
+  }
+  // the CTA's sums: the eight row lanes of a column in butterfly order, then the warps in order (fixed: deterministic)
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+    for (int e = 0; e < 2; ++e)
+#pragma unroll
+      for (int sh = 4; sh < 32; sh <<= 1) {
+        dgam[nt][e] += __shfl_xor_sync(0xffffffffu, dgam[nt][e], sh);
+        dbet[nt][e] += __shfl_xor_sync(0xffffffffu, dbet[nt][e], sh);
+      }
+  __syncthreads();                                                 // every warp is done with the fragment store
+  float* s_red = reinterpret_cast<float*>(s_b);                    // (warps, 2 DM)
+  if (gq == 0) {
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        s_red[warp * 2 * DM + 8 * nt + 2 * t + e] = dgam[nt][e];
+        s_red[warp * 2 * DM + DM + 8 * nt + 2 * t + e] = dbet[nt][e];
+      }
+  }
+  __syncthreads();
+  if (tid < 2 * DM) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < kAbMmaWarps; ++w) s += s_red[w * 2 * DM + tid];
+    partial[(size_t)blockIdx.x * 2 * DM + tid] = s;
+  }
+}
+
 // d gamma / d beta = fixed-order sum over the CTAs' partials (ctas, 2 DM): one CTA, tree over 256 strided sums
 __global__ void __launch_bounds__(256) ln_params_reduce_kernel(const float* __restrict__ partial, int ctas, int DM,
                                                                float* __restrict__ dgamma, float* __restrict__ dbeta) {
@@ -306,8 +496,7 @@ template <int DM, int OW>
 static int launch_qkv_bwd(const float* x, const float* xn, const float* gamma, const float* wt, const float* dq, const float* dk,
                           const float* dv, int N, int H, int D, float eps, float* dx, float* dgamma, float* dbeta, float* dwq,
                           float* dwk, float* dwv, float* ws, size_t ws_floats, cudaStream_t st) {
-  const size_t smem = sizeof(float) * (3 * (size_t)DM * (OW + 4) + (size_t)kAbBwdHits * (48 + 4));
-  static_assert(kAbBwdHits * (48 + 4) >= 64 * 2 * DM, "the staging buffer doubles as the reduction buffer");
+  const size_t smem = sizeof(float) * kAbBwdStages * (size_t)(kAbBwdHits + DM) * (kAbBwdKc + 4);
   static DeviceOnce configured;
   if (configured.needed()) {
     cudaError_t e = cudaFuncSetAttribute(ln_qkv_bwd_input_kernel<DM, OW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

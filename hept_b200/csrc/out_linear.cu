@@ -10,6 +10,7 @@
 //   out_linear_bwd_params dW = g^T out_pre, db = sum_n g: per-CTA partials over slabs of hits, then a fixed-order
 //                         reduction over CTAs (deterministic, no floating-point atomics)
 #include "common.cuh"
+#include "mma_tf32.cuh"
 
 namespace hept {
 
@@ -401,7 +402,8 @@ __global__ void __launch_bounds__(kPgGroups * (OUT / 8) * (IN / 8), 2) out_linea
 #pragma unroll 2
     for (int r = p; r < rows; r += kPgGroups) {
       const float4 g0 = *reinterpret_cast<const float4*>(gs + r * GS + 8 * jt), g1 = *reinterpret_cast<const float4*>(gs + r * GS + 8 * jt + 4);
-      const float4 x0 = *reinterpret_cast<const float4*>(xs + r * XS + 8 * ct), x1 = *reinterpret_cast<const float4*>(xs + r * XS + 8 * ct + 4);
+      // the thread's eight columns are 4 ct .. 4 ct + 3 and IN / 2 + 4 ct ..: a warp's 128-bit loads cover consecutive words
+      const float4 x0 = *reinterpret_cast<const float4*>(xs + r * XS + 4 * ct), x1 = *reinterpret_cast<const float4*>(xs + r * XS + IN / 2 + 4 * ct);
       const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
       const float2 xv[4] = {make_float2(x0.x, x0.y), make_float2(x0.z, x0.w), make_float2(x1.x, x1.y), make_float2(x1.z, x1.w)};
 #pragma unroll
@@ -421,11 +423,12 @@ __global__ void __launch_bounds__(kPgGroups * (OUT / 8) * (IN / 8), 2) out_linea
     if (p == turn) {
 #pragma unroll
       for (int a = 0; a < 8; ++a) {
-        float* dst = s_acc + (8 * jt + a) * IN + 8 * ct;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          dst[2 * c] = turn == 0 ? acc[a][c].x : dst[2 * c] + acc[a][c].x;
-          dst[2 * c + 1] = turn == 0 ? acc[a][c].y : dst[2 * c + 1] + acc[a][c].y;
+        for (int h = 0; h < 2; ++h) {
+          float4* dst = reinterpret_cast<float4*>(s_acc + (8 * jt + a) * IN + h * (IN / 2) + 4 * ct);
+          float4 v = make_float4(acc[a][2 * h].x, acc[a][2 * h].y, acc[a][2 * h + 1].x, acc[a][2 * h + 1].y);
+          if (turn != 0) { const float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+          *dst = v;
         }
         if (ct == 0) s_acc[OUT * IN + 8 * jt + a] = turn == 0 ? bsum[a] : s_acc[OUT * IN + 8 * jt + a] + bsum[a];
       }
@@ -436,20 +439,181 @@ __global__ void __launch_bounds__(kPgGroups * (OUT / 8) * (IN / 8), 2) out_linea
   for (int i = tid; i < OUT * IN + OUT; i += THREADS) dstp[i] = s_acc[i];
 }
 
+// The same product on the legacy tensor path (mma.sync m16n8k8, 3xTF32: lo*hi + hi*lo + hi*hi with fp32 accumulation): the
+// CUDA-core kernel above is bound by its shared-memory wavefronts (70 % of the LSU data pipe, profiles/r2_ncu_prof_front_r2.csv),
+// an mma needs an eighth of the operand loads per product.  P[c][j] = sum_n x[n][c] g[n][j]: M = the IN columns of x, N = the
+// OUT columns of g, K = hits.  Slabs of 32 hits go through a cp.async ring of three slots (two slabs in flight per CTA, two
+// CTAs per SM: 120 KB of loads in flight per SM); a warp = (k half hg, column group mg) multiplies 48 columns (three M tiles) x
+// all OUT columns (three N tiles) over two of a slab's four k-steps.  k-slot t of k-step s is hit 4 s + t of the slab, k-slot
+// t + 4 is hit 16 + 4 s + t (K is the contraction index: any bijection will do) -- with rows padded to 8 mod 32 words every
+// fragment load is conflict-free.  blockIdx.y selects one of up to three operand pairs (the q / k / v weight gradients of the
+// attention block in ONE launch).  The depth of one accumulation chain is N / (2 gridDim.x) hits; the CTAs' partials are
+// added by out_linear_reduce_kernel in fixed order.
+constexpr int kPmWarps = 8, kPmThreads = 32 * kPmWarps, kPmHalves = 2, kPmRows = 32, kPmStages = 3;
+struct PgOperands {
+  const float* g[3];       // (N, OUT)
+  const float* x[3];       // (N, IN)
+};
+template <int OUT, int IN>
+constexpr size_t params_mma_smem_bytes() { return sizeof(float) * kPmStages * (size_t)kPmRows * (IN + 8 + OUT + 16); }
+
+template <int OUT, int IN, bool BIAS>
+__global__ void __launch_bounds__(kPmThreads, 2) out_linear_bwd_params_mma_kernel(PgOperands ops, int N, float* __restrict__ partial) {
+  constexpr int NT = OUT / 8, MG = kPmWarps / kPmHalves, MT = IN / (16 * MG);
+  constexpr int XS = IN + 8, GS = OUT + 16, SLAB = kPmRows * (XS + GS);
+  static_assert(OUT % 8 == 0 && IN % (16 * MG) == 0 && XS % 32 == 8 && GS % 32 == 8, "tile shape / bank padding");
+  static_assert(kPmStages * SLAB >= MG * (MT * NT * 4 + NT) * 32, "the ring doubles as the reduction buffer");
+  extern __shared__ __align__(16) float s_dyn[];   // kPmStages x [ (32, XS) | (32, GS) ]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int mg = warp % MG, hg = warp / MG;
+  const int gq = lane >> 2, t = lane & 3;
+  const int pair = blockIdx.y;                   // selects, not a dynamic index: the struct stays in parameter space
+  const float* __restrict__ g = pair == 0 ? ops.g[0] : (pair == 1 ? ops.g[1] : ops.g[2]);
+  const float* __restrict__ x = pair == 0 ? ops.x[0] : (pair == 1 ? ops.x[1] : ops.x[2]);
+  float acc[MT][NT][4];
+  float bs[NT];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    bs[nt] = 0.f;
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
+  }
+  const int slabs = (N + kPmRows - 1) / kPmRows;
+  // a thread's share of a slab: x rows tr, tr + 16 x column quads tc, tc + 16, .. (all offsets are constants from here on),
+  // and one quad of g for the first 32 (OUT / 4) threads
+  static_assert(kPmThreads == 256 && kPmRows == 32 && (IN / 4) % 16 == 0 && kPmRows * (OUT / 4) <= kPmThreads, "slab load mapping");
+  const int tr = tid >> 4, tc = tid & 15;
+  const int gr = tid / (OUT / 4), gj = tid - gr * (OUT / 4);
+  auto load_slab = [&](int slab, int slot) {
+    float* xs = s_dyn + slot * SLAB;
+    float* gs = xs + kPmRows * XS;
+    const int n0 = slab * kPmRows, rows = min(kPmRows, N - n0);
+    const float* xsrc = x + (size_t)n0 * IN;
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int r = tr + 16 * a;
+#pragma unroll
+      for (int q = 0; q < IN / 64; ++q) {
+        const int c4 = tc + 16 * q;
+        if (r < rows) cp_async16_cg(xs + r * XS + 4 * c4, xsrc + (size_t)r * IN + 4 * c4);
+        else *reinterpret_cast<float4*>(xs + r * XS + 4 * c4) = make_float4(0.f, 0.f, 0.f, 0.f);   // a short last slab adds zeros
+      }
+    }
+    if (gr < kPmRows) {
+      if (gr < rows) cp_async16_cg(gs + gr * GS + 4 * gj, g + (size_t)(n0 + gr) * OUT + 4 * gj);
+      else *reinterpret_cast<float4*>(gs + gr * GS + 4 * gj) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+#pragma unroll
+  for (int pre = 0; pre < kPmStages - 1; ++pre) {      // one commit group per slab, empty ones included: the waits count groups
+    const int slab = blockIdx.x + pre * (int)gridDim.x;
+    if (slab < slabs) load_slab(slab, pre);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  int it = 0;
+#pragma unroll 1
+  for (int slab = blockIdx.x; slab < slabs; slab += gridDim.x, ++it) {
+    asm volatile("cp.async.wait_group %0;" :: "n"(kPmStages - 2) : "memory");
+    __syncthreads();                                   // this slab has landed for every thread; the previous one's slot is free
+    const int next = slab + (kPmStages - 1) * (int)gridDim.x;
+    if (next < slabs) load_slab(next, (it + kPmStages - 1) % kPmStages);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    const float* xs = s_dyn + (it % kPmStages) * SLAB + 16 * MT * mg + gq;
+    const float* gs = s_dyn + (it % kPmStages) * SLAB + kPmRows * XS + gq;
+#pragma unroll
+    for (int sh = 0; sh < 4 / kPmHalves; ++sh) {
+      const int ra = 4 * ((4 / kPmHalves) * hg + sh) + t, rb = ra + 16;
+      uint32_t bh[NT][2], bl[NT][2];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const float b0 = gs[ra * GS + 8 * nt], b1 = gs[rb * GS + 8 * nt];
+        split_tf32(b0, bh[nt][0], bl[nt][0]);
+        split_tf32(b1, bh[nt][1], bl[nt][1]);
+        if (BIAS) bs[nt] += b0 + b1;
+      }
+      uint32_t ah[MT][4], al[MT][4];
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        const float a[4] = {xs[ra * XS + 16 * mt], xs[ra * XS + 16 * mt + 8], xs[rb * XS + 16 * mt], xs[rb * XS + 16 * mt + 8]};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) split_tf32(a[e], ah[mt][e], al[mt][e]);
+      }
+      // the small terms first; product kind outermost, so that consecutive mma write different accumulators
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) mma_tf32(acc[mt][nt], al[mt], bh[nt][0], bh[nt][1]);
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) mma_tf32(acc[mt][nt], ah[mt], bl[nt][0], bl[nt][1]);
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) mma_tf32(acc[mt][nt], ah[mt], bh[nt][0], bh[nt][1]);
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  if (BIAS) {
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {                          // the four k-slot lanes of a column: fixed order
+      bs[nt] += __shfl_xor_sync(0xffffffffu, bs[nt], 1);
+      bs[nt] += __shfl_xor_sync(0xffffffffu, bs[nt], 2);
+    }
+  }
+  __syncthreads();                                             // the ring is free: the second k half parks its sums in it
+  float* s_acc = s_dyn + mg * (MT * NT * 4 + NT) * 32;
+  if (hg == 1) {
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) s_acc[((mt * NT + nt) * 4 + e) * 32 + lane] = acc[mt][nt][e];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) s_acc[(MT * NT * 4 + nt) * 32 + lane] = bs[nt];
+  }
+  __syncthreads();
+  if (hg == 0) {
+    float* dstp = partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (OUT + 1) * IN;
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const int c = 16 * MT * mg + 16 * mt + gq, j = 8 * nt + 2 * t;
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = acc[mt][nt][e] + s_acc[((mt * NT + nt) * 4 + e) * 32 + lane];
+        dstp[(size_t)j * IN + c] = v[0];
+        dstp[(size_t)(j + 1) * IN + c] = v[1];
+        dstp[(size_t)j * IN + c + 8] = v[2];
+        dstp[(size_t)(j + 1) * IN + c + 8] = v[3];
+      }
+    if (BIAS && mg == 0 && t == 0) {
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) dstp[(size_t)OUT * IN + 8 * nt + gq] = bs[nt] + s_acc[(MT * NT * 4 + nt) * 32 + lane];
+    }
+  }
+}
+
 // Stage 2: fixed-order sum over CTAs.  A CTA of 512 threads = 32 entries of (OUT + 1, IN) x 16 parts; part p sums the
 // partials p, p + 16, ... in order (eight loads in flight ahead of the adds), then the sixteen sums are added in order.
 // Entries [OUT][OUT..IN) are unused.
 constexpr int kOlParts = 16;
+struct PgResults { float* dw[3]; };     // blockIdx.y selects the operand pair; db belongs to pair 0
 __global__ void __launch_bounds__(32 * kOlParts) out_linear_reduce_kernel(const float* __restrict__ partial, int ctas, int OUT,
-                                                                          int IN, float* __restrict__ dw, float* __restrict__ db,
+                                                                          int IN, PgResults res, float* __restrict__ db,
                                                                           bool transposed = false) {
   __shared__ float red[kOlParts][32];
   const int e = threadIdx.x & 31, part = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + e;
   const int entries = (OUT + 1) * IN;
   float s = 0.f;
+  float* __restrict__ dw = blockIdx.y == 0 ? res.dw[0] : (blockIdx.y == 1 ? res.dw[1] : res.dw[2]);
   if (i < entries) {
-    const float* src = partial + i;
+    const float* src = partial + (size_t)blockIdx.y * ctas * entries + i;
     int b = part;
     for (; b + 7 * kOlParts < ctas; b += 8 * kOlParts) {
       float v[8];
@@ -468,8 +632,56 @@ __global__ void __launch_bounds__(32 * kOlParts) out_linear_reduce_kernel(const 
     for (int p = 1; p < kOlParts; ++p) t += red[p][e];
     const int j = i / IN, c = i - j * IN;
     if (j < OUT) dw[transposed ? c * OUT + j : i] = t;     // transposed: dw is (IN, OUT)
-    else if (c < OUT && db) db[c] = t;
+    else if (c < OUT && db && blockIdx.y == 0) db[c] = t;
   }
+}
+
+// HEPT_PG_STAGED=1 selects the staged CUDA-core kernel (A/B against the tensor-path one); read once.
+static bool pg_staged() {
+  static const bool v = [] { const char* e = getenv("HEPT_PG_STAGED"); return e && e[0] == '1'; }();
+  return v;
+}
+// CTAs per operand pair: two resident CTAs per SM over all pairs
+static int pg_ctas(int sms, int slabs, int pairs) {
+  int ctas = pg_staged() ? 2 * sms : 2 * sms / pairs;
+  if (ctas > slabs) ctas = slabs;
+  return ctas > kOlMaxCtas / pairs ? kOlMaxCtas / pairs : ctas;     // the workspace holds kOlMaxCtas partials
+}
+// partial sums of `pairs` products g[m]^T x[m] -> partial (pairs, ctas, (OUT + 1) IN), then their fixed-order sums -> res
+template <int OUT, int TIN>
+static int launch_pg(const PgOperands& ops, int pairs, int N, float* partial, int ctas, const PgResults& res, float* db,
+                     bool transposed, cudaStream_t st, const char* what) {
+  const int entries = (OUT + 1) * TIN;
+  if (pg_staged()) {
+    constexpr int THREADS = kPgGroups * (OUT / 8) * (TIN / 8);
+    const size_t tsmem = sizeof(float) * kPgStages * (size_t)kPgRows * (TIN + 4 + OUT + 4);
+    static DeviceOnce configured;
+    if (configured.needed()) {
+      cudaError_t e = cudaFuncSetAttribute(out_linear_bwd_params_tiled_kernel<OUT, TIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem);
+      HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "%s: %s", what, cudaGetErrorString(e));
+      configured.mark();
+    }
+    for (int m = 0; m < pairs; ++m)
+      out_linear_bwd_params_tiled_kernel<OUT, TIN><<<ctas, THREADS, tsmem, st>>>(ops.g[m], ops.x[m], N, partial + (size_t)m * ctas * entries);
+  } else {
+    const size_t msmem = params_mma_smem_bytes<OUT, TIN>();
+    static DeviceOnce configured;
+    if (configured.needed()) {
+      cudaError_t e = cudaFuncSetAttribute(out_linear_bwd_params_mma_kernel<OUT, TIN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(out_linear_bwd_params_mma_kernel<OUT, TIN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem);
+      HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "%s: %s", what, cudaGetErrorString(e));
+      configured.mark();
+    }
+    if (db) out_linear_bwd_params_mma_kernel<OUT, TIN, true><<<dim3(ctas, pairs), kPmThreads, msmem, st>>>(ops, N, partial);
+    else out_linear_bwd_params_mma_kernel<OUT, TIN, false><<<dim3(ctas, pairs), kPmThreads, msmem, st>>>(ops, N, partial);
+  }
+  cudaError_t e = cudaGetLastError();
+  HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "%s (partial sums): %s", what, cudaGetErrorString(e));
+  out_linear_reduce_kernel<<<dim3((entries + 31) / 32, pairs), 32 * kOlParts, 0, st>>>(partial, ctas, OUT, TIN, res, db, transposed);
+  e = cudaGetLastError();
+  HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "%s (reduce): %s", what, cudaGetErrorString(e));
+  return HEPT_OK;
 }
 
 template <int OUT, int OUTS, int HT>
@@ -543,29 +755,20 @@ static int launch_ol_bwd(const hept_shape* s, const float* g, const float* w, co
   int ctas = sms * 4;
   if (ctas > slabs) ctas = slabs;
   if (ctas > kOlMaxCtas) ctas = kOlMaxCtas;
-  bool ptiled = false;
   if constexpr (OUT == 24) if (IN == OUT * 8) {
-    ptiled = true;
-    constexpr int TIN = OUT * 8, THREADS = kPgGroups * (OUT / 8) * (TIN / 8);
-    const size_t tsmem = sizeof(float) * kPgStages * (size_t)kPgRows * (TIN + 4 + OUT + 4);
-    static DeviceOnce tconfigured;
-    if (tconfigured.needed()) {
-      cudaError_t e = cudaFuncSetAttribute(out_linear_bwd_params_tiled_kernel<OUT, TIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem);
-      HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "out_linear_bwd: %s", cudaGetErrorString(e));
-      tconfigured.mark();
-    }
-    const int tslabs = (s->N + kPgRows - 1) / kPgRows;
-    ctas = sms * 2 < tslabs ? sms * 2 : tslabs;
-    if (ctas > kOlMaxCtas) ctas = kOlMaxCtas;
-    out_linear_bwd_params_tiled_kernel<OUT, TIN><<<ctas, THREADS, tsmem, st>>>(g, x, s->N, partial);
+    constexpr int TIN = OUT * 8;
+    PgOperands ops{};
+    PgResults res{};
+    ops.g[0] = g; ops.x[0] = x; res.dw[0] = dw;
+    return launch_pg<OUT, TIN>(ops, 1, s->N, partial, pg_ctas(sms, (s->N + kPgRows - 1) / kPgRows, 1), res, db, false, st, "out_linear_bwd");
   }
-  if (!ptiled) {
-    const size_t psmem = sizeof(float) * ((size_t)kOlRows * OUT + (size_t)OUT * IN);
-    out_linear_bwd_params_kernel<OUT><<<ctas, kOlThreads, psmem, st>>>(g, x, s->N, IN, partial);
-  }
+  const size_t psmem = sizeof(float) * ((size_t)kOlRows * OUT + (size_t)OUT * IN);
+  out_linear_bwd_params_kernel<OUT><<<ctas, kOlThreads, psmem, st>>>(g, x, s->N, IN, partial);
   HEPT_CHECK_LAUNCH("out_linear_bwd_params");
   const int entries = (OUT + 1) * IN;
-  out_linear_reduce_kernel<<<(entries + 31) / 32, 32 * kOlParts, 0, st>>>(partial, ctas, OUT, IN, dw, db);
+  PgResults res{};
+  res.dw[0] = dw;
+  out_linear_reduce_kernel<<<(entries + 31) / 32, 32 * kOlParts, 0, st>>>(partial, ctas, OUT, IN, res, db);
   HEPT_CHECK_LAUNCH("out_linear_reduce");
   return HEPT_OK;
 }
@@ -578,29 +781,15 @@ int qkv_weight_grads(const float* xn, const float* dq, const float* dk, const fl
                      float* dwk, float* dwv, float* partial, size_t partial_floats, cudaStream_t st) {
   HEPT_REQUIRE(D == 24 && H == 8, HEPT_EUNSUPPORTED, "qkv_weight_grads: (H=%d, D=%d) not compiled in", H, D);
   HEPT_REQUIRE(partial_floats >= qkv_weight_grads_partial_floats(H, D), HEPT_EWORKSPACE, "qkv_weight_grads: workspace too small");
-  constexpr int OUT = 24, TIN = 192, THREADS = kPgGroups * (OUT / 8) * (TIN / 8);
-  const size_t tsmem = sizeof(float) * kPgStages * (size_t)kPgRows * (TIN + 4 + OUT + 4);
-  static DeviceOnce configured;
-  if (configured.needed()) {
-    cudaError_t e = cudaFuncSetAttribute(out_linear_bwd_params_tiled_kernel<OUT, TIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem);
-    HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "qkv_weight_grads: %s", cudaGetErrorString(e));
-    configured.mark();
-  }
+  constexpr int OUT = 24, TIN = 192;
   const int sms = sm_count();
   HEPT_REQUIRE(sms > 0, HEPT_ECUDA, "qkv_weight_grads: cannot read the SM count");
-  const int tslabs = (N + kPgRows - 1) / kPgRows;
-  int ctas = sms * 2 < tslabs ? sms * 2 : tslabs;
-  if (ctas > kOlMaxCtas) ctas = kOlMaxCtas;
-  const int entries = (OUT + 1) * TIN;
+  PgOperands ops{};
+  PgResults res{};
   const float* src[3] = {dq, dk, dv};
   float* dst[3] = {dwq, dwk, dwv};
-  for (int m = 0; m < 3; ++m) {     // one partial buffer, reused: the launches are ordered on the stream
-    out_linear_bwd_params_tiled_kernel<OUT, TIN><<<ctas, THREADS, tsmem, st>>>(xn, src[m], N, partial);
-    HEPT_CHECK_LAUNCH("qkv_weight_grads");
-    out_linear_reduce_kernel<<<(entries + 31) / 32, 32 * kOlParts, 0, st>>>(partial, ctas, OUT, TIN, dst[m], nullptr, true);
-    HEPT_CHECK_LAUNCH("qkv_weight_reduce");
-  }
-  return HEPT_OK;
+  for (int m = 0; m < 3; ++m) { ops.g[m] = xn; ops.x[m] = src[m]; res.dw[m] = dst[m]; }
+  return launch_pg<OUT, TIN>(ops, 3, N, partial, pg_ctas(sms, (N + kPgRows - 1) / kPgRows, 3), res, nullptr, true, st, "qkv_weight_grads");
 }
 
 }  // namespace hept
