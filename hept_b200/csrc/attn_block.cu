@@ -26,6 +26,8 @@ int qkv_weight_grads(const float* xn, const float* dq, const float* dk, const fl
 size_t qkv_weight_grads_partial_floats(int H, int D);
 
 constexpr int kAbHits = 128, kAbThreads = 128;
+// the tensor-path kernels: a warp per 16-hit tile, 16 warps per persistent CTA, gradient blocks in flight per warp
+constexpr int kAbMmaWarps = 16, kAbMmaThreads = 32 * kAbMmaWarps, kAbMmaTile = 16, kAbMmaAhead = 3;
 
 // Wt[m][j][c] = W_m[c][j]
 __global__ void __launch_bounds__(256) qkv_weights_t_kernel(const float* __restrict__ wq, const float* __restrict__ wk,
@@ -127,6 +129,124 @@ __global__ void __launch_bounds__(kAbThreads, 4) ln_qkv_fwd_kernel(const float* 
         const int r = hq + 32 * t;
         if (r < rows) {
           st_global_v8(out + (size_t)(n0 + r) * OW + 8 * cg, a0[t], a1[t]);
+        }
+      }
+    }
+  }
+}
+
+// The same on the legacy tensor path (mma_tf32.cuh): q / k / v (hits x OW) = xn (hits x DM) W_m^T.  One persistent CTA per SM; a
+// warp owns 16-hit tiles as in the backward kernel below (same tile order):
+//   A  a quad's lane t holds the six activations 6 t .. 6 t + 5 of its two hits (k-slot t of k-step s is column 6 t + 2 s,
+//      k-slot t + 4 is 6 t + 2 s + 1); the LayerNorm sums go over the quad by shuffles; xn is split into tf32 hi / lo once.
+//   B  the three weights, split ONCE per CTA and parked in shared memory in fragment order, s_b[m][n-tile][k-step][lane] =
+//      {b0 hi, b0 lo, b1 hi, b1 lo}.  Fragment column j of the n-tile pair (p, q) is output column 16 p + 4 (j / 2) + 2 q + j % 2,
+//      so that a thread's C fragments of a pair are four adjacent outputs: one 16-byte store per hit and pair.
+template <int DM, int OW>
+constexpr size_t ln_qkv_fwd_mma_smem_bytes() { return sizeof(uint4) * 3 * (OW / 8) * (DM / 8) * 32; }
+
+template <int DM, int OW>
+__global__ void __launch_bounds__(kAbMmaThreads, 1) ln_qkv_fwd_mma_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                                        const float* __restrict__ beta, const float* __restrict__ wq,
+                                                                        const float* __restrict__ wk, const float* __restrict__ wv,
+                                                                        int N, float eps, float* __restrict__ xn_out,
+                                                                        float* __restrict__ q, float* __restrict__ k, float* __restrict__ v) {
+  constexpr int NT = OW / 8, KS = DM / 8, PERL = DM / 4;           // n-tiles per matrix, k-steps, activations per lane
+  static_assert(DM % 8 == 0 && OW % 32 == 0 && PERL == 2 * KS, "tile shape");
+  extern __shared__ __align__(16) uint4 s_b[];                     // (3, NT, KS, 32)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gq = lane >> 2, t = lane & 3;
+  {
+    constexpr int TOTAL = 3 * NT * KS * 32, PER = (TOTAL + kAbMmaThreads - 1) / kAbMmaThreads;
+    float2 w[PER];
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {                                // all of a thread's (L2-resident) loads in flight at once
+      const int i = tid + u * kAbMmaThreads;
+      const int l = i & 31, ks = (i >> 5) % KS, nt = (i / (32 * KS)) % NT, m = i / (32 * KS * NT);
+      const int j = l >> 2, col = 16 * (nt >> 1) + 4 * (j >> 1) + 2 * (nt & 1) + (j & 1);
+      const float* wm = m == 0 ? wq : (m == 1 ? wk : wv);
+      w[u] = i < TOTAL ? ldg2(wm + (size_t)col * DM + PERL * (l & 3) + 2 * ks) : make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+      const int i = tid + u * kAbMmaThreads;
+      uint4 f;
+      split_tf32(w[u].x, f.x, f.y);
+      split_tf32(w[u].y, f.z, f.w);
+      if (i < TOTAL) s_b[i] = f;
+    }
+  }
+  __syncthreads();
+  float gam[PERL], bet[PERL];
+#pragma unroll
+  for (int u = 0; u < PERL; ++u) { gam[u] = __ldg(gamma + PERL * t + u); bet[u] = __ldg(beta + PERL * t + u); }
+  const int tiles = (N + kAbMmaTile - 1) / kAbMmaTile;
+#pragma unroll 1
+  for (int tile = blockIdx.x + gridDim.x * warp; tile < tiles; tile += gridDim.x * kAbMmaWarps) {
+    const int rows[2] = {tile * kAbMmaTile + gq, tile * kAbMmaTile + gq + 8};
+    uint32_t ah[KS][4], al[KS][4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {                                  // LayerNorm of the quad's hit: two-pass variance, eps inside the root
+      const bool live = rows[h] < N;
+      float xv[PERL];
+#pragma unroll
+      for (int u2 = 0; u2 < PERL / 2; ++u2) {
+        const float2 tt = live ? ldg2(x + (size_t)rows[h] * DM + PERL * t + 2 * u2) : make_float2(0.f, 0.f);
+        xv[2 * u2] = tt.x; xv[2 * u2 + 1] = tt.y;
+      }
+      float sum = 0.f;
+#pragma unroll
+      for (int u = 0; u < PERL; ++u) sum += xv[u];
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      const float mean = sum * (1.f / DM);
+      float var = 0.f;
+#pragma unroll
+      for (int u = 0; u < PERL; ++u) { const float dlt = xv[u] - mean; var = fmaf(dlt, dlt, var); }
+      var += __shfl_xor_sync(0xffffffffu, var, 1);
+      var += __shfl_xor_sync(0xffffffffu, var, 2);
+      const float rstd = 1.f / sqrtf(var * (1.f / DM) + eps);
+#pragma unroll
+      for (int u = 0; u < PERL; ++u) xv[u] = fmaf((xv[u] - mean) * rstd, gam[u], bet[u]);
+      if (live) {
+#pragma unroll
+        for (int u2 = 0; u2 < PERL / 2; ++u2)
+          *reinterpret_cast<float2*>(xn_out + (size_t)rows[h] * DM + PERL * t + 2 * u2) = make_float2(xv[2 * u2], xv[2 * u2 + 1]);
+      }
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {                            // a0 / a1 = rows g / g + 8 at k-slot t, a2 / a3 at k-slot t + 4
+        split_tf32(xv[2 * ks], ah[ks][h], al[ks][h]);
+        split_tf32(xv[2 * ks + 1], ah[ks][2 + h], al[ks][2 + h]);
+      }
+    }
+#pragma unroll 1
+    for (int m = 0; m < 3; ++m) {
+      float* __restrict__ out = m == 0 ? q : (m == 1 ? k : v);
+      const uint4* bm = s_b + (size_t)m * NT * KS * 32 + lane;
+#pragma unroll 2
+      for (int n4 = 0; n4 < NT / 4; ++n4) {                        // four n-tiles (two pairs) at a time: twelve independent mma chains
+        float acc[4][4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[c][e] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+          uint4 b[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) b[c] = bm[((4 * n4 + c) * KS + ks) * 32];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) mma_tf32(acc[c], al[ks], b[c].x, b[c].z);     // the small terms first
+#pragma unroll
+          for (int c = 0; c < 4; ++c) mma_tf32(acc[c], ah[ks], b[c].y, b[c].w);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) mma_tf32(acc[c], ah[ks], b[c].x, b[c].z);
+        }
+#pragma unroll
+        for (int pr = 0; pr < 2; ++pr) {
+          const int col = 16 * (2 * n4 + pr) + 4 * t;
+          if (rows[0] < N) *reinterpret_cast<float4*>(out + (size_t)rows[0] * OW + col) = make_float4(acc[2 * pr][0], acc[2 * pr][1], acc[2 * pr + 1][0], acc[2 * pr + 1][1]);
+          if (rows[1] < N) *reinterpret_cast<float4*>(out + (size_t)rows[1] * OW + col) = make_float4(acc[2 * pr][2], acc[2 * pr][3], acc[2 * pr + 1][2], acc[2 * pr + 1][3]);
         }
       }
     }
@@ -279,7 +399,8 @@ __global__ void __launch_bounds__(kAbBwdThreads, 2) ln_qkv_bwd_input_kernel(cons
 
 // The same on the legacy tensor path (mma_tf32.cuh): dxn (hits x DM) = [dq | dk | dv] (hits x 3 OW) * [Wq; Wk; Wv] (3 OW x DM).
 // One persistent CTA of 16 warps per SM; a warp owns 16-hit tiles (tile = blockIdx.x + gridDim.x (warp + 16 j): every SM gets
-// the same number of tiles to within one) and needs no CTA barrier inside the loop:
+// the same number of tiles to within one) and needs no CTA barrier inside the loop (13 warps, which would fill the last round
+// of a 60 000-hit event's 25.3 tiles per SM exactly, measured 5 % slower than 16: the tensor pipe wants the warps).
 //   B  the three weights, split into tf32 hi / lo ONCE per CTA and parked in shared memory in fragment order:
 //      s_b[k-step][n-tile][lane] = {b0 hi, b0 lo, b1 hi, b1 lo} -- one conflict-free 128-bit load per (k-step, n-tile)
 //   A  the gradient rows, read straight from global memory: within a block of 32 columns lane t of a row's quad holds the
@@ -288,7 +409,6 @@ __global__ void __launch_bounds__(kAbBwdThreads, 2) ln_qkv_bwd_input_kernel(cons
 //      blocks (12 vectors per thread) are in flight ahead of the one being multiplied.
 //   C  a thread ends with 6 of the 24 dxn of two hits (the C fragment); the four lanes of a quad share a hit exactly as in
 //      the CUDA-core kernel above, and the LayerNorm backward / d gamma / d beta follow it line by line.
-constexpr int kAbMmaWarps = 16, kAbMmaThreads = 32 * kAbMmaWarps, kAbMmaTile = 16, kAbMmaAhead = 3;
 template <int DM, int OW>
 constexpr size_t ln_qkv_bwd_mma_smem_bytes() { return sizeof(uint4) * (3 * OW / 8) * (DM / 8) * 32; }
 
@@ -304,50 +424,72 @@ __global__ void __launch_bounds__(kAbMmaThreads, 1) ln_qkv_bwd_input_mma_kernel(
   extern __shared__ __align__(16) uint4 s_b[];                     // (KS, NT, 32)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gq = lane >> 2, t = lane & 3;
-  for (int i = tid; i < KS * NT * 32; i += kAbMmaThreads) {
-    const int l = i & 31, nt = (i >> 5) % NT, ks = i / (32 * NT);
-    const int m = ks / (OW / 8), kk = ks - m * (OW / 8);
-    const int k0 = 32 * (kk >> 2) + 4 * (l & 3) + (kk & 3), n = 8 * nt + (l >> 2);
-    const float* wrow = wt + ((size_t)m * DM + n) * OW;            // Wt[m][n][k] = W_m[k][n]
-    uint4 v;
-    split_tf32(__ldg(wrow + k0), v.x, v.y);
-    split_tf32(__ldg(wrow + k0 + 16), v.z, v.w);
-    s_b[i] = v;
+  {
+    constexpr int TOTAL = KS * NT * 32, PER = (TOTAL + kAbMmaThreads - 1) / kAbMmaThreads;
+    float w0[PER], w1[PER];
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {                                // all of a thread's (L2-resident) loads in flight at once
+      const int i = tid + u * kAbMmaThreads;
+      const int l = i & 31, nt = (i >> 5) % NT, ks = i / (32 * NT);
+      const int m = ks / (OW / 8), kk = ks - m * (OW / 8);
+      const int k0 = 32 * (kk >> 2) + 4 * (l & 3) + (kk & 3), n = 8 * nt + (l >> 2);
+      const float* wrow = wt + ((size_t)m * DM + n) * OW;          // Wt[m][n][k] = W_m[k][n]
+      w0[u] = i < TOTAL ? __ldg(wrow + k0) : 0.f;
+      w1[u] = i < TOTAL ? __ldg(wrow + k0 + 16) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+      const int i = tid + u * kAbMmaThreads;
+      uint4 v;
+      split_tf32(w0[u], v.x, v.y);
+      split_tf32(w1[u], v.z, v.w);
+      if (i < TOTAL) s_b[i] = v;
+    }
   }
-  __syncthreads();
   float gam[NT][2], dgam[NT][2], dbet[NT][2];
 #pragma unroll
   for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
     for (int e = 0; e < 2; ++e) { gam[nt][e] = __ldg(gamma + 8 * nt + 2 * t + e); dgam[nt][e] = 0.f; dbet[nt][e] = 0.f; }
   const int tiles = (N + kAbMmaTile - 1) / kAbMmaTile;
+  // dead rows (beyond N, or beyond the warp's last tile) read row 0 and are dropped below
+  auto row_offset = [&](int r) { return (size_t)(r < N ? r : 0) * OW + 4 * t; };
+  float4 ring[kAbMmaAhead][4];      // [block in flight][row a slot t, row b slot t, row a slot t + 4, row b slot t + 4]
+  auto load_block = [&](int blk, size_t oa, size_t ob, float4 (&dst)[4]) {
+    const int m = blk / KB, kb = blk - m * KB;
+    const float* src = m == 0 ? dq : (m == 1 ? dk : dv);
+    dst[0] = ldg4(src + oa + 32 * kb);
+    dst[1] = ldg4(src + ob + 32 * kb);
+    dst[2] = ldg4(src + oa + 32 * kb + 16);
+    dst[3] = ldg4(src + ob + 32 * kb + 16);
+  };
+  int tile = blockIdx.x + gridDim.x * warp;
+  size_t oa = row_offset(tile * kAbMmaTile + gq), ob = row_offset(tile * kAbMmaTile + gq + 8);
+  if (tile < tiles) {               // the first tile's first blocks fly while the fragment store settles
+#pragma unroll
+    for (int pre = 0; pre < kAbMmaAhead; ++pre) load_block(pre, oa, ob, ring[pre]);
+  }
+  __syncthreads();
 #pragma unroll 1
-  for (int tile = blockIdx.x + gridDim.x * warp; tile < tiles; tile += gridDim.x * kAbMmaWarps) {
+  for (; tile < tiles; tile += gridDim.x * kAbMmaWarps) {
     const int ra = tile * kAbMmaTile + gq, rb = ra + 8;
     const bool la = ra < N, lb = rb < N;
-    const size_t oa = (size_t)(la ? ra : 0) * OW + 4 * t, ob = (size_t)(lb ? rb : 0) * OW + 4 * t;   // dead rows read row 0, dropped below
+    const int next = tile + gridDim.x * kAbMmaWarps;
+    const size_t na = row_offset(next * kAbMmaTile + gq), nb = row_offset(next * kAbMmaTile + gq + 8);
     float acc[NT][4];
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
       for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
-    float4 ring[kAbMmaAhead][4];                                    // [block in flight][row a slot t, row b slot t, row a slot t + 4, row b slot t + 4]
-    auto load_block = [&](int blk, float4 (&dst)[4]) {
-      const int m = blk / KB, kb = blk - m * KB;
-      const float* src = m == 0 ? dq : (m == 1 ? dk : dv);
-      dst[0] = ldg4(src + oa + 32 * kb);
-      dst[1] = ldg4(src + ob + 32 * kb);
-      dst[2] = ldg4(src + oa + 32 * kb + 16);
-      dst[3] = ldg4(src + ob + 32 * kb + 16);
-    };
-#pragma unroll
-    for (int pre = 0; pre < kAbMmaAhead; ++pre) load_block(pre, ring[pre]);
 #pragma unroll
     for (int blk = 0; blk < 3 * KB; ++blk) {
       float4 cur[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) cur[e] = ring[blk % kAbMmaAhead][e];
-      if (blk + kAbMmaAhead < 3 * KB) load_block(blk + kAbMmaAhead, ring[blk % kAbMmaAhead]);
+      // the slot just read takes the block three ahead -- of this tile, or of the warp's next one (its first blocks are
+      // on their way while this tile's LayerNorm backward runs)
+      if (blk + kAbMmaAhead < 3 * KB) load_block(blk + kAbMmaAhead, oa, ob, ring[blk % kAbMmaAhead]);
+      else if (next < tiles) load_block(blk + kAbMmaAhead - 3 * KB, na, nb, ring[blk % kAbMmaAhead]);
 #pragma unroll
       for (int s = 0; s < 4; ++s) {
         uint32_t ah[4], al[4];
@@ -368,6 +510,8 @@ __global__ void __launch_bounds__(kAbMmaThreads, 1) ln_qkv_bwd_input_mma_kernel(
         for (int nt = 0; nt < NT; ++nt) mma_tf32(acc[nt], ah, b[nt].x, b[nt].z);
       }
     }
+    oa = na;
+    ob = nb;
     // LayerNorm backward of the two hits: y = xhat gamma + beta, xhat = (x - mean) rstd
     //   dx = rstd (g - mean(g) - xhat mean(g xhat)), g = dxn gamma;  d gamma += dxn xhat;  d beta += dxn
 #pragma unroll
@@ -475,38 +619,80 @@ __global__ void __launch_bounds__(256) ln_params_reduce_kernel(const float* __re
   }
 }
 
+// HEPT_QKV_SIMT=1 selects the CUDA-core kernels (A/B against the tensor-path ones); read once
+static bool qkv_simt() {
+  static const bool v = [] { const char* e = getenv("HEPT_QKV_SIMT"); return e && e[0] == '1'; }();
+  return v;
+}
 template <int DM, int OW>
 static int launch_qkv_fwd(const float* x, const float* gamma, const float* beta, const float* wq, const float* wk, const float* wv,
                           int N, float eps, float* wt, float* xn, float* q, float* k, float* v, cudaStream_t st) {
-  const size_t smem = sizeof(float) * ((size_t)DM * OW + (size_t)kAbHits * (DM + 4));
-  static DeviceOnce configured;
-  if (configured.needed()) {
-    cudaError_t e = cudaFuncSetAttribute(ln_qkv_fwd_kernel<DM, OW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "attn_qkv_fwd: cannot reserve %zu B of shared memory: %s", smem, cudaGetErrorString(e));
-    configured.mark();
-  }
   qkv_weights_t_kernel<<<(3 * DM * OW + 255) / 256, 256, 0, st>>>(wq, wk, wv, DM, OW, wt);
   HEPT_CHECK_LAUNCH("qkv_weights_t");
-  ln_qkv_fwd_kernel<DM, OW><<<dim3((N + kAbHits - 1) / kAbHits, 3), kAbThreads, smem, st>>>(x, gamma, beta, wt, N, eps, xn, q, k, v);
+  if (qkv_simt()) {
+    const size_t smem = sizeof(float) * ((size_t)DM * OW + (size_t)kAbHits * (DM + 4));
+    static DeviceOnce configured;
+    if (configured.needed()) {
+      cudaError_t e = cudaFuncSetAttribute(ln_qkv_fwd_kernel<DM, OW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "attn_qkv_fwd: cannot reserve %zu B of shared memory: %s", smem, cudaGetErrorString(e));
+      configured.mark();
+    }
+    ln_qkv_fwd_kernel<DM, OW><<<dim3((N + kAbHits - 1) / kAbHits, 3), kAbThreads, smem, st>>>(x, gamma, beta, wt, N, eps, xn, q, k, v);
+  } else {
+    const size_t smem = ln_qkv_fwd_mma_smem_bytes<DM, OW>();
+    static DeviceOnce configured;
+    if (configured.needed()) {
+      cudaError_t e = cudaFuncSetAttribute(ln_qkv_fwd_mma_kernel<DM, OW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "attn_qkv_fwd: cannot reserve %zu B of shared memory: %s", smem, cudaGetErrorString(e));
+      configured.mark();
+    }
+    const int sms = sm_count();
+    HEPT_REQUIRE(sms > 0, HEPT_ECUDA, "attn_qkv_fwd: cannot read the SM count");
+    const int tiles = (N + kAbMmaTile - 1) / kAbMmaTile, ctas = sms < tiles ? sms : tiles;
+    ln_qkv_fwd_mma_kernel<DM, OW><<<ctas, kAbMmaThreads, smem, st>>>(x, gamma, beta, wq, wk, wv, N, eps, xn, q, k, v);
+  }
   HEPT_CHECK_LAUNCH("ln_qkv_fwd");
   return HEPT_OK;
+}
+
+// rows of the (ctas, 2 DM) buffer of LayerNorm parameter partials: either kernel's grid fits
+constexpr int kAbMaxCtas = 1024;
+static size_t ln_partial_rows(int N) {
+  const int simt = (N + kAbBwdHits - 1) / kAbBwdHits;
+  return (size_t)(simt > kAbMaxCtas ? simt : kAbMaxCtas);
 }
 
 template <int DM, int OW>
 static int launch_qkv_bwd(const float* x, const float* xn, const float* gamma, const float* wt, const float* dq, const float* dk,
                           const float* dv, int N, int H, int D, float eps, float* dx, float* dgamma, float* dbeta, float* dwq,
                           float* dwk, float* dwv, float* ws, size_t ws_floats, cudaStream_t st) {
-  const size_t smem = sizeof(float) * kAbBwdStages * (size_t)(kAbBwdHits + DM) * (kAbBwdKc + 4);
-  static DeviceOnce configured;
-  if (configured.needed()) {
-    cudaError_t e = cudaFuncSetAttribute(ln_qkv_bwd_input_kernel<DM, OW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "attn_qkv_bwd: cannot reserve %zu B of shared memory: %s", smem, cudaGetErrorString(e));
-    configured.mark();
-  }
-  const int ctas = (N + kAbBwdHits - 1) / kAbBwdHits;
-  const size_t ln_floats = (size_t)ctas * 2 * DM;
+  const bool simt = qkv_simt();
+  const int sms = sm_count();
+  HEPT_REQUIRE(sms > 0, HEPT_ECUDA, "attn_qkv_bwd: cannot read the SM count");
+  const int tiles = (N + kAbMmaTile - 1) / kAbMmaTile;
+  const int ctas = simt ? (N + kAbBwdHits - 1) / kAbBwdHits : (sms < tiles ? sms : tiles);
+  HEPT_REQUIRE(sms <= kAbMaxCtas, HEPT_EUNSUPPORTED, "attn_qkv_bwd: %d SMs, at most %d supported", sms, kAbMaxCtas);
+  const size_t ln_floats = ln_partial_rows(N) * 2 * DM;
   HEPT_REQUIRE(ws_floats >= ln_floats + qkv_weight_grads_partial_floats(H, D), HEPT_EWORKSPACE, "attn_qkv_bwd: workspace too small");
-  ln_qkv_bwd_input_kernel<DM, OW><<<ctas, kAbBwdThreads, smem, st>>>(dq, dk, dv, wt, x, gamma, N, eps, dx, ws);
+  if (simt) {
+    const size_t smem = sizeof(float) * kAbBwdStages * (size_t)(kAbBwdHits + DM) * (kAbBwdKc + 4);
+    static DeviceOnce configured;
+    if (configured.needed()) {
+      cudaError_t e = cudaFuncSetAttribute(ln_qkv_bwd_input_kernel<DM, OW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "attn_qkv_bwd: cannot reserve %zu B of shared memory: %s", smem, cudaGetErrorString(e));
+      configured.mark();
+    }
+    ln_qkv_bwd_input_kernel<DM, OW><<<ctas, kAbBwdThreads, smem, st>>>(dq, dk, dv, wt, x, gamma, N, eps, dx, ws);
+  } else {
+    const size_t smem = ln_qkv_bwd_mma_smem_bytes<DM, OW>();
+    static DeviceOnce configured;
+    if (configured.needed()) {
+      cudaError_t e = cudaFuncSetAttribute(ln_qkv_bwd_input_mma_kernel<DM, OW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "attn_qkv_bwd: cannot reserve %zu B of shared memory: %s", smem, cudaGetErrorString(e));
+      configured.mark();
+    }
+    ln_qkv_bwd_input_mma_kernel<DM, OW><<<ctas, kAbMmaThreads, smem, st>>>(dq, dk, dv, wt, x, gamma, N, eps, dx, ws);
+  }
   HEPT_CHECK_LAUNCH("ln_qkv_bwd_input");
   ln_params_reduce_kernel<<<2 * DM, 256, 0, st>>>(ws, ctas, DM, dgamma, dbeta);
   HEPT_CHECK_LAUNCH("ln_params_reduce");
@@ -521,7 +707,7 @@ extern "C" int hept_attn_qkv_supported(int32_t H, int32_t D) { return H == 8 && 
 
 extern "C" size_t hept_attn_qkv_bwd_workspace_bytes(int32_t N, int32_t H, int32_t D) {
   if (N <= 0 || H <= 0 || D <= 0) return 0;
-  return sizeof(float) * ((size_t)((N + kAbBwdHits - 1) / kAbBwdHits) * 2 * D + qkv_weight_grads_partial_floats(H, D));
+  return sizeof(float) * (ln_partial_rows(N) * 2 * D + qkv_weight_grads_partial_floats(H, D));
 }
 
 extern "C" int hept_attn_qkv_fwd(const float* x, const float* norm_weight, const float* norm_bias, const float* w_q,
