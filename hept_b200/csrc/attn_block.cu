@@ -1,21 +1,25 @@
 // The caller's side of the boundary: the front of the reference's Attn block,
 //     x_normed = norm1(x);  q, k, v = w_q(x_normed), w_k(x_normed), w_v(x_normed)        example/transformer.py:157-158
-// (src/models/baselines/transformer.py:209-212), forward and backward, as streaming fp32 kernels, so that a hit enters the
-// library as its 96-byte activation row instead of three 768-byte q / k / v rows: with host-resident inputs the call is
-// no longer a PCIe benchmark (2 520 -> 312 bytes per hit over the link), and on the device the three projections stop
-// being library GEMM launches.  q, k, v are still materialised in HBM (they are what the hash and tile kernels gather).
+// (src/models/baselines/transformer.py:209-212), forward and backward, so that a hit enters the library as its 96-byte
+// activation row instead of three 768-byte q / k / v rows: with host-resident inputs the call is no longer a PCIe benchmark
+// (2 520 -> 312 bytes per hit over the link), and on the device the three projections stop being library GEMM launches.
+// q, k, v are still materialised in HBM (they are what the hash and tile kernels gather).
 //
-//   qkv_weights_t        Wt (3, DM, OW) = the three (OW, DM) weights transposed once per call (the row-wise products below
-//                        want the DM rows of a matrix contiguous over its OW columns)
-//   ln_qkv_fwd           128 hits per CTA: LayerNorm of the rows (two-pass variance, eps inside the square root like
-//                        torch.nn.functional.layer_norm), xn kept for the backward, then q / k / v = xn Wt with 4-hit x 8-column
-//                        register tiles (packed fp32 FMAs), weights and xn rows in shared memory
-//   ln_qkv_bwd_input     dxn = dq Wq + dk Wk + dv Wv with 4-hit x 6-output register tiles over cp.async-staged gradient rows,
-//                        then the LayerNorm backward of the row (4 adjacent lanes share a hit) -> dx, and the CTA's partial
-//                        sums of d gamma / d beta (fixed order: deterministic)
+// The three products of a call (hits x 24 by 24 x 576, its transpose, and the 576 x hits by hits x 24 weight gradient) are
+// 0.83 GFMA each against 138 MB of q / k / v traffic: on CUDA cores they sit on the FMA pipe's floor (23 us at 128 FMA per
+// clock and SM; FFMA2 occupies the pipe for two cycles, it only saves issue slots) and, in practice, on shared-memory
+// wavefronts -- the first versions measured 54 / 80 / 3 x 40 us.  They run on the legacy tensor path instead (mma.sync
+// m16n8k8, 3xTF32, fp32 accumulation: 2.2 clocks per mma and SM measured, tools/micro/mma_rate.cu, i.e. an 18 us floor per
+// product next to the 21 us HBM floor): 40 / 43 / 42 us.  A tcgen05 pipeline would lift the arithmetic floor, not the HBM one.
+//
+//   qkv_weights_t        Wt (3, DM, OW) = the three (OW, DM) weights transposed once per call, saved for the backward
+//   ln_qkv_fwd           LayerNorm + the three projections: a warp per 16-hit tile, weights as pre-split fragments in shared memory
+//   ln_qkv_bwd_input     dxn = dq Wq + dk Wk + dv Wv the same way, gradient rows read straight from global memory three
+//                        32-column blocks ahead, then the LayerNorm backward of the row -> dx, and the CTA's partial sums of
+//                        d gamma / d beta (fixed order: deterministic)
 //   ln_params_reduce     fixed-order sum of those partials
-//   weight gradients     dW_m = dq_m^T xn: the out_linear parameter-gradient kernels (out_linear.cu) with the roles of the
-//                        operands exchanged, result written transposed
+//   weight gradients     dW_m = dq_m^T xn: the out_linear parameter-gradient kernel (out_linear.cu) with the roles of the
+//                        operands exchanged, the three matrices in one launch, result written transposed
 #include "common.cuh"
 #include "mma_tf32.cuh"
 
@@ -25,7 +29,6 @@ int qkv_weight_grads(const float* xn, const float* dq, const float* dk, const fl
                      float* dwk, float* dwv, float* partial, size_t partial_floats, cudaStream_t st);
 size_t qkv_weight_grads_partial_floats(int H, int D);
 
-constexpr int kAbHits = 128, kAbThreads = 128;
 // the tensor-path kernels: a warp per 16-hit tile, 16 warps per persistent CTA, gradient blocks in flight per warp
 constexpr int kAbMmaWarps = 16, kAbMmaThreads = 32 * kAbMmaWarps, kAbMmaTile = 16, kAbMmaAhead = 3;
 
@@ -41,123 +44,32 @@ __global__ void __launch_bounds__(256) qkv_weights_t_kernel(const float* __restr
   wt[i] = __ldg(w + (size_t)c * DM + j);
 }
 
-template <int DM, int OW>
-__global__ void __launch_bounds__(kAbThreads, 4) ln_qkv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
-                                                                   const float* __restrict__ beta, const float* __restrict__ wt,
-                                                                   int N, float eps, float* __restrict__ xn_out,
-                                                                   float* __restrict__ q, float* __restrict__ k, float* __restrict__ v) {
-  constexpr int XS = DM + 4;
-  static_assert(DM % 4 == 0 && OW % 32 == 0, "tile shape");
-  extern __shared__ __align__(16) float s_dyn[];
-  // one CTA = 128 hits x ONE of the three matrices (blockIdx.y): 32 KB of shared memory instead of 70, so four CTAs fit an
-  // SM and the 3 x 469 small CTAs of a 60k-hit event leave no half-empty last wave (the normalisation is repeated per
-  // matrix: 24 floats per hit)
-  float* s_w = s_dyn;                        // (DM, OW) of matrix m
-  float* s_x = s_w + DM * OW;                // (kAbHits, XS) normalised rows
-  const int tid = threadIdx.x;
-  const int m = blockIdx.y;
-  const int n0 = blockIdx.x * kAbHits;
-  const int rows = min(kAbHits, N - n0);
-  for (int i = tid; i < DM * OW / 4; i += kAbThreads)
-    reinterpret_cast<float4*>(s_w)[i] = __ldg(reinterpret_cast<const float4*>(wt + (size_t)m * DM * OW) + i);
-  {  // LayerNorm: one hit per thread
-    const int r = tid;
-    float xv[DM];
-    if (r < rows) {
-#pragma unroll
-      for (int c4 = 0; c4 < DM / 4; ++c4) {
-        const float4 t = ldg4(x + (size_t)(n0 + r) * DM + 4 * c4);
-        xv[4 * c4] = t.x; xv[4 * c4 + 1] = t.y; xv[4 * c4 + 2] = t.z; xv[4 * c4 + 3] = t.w;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < DM; ++j) xv[j] = 0.f;
-    }
-    float mean = 0.f;
-#pragma unroll
-    for (int j = 0; j < DM; ++j) mean += xv[j];
-    mean *= 1.f / DM;
-    float var = 0.f;
-#pragma unroll
-    for (int j = 0; j < DM; ++j) { const float dlt = xv[j] - mean; var = fmaf(dlt, dlt, var); }
-    const float rstd = 1.f / sqrtf(var * (1.f / DM) + eps);
-#pragma unroll
-    for (int j = 0; j < DM; ++j) xv[j] = fmaf((xv[j] - mean) * rstd, __ldg(gamma + j), __ldg(beta + j));
-#pragma unroll
-    for (int c4 = 0; c4 < DM / 4; ++c4) {
-      const float4 t = make_float4(xv[4 * c4], xv[4 * c4 + 1], xv[4 * c4 + 2], xv[4 * c4 + 3]);
-      *reinterpret_cast<float4*>(s_x + r * XS + 4 * c4) = t;
-      if (r < rows && m == 0) *reinterpret_cast<float4*>(xn_out + (size_t)(n0 + r) * DM + 4 * c4) = t;
-    }
-  }
-  __syncthreads();
-  // thread = (hq = tid / 4, c0 = tid % 4): hits hq + 32 t x columns [8 cg, 8 cg + 8), cg = c0 + 4 i
-  const int hq = tid >> 2, c0 = tid & 3;
-  {
-    float* __restrict__ out = m == 0 ? q : (m == 1 ? k : v);
-    const float* wm = s_w;
-#pragma unroll 1
-    for (int i = 0; i < OW / 32; ++i) {
-      asm volatile("" ::: "memory");           // keep the xn rows in shared memory (hoisting them costs 96 registers)
-      const int cg = c0 + 4 * i;
-      float4 a0[4], a1[4];
-#pragma unroll
-      for (int t = 0; t < 4; ++t) { a0[t] = make_float4(0.f, 0.f, 0.f, 0.f); a1[t] = a0[t]; }
-#pragma unroll
-      for (int j4 = 0; j4 < DM / 4; ++j4) {
-        float4 gv[4];
-#pragma unroll
-        for (int t = 0; t < 4; ++t) gv[t] = *reinterpret_cast<const float4*>(s_x + (hq + 32 * t) * XS + 4 * j4);
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          const float4 w0 = *reinterpret_cast<const float4*>(wm + (4 * j4 + jj) * OW + 8 * cg);
-          const float4 w1 = *reinterpret_cast<const float4*>(wm + (4 * j4 + jj) * OW + 8 * cg + 4);
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const float gj = jj == 0 ? gv[t].x : (jj == 1 ? gv[t].y : (jj == 2 ? gv[t].z : gv[t].w));
-            const float2 g2 = make_float2(gj, gj);
-            float2 r;
-            r = __ffma2_rn(g2, make_float2(w0.x, w0.y), make_float2(a0[t].x, a0[t].y)); a0[t].x = r.x; a0[t].y = r.y;
-            r = __ffma2_rn(g2, make_float2(w0.z, w0.w), make_float2(a0[t].z, a0[t].w)); a0[t].z = r.x; a0[t].w = r.y;
-            r = __ffma2_rn(g2, make_float2(w1.x, w1.y), make_float2(a1[t].x, a1[t].y)); a1[t].x = r.x; a1[t].y = r.y;
-            r = __ffma2_rn(g2, make_float2(w1.z, w1.w), make_float2(a1[t].z, a1[t].w)); a1[t].z = r.x; a1[t].w = r.y;
-          }
-        }
-      }
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const int r = hq + 32 * t;
-        if (r < rows) {
-          st_global_v8(out + (size_t)(n0 + r) * OW + 8 * cg, a0[t], a1[t]);
-        }
-      }
-    }
-  }
-}
-
-// The same on the legacy tensor path (mma_tf32.cuh): q / k / v (hits x OW) = xn (hits x DM) W_m^T.  One persistent CTA per SM; a
-// warp owns 16-hit tiles as in the backward kernel below (same tile order):
+// LayerNorm of the rows (two-pass variance, eps inside the square root like torch.nn.functional.layer_norm), xn kept for the
+// backward, then q / k / v (hits x OW) = xn (hits x DM) W_m^T on the legacy tensor path (mma_tf32.cuh).  One persistent CTA per
+// SM; a warp owns 16-hit tiles as in the backward kernel below (same tile order):
 //   A  a quad's lane t holds the six activations 6 t .. 6 t + 5 of its two hits (k-slot t of k-step s is column 6 t + 2 s,
 //      k-slot t + 4 is 6 t + 2 s + 1); the LayerNorm sums go over the quad by shuffles; xn is split into tf32 hi / lo once.
 //   B  the three weights, split ONCE per CTA and parked in shared memory in fragment order, s_b[m][n-tile][k-step][lane] =
 //      {b0 hi, b0 lo, b1 hi, b1 lo}.  Fragment column j of the n-tile pair (p, q) is output column 16 p + 4 (j / 2) + 2 q + j % 2,
 //      so that a thread's C fragments of a pair are four adjacent outputs: one 16-byte store per hit and pair.
-template <int DM, int OW>
-constexpr size_t ln_qkv_fwd_mma_smem_bytes() { return sizeof(uint4) * 3 * (OW / 8) * (DM / 8) * 32; }
+// NMAT = 3, LN: the block's front.  NMAT = 1, no LayerNorm, WT (the weight is (DM, OW): element (column, k) at w[k OW + column]):
+// out_linear's input gradient d out_pre = d out W (out_linear.cu).
+template <int DM, int OW, int NMAT>
+constexpr size_t rows_wide_smem_bytes() { return sizeof(uint4) * NMAT * (OW / 8) * (DM / 8) * 32; }
 
-template <int DM, int OW>
-__global__ void __launch_bounds__(kAbMmaThreads, 1) ln_qkv_fwd_mma_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
-                                                                        const float* __restrict__ beta, const float* __restrict__ wq,
-                                                                        const float* __restrict__ wk, const float* __restrict__ wv,
-                                                                        int N, float eps, float* __restrict__ xn_out,
-                                                                        float* __restrict__ q, float* __restrict__ k, float* __restrict__ v) {
+template <int DM, int OW, int NMAT, bool LN, bool WT>
+__global__ void __launch_bounds__(kAbMmaThreads, 1) rows_wide_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                                       const float* __restrict__ beta, const float* __restrict__ wq,
+                                                                       const float* __restrict__ wk, const float* __restrict__ wv,
+                                                                       int N, float eps, float* __restrict__ xn_out,
+                                                                       float* __restrict__ q, float* __restrict__ k, float* __restrict__ v) {
   constexpr int NT = OW / 8, KS = DM / 8, PERL = DM / 4;           // n-tiles per matrix, k-steps, activations per lane
   static_assert(DM % 8 == 0 && OW % 32 == 0 && PERL == 2 * KS, "tile shape");
-  extern __shared__ __align__(16) uint4 s_b[];                     // (3, NT, KS, 32)
+  extern __shared__ __align__(16) uint4 s_b[];                     // (NMAT, NT, KS, 32)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gq = lane >> 2, t = lane & 3;
   {
-    constexpr int TOTAL = 3 * NT * KS * 32, PER = (TOTAL + kAbMmaThreads - 1) / kAbMmaThreads;
+    constexpr int TOTAL = NMAT * NT * KS * 32, PER = (TOTAL + kAbMmaThreads - 1) / kAbMmaThreads;
     float2 w[PER];
 #pragma unroll
     for (int u = 0; u < PER; ++u) {                                // all of a thread's (L2-resident) loads in flight at once
@@ -165,7 +77,10 @@ __global__ void __launch_bounds__(kAbMmaThreads, 1) ln_qkv_fwd_mma_kernel(const 
       const int l = i & 31, ks = (i >> 5) % KS, nt = (i / (32 * KS)) % NT, m = i / (32 * KS * NT);
       const int j = l >> 2, col = 16 * (nt >> 1) + 4 * (j >> 1) + 2 * (nt & 1) + (j & 1);
       const float* wm = m == 0 ? wq : (m == 1 ? wk : wv);
-      w[u] = i < TOTAL ? ldg2(wm + (size_t)col * DM + PERL * (l & 3) + 2 * ks) : make_float2(0.f, 0.f);
+      const int k0 = PERL * (l & 3) + 2 * ks;
+      if (i >= TOTAL) w[u] = make_float2(0.f, 0.f);
+      else if (WT) w[u] = make_float2(__ldg(wm + (size_t)k0 * OW + col), __ldg(wm + (size_t)(k0 + 1) * OW + col));
+      else w[u] = ldg2(wm + (size_t)col * DM + k0);
     }
 #pragma unroll
     for (int u = 0; u < PER; ++u) {
@@ -179,7 +94,7 @@ __global__ void __launch_bounds__(kAbMmaThreads, 1) ln_qkv_fwd_mma_kernel(const 
   __syncthreads();
   float gam[PERL], bet[PERL];
 #pragma unroll
-  for (int u = 0; u < PERL; ++u) { gam[u] = __ldg(gamma + PERL * t + u); bet[u] = __ldg(beta + PERL * t + u); }
+  for (int u = 0; u < PERL; ++u) { gam[u] = LN ? __ldg(gamma + PERL * t + u) : 1.f; bet[u] = LN ? __ldg(beta + PERL * t + u) : 0.f; }
   const int tiles = (N + kAbMmaTile - 1) / kAbMmaTile;
 #pragma unroll 1
   for (int tile = blockIdx.x + gridDim.x * warp; tile < tiles; tile += gridDim.x * kAbMmaWarps) {
@@ -194,24 +109,26 @@ __global__ void __launch_bounds__(kAbMmaThreads, 1) ln_qkv_fwd_mma_kernel(const 
         const float2 tt = live ? ldg2(x + (size_t)rows[h] * DM + PERL * t + 2 * u2) : make_float2(0.f, 0.f);
         xv[2 * u2] = tt.x; xv[2 * u2 + 1] = tt.y;
       }
-      float sum = 0.f;
+      if (LN) {
+        float sum = 0.f;
 #pragma unroll
-      for (int u = 0; u < PERL; ++u) sum += xv[u];
-      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-      const float mean = sum * (1.f / DM);
-      float var = 0.f;
+        for (int u = 0; u < PERL; ++u) sum += xv[u];
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        const float mean = sum * (1.f / DM);
+        float var = 0.f;
 #pragma unroll
-      for (int u = 0; u < PERL; ++u) { const float dlt = xv[u] - mean; var = fmaf(dlt, dlt, var); }
-      var += __shfl_xor_sync(0xffffffffu, var, 1);
-      var += __shfl_xor_sync(0xffffffffu, var, 2);
-      const float rstd = 1.f / sqrtf(var * (1.f / DM) + eps);
+        for (int u = 0; u < PERL; ++u) { const float dlt = xv[u] - mean; var = fmaf(dlt, dlt, var); }
+        var += __shfl_xor_sync(0xffffffffu, var, 1);
+        var += __shfl_xor_sync(0xffffffffu, var, 2);
+        const float rstd = 1.f / sqrtf(var * (1.f / DM) + eps);
 #pragma unroll
-      for (int u = 0; u < PERL; ++u) xv[u] = fmaf((xv[u] - mean) * rstd, gam[u], bet[u]);
-      if (live) {
+        for (int u = 0; u < PERL; ++u) xv[u] = fmaf((xv[u] - mean) * rstd, gam[u], bet[u]);
+        if (live) {
 #pragma unroll
-        for (int u2 = 0; u2 < PERL / 2; ++u2)
-          *reinterpret_cast<float2*>(xn_out + (size_t)rows[h] * DM + PERL * t + 2 * u2) = make_float2(xv[2 * u2], xv[2 * u2 + 1]);
+          for (int u2 = 0; u2 < PERL / 2; ++u2)
+            *reinterpret_cast<float2*>(xn_out + (size_t)rows[h] * DM + PERL * t + 2 * u2) = make_float2(xv[2 * u2], xv[2 * u2 + 1]);
+        }
       }
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) {                            // a0 / a1 = rows g / g + 8 at k-slot t, a2 / a3 at k-slot t + 4
@@ -220,7 +137,7 @@ __global__ void __launch_bounds__(kAbMmaThreads, 1) ln_qkv_fwd_mma_kernel(const 
       }
     }
 #pragma unroll 1
-    for (int m = 0; m < 3; ++m) {
+    for (int m = 0; m < NMAT; ++m) {
       float* __restrict__ out = m == 0 ? q : (m == 1 ? k : v);
       const uint4* bm = s_b + (size_t)m * NT * KS * 32 + lane;
 #pragma unroll 2
@@ -253,151 +170,8 @@ __global__ void __launch_bounds__(kAbMmaThreads, 1) ln_qkv_fwd_mma_kernel(const 
   }
 }
 
-// dxn = dq Wq + dk Wk + dv Wv, then the LayerNorm backward.  thread = (hq = tid / 4, og = tid % 4): hits hq + 64 t x outputs
-// [PER og, PER og + PER), PER = DM / 4; the four threads of a hit are adjacent lanes.
-constexpr int kAbBwdHits = 256, kAbBwdThreads = 256;   // two CTAs of 8 warps per SM: a 60k-hit event is ONE wave of 235 CTAs
-constexpr int kAbBwdKc = 24, kAbBwdStages = 3;         // ring of three 24-column chunks: 94 KB per CTA
-template <int DM, int OW>
-__global__ void __launch_bounds__(kAbBwdThreads, 2) ln_qkv_bwd_input_kernel(const float* __restrict__ dq, const float* __restrict__ dk,
-                                                                         const float* __restrict__ dv, const float* __restrict__ wt,
-                                                                         const float* __restrict__ x, const float* __restrict__ gamma,
-                                                                         int N, float eps, float* __restrict__ dx,
-                                                                         float* __restrict__ partial) {
-  constexpr int KC = kAbBwdKc, NCH = OW / KC, XS = KC + 4, PER = DM / 4, STAGES = kAbBwdStages;
-  constexpr int STAGE = (kAbBwdHits + DM) * XS;    // floats per ring slot: the gradient rows' chunk | the weights' chunk
-  static_assert(OW % KC == 0 && DM % 4 == 0 && PER % 2 == 0 && KC % 4 == 0, "tile shape");
-  static_assert(STAGES * STAGE >= 64 * 2 * DM, "the ring doubles as the reduction buffer");
-  extern __shared__ __align__(16) float s_dyn[];   // STAGES x [ (kAbBwdHits, XS) | (DM, XS) ]: a ring over the 3 NCH chunks; the
-                                                   // loads of STAGES - 1 chunks are in flight while one is consumed
-  float* s_red = s_dyn;                            // reused at the end: (64, 2 DM) per-hit-group sums of d gamma / d beta
-  const int tid = threadIdx.x, hq = tid >> 2, og = tid & 3;
-  const int n0 = blockIdx.x * kAbBwdHits;
-  const int rows = min(kAbBwdHits, N - n0);
-  auto load_chunk = [&](int ch) {
-    const int m = ch / NCH, kc = ch - m * NCH;
-    float* sx = s_dyn + (ch % STAGES) * STAGE;
-    float* sw = sx + kAbBwdHits * XS;
-    const float* src = m == 0 ? dq : (m == 1 ? dk : dv);
-    for (int i = tid; i < kAbBwdHits * (KC / 4); i += kAbBwdThreads) {
-      const int r = i / (KC / 4), c4 = i - r * (KC / 4);
-      if (r < rows) cp_async16_cg(sx + r * XS + 4 * c4, src + (size_t)(n0 + r) * OW + kc * KC + 4 * c4);
-    }
-    for (int i = tid; i < DM * (KC / 4); i += kAbBwdThreads) {     // Wt[m][j][kc KC ..): L2-resident, 55 KB in all
-      const int j = i / (KC / 4), c4 = i - j * (KC / 4);
-      cp_async16_cg(sw + j * XS + 4 * c4, wt + ((size_t)m * DM + j) * OW + kc * KC + 4 * c4);
-    }
-  };
-  if (rows < kAbBwdHits)                           // a short last tile: its dead rows are read by the FMAs below (and dropped)
-    for (int i = tid; i < STAGES * STAGE; i += kAbBwdThreads) s_dyn[i] = 0.f;
-  __syncthreads();
-#pragma unroll
-  for (int pre = 0; pre < STAGES - 1; ++pre) {     // one commit group per chunk, empty ones included: the waits count groups
-    if (pre < 3 * NCH) load_chunk(pre);
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  }
-  float2 acc[4][PER];
-#pragma unroll
-  for (int u = 0; u < PER; ++u)
-#pragma unroll
-    for (int t = 0; t < 4; ++t) acc[t][u] = make_float2(0.f, 0.f);
-#pragma unroll 1
-  for (int ch = 0; ch < 3 * NCH; ++ch) {
-    asm volatile("cp.async.wait_group %0;" :: "n"(STAGES - 2) : "memory");
-    __syncthreads();                               // chunk ch has landed for every thread; the slot of chunk ch - 1 is free
-    if (ch + STAGES - 1 < 3 * NCH) load_chunk(ch + STAGES - 1);
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    const float* xs = s_dyn + (ch % STAGES) * STAGE + hq * XS;
-    const float* ws = s_dyn + (ch % STAGES) * STAGE + kAbBwdHits * XS + og * PER * XS;
-#pragma unroll
-    for (int c4 = 0; c4 < KC / 4; ++c4) {
-      float4 xv[4];
-#pragma unroll
-      for (int t = 0; t < 4; ++t) xv[t] = *reinterpret_cast<const float4*>(xs + 64 * t * XS + 4 * c4);
-#pragma unroll
-      for (int u = 0; u < PER; ++u) {
-        const float4 wv = *reinterpret_cast<const float4*>(ws + u * XS + 4 * c4);
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          acc[t][u] = __ffma2_rn(make_float2(xv[t].x, xv[t].y), make_float2(wv.x, wv.y), acc[t][u]);
-          acc[t][u] = __ffma2_rn(make_float2(xv[t].z, xv[t].w), make_float2(wv.z, wv.w), acc[t][u]);
-        }
-      }
-    }
-  }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  // LayerNorm backward of each hit: y = xhat gamma + beta, xhat = (x - mean) rstd
-  //   dx = rstd (g - mean(g) - xhat mean(g xhat)), g = dxn gamma;  d gamma += dxn xhat;  d beta += dxn
-  float gam[PER], dgam[PER], dbet[PER];
-#pragma unroll
-  for (int u = 0; u < PER; ++u) { gam[u] = __ldg(gamma + og * PER + u); dgam[u] = 0.f; dbet[u] = 0.f; }
-#pragma unroll
-  for (int t = 0; t < 4; ++t) {
-    const int r = hq + 64 * t;
-    const bool live = r < rows;
-    float xv[PER], dxn[PER];
-#pragma unroll
-    for (int u2 = 0; u2 < PER / 2; ++u2) {
-      const float2 tt = live ? ldg2(x + (size_t)(n0 + r) * DM + og * PER + 2 * u2) : make_float2(0.f, 0.f);
-      xv[2 * u2] = tt.x; xv[2 * u2 + 1] = tt.y;
-    }
-#pragma unroll
-    for (int u = 0; u < PER; ++u) dxn[u] = acc[t][u].x + acc[t][u].y;
-    float s = 0.f;
-#pragma unroll
-    for (int u = 0; u < PER; ++u) s += xv[u];
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    const float mean = s * (1.f / DM);
-    float vs = 0.f;
-#pragma unroll
-    for (int u = 0; u < PER; ++u) { const float dlt = xv[u] - mean; vs = fmaf(dlt, dlt, vs); }
-    vs += __shfl_xor_sync(0xffffffffu, vs, 1);
-    vs += __shfl_xor_sync(0xffffffffu, vs, 2);
-    const float rstd = 1.f / sqrtf(vs * (1.f / DM) + eps);
-    float xh[PER], g[PER], m1 = 0.f, m2 = 0.f;
-#pragma unroll
-    for (int u = 0; u < PER; ++u) {
-      xh[u] = (xv[u] - mean) * rstd;
-      g[u] = dxn[u] * gam[u];
-      m1 += g[u];
-      m2 = fmaf(g[u], xh[u], m2);
-    }
-    m1 += __shfl_xor_sync(0xffffffffu, m1, 1);
-    m1 += __shfl_xor_sync(0xffffffffu, m1, 2);
-    m2 += __shfl_xor_sync(0xffffffffu, m2, 1);
-    m2 += __shfl_xor_sync(0xffffffffu, m2, 2);
-    m1 *= 1.f / DM;
-    m2 *= 1.f / DM;
-    if (live) {
-      float o[PER];
-#pragma unroll
-      for (int u = 0; u < PER; ++u) {
-        o[u] = rstd * (g[u] - m1 - xh[u] * m2);
-        dgam[u] = fmaf(dxn[u], xh[u], dgam[u]);
-        dbet[u] += dxn[u];
-      }
-#pragma unroll
-      for (int u2 = 0; u2 < PER / 2; ++u2)
-        *reinterpret_cast<float2*>(dx + (size_t)(n0 + r) * DM + og * PER + 2 * u2) = make_float2(o[2 * u2], o[2 * u2 + 1]);
-    }
-  }
-  // the CTA's sums: hit groups in order 0 .. 63 (fixed order)
-  __syncthreads();
-#pragma unroll
-  for (int u = 0; u < PER; ++u) {
-    s_red[hq * 2 * DM + og * PER + u] = dgam[u];
-    s_red[hq * 2 * DM + DM + og * PER + u] = dbet[u];
-  }
-  __syncthreads();
-  if (tid < 2 * DM) {
-    float s = 0.f;
-#pragma unroll 8
-    for (int g2 = 0; g2 < 64; ++g2) s += s_red[g2 * 2 * DM + tid];
-    partial[(size_t)blockIdx.x * 2 * DM + tid] = s;
-  }
-}
-
-// The same on the legacy tensor path (mma_tf32.cuh): dxn (hits x DM) = [dq | dk | dv] (hits x 3 OW) * [Wq; Wk; Wv] (3 OW x DM).
+// dxn (hits x DM) = [dq | dk | dv] (hits x 3 OW) * [Wq; Wk; Wv] (3 OW x DM) on the legacy tensor path (mma_tf32.cuh), then the
+// LayerNorm backward of the row and the CTA's partial sums of d gamma / d beta.
 // One persistent CTA of 16 warps per SM; a warp owns 16-hit tiles (tile = blockIdx.x + gridDim.x (warp + 16 j): every SM gets
 // the same number of tiles to within one) and needs no CTA barrier inside the loop (13 warps, which would fill the last round
 // of a 60 000-hit event's 25.3 tiles per SM exactly, measured 5 % slower than 16: the tensor pipe wants the warps).
@@ -408,17 +182,19 @@ __global__ void __launch_bounds__(kAbBwdThreads, 2) ln_qkv_bwd_input_kernel(cons
 //      bijection will do, and this one makes every load a full 16-byte vector, a row's quad cover whole sectors.  Three
 //      blocks (12 vectors per thread) are in flight ahead of the one being multiplied.
 //   C  a thread ends with 6 of the 24 dxn of two hits (the C fragment); the four lanes of a quad share a hit exactly as in
-//      the CUDA-core kernel above, and the LayerNorm backward / d gamma / d beta follow it line by line.
-template <int DM, int OW>
-constexpr size_t ln_qkv_bwd_mma_smem_bytes() { return sizeof(uint4) * (3 * OW / 8) * (DM / 8) * 32; }
+//      the forward kernel; the LayerNorm backward runs on the fragment, the sums over the quad by shuffles.
+// NMAT = 3, LN: the block's front.  NMAT = 1, no LayerNorm: out_linear's forward out = out_pre W^T + b (out_linear.cu; `wt` is
+// the (DM, OW) weight itself, `gamma` its bias, `dx` the output).
+template <int DM, int OW, int NMAT>
+constexpr size_t rows_narrow_smem_bytes() { return sizeof(uint4) * (NMAT * OW / 8) * (DM / 8) * 32; }
 
-template <int DM, int OW>
-__global__ void __launch_bounds__(kAbMmaThreads, 1) ln_qkv_bwd_input_mma_kernel(const float* __restrict__ dq, const float* __restrict__ dk,
+template <int DM, int OW, int NMAT, bool LN>
+__global__ void __launch_bounds__(kAbMmaThreads, 1) rows_narrow_kernel(const float* __restrict__ dq, const float* __restrict__ dk,
                                                                               const float* __restrict__ dv, const float* __restrict__ wt,
                                                                               const float* __restrict__ x, const float* __restrict__ gamma,
                                                                               int N, float eps, float* __restrict__ dx,
                                                                               float* __restrict__ partial) {
-  constexpr int NT = DM / 8, KB = OW / 32, KS = 3 * OW / 8;       // n-tiles, 32-column blocks per matrix, k-steps in all
+  constexpr int NT = DM / 8, KB = OW / 32, KS = NMAT * OW / 8;    // n-tiles, 32-column blocks per matrix, k-steps in all
   static_assert(DM % 8 == 0 && OW % 32 == 0, "tile shape");
   static_assert(KS * NT * 32 * 4 >= kAbMmaWarps * 2 * DM, "the fragment store doubles as the reduction buffer");
   extern __shared__ __align__(16) uint4 s_b[];                     // (KS, NT, 32)
@@ -482,14 +258,14 @@ __global__ void __launch_bounds__(kAbMmaThreads, 1) ln_qkv_bwd_input_mma_kernel(
 #pragma unroll
       for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
 #pragma unroll
-    for (int blk = 0; blk < 3 * KB; ++blk) {
+    for (int blk = 0; blk < NMAT * KB; ++blk) {
       float4 cur[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) cur[e] = ring[blk % kAbMmaAhead][e];
       // the slot just read takes the block three ahead -- of this tile, or of the warp's next one (its first blocks are
       // on their way while this tile's LayerNorm backward runs)
-      if (blk + kAbMmaAhead < 3 * KB) load_block(blk + kAbMmaAhead, oa, ob, ring[blk % kAbMmaAhead]);
-      else if (next < tiles) load_block(blk + kAbMmaAhead - 3 * KB, na, nb, ring[blk % kAbMmaAhead]);
+      if (blk + kAbMmaAhead < NMAT * KB) load_block(blk + kAbMmaAhead, oa, ob, ring[blk % kAbMmaAhead]);
+      else if (next < tiles) load_block(blk + kAbMmaAhead - NMAT * KB, na, nb, ring[blk % kAbMmaAhead]);
 #pragma unroll
       for (int s = 0; s < 4; ++s) {
         uint32_t ah[4], al[4];
@@ -512,91 +288,105 @@ __global__ void __launch_bounds__(kAbMmaThreads, 1) ln_qkv_bwd_input_mma_kernel(
     }
     oa = na;
     ob = nb;
-    // LayerNorm backward of the two hits: y = xhat gamma + beta, xhat = (x - mean) rstd
-    //   dx = rstd (g - mean(g) - xhat mean(g xhat)), g = dxn gamma;  d gamma += dxn xhat;  d beta += dxn
+    if constexpr (!LN) {                                             // out = acc + bias
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int r = h == 0 ? ra : rb;
-      const bool live = h == 0 ? la : lb;
-      float xv[NT][2], dxn[NT][2];
+      for (int h = 0; h < 2; ++h) {
+        const int r = h == 0 ? ra : rb;
+        if (h == 0 ? la : lb) {
 #pragma unroll
-      for (int nt = 0; nt < NT; ++nt) {
-        const float2 tt = live ? ldg2(x + (size_t)r * DM + 8 * nt + 2 * t) : make_float2(0.f, 0.f);
-        xv[nt][0] = tt.x; xv[nt][1] = tt.y;
-        dxn[nt][0] = acc[nt][2 * h]; dxn[nt][1] = acc[nt][2 * h + 1];
-      }
-      float sum = 0.f;
-#pragma unroll
-      for (int nt = 0; nt < NT; ++nt) sum += xv[nt][0] + xv[nt][1];
-      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-      const float mean = sum * (1.f / DM);
-      float vs = 0.f;
-#pragma unroll
-      for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) { const float dlt = xv[nt][e] - mean; vs = fmaf(dlt, dlt, vs); }
-      vs += __shfl_xor_sync(0xffffffffu, vs, 1);
-      vs += __shfl_xor_sync(0xffffffffu, vs, 2);
-      const float rstd = 1.f / sqrtf(vs * (1.f / DM) + eps);
-      float xh[NT][2], gg[NT][2], m1 = 0.f, m2 = 0.f;
-#pragma unroll
-      for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          xh[nt][e] = (xv[nt][e] - mean) * rstd;
-          gg[nt][e] = dxn[nt][e] * gam[nt][e];
-          m1 += gg[nt][e];
-          m2 = fmaf(gg[nt][e], xh[nt][e], m2);
+          for (int nt = 0; nt < NT; ++nt)
+            *reinterpret_cast<float2*>(dx + (size_t)r * DM + 8 * nt + 2 * t) = make_float2(acc[nt][2 * h] + gam[nt][0], acc[nt][2 * h + 1] + gam[nt][1]);
         }
-      m1 += __shfl_xor_sync(0xffffffffu, m1, 1);
-      m1 += __shfl_xor_sync(0xffffffffu, m1, 2);
-      m2 += __shfl_xor_sync(0xffffffffu, m2, 1);
-      m2 += __shfl_xor_sync(0xffffffffu, m2, 2);
-      m1 *= 1.f / DM;
-      m2 *= 1.f / DM;
-      if (live) {
+      }
+    } else {
+      // LayerNorm backward of the two hits: y = xhat gamma + beta, xhat = (x - mean) rstd
+      //   dx = rstd (g - mean(g) - xhat mean(g xhat)), g = dxn gamma;  d gamma += dxn xhat;  d beta += dxn
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int r = h == 0 ? ra : rb;
+        const bool live = h == 0 ? la : lb;
+        float xv[NT][2], dxn[NT][2];
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
-          float o[2];
+          const float2 tt = live ? ldg2(x + (size_t)r * DM + 8 * nt + 2 * t) : make_float2(0.f, 0.f);
+          xv[nt][0] = tt.x; xv[nt][1] = tt.y;
+          dxn[nt][0] = acc[nt][2 * h]; dxn[nt][1] = acc[nt][2 * h + 1];
+        }
+        float sum = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) sum += xv[nt][0] + xv[nt][1];
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        const float mean = sum * (1.f / DM);
+        float vs = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) { const float dlt = xv[nt][e] - mean; vs = fmaf(dlt, dlt, vs); }
+        vs += __shfl_xor_sync(0xffffffffu, vs, 1);
+        vs += __shfl_xor_sync(0xffffffffu, vs, 2);
+        const float rstd = 1.f / sqrtf(vs * (1.f / DM) + eps);
+        float xh[NT][2], gg[NT][2], m1 = 0.f, m2 = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
-            o[e] = rstd * (gg[nt][e] - m1 - xh[nt][e] * m2);
-            dgam[nt][e] = fmaf(dxn[nt][e], xh[nt][e], dgam[nt][e]);
-            dbet[nt][e] += dxn[nt][e];
+            xh[nt][e] = (xv[nt][e] - mean) * rstd;
+            gg[nt][e] = dxn[nt][e] * gam[nt][e];
+            m1 += gg[nt][e];
+            m2 = fmaf(gg[nt][e], xh[nt][e], m2);
           }
-          *reinterpret_cast<float2*>(dx + (size_t)r * DM + 8 * nt + 2 * t) = make_float2(o[0], o[1]);
+        m1 += __shfl_xor_sync(0xffffffffu, m1, 1);
+        m1 += __shfl_xor_sync(0xffffffffu, m1, 2);
+        m2 += __shfl_xor_sync(0xffffffffu, m2, 1);
+        m2 += __shfl_xor_sync(0xffffffffu, m2, 2);
+        m1 *= 1.f / DM;
+        m2 *= 1.f / DM;
+        if (live) {
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) {
+            float o[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              o[e] = rstd * (gg[nt][e] - m1 - xh[nt][e] * m2);
+              dgam[nt][e] = fmaf(dxn[nt][e], xh[nt][e], dgam[nt][e]);
+              dbet[nt][e] += dxn[nt][e];
+            }
+            *reinterpret_cast<float2*>(dx + (size_t)r * DM + 8 * nt + 2 * t) = make_float2(o[0], o[1]);
+          }
         }
       }
     }
   }
-  // the CTA's sums: the eight row lanes of a column in butterfly order, then the warps in order (fixed: deterministic)
-#pragma unroll
-  for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-    for (int e = 0; e < 2; ++e)
-#pragma unroll
-      for (int sh = 4; sh < 32; sh <<= 1) {
-        dgam[nt][e] += __shfl_xor_sync(0xffffffffu, dgam[nt][e], sh);
-        dbet[nt][e] += __shfl_xor_sync(0xffffffffu, dbet[nt][e], sh);
-      }
-  __syncthreads();                                                 // every warp is done with the fragment store
-  float* s_red = reinterpret_cast<float*>(s_b);                    // (warps, 2 DM)
-  if (gq == 0) {
+  if constexpr (LN) {
+    // the CTA's sums: the eight row lanes of a column in butterfly order, then the warps in order (fixed: deterministic)
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        s_red[warp * 2 * DM + 8 * nt + 2 * t + e] = dgam[nt][e];
-        s_red[warp * 2 * DM + DM + 8 * nt + 2 * t + e] = dbet[nt][e];
-      }
-  }
-  __syncthreads();
-  if (tid < 2 * DM) {
-    float s = 0.f;
+      for (int e = 0; e < 2; ++e)
 #pragma unroll
-    for (int w = 0; w < kAbMmaWarps; ++w) s += s_red[w * 2 * DM + tid];
-    partial[(size_t)blockIdx.x * 2 * DM + tid] = s;
+        for (int sh = 4; sh < 32; sh <<= 1) {
+          dgam[nt][e] += __shfl_xor_sync(0xffffffffu, dgam[nt][e], sh);
+          dbet[nt][e] += __shfl_xor_sync(0xffffffffu, dbet[nt][e], sh);
+        }
+    __syncthreads();                                                 // every warp is done with the fragment store
+    float* s_red = reinterpret_cast<float*>(s_b);                    // (warps, 2 DM)
+    if (gq == 0) {
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          s_red[warp * 2 * DM + 8 * nt + 2 * t + e] = dgam[nt][e];
+          s_red[warp * 2 * DM + DM + 8 * nt + 2 * t + e] = dbet[nt][e];
+        }
+    }
+    __syncthreads();
+    if (tid < 2 * DM) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < kAbMmaWarps; ++w) s += s_red[w * 2 * DM + tid];
+      partial[(size_t)blockIdx.x * 2 * DM + tid] = s;
+    }
   }
 }
 
@@ -619,84 +409,90 @@ __global__ void __launch_bounds__(256) ln_params_reduce_kernel(const float* __re
   }
 }
 
-// HEPT_QKV_SIMT=1 selects the CUDA-core kernels (A/B against the tensor-path ones); read once
-static bool qkv_simt() {
-  static const bool v = [] { const char* e = getenv("HEPT_QKV_SIMT"); return e && e[0] == '1'; }();
-  return v;
-}
 template <int DM, int OW>
 static int launch_qkv_fwd(const float* x, const float* gamma, const float* beta, const float* wq, const float* wk, const float* wv,
                           int N, float eps, float* wt, float* xn, float* q, float* k, float* v, cudaStream_t st) {
   qkv_weights_t_kernel<<<(3 * DM * OW + 255) / 256, 256, 0, st>>>(wq, wk, wv, DM, OW, wt);
   HEPT_CHECK_LAUNCH("qkv_weights_t");
-  if (qkv_simt()) {
-    const size_t smem = sizeof(float) * ((size_t)DM * OW + (size_t)kAbHits * (DM + 4));
-    static DeviceOnce configured;
-    if (configured.needed()) {
-      cudaError_t e = cudaFuncSetAttribute(ln_qkv_fwd_kernel<DM, OW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "attn_qkv_fwd: cannot reserve %zu B of shared memory: %s", smem, cudaGetErrorString(e));
-      configured.mark();
-    }
-    ln_qkv_fwd_kernel<DM, OW><<<dim3((N + kAbHits - 1) / kAbHits, 3), kAbThreads, smem, st>>>(x, gamma, beta, wt, N, eps, xn, q, k, v);
-  } else {
-    const size_t smem = ln_qkv_fwd_mma_smem_bytes<DM, OW>();
-    static DeviceOnce configured;
-    if (configured.needed()) {
-      cudaError_t e = cudaFuncSetAttribute(ln_qkv_fwd_mma_kernel<DM, OW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "attn_qkv_fwd: cannot reserve %zu B of shared memory: %s", smem, cudaGetErrorString(e));
-      configured.mark();
-    }
-    const int sms = sm_count();
-    HEPT_REQUIRE(sms > 0, HEPT_ECUDA, "attn_qkv_fwd: cannot read the SM count");
-    const int tiles = (N + kAbMmaTile - 1) / kAbMmaTile, ctas = sms < tiles ? sms : tiles;
-    ln_qkv_fwd_mma_kernel<DM, OW><<<ctas, kAbMmaThreads, smem, st>>>(x, gamma, beta, wq, wk, wv, N, eps, xn, q, k, v);
+  const size_t smem = rows_wide_smem_bytes<DM, OW, 3>();
+  static DeviceOnce configured;
+  if (configured.needed()) {
+    cudaError_t e = cudaFuncSetAttribute(rows_wide_kernel<DM, OW, 3, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "attn_qkv_fwd: cannot reserve %zu B of shared memory: %s", smem, cudaGetErrorString(e));
+    configured.mark();
   }
+  const int sms = sm_count();
+  HEPT_REQUIRE(sms > 0, HEPT_ECUDA, "attn_qkv_fwd: cannot read the SM count");
+  const int tiles = (N + kAbMmaTile - 1) / kAbMmaTile;
+  rows_wide_kernel<DM, OW, 3, true, false><<<sms < tiles ? sms : tiles, kAbMmaThreads, smem, st>>>(x, gamma, beta, wq, wk, wv, N, eps, xn, q, k, v);
   HEPT_CHECK_LAUNCH("ln_qkv_fwd");
   return HEPT_OK;
 }
 
-// rows of the (ctas, 2 DM) buffer of LayerNorm parameter partials: either kernel's grid fits
+// rows of the (ctas, 2 DM) buffer of LayerNorm parameter partials: one per persistent CTA, i.e. per SM
 constexpr int kAbMaxCtas = 1024;
-static size_t ln_partial_rows(int N) {
-  const int simt = (N + kAbBwdHits - 1) / kAbBwdHits;
-  return (size_t)(simt > kAbMaxCtas ? simt : kAbMaxCtas);
-}
 
 template <int DM, int OW>
 static int launch_qkv_bwd(const float* x, const float* xn, const float* gamma, const float* wt, const float* dq, const float* dk,
                           const float* dv, int N, int H, int D, float eps, float* dx, float* dgamma, float* dbeta, float* dwq,
                           float* dwk, float* dwv, float* ws, size_t ws_floats, cudaStream_t st) {
-  const bool simt = qkv_simt();
   const int sms = sm_count();
   HEPT_REQUIRE(sms > 0, HEPT_ECUDA, "attn_qkv_bwd: cannot read the SM count");
-  const int tiles = (N + kAbMmaTile - 1) / kAbMmaTile;
-  const int ctas = simt ? (N + kAbBwdHits - 1) / kAbBwdHits : (sms < tiles ? sms : tiles);
   HEPT_REQUIRE(sms <= kAbMaxCtas, HEPT_EUNSUPPORTED, "attn_qkv_bwd: %d SMs, at most %d supported", sms, kAbMaxCtas);
-  const size_t ln_floats = ln_partial_rows(N) * 2 * DM;
+  const int tiles = (N + kAbMmaTile - 1) / kAbMmaTile;
+  const int ctas = sms < tiles ? sms : tiles;
+  const size_t ln_floats = (size_t)kAbMaxCtas * 2 * DM;
   HEPT_REQUIRE(ws_floats >= ln_floats + qkv_weight_grads_partial_floats(H, D), HEPT_EWORKSPACE, "attn_qkv_bwd: workspace too small");
-  if (simt) {
-    const size_t smem = sizeof(float) * kAbBwdStages * (size_t)(kAbBwdHits + DM) * (kAbBwdKc + 4);
-    static DeviceOnce configured;
-    if (configured.needed()) {
-      cudaError_t e = cudaFuncSetAttribute(ln_qkv_bwd_input_kernel<DM, OW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "attn_qkv_bwd: cannot reserve %zu B of shared memory: %s", smem, cudaGetErrorString(e));
-      configured.mark();
-    }
-    ln_qkv_bwd_input_kernel<DM, OW><<<ctas, kAbBwdThreads, smem, st>>>(dq, dk, dv, wt, x, gamma, N, eps, dx, ws);
-  } else {
-    const size_t smem = ln_qkv_bwd_mma_smem_bytes<DM, OW>();
-    static DeviceOnce configured;
-    if (configured.needed()) {
-      cudaError_t e = cudaFuncSetAttribute(ln_qkv_bwd_input_mma_kernel<DM, OW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "attn_qkv_bwd: cannot reserve %zu B of shared memory: %s", smem, cudaGetErrorString(e));
-      configured.mark();
-    }
-    ln_qkv_bwd_input_mma_kernel<DM, OW><<<ctas, kAbMmaThreads, smem, st>>>(dq, dk, dv, wt, x, gamma, N, eps, dx, ws);
+  const size_t smem = rows_narrow_smem_bytes<DM, OW, 3>();
+  static DeviceOnce configured;
+  if (configured.needed()) {
+    cudaError_t e = cudaFuncSetAttribute(rows_narrow_kernel<DM, OW, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "attn_qkv_bwd: cannot reserve %zu B of shared memory: %s", smem, cudaGetErrorString(e));
+    configured.mark();
   }
+  rows_narrow_kernel<DM, OW, 3, true><<<ctas, kAbMmaThreads, smem, st>>>(dq, dk, dv, wt, x, gamma, N, eps, dx, ws);
   HEPT_CHECK_LAUNCH("ln_qkv_bwd_input");
   ln_params_reduce_kernel<<<2 * DM, 256, 0, st>>>(ws, ctas, DM, dgamma, dbeta);
   HEPT_CHECK_LAUNCH("ln_params_reduce");
   return qkv_weight_grads(xn, dq, dk, dv, N, H, D, dwq, dwk, dwv, ws + ln_floats, ws_floats - ln_floats, st);
+}
+
+// out_linear (out_linear.cu) on the same two kernels, for the shipped H = 8, D = 24 shape: out = out_pre W^T + b and
+// d out_pre = d out W, W (24, 192)
+int out_linear_fwd_rows(const float* out_pre, const float* w, const float* b, int N, float* out, cudaStream_t st) {
+  constexpr int DM = 24, OW = 192;
+  const size_t smem = rows_narrow_smem_bytes<DM, OW, 1>();
+  static DeviceOnce configured;
+  if (configured.needed()) {
+    cudaError_t e = cudaFuncSetAttribute(rows_narrow_kernel<DM, OW, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "out_linear_fwd: cannot reserve %zu B of shared memory: %s", smem, cudaGetErrorString(e));
+    configured.mark();
+  }
+  const int sms = sm_count();
+  HEPT_REQUIRE(sms > 0, HEPT_ECUDA, "out_linear_fwd: cannot read the SM count");
+  const int tiles = (N + kAbMmaTile - 1) / kAbMmaTile;
+  rows_narrow_kernel<DM, OW, 1, false><<<sms < tiles ? sms : tiles, kAbMmaThreads, smem, st>>>(out_pre, nullptr, nullptr, w, nullptr, b, N, 0.f,
+                                                                                             out, nullptr);
+  HEPT_CHECK_LAUNCH("out_linear_fwd");
+  return HEPT_OK;
+}
+
+int out_linear_bwd_input_rows(const float* g, const float* w, int N, float* dx, cudaStream_t st) {
+  constexpr int DM = 24, OW = 192;
+  const size_t smem = rows_wide_smem_bytes<DM, OW, 1>();
+  static DeviceOnce configured;
+  if (configured.needed()) {
+    cudaError_t e = cudaFuncSetAttribute(rows_wide_kernel<DM, OW, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "out_linear_bwd: cannot reserve %zu B of shared memory: %s", smem, cudaGetErrorString(e));
+    configured.mark();
+  }
+  const int sms = sm_count();
+  HEPT_REQUIRE(sms > 0, HEPT_ECUDA, "out_linear_bwd: cannot read the SM count");
+  const int tiles = (N + kAbMmaTile - 1) / kAbMmaTile;
+  rows_wide_kernel<DM, OW, 1, false, true><<<sms < tiles ? sms : tiles, kAbMmaThreads, smem, st>>>(g, nullptr, nullptr, w, nullptr, nullptr, N, 0.f,
+                                                                                                 nullptr, dx, nullptr, nullptr);
+  HEPT_CHECK_LAUNCH("out_linear_bwd_input");
+  return HEPT_OK;
 }
 
 }  // namespace hept
@@ -707,7 +503,7 @@ extern "C" int hept_attn_qkv_supported(int32_t H, int32_t D) { return H == 8 && 
 
 extern "C" size_t hept_attn_qkv_bwd_workspace_bytes(int32_t N, int32_t H, int32_t D) {
   if (N <= 0 || H <= 0 || D <= 0) return 0;
-  return sizeof(float) * (ln_partial_rows(N) * 2 * D + qkv_weight_grads_partial_floats(H, D));
+  return sizeof(float) * ((size_t)kAbMaxCtas * 2 * D + qkv_weight_grads_partial_floats(H, D));
 }
 
 extern "C" int hept_attn_qkv_fwd(const float* x, const float* norm_weight, const float* norm_bias, const float* w_q,

@@ -1,18 +1,22 @@
 // a12, second half: the output projection out = out_pre W^T + b (example/hept.py:80, nn.Linear(H*D, D)) and its
-// backward, as streaming fp32 kernels.  The library GEMMs this replaces were 12 % of a tracking-60k step: the
-// 24 x 60000 x 192 weight-gradient product alone took 132 us in cuBLAS (one long reduction, poorly split), the
-// two 60000 x 192 x 24 products 29 us each.  All three are HBM-sized problems (46 MB of out_pre / d_out_pre):
-//   out_linear_fwd        reads out_pre once, W from shared memory                      -> out (N, D)        44 us
-//   out_linear_bwd_input  d_out_pre = g W, W from shared memory                         -> d_out_pre (N, H*D) 41 us
-// (measured at 60k hits; both are bound by the L1 tag stage: a lane-per-hit LDG.128 / STG.128 touches 32 lines.  Staging
-// the rows through shared memory with cp.async is the next step; tile-shape variants HEPT_OL_OUTS / HEPT_OL_HT do not
-// move them.)
-//   out_linear_bwd_params dW = g^T out_pre, db = sum_n g: per-CTA partials over slabs of hits, then a fixed-order
-//                         reduction over CTAs (deterministic, no floating-point atomics)
+// backward.  The library GEMMs this replaces were 12 % of a tracking-60k step: the 24 x 60000 x 192 weight-gradient
+// product alone took 132 us in cuBLAS (one long reduction, poorly split), the two 60000 x 192 x 24 products 29 us each.
+// All three are HBM-sized problems (46 MB of out_pre / d_out_pre, 0.28 GFMA).  For the shipped (H, D) = (8, 24) shape they run
+// on the legacy tensor path (mma.sync m16n8k8, 3xTF32, fp32 accumulation -- mma_tf32.cuh):
+//   out_linear_fwd        the narrow row kernel of attn_block.cu (K = 192 -> 24 outputs, + bias)          17 us
+//   out_linear_bwd_input  the wide row kernel of attn_block.cu (K = 24 -> 192 outputs)                    16 us
+//   out_linear_bwd_params dW = g^T out_pre, db = sum_n g: per-CTA partials over slabs of hits (below),    16 + 6 us
+//                         then a fixed-order reduction over CTAs (deterministic, no floating-point atomics)
+// (60k hits, ncu launch list.)  Other shapes take the CUDA-core kernels below: a hit per lane, weights broadcast from shared
+// memory (44 / 41 us at 60k hits; bound by the L1 tag stage -- a lane-per-hit LDG.128 / STG.128 touches 32 lines).
 #include "common.cuh"
 #include "mma_tf32.cuh"
 
 namespace hept {
+
+// the tensor-path row kernels of attn_block.cu, for the shipped (H, D) = (8, 24) shape
+int out_linear_fwd_rows(const float* out_pre, const float* w, const float* b, int N, float* out, cudaStream_t st);
+int out_linear_bwd_input_rows(const float* g, const float* w, int N, float* dx, cudaStream_t st);
 
 #ifndef HEPT_OL_OUTS
 #define HEPT_OL_OUTS 12
@@ -206,242 +210,10 @@ __global__ void __launch_bounds__(kOlThreads) out_linear_bwd_params_kernel(const
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// Register-tiled versions for IN = 8 OUT (the shipped H = 8 shapes).  The row-per-lane kernels above are bound by the
-// L1 tag stage (a warp's 16-byte accesses touch 32 lines) and by the 128 B/clk shared-memory return path (one
-// LDS.128 — broadcast or not — delivers 512 B per warp for 4 FMAs per lane).  Here the rows travel global -> shared
-// with fully coalesced cp.async (double-buffered), and a thread owns a 4-hit x 6-output (forward), 4-hit x 8-column
-// (input gradient) or 8 x 8 (weight gradient) register tile, so a 16-byte shared-memory load feeds 16-32 FMAs.
-// ---------------------------------------------------------------------------------------------------------------
-constexpr int kTlHits = 128;                       // hits per CTA tile (forward, input gradient)
-constexpr int kTlThreads = 128;
-
-// forward: thread = (q = tid / 4, og = tid % 4): hits q, q+32, q+64, q+96 x outputs [6 og, 6 og + 6)
-template <int OUT, int IN>
-__global__ void __launch_bounds__(kTlThreads) out_linear_fwd_tiled_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                                          const float* __restrict__ b, int N, float* __restrict__ out) {
-  constexpr int KC = 48, NCH = IN / KC, XS = KC + 4, WS = IN + 4, PER = OUT / 4;
-  static_assert(IN % KC == 0 && OUT % 4 == 0 && PER % 2 == 0, "tile shape");
-  extern __shared__ __align__(16) float s_dyn[];
-  float* s_w = s_dyn;                              // (OUT, WS)
-  float* s_x = s_w + OUT * WS;                     // (kTlHits, XS): one buffer; 45 KB per CTA -> 5 CTAs per SM, so the 469 tiles
-                                                   // of a 60k-hit event are ONE wave and other CTAs cover a CTA's load latency
-  const int tid = threadIdx.x, q = tid >> 2, og = tid & 3;
-  const int n0 = blockIdx.x * kTlHits;
-  const int rows = min(kTlHits, N - n0);
-  auto load_chunk = [&](int kc) {
-    float* dst = s_x;
-    for (int i = tid; i < kTlHits * (KC / 4); i += kTlThreads) {
-      const int r = i / (KC / 4), c4 = i - r * (KC / 4);
-      if (r < rows) cp_async16_cg(dst + r * XS + 4 * c4, x + (size_t)(n0 + r) * IN + kc * KC + 4 * c4);
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-  load_chunk(0);
-  for (int i = tid; i < OUT * (IN / 4); i += kTlThreads) {
-    const int j = i / (IN / 4), c4 = i - j * (IN / 4);
-    *reinterpret_cast<float4*>(s_w + j * WS + 4 * c4) = ldg4(w + (size_t)j * IN + 4 * c4);
-  }
-  // packed fp32 FMAs (fma.rn.f32x2, sm_100): an accumulator pair holds the sums over the even and the odd k of a
-  // 16-byte chunk pair; two FMAs per issue slot, the halves are added at the end
-  float2 acc[4][PER];
-#pragma unroll
-  for (int u = 0; u < PER; ++u) {
-    const float bu = __ldg(b + og * PER + u);
-#pragma unroll
-    for (int t = 0; t < 4; ++t) acc[t][u] = make_float2(bu, 0.f);
-  }
-#pragma unroll 1
-  for (int kc = 0; kc < NCH; ++kc) {
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
-    const float* xs = s_x + q * XS;
-    const float* ws = s_w + og * PER * WS + kc * KC;
-#pragma unroll 4
-    for (int c4 = 0; c4 < KC / 4; ++c4) {
-      float4 xv[4];
-#pragma unroll
-      for (int t = 0; t < 4; ++t) xv[t] = *reinterpret_cast<const float4*>(xs + 32 * t * XS + 4 * c4);
-#pragma unroll
-      for (int u = 0; u < PER; ++u) {
-        const float4 wv = *reinterpret_cast<const float4*>(ws + u * WS + 4 * c4);
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          acc[t][u] = __ffma2_rn(make_float2(xv[t].x, xv[t].y), make_float2(wv.x, wv.y), acc[t][u]);
-          acc[t][u] = __ffma2_rn(make_float2(xv[t].z, xv[t].w), make_float2(wv.z, wv.w), acc[t][u]);
-        }
-      }
-    }
-    __syncthreads();
-    if (kc + 1 < NCH) load_chunk(kc + 1);
-  }
-#pragma unroll
-  for (int t = 0; t < 4; ++t) {
-    const int r = q + 32 * t;
-    if (r < rows) {
-      float2* dst = reinterpret_cast<float2*>(out + (size_t)(n0 + r) * OUT + og * PER);
-#pragma unroll
-      for (int u2 = 0; u2 < PER / 2; ++u2)
-        dst[u2] = make_float2(acc[t][2 * u2].x + acc[t][2 * u2].y, acc[t][2 * u2 + 1].x + acc[t][2 * u2 + 1].y);
-    }
-  }
-}
-
-// input gradient: thread = (q = tid / 4, cg = tid % 4 + 4 i): hits q + 32 u x columns [8 cg, 8 cg + 8), i < IN / 32
-template <int OUT, int IN>
-__global__ void __launch_bounds__(kTlThreads, 4) out_linear_bwd_input_tiled_kernel(const float* __restrict__ g,
-                                                                                const float* __restrict__ w, int N,
-                                                                                float* __restrict__ dx) {
-  constexpr int GS = OUT + 4;
-  static_assert(OUT % 4 == 0 && IN % 32 == 0, "tile shape");
-  extern __shared__ __align__(16) float s_dyn[];
-  float* s_w = s_dyn;                              // (OUT, IN)
-  float* s_g = s_w + OUT * IN;                     // (kTlHits, GS)
-  const int tid = threadIdx.x, q = tid >> 2, c0 = tid & 3;
-  const int n0 = blockIdx.x * kTlHits;
-  const int rows = min(kTlHits, N - n0);
-  for (int i = tid; i < OUT * IN / 4; i += kTlThreads) reinterpret_cast<float4*>(s_w)[i] = __ldg(reinterpret_cast<const float4*>(w) + i);
-  for (int i = tid; i < kTlHits * (OUT / 4); i += kTlThreads) {
-    const int r = i / (OUT / 4), j4 = i - r * (OUT / 4);
-    *reinterpret_cast<float4*>(s_g + r * GS + 4 * j4) =
-        r < rows ? ldg4(g + (size_t)(n0 + r) * OUT + 4 * j4) : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  __syncthreads();
-#pragma unroll 1
-  for (int i = 0; i < IN / 32; ++i) {
-    asm volatile("" ::: "memory");                 // keep the gradient rows in shared memory: hoisting their loads out of
-                                                   // this loop costs 96 registers (spills, one CTA less per SM)
-    const int cg = c0 + 4 * i;
-    float4 a0[4], a1[4];
-#pragma unroll
-    for (int t = 0; t < 4; ++t) { a0[t] = make_float4(0.f, 0.f, 0.f, 0.f); a1[t] = a0[t]; }
-#pragma unroll
-    for (int j4 = 0; j4 < OUT / 4; ++j4) {
-      float4 gv[4];
-#pragma unroll
-      for (int t = 0; t < 4; ++t) gv[t] = *reinterpret_cast<const float4*>(s_g + (q + 32 * t) * GS + 4 * j4);
-#pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
-        const float4 w0 = *reinterpret_cast<const float4*>(s_w + (4 * j4 + jj) * IN + 8 * cg);
-        const float4 w1 = *reinterpret_cast<const float4*>(s_w + (4 * j4 + jj) * IN + 8 * cg + 4);
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const float gj = jj == 0 ? gv[t].x : (jj == 1 ? gv[t].y : (jj == 2 ? gv[t].z : gv[t].w));
-          const float2 g2 = make_float2(gj, gj);     // packed fp32 FMAs: two columns per issue slot, same sums per element
-          float2 r;
-          r = __ffma2_rn(g2, make_float2(w0.x, w0.y), make_float2(a0[t].x, a0[t].y)); a0[t].x = r.x; a0[t].y = r.y;
-          r = __ffma2_rn(g2, make_float2(w0.z, w0.w), make_float2(a0[t].z, a0[t].w)); a0[t].z = r.x; a0[t].w = r.y;
-          r = __ffma2_rn(g2, make_float2(w1.x, w1.y), make_float2(a1[t].x, a1[t].y)); a1[t].x = r.x; a1[t].y = r.y;
-          r = __ffma2_rn(g2, make_float2(w1.z, w1.w), make_float2(a1[t].z, a1[t].w)); a1[t].z = r.x; a1[t].w = r.y;
-        }
-      }
-    }
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const int r = q + 32 * t;
-      if (r < rows) {
-        st_global_v8(dx + (size_t)(n0 + r) * IN + 8 * cg, a0[t], a1[t]);
-      }
-    }
-  }
-}
-
-// weight / bias gradient, stage 1: a CTA = kPgGroups hit groups x (OUT / 8) x (IN / 8) threads; a thread owns an 8 x 8 tile
-// of dW; slabs of kPgRows hits are staged in shared memory (double-buffered cp.async); group p takes the hits p, p + G, ...
-// of a slab.  The groups' tiles are added through shared memory in group order (deterministic), db by the ct == 0 threads.
-constexpr int kPgGroups = 4, kPgRows = 32, kPgStages = 2;   // (three stages measured: no gain, the loop is barrier-bound)
-template <int OUT, int IN>
-__global__ void __launch_bounds__(kPgGroups * (OUT / 8) * (IN / 8), 2) out_linear_bwd_params_tiled_kernel(
-    const float* __restrict__ g, const float* __restrict__ x, int N, float* __restrict__ partial) {
-  constexpr int JT = OUT / 8, CT = IN / 8, PER = JT * CT, THREADS = kPgGroups * PER;
-  constexpr int XS = IN + 4, GS = OUT + 4, SLAB = kPgRows * (XS + GS);
-  static_assert(2 * SLAB >= (OUT + 1) * IN, "the staging buffers double as the reduction buffer");
-  extern __shared__ __align__(16) float s_dyn[];   // kPgStages x [ (kPgRows, XS) | (kPgRows, GS) ]: the loads of two slabs are in
-                                                   // flight while one is consumed (a slab's compute is shorter than its load latency)
-  const int tid = threadIdx.x, p = tid / PER, u = tid % PER;
-  const int jt = u / CT, ct = u % CT;
-  float2 acc[8][4];                                // 8 x 8 tile as column pairs: packed fp32 FMAs, two columns per issue slot
-  float bsum[8];
-#pragma unroll
-  for (int a = 0; a < 8; ++a) {
-    bsum[a] = 0.f;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) acc[a][c] = make_float2(0.f, 0.f);
-  }
-  const int slabs = (N + kPgRows - 1) / kPgRows;
-  auto load_slab = [&](int slab, int buf) {
-    float* xs = s_dyn + buf * SLAB;
-    float* gs = xs + kPgRows * XS;
-    const int n0 = slab * kPgRows, rows = min(kPgRows, N - n0);
-    for (int i = tid; i < kPgRows * (IN / 4); i += THREADS) {
-      const int r = i / (IN / 4), c4 = i - r * (IN / 4);
-      if (r < rows) cp_async16_cg(xs + r * XS + 4 * c4, x + (size_t)(n0 + r) * IN + 4 * c4);
-    }
-    for (int i = tid; i < kPgRows * (OUT / 4); i += THREADS) {
-      const int r = i / (OUT / 4), j4 = i - r * (OUT / 4);
-      if (r < rows) cp_async16_cg(gs + r * GS + 4 * j4, g + (size_t)(n0 + r) * OUT + 4 * j4);
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-  int slab = blockIdx.x, it = 0;
-#pragma unroll
-  for (int pre = 0; pre < kPgStages - 1; ++pre) {      // one commit group per stage, empty ones included: the waits count groups
-    if (slab + pre * (int)gridDim.x < slabs) load_slab(slab + pre * gridDim.x, pre);
-    else asm volatile("cp.async.commit_group;" ::: "memory");
-  }
-#pragma unroll 1
-  for (; slab < slabs; slab += gridDim.x, ++it) {
-    const int next = slab + (kPgStages - 1) * (int)gridDim.x;
-    if (next < slabs) load_slab(next, (it + kPgStages - 1) % kPgStages);
-    else asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group %0;" :: "n"(kPgStages - 1) : "memory");
-    __syncthreads();
-    const float* xs = s_dyn + (it % kPgStages) * SLAB;
-    const float* gs = xs + kPgRows * XS;
-    const int rows = min(kPgRows, N - slab * kPgRows);
-#pragma unroll 2
-    for (int r = p; r < rows; r += kPgGroups) {
-      const float4 g0 = *reinterpret_cast<const float4*>(gs + r * GS + 8 * jt), g1 = *reinterpret_cast<const float4*>(gs + r * GS + 8 * jt + 4);
-      // the thread's eight columns are 4 ct .. 4 ct + 3 and IN / 2 + 4 ct ..: a warp's 128-bit loads cover consecutive words
-      const float4 x0 = *reinterpret_cast<const float4*>(xs + r * XS + 4 * ct), x1 = *reinterpret_cast<const float4*>(xs + r * XS + IN / 2 + 4 * ct);
-      const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-      const float2 xv[4] = {make_float2(x0.x, x0.y), make_float2(x0.z, x0.w), make_float2(x1.x, x1.y), make_float2(x1.z, x1.w)};
-#pragma unroll
-      for (int a = 0; a < 8; ++a) {
-        const float2 g2 = make_float2(gv[a], gv[a]);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) acc[a][c] = __ffma2_rn(g2, xv[c], acc[a][c]);
-        bsum[a] += gv[a];                          // only the ct == 0 threads' sums are used
-      }
-    }
-    __syncthreads();
-  }
-  // groups add their tiles in order 0, 1, ... through shared memory (the staging buffers are free now)
-  float* s_acc = s_dyn;                            // (OUT + 1, IN)
-#pragma unroll 1
-  for (int turn = 0; turn < kPgGroups; ++turn) {
-    if (p == turn) {
-#pragma unroll
-      for (int a = 0; a < 8; ++a) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          float4* dst = reinterpret_cast<float4*>(s_acc + (8 * jt + a) * IN + h * (IN / 2) + 4 * ct);
-          float4 v = make_float4(acc[a][2 * h].x, acc[a][2 * h].y, acc[a][2 * h + 1].x, acc[a][2 * h + 1].y);
-          if (turn != 0) { const float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
-          *dst = v;
-        }
-        if (ct == 0) s_acc[OUT * IN + 8 * jt + a] = turn == 0 ? bsum[a] : s_acc[OUT * IN + 8 * jt + a] + bsum[a];
-      }
-    }
-    __syncthreads();
-  }
-  float* dstp = partial + (size_t)blockIdx.x * (OUT + 1) * IN;
-  for (int i = tid; i < OUT * IN + OUT; i += THREADS) dstp[i] = s_acc[i];
-}
-
-// The same product on the legacy tensor path (mma.sync m16n8k8, 3xTF32: lo*hi + hi*lo + hi*hi with fp32 accumulation): the
-// CUDA-core kernel above is bound by its shared-memory wavefronts (70 % of the LSU data pipe, profiles/r2_ncu_prof_front_r2.csv),
-// an mma needs an eighth of the operand loads per product.  P[c][j] = sum_n x[n][c] g[n][j]: M = the IN columns of x, N = the
+// weight / bias gradient, stage 1, on the legacy tensor path (mma_tf32.cuh: mma.sync m16n8k8, 3xTF32 with fp32 accumulation).
+// The CUDA-core version of this product (8 x 8 register tiles over staged slabs) was bound by its shared-memory wavefronts
+// (70 % of the LSU data pipe, profiles/r2_ncu_prof_front_r2.csv: 33.6 us); an mma needs an eighth of the operand loads per
+// product (15.5 us).  P[c][j] = sum_n x[n][c] g[n][j]: M = the IN columns of x, N = the
 // OUT columns of g, K = hits.  Slabs of 32 hits go through a cp.async ring of three slots (two slabs in flight per CTA, two
 // CTAs per SM: 120 KB of loads in flight per SM); a warp = (k half hg, column group mg) multiplies 48 columns (three M tiles) x
 // all OUT columns (three N tiles) over two of a slab's four k-steps.  k-slot t of k-step s is hit 4 s + t of the slab, k-slot
@@ -636,14 +408,9 @@ __global__ void __launch_bounds__(32 * kOlParts) out_linear_reduce_kernel(const 
   }
 }
 
-// HEPT_PG_STAGED=1 selects the staged CUDA-core kernel (A/B against the tensor-path one); read once.
-static bool pg_staged() {
-  static const bool v = [] { const char* e = getenv("HEPT_PG_STAGED"); return e && e[0] == '1'; }();
-  return v;
-}
 // CTAs per operand pair: two resident CTAs per SM over all pairs
 static int pg_ctas(int sms, int slabs, int pairs) {
-  int ctas = pg_staged() ? 2 * sms : 2 * sms / pairs;
+  int ctas = 2 * sms / pairs;
   if (ctas > slabs) ctas = slabs;
   return ctas > kOlMaxCtas / pairs ? kOlMaxCtas / pairs : ctas;     // the workspace holds kOlMaxCtas partials
 }
@@ -652,30 +419,17 @@ template <int OUT, int TIN>
 static int launch_pg(const PgOperands& ops, int pairs, int N, float* partial, int ctas, const PgResults& res, float* db,
                      bool transposed, cudaStream_t st, const char* what) {
   const int entries = (OUT + 1) * TIN;
-  if (pg_staged()) {
-    constexpr int THREADS = kPgGroups * (OUT / 8) * (TIN / 8);
-    const size_t tsmem = sizeof(float) * kPgStages * (size_t)kPgRows * (TIN + 4 + OUT + 4);
-    static DeviceOnce configured;
-    if (configured.needed()) {
-      cudaError_t e = cudaFuncSetAttribute(out_linear_bwd_params_tiled_kernel<OUT, TIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem);
-      HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "%s: %s", what, cudaGetErrorString(e));
-      configured.mark();
-    }
-    for (int m = 0; m < pairs; ++m)
-      out_linear_bwd_params_tiled_kernel<OUT, TIN><<<ctas, THREADS, tsmem, st>>>(ops.g[m], ops.x[m], N, partial + (size_t)m * ctas * entries);
-  } else {
-    const size_t msmem = params_mma_smem_bytes<OUT, TIN>();
-    static DeviceOnce configured;
-    if (configured.needed()) {
-      cudaError_t e = cudaFuncSetAttribute(out_linear_bwd_params_mma_kernel<OUT, TIN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem);
-      if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(out_linear_bwd_params_mma_kernel<OUT, TIN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem);
-      HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "%s: %s", what, cudaGetErrorString(e));
-      configured.mark();
-    }
-    if (db) out_linear_bwd_params_mma_kernel<OUT, TIN, true><<<dim3(ctas, pairs), kPmThreads, msmem, st>>>(ops, N, partial);
-    else out_linear_bwd_params_mma_kernel<OUT, TIN, false><<<dim3(ctas, pairs), kPmThreads, msmem, st>>>(ops, N, partial);
+  const size_t msmem = params_mma_smem_bytes<OUT, TIN>();
+  static DeviceOnce configured;
+  if (configured.needed()) {
+    cudaError_t e = cudaFuncSetAttribute(out_linear_bwd_params_mma_kernel<OUT, TIN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(out_linear_bwd_params_mma_kernel<OUT, TIN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem);
+    HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "%s: %s", what, cudaGetErrorString(e));
+    configured.mark();
   }
+  if (db) out_linear_bwd_params_mma_kernel<OUT, TIN, true><<<dim3(ctas, pairs), kPmThreads, msmem, st>>>(ops, N, partial);
+  else out_linear_bwd_params_mma_kernel<OUT, TIN, false><<<dim3(ctas, pairs), kPmThreads, msmem, st>>>(ops, N, partial);
   cudaError_t e = cudaGetLastError();
   HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "%s (partial sums): %s", what, cudaGetErrorString(e));
   out_linear_reduce_kernel<<<dim3((entries + 31) / 32, pairs), 32 * kOlParts, 0, st>>>(partial, ctas, OUT, TIN, res, db, transposed);
@@ -695,19 +449,8 @@ static int launch_ol_fwd(const hept_shape* s, const float* x, const float* w, co
     configured.mark();
   }
   HEPT_REQUIRE(smem <= 96 * 1024 && IN % 4 == 0, HEPT_EUNSUPPORTED, "out_linear_fwd: H*D=%d not supported", IN);
-  if constexpr (OUT == 24) if (IN == OUT * 8) {    // the shipped H = 8, D = 24 shape: staged, register-tiled
-    constexpr int TIN = OUT * 8;
-    const size_t tsmem = sizeof(float) * ((size_t)OUT * (TIN + 4) + (size_t)kTlHits * (48 + 4));
-    static DeviceOnce tconfigured;
-    if (tconfigured.needed()) {
-      cudaError_t e = cudaFuncSetAttribute(out_linear_fwd_tiled_kernel<OUT, TIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem);
-      HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "out_linear_fwd: %s", cudaGetErrorString(e));
-      tconfigured.mark();
-    }
-    out_linear_fwd_tiled_kernel<OUT, TIN><<<(s->N + kTlHits - 1) / kTlHits, kTlThreads, tsmem, st>>>(x, w, b, s->N, out);
-    HEPT_CHECK_LAUNCH("out_linear_fwd");
-    return HEPT_OK;
-  }
+  if constexpr (OUT == 24) if (IN == OUT * 8)      // the shipped H = 8, D = 24 shape: the tensor-path row kernels (attn_block.cu)
+    return out_linear_fwd_rows(x, w, b, s->N, out, st);
   const int units = (s->N + 32 * HT - 1) / (32 * HT) * (OUT / OUTS);
   out_linear_fwd_kernel<OUT, OUTS, HT><<<(units + kOlWarps - 1) / kOlWarps, 32 * kOlWarps, smem, st>>>(x, w, b, s->N, IN, out);
   HEPT_CHECK_LAUNCH("out_linear_fwd");
@@ -731,20 +474,12 @@ static int launch_ol_bwd(const hept_shape* s, const float* g, const float* w, co
       configured.mark();
     }
     HEPT_REQUIRE(smem <= 96 * 1024, HEPT_EUNSUPPORTED, "out_linear_bwd: H*D=%d too wide", IN);
-    bool tiled = false;
+    bool rows = false;
     if constexpr (OUT == 24) if (IN == OUT * 8) {
-      tiled = true;
-      constexpr int TIN = OUT * 8;
-      const size_t tsmem = sizeof(float) * ((size_t)OUT * TIN + (size_t)kTlHits * (OUT + 4));
-      static DeviceOnce tconfigured;
-      if (tconfigured.needed()) {
-        cudaError_t e = cudaFuncSetAttribute(out_linear_bwd_input_tiled_kernel<OUT, TIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem);
-        HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "out_linear_bwd: %s", cudaGetErrorString(e));
-        tconfigured.mark();
-      }
-      out_linear_bwd_input_tiled_kernel<OUT, TIN><<<(s->N + kTlHits - 1) / kTlHits, kTlThreads, tsmem, st>>>(g, w, s->N, dx);
+      rows = true;
+      if (int rc = out_linear_bwd_input_rows(g, w, s->N, dx, st)) return rc;
     }
-    if (!tiled) {
+    if (!rows) {
       const int units = (s->N + 63) / 64 * SPLIT;
       const unsigned grid = (unsigned)((units + kOlWarps - 1) / kOlWarps);
       out_linear_bwd_input_kernel<OUT, SPLIT><<<grid, 32 * kOlWarps, smem, st>>>(g, w, s->N, IN, dx);
@@ -760,7 +495,7 @@ static int launch_ol_bwd(const hept_shape* s, const float* g, const float* w, co
     PgOperands ops{};
     PgResults res{};
     ops.g[0] = g; ops.x[0] = x; res.dw[0] = dw;
-    return launch_pg<OUT, TIN>(ops, 1, s->N, partial, pg_ctas(sms, (s->N + kPgRows - 1) / kPgRows, 1), res, db, false, st, "out_linear_bwd");
+    return launch_pg<OUT, TIN>(ops, 1, s->N, partial, pg_ctas(sms, (s->N + kPmRows - 1) / kPmRows, 1), res, db, false, st, "out_linear_bwd");
   }
   const size_t psmem = sizeof(float) * ((size_t)kOlRows * OUT + (size_t)OUT * IN);
   out_linear_bwd_params_kernel<OUT><<<ctas, kOlThreads, psmem, st>>>(g, x, s->N, IN, partial);
@@ -789,7 +524,7 @@ int qkv_weight_grads(const float* xn, const float* dq, const float* dk, const fl
   const float* src[3] = {dq, dk, dv};
   float* dst[3] = {dwq, dwk, dwv};
   for (int m = 0; m < 3; ++m) { ops.g[m] = xn; ops.x[m] = src[m]; res.dw[m] = dst[m]; }
-  return launch_pg<OUT, TIN>(ops, 3, N, partial, pg_ctas(sms, (N + kPgRows - 1) / kPgRows, 3), res, nullptr, true, st, "qkv_weight_grads");
+  return launch_pg<OUT, TIN>(ops, 3, N, partial, pg_ctas(sms, (N + kPmRows - 1) / kPmRows, 3), res, nullptr, true, st, "qkv_weight_grads");
 }
 
 }  // namespace hept
