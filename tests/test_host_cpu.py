@@ -140,7 +140,8 @@ def _gloo_worker(rank, world, port, out):
     x = torch.stack([torch.full((5,), float(e + 1)) for e in events])
     lin(x).sum().backward()
     nbytes = sharding.allreduce_gradients([lin.weight, lin.bias, frozen, None], average=False)
-    out.put((rank, lin.weight.grad.clone(), lin.bias.grad.clone(), nbytes))
+    # plain lists, not tensors: a tensor in a queue is a handle to the sender's shared memory, gone if the sender exits first
+    out.put((rank, lin.weight.grad.tolist(), lin.bias.grad.tolist(), nbytes))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -164,7 +165,7 @@ def test_gradient_allreduce_two_ranks_gloo():
     x = torch.stack([torch.full((5,), float(e + 1)) for e in range(6)])
     lin(x).sum().backward()
     for rank, gw, gb, nbytes in got:
-        assert torch.allclose(gw, lin.weight.grad) and torch.allclose(gb, lin.bias.grad)
+        assert torch.allclose(torch.tensor(gw), lin.weight.grad) and torch.allclose(torch.tensor(gb), lin.bias.grad)
         assert nbytes == (15 + 3) * 4
 
 
@@ -185,7 +186,7 @@ def _bucket_worker(rank, world, port, out):
         lin(x).sum().backward()
         assert bucket.attached()
         bucket.allreduce(average=True)
-        res.append((lin.weight.grad.clone(), lin.bias.grad.clone(), unused.grad.clone()))
+        res.append((lin.weight.grad.tolist(), lin.bias.grad.tolist(), unused.grad.tolist()))
     out.put((rank, res, bucket.nbytes))
     dist.barrier()
     dist.destroy_process_group()
@@ -213,8 +214,8 @@ def test_flat_gradient_bucket_two_ranks_gloo():
         lin(x).sum().backward()
         for rank, res, nbytes in got:
             gw, gb, gu = res[step]
-            assert torch.allclose(gw, lin.weight.grad / 2) and torch.allclose(gb, lin.bias.grad / 2)
-            assert bool((gu == 0).all()) and nbytes == (15 + 3 + 4) * 4
+            assert torch.allclose(torch.tensor(gw), lin.weight.grad / 2) and torch.allclose(torch.tensor(gb), lin.bias.grad / 2)
+            assert all(v == 0 for v in gu) and nbytes == (15 + 3 + 4) * 4
 
 
 def test_trace_variant_of_the_library_builds():

@@ -13,7 +13,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-fil
 # (3) --set full of the two tile kernels (second repetition) and of the new streaming kernels
 ncu --set full --clock-control none --import-source on -k regex:block_attn -s 2 -c 2 -f -o gpurun_out/prof_tiles_r2 \
     python tools/profile_step.py > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"ln_qkv|qkv_weights|params_tiled|ln_params" -s 5 -c 6 -f -o gpurun_out/prof_front_r2 \
+ncu --set full --clock-control none --import-source on -k regex:"rows_wide|rows_narrow|qkv_weights|params_mma|ln_params" -s 7 -c 8 -f -o gpurun_out/prof_front_r2 \
     python tools/profile_block.py 60000 2 > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"prep_|cluster_sort" -c 12 -f -o gpurun_out/prof_prepare_r2 \
     python tools/prof_prepare.py > /dev/null 2>&1
