@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(kOlThreads) out_linear_bwd_params_kernel(const
 
 // weight / bias gradient, stage 1, on the legacy tensor path (mma_tf32.cuh: mma.sync m16n8k8, 3xTF32 with fp32 accumulation).
 // The CUDA-core version of this product (8 x 8 register tiles over staged slabs) was bound by its shared-memory wavefronts
-// (70 % of the LSU data pipe, profiles/r2_ncu_prof_front_r2.csv: 33.6 us); an mma needs an eighth of the operand loads per
+// (70 % of the LSU data pipe, profiles/r2a_ncu_prof_front_cudacore.csv: 33.6 us); an mma needs an eighth of the operand loads per
 // product (15.5 us).  P[c][j] = sum_n x[n][c] g[n][j]: M = the IN columns of x, N = the
 // OUT columns of g, K = hits.  Slabs of 32 hits go through a cp.async ring of three slots (two slabs in flight per CTA, two
 // CTAs per SM: 120 KB of loads in flight per SM); a warp = (k half hg, column group mg) multiplies 48 columns (three M tiles) x
