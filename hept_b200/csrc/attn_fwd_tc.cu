@@ -19,16 +19,18 @@
 // small cross terms are accumulated first and the hi*hi steps are split over two accumulators that the epilogue adds
 // in fp32 (S0: cross terms + first half of the k-steps, S1: the rest).
 //
-// Warp roles (896 threads = 7 warpgroups, register budgets rebalanced with setmaxnreg):
+// Warp roles (896 threads = 7 warpgroups, register budgets 96 / 64 / 56 rebalanced with setmaxnreg):
 //   warps 0-7   epilogue: TMEM lane = (warp & 3) * 32 + lane, columns split in two parts (warp >> 2); software
 //               pipelined: P of tile n+1 is produced before the output rows of tile n are read and scattered, so the
-//               P V MMAs of tile n run under SIMT work.  The same warps own the value operand: raw v rows travel
-//               global -> shared with cp.async four tiles ahead, and right after O of tile n has been read out (its
-//               P V MMAs are done, so the value tiles of that stage are free) each thread splits its own chunks into
-//               the MN-major (hi, lo) value tiles of tile n+2
+//               P V MMAs of tile n run under SIMT work
 //   warps 8-23  producer: gather q^ / k^ rows through the sort permutation into registers (one tile ahead), centre,
 //               split, write the K-major operand tiles of stage n & 1 as soon as the score MMAs of tile n-2 are done
 //   warp 24     one elected lane issues every tcgen05.mma: S(n+1), then P V(n)
+//   warps 25-27 value operand: raw v rows travel global -> shared with cp.async four tiles ahead; as soon as P V of tile
+//               n is done (its value tiles are free) each thread splits its own chunks into the MN-major (hi, lo) value
+//               tiles of tile n+2.  (Until round 2 the epilogue warps did this between two tiles: with 16 producer warps
+//               the epilogue was the kernel's serial chain -- 2 000 of its 6 200 traced cycles per tile -- and these
+//               three warps idle: 288 -> 271 us.)
 // TMEM: two tile slots of 256 columns (S0 | S1 | O).  Hand-offs are mbarriers that complete once per use of a slot /
 // stage, so the wait parity is bit 1 of the tile counter.
 #include "tile.cuh"
@@ -48,7 +50,8 @@ constexpr int kFtParts = kFtEpiThreads / 128;
 // The gather / centre / split work of the producer is latency bound (ncu: every producer warp busy or stalled on its
 // own loads the whole time, the epilogue waiting for scores), so it gets 16 warps: two 64-row passes per tile.
 constexpr int kFtLaunchRegs = 72;
-constexpr int kFtRegsEpi = 104, kFtRegsProd = 64, kFtRegsMma = 24;
+constexpr int kFtRegsEpi = 96, kFtRegsProd = 64, kFtRegsMma = 56;
+constexpr int kFtVWarps = 3, kFtVThreads = 32 * kFtVWarps;   // the MMA warp's three siblings prepare the value operand
 static_assert(kFtEpiThreads * kFtRegsEpi + kFtProdThreads * kFtRegsProd + 128 * kFtRegsMma <= kFtThreads * kFtLaunchRegs, "register pool");
 
 template <int D, int C, int B>
@@ -111,7 +114,7 @@ __global__ void __launch_bounds__(kFtThreads, 1)
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
       umma::mbar_init(&mbar[QKFULL + s], PW);
-      umma::mbar_init(&mbar[VFULL + s], EW);           // the epilogue warps own the value operand
+      umma::mbar_init(&mbar[VFULL + s], kFtVWarps);    // the value warps own the value operand
       umma::mbar_init(&mbar[QKFREE + s], 1);
       umma::mbar_init(&mbar[VFREE + s], 1);
       umma::mbar_init(&mbar[SREADY + s], 1);
@@ -211,76 +214,9 @@ __global__ void __launch_bounds__(kFtThreads, 1)
       if (warp == 0) HEPT_TRACE_EVENT(EV_E_PREADY, it);
     };
 
-    // ---- the value operand is the epilogue's job: it waits on S for a good third of a tile, the producer warps, which
-    // bound the kernel, do not.  Raw v rows travel global -> shared with cp.async (no registers) four tiles before they
-    // are used; thread <-> items (row r, chunk c < D / 4) idx = tid, tid + 256, ...; a thread splits its own items into
-    // (hi, lo) and writes the MN-major tiles of stage it & 1 right after it has read O of tile it - 2 out (P V done).
-    constexpr int ITEMS = B * VCH, VPER = (ITEMS + kFtEpiThreads - 1) / kFtEpiThreads;
-    const int g = (int)gridDim.x;
-    int hit[VPER];                                     // key-side hit index of this thread's items, loaded one step before `v_issue`
-    auto v_hits = [&](int tile) {
-      int h, t, blk;
-      decode(tile, h, t, blk);
-      const int32_t* kpos = positions + ((size_t)T * H + t * H + h) * N + (size_t)blk * B;
-#pragma unroll
-      for (int u = 0; u < VPER; ++u) {
-        const int idx = tid + u * kFtEpiThreads;
-        hit[u] = idx < ITEMS ? __ldg(kpos + idx / VCH) : -1;
-      }
-    };
-    auto v_issue = [&](int tile, int set) {            // uses hit[] loaded for `tile`; always commits one group
-      if (tile < total_tiles) {
-        int h, t, blk;
-        decode(tile, h, t, blk);
-        float4* stg = reinterpret_cast<float4*>(smem + CF::OFF_VSTG + set * CF::VSTG);
-        const float* vh = v + (size_t)h * D;
-#pragma unroll
-        for (int u = 0; u < VPER; ++u) {
-          const int idx = tid + u * kFtEpiThreads;
-          if (idx < ITEMS) {
-            const int n = hit[u];
-            const bool ok = n < raw_size;
-            umma::cp_async16(stg + idx, ok ? vh + (size_t)n * H * D + 4 * (idx % VCH) : v, ok ? 16 : 0);
-          }
-        }
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    auto v_write = [&](int vit) {                      // value tiles of tile number `vit` (stage vit & 1) from staging set vit & 1
-      const int st = vit & 1;
-      uint8_t* vm = smem + CF::OFF_V + st * 2 * CF::TILE;
-      const float4* stg = reinterpret_cast<const float4*>(smem + CF::OFF_VSTG + st * CF::VSTG);
-#pragma unroll
-      for (int u = 0; u < VPER; ++u) {
-        const int idx = tid + u * kFtEpiThreads;
-        if (idx < ITEMS) {
-          float4 hi, lo;
-          split4(stg[idx], hi, lo);
-          const uint32_t omn = umma::sw128b32_offset(idx / VCH, idx % VCH);
-          *reinterpret_cast<float4*>(vm + omn) = hi;
-          *reinterpret_cast<float4*>(vm + CF::TILE + omn) = lo;
-        }
-      }
-      umma::fence_async_smem();
-      __syncwarp();
-      if (lane == 0) umma::mbar_arrive(&mbar[VFULL + st]);
-      if (warp == 0) HEPT_TRACE_EVENT(EV_P_VFULL, vit);
-    };
-    // prologue: rows of tiles 0, 1 (written before the loop), 2, 3 (in flight); groups are committed in tile order
-    const int tile0 = blockIdx.x;
-#pragma unroll 1
-    for (int j = 0; j < 4; ++j) {
-      if (tile0 + j * g < total_tiles) v_hits(tile0 + j * g);
-      if (j == 2) {                                    // sets are reused: tiles 0 and 1 must be out of them first
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        if (tile0 < total_tiles) v_write(0);
-        if (tile0 + g < total_tiles) v_write(1);
-      }
-      v_issue(tile0 + j * g, j & 1);
-    }
-    if (tile0 + 4 * g < total_tiles) v_hits(tile0 + 4 * g);
-
     int it = 0;
+    // (tried: the read-out below on the producer warps, which wait for the score MMAs most of a tile -- their wait for
+    // P V then delays the next tile's operands, and three parties on the TMEM port stretch the P V MMAs: 283 us against 271)
     if ((int)blockIdx.x < total_tiles) make_p(0);
 #pragma unroll 1
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -306,15 +242,7 @@ __global__ void __launch_bounds__(kFtThreads, 1)
           if (4 * part + cc < WR) dst[4 * part + cc] = make_float4(ov[4 * cc], ov[4 * cc + 1], ov[4 * cc + 2], ov[4 * cc + 3]);
       }
       if (warp == 0) HEPT_TRACE_EVENT(EV_E_OUT, it);
-      // ---- P V of this tile is done (ODONE): its value tiles are free -> write those of tile it + 2, refill the set -----
-      if (tile + 2 * g < total_tiles) {
-        asm volatile("cp.async.wait_group 1;" ::: "memory");     // rows of tile it + 2 have landed (it + 3 may be in flight)
-        v_write(it + 2);
-      }
-      v_issue(tile + 4 * g, it & 1);                             // hit[] holds tile it + 4
-      if (tile + 5 * g < total_tiles) v_hits(tile + 5 * g);
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
   } else if (warp < EW + PW) {
     // =========================================== producer warps =================================================
     umma::setmaxnreg_dec<kFtRegsProd>();
@@ -428,6 +356,94 @@ __global__ void __launch_bounds__(kFtThreads, 1)
     }
   } else {
     umma::setmaxnreg_dec<kFtRegsMma>();
+  }
+  if (warp > EW + PW) {
+    // =========================================== value warps ===================================================
+    const int vt = tid - (kFtEpiThreads + kFtProdThreads + 32);
+    // ---- the value operand: raw v rows travel global -> shared with cp.async (no registers) four tiles before they are
+    // used; thread <-> items (row r, chunk c < D / 4) idx = vt, vt + 96, ...; a thread splits its own items into (hi, lo)
+    // and writes the MN-major tiles of stage it & 1 as soon as P V of tile it - 2 is done (VFREE).  Round 1 gave this to the
+    // epilogue warps, when the producers bounded the kernel; with 16 producer warps the epilogue became the serial chain
+    // (pipeline trace: 2 000 of its 6 200 cycles per tile went here while S of the next tile sat ready in TMEM), and the MMA
+    // warp's three siblings were idle.
+    constexpr int ITEMS = B * VCH, VPER = (ITEMS + kFtVThreads - 1) / kFtVThreads;
+    const int g = (int)gridDim.x;
+    int hit[VPER];                                     // key-side hit index of this thread's items, loaded one step before `v_issue`
+    auto v_hits = [&](int tile) {
+      int h, t, blk;
+      decode(tile, h, t, blk);
+      const int32_t* kpos = positions + ((size_t)T * H + t * H + h) * N + (size_t)blk * B;
+#pragma unroll
+      for (int u = 0; u < VPER; ++u) {
+        const int idx = vt + u * kFtVThreads;
+        hit[u] = idx < ITEMS ? __ldg(kpos + idx / VCH) : -1;
+      }
+    };
+    auto v_issue = [&](int tile, int set) {            // uses hit[] loaded for `tile`; always commits one group
+      if (tile < total_tiles) {
+        int h, t, blk;
+        decode(tile, h, t, blk);
+        float4* stg = reinterpret_cast<float4*>(smem + CF::OFF_VSTG + set * CF::VSTG);
+        const float* vh = v + (size_t)h * D;
+#pragma unroll
+        for (int u = 0; u < VPER; ++u) {
+          const int idx = vt + u * kFtVThreads;
+          if (idx < ITEMS) {
+            const int n = hit[u];
+            const bool ok = n < raw_size;
+            umma::cp_async16(stg + idx, ok ? vh + (size_t)n * H * D + 4 * (idx % VCH) : v, ok ? 16 : 0);
+          }
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto v_write = [&](int vit) {                      // value tiles of tile number `vit` (stage vit & 1) from staging set vit & 1
+      const int st = vit & 1;
+      uint8_t* vm = smem + CF::OFF_V + st * 2 * CF::TILE;
+      const float4* stg = reinterpret_cast<const float4*>(smem + CF::OFF_VSTG + st * CF::VSTG);
+#pragma unroll
+      for (int u = 0; u < VPER; ++u) {
+        const int idx = vt + u * kFtVThreads;
+        if (idx < ITEMS) {
+          float4 hi, lo;
+          split4(stg[idx], hi, lo);
+          const uint32_t omn = umma::sw128b32_offset(idx / VCH, idx % VCH);
+          *reinterpret_cast<float4*>(vm + omn) = hi;
+          *reinterpret_cast<float4*>(vm + CF::TILE + omn) = lo;
+        }
+      }
+      umma::fence_async_smem();
+      __syncwarp();
+      if (lane == 0) umma::mbar_arrive(&mbar[VFULL + st]);
+      if (warp == EW + PW + 1) HEPT_TRACE_EVENT(EV_P_VFULL, vit);
+    };
+    // prologue: rows of tiles 0, 1 (written before the loop), 2, 3 (in flight); groups are committed in tile order
+    const int tile0 = blockIdx.x;
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+      if (tile0 + j * g < total_tiles) v_hits(tile0 + j * g);
+      if (j == 2) {                                    // sets are reused: tiles 0 and 1 must be out of them first
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (tile0 < total_tiles) v_write(0);
+        if (tile0 + g < total_tiles) v_write(1);
+      }
+      v_issue(tile0 + j * g, j & 1);
+    }
+    if (tile0 + 4 * g < total_tiles) v_hits(tile0 + 4 * g);
+
+    int it = 0;
+#pragma unroll 1
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      if (tile + 2 * g < total_tiles) {
+        umma::mbar_wait_parked(&mbar[VFREE + (it & 1)], (it >> 1) & 1);   // P V of this tile is done: its value tiles are free
+        umma::fence_after_sync();
+        asm volatile("cp.async.wait_group 1;" ::: "memory");     // rows of tile it + 2 have landed (it + 3 may be in flight)
+        v_write(it + 2);
+      }
+      v_issue(tile + 4 * g, it & 1);                             // hit[] holds tile it + 4
+      if (tile + 5 * g < total_tiles) v_hits(tile + 5 * g);
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
   if (warp == EW + PW) {
     // =========================================== MMA issuer ====================================================

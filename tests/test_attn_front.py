@@ -42,7 +42,7 @@ def _problem(n, seed, trained):
 
 
 @pytest.mark.parametrize("trained", [False, True], ids=["default-init", "checkpoint-layer0"])
-@pytest.mark.parametrize("n", [1, 127, 128, 1300, 6100, 60000])
+@pytest.mark.parametrize("n", [1, 15, 17, 33, 127, 128, 1300, 6100, 60000])   # 16-hit tiles, 32-hit slabs: both sides of each edge
 def test_attn_front_forward_backward(n, trained):
     from hept_b200 import ops
 

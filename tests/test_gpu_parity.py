@@ -141,7 +141,7 @@ def test_coord_scale_forward_backward(name):
     assert rel_err(dw.cpu(), w.grad) < 1e-5
 
 
-@pytest.mark.parametrize("shape", [(1300, 8, 24), (60000, 8, 24), (70, 2, 8), (6437, 8, 24)])
+@pytest.mark.parametrize("shape", [(1300, 8, 24), (60000, 8, 24), (70, 2, 8), (6437, 8, 24), (1, 8, 24), (17, 8, 24), (33, 8, 24)])
 def test_out_linear_forward_backward(shape):
     """a12 projection (example/hept.py:80) on the library's streaming kernels vs a float64 evaluation: an fp32 dot product
     of H*D terms; 2e-6 relative (Frobenius) is ~10 ulp of headroom over sqrt(192) * 2^-24.  Deterministic bit for bit."""
