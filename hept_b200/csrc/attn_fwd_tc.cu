@@ -19,7 +19,7 @@
 // small cross terms are accumulated first and the hi*hi steps are split over two accumulators that the epilogue adds
 // in fp32 (S0: cross terms + first half of the k-steps, S1: the rest).
 //
-// Warp roles (896 threads = 7 warpgroups, register budgets 96 / 64 / 56 rebalanced with setmaxnreg):
+// Warp roles (896 threads = 7 warpgroups, register budgets 104 / 56 / 56 rebalanced with setmaxnreg):
 //   warps 0-7   epilogue: TMEM lane = (warp & 3) * 32 + lane, columns split in two parts (warp >> 2); software
 //               pipelined: P of tile n+1 is produced before the output rows of tile n are read and scattered, so the
 //               P V MMAs of tile n run under SIMT work
@@ -50,7 +50,7 @@ constexpr int kFtParts = kFtEpiThreads / 128;
 // The gather / centre / split work of the producer is latency bound (ncu: every producer warp busy or stalled on its
 // own loads the whole time, the epilogue waiting for scores), so it gets 16 warps: two 64-row passes per tile.
 constexpr int kFtLaunchRegs = 72;
-constexpr int kFtRegsEpi = 96, kFtRegsProd = 64, kFtRegsMma = 56;
+constexpr int kFtRegsEpi = 104, kFtRegsProd = 56, kFtRegsMma = 56;
 constexpr int kFtVWarps = 3, kFtVThreads = 32 * kFtVWarps;   // the MMA warp's three siblings prepare the value operand
 static_assert(kFtEpiThreads * kFtRegsEpi + kFtProdThreads * kFtRegsProd + 128 * kFtRegsMma <= kFtThreads * kFtLaunchRegs, "register pool");
 
@@ -181,20 +181,22 @@ __global__ void __launch_bounds__(kFtThreads, 1)
       umma::fence_after_sync();
       if (warp == 0) HEPT_TRACE_EVENT(EV_E_SREADY, it);
       const float nq2 = s_nq2[(it & 3) * 128 + row];
+      // (issuing the loads of chunk ci + 1 before chunk ci is turned into P measured 2 % SLOWER: the TMEM port is shared
+      // with the P V MMAs of the other slot, spreading the loads does not help)
 #pragma unroll
       for (int ci = 0; ci < MAXCH; ++ci) {
         const int ch = part + ci * kFtParts;
         if (ch < KSTEPS) {
-          uint32_t ra[8], rb[8];
-          umma::tmem_ld8_nowait(tS0 + lane_base + 8 * ch, ra);
-          umma::tmem_ld8_nowait(tS1 + lane_base + 8 * ch, rb);
-          umma::tmem_wait_ld(ra, rb);
+          uint32_t xa[8], xb[8];
+          umma::tmem_ld8_nowait(tS0 + lane_base + 8 * ch, xa);
+          umma::tmem_ld8_nowait(tS1 + lane_base + 8 * ch, xb);
+          umma::tmem_wait_ld(xa, xb);
           float ph[8], pl[8];
           // two elements per issue slot where the ISA has packed fp32 (add, fma: sm_100); same IEEE results per element
 #pragma unroll
           for (int u = 0; u < 8; u += 2) {
-            const float2 s2 = __fadd2_rn(make_float2(__uint_as_float(ra[u]), __uint_as_float(ra[u + 1])),
-                                         make_float2(__uint_as_float(rb[u]), __uint_as_float(rb[u + 1])));
+            const float2 s2 = __fadd2_rn(make_float2(__uint_as_float(xa[u]), __uint_as_float(xa[u + 1])),
+                                         make_float2(__uint_as_float(xb[u]), __uint_as_float(xb[u + 1])));
             const float2 x2 = __ffma2_rn(s2, make_float2(kLog2e, kLog2e), make_float2(nq2, nq2));
             const float p0 = exp2_fast(fminf(x2.x, 0.f)), p1 = exp2_fast(fminf(x2.y, 0.f));   // exp(min(S, 0)), example/hept.py:12
             ph[u] = __uint_as_float(__float_as_uint(p0) & 0xffffe000u);
