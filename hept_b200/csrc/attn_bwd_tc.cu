@@ -420,15 +420,26 @@ __global__ void __launch_bounds__(kBtThreads, 1)
             if (part == (D + cc) / 16) dsc[cc] = fmaf(xr[(D + cc) % 16], o[(D + cc) % 16], dsc[cc]);
         }
       };
-      // a 64-column accumulator = [hi*hi | hi*lo + lo*hi]: this thread's 16 columns of the sum of the two halves
-      auto ld_acc = [&](uint32_t taddr, float (&acc)[16]) {
-        float lo[16];
-        umma::tmem_ld16(taddr + lane_base + 16 * part, acc);
-        umma::tmem_ld16(taddr + 32 + lane_base + 16 * part, lo);
+      // a 64-column accumulator = [hi*hi | hi*lo + lo*hi]: this thread's 16 columns of the sum of the two halves, and (SUM)
+      // column E of both halves -- every load is issued before the one wait (four waits cost four TMEM round trips)
+      auto ld_acc = [&](uint32_t taddr, float (&acc)[16], float* sum) {
+        uint32_t a[16], l[16], s0 = 0, s1 = 0;
+        umma::tmem_ld16_nowait(taddr + lane_base + 16 * part, a);
+        umma::tmem_ld16_nowait(taddr + 32 + lane_base + 16 * part, l);
+        if (sum) {
+          umma::tmem_ld1_nowait(taddr + lane_base + E, s0);
+          umma::tmem_ld1_nowait(taddr + 32 + lane_base + E, s1);
+        }
+        umma::tmem_wait_ld();
+        umma::tmem_tie(a);
+        umma::tmem_tie(l);
+        if (sum) {
+          umma::tmem_tie(s0, s1);
+          *sum = __uint_as_float(s0) + __uint_as_float(s1);
+        }
 #pragma unroll
-        for (int u = 0; u < 16; ++u) acc[u] += lo[u];
+        for (int u = 0; u < 16; ++u) acc[u] = __uint_as_float(a[u]) + __uint_as_float(l[u]);
       };
-      auto ld_sum = [&](uint32_t taddr) { return umma::tmem_ld1(taddr + lane_base + E) + umma::tmem_ld1(taddr + 32 + lane_base + E); };
 
       // ---- dv rows (dV was the first product into tO) ------------------------------------------------------------------
       umma::mbar_wait(&mbar[DVDONE], ph);
@@ -457,7 +468,7 @@ __global__ void __launch_bounds__(kBtThreads, 1)
       }
       {
         float acc[16];
-        ld_acc(tO, acc);
+        ld_acc(tO, acc, nullptr);
         const int n = row < B ? kidx[row] : -1;
         if (n >= 0) {
           float4* dst = reinterpret_cast<float4*>(stage_dv + (DIRECT ? ((size_t)n * H + h) * D : (((size_t)h * N + n) * T + t) * D));
@@ -499,9 +510,8 @@ __global__ void __launch_bounds__(kBtThreads, 1)
 
       // ---- dq^ rows: dQ was accumulated over the first columns of the (consumed) P^T region ---------------------------
       {
-        float acc[16], xr[16];
-        ld_acc(tST, acc);
-        const float rs = ld_sum(tST);                              // column E of dQ: sum_j dS_ij
+        float acc[16], xr[16], rs;
+        ld_acc(tST, acc, &rs);                                     // rs = column E of dQ: sum_j dS_ij
         umma::fence_before_sync();
         __syncwarp();
         if (lane == 0) umma::mbar_arrive(&mbar[STFREE]);           // the next tile's key-side scores may overwrite tST
@@ -515,15 +525,14 @@ __global__ void __launch_bounds__(kBtThreads, 1)
       umma::fence_after_sync();
       if (warp == 0) HEPT_TRACE_EVENT(BE_DKDONE, it);
       {
-        float acc[16], xr[16];
-        ld_acc(tO, acc);
-        const float cs = ld_sum(tO);                               // column E of dK: sum_i dS_ij
+        float acc[16], xr[16], cs;
+        ld_acc(tO, acc, &cs);                                      // cs = column E of dK: sum_i dS_ij
         centred_row(CF::MKH, CF::MKL, xr);
+        umma::fence_before_sync();                       // the TMEM loads above precede the next tile's MMAs into tO
+        __syncwarp();
+        if (lane == 0) umma::mbar_arrive(&mbar[MFREE]);  // this warp is done with the MN-major tiles (its rows are in registers)
         finish_rows(acc, xr, cs, row < B ? kidx[row] : -1, stage_dk);
       }
-      umma::fence_before_sync();                         // the TMEM loads above precede the next tile's MMAs into tO
-      __syncwarp();
-      if (lane == 0) umma::mbar_arrive(&mbar[MFREE]);    // this warp is done with the MN-major tiles
       if (DIRECT) {
         // last tile of this CTA in the group: sums handed in, and the count the next group depends on asked for, now
         int hn = -1, tn = 0, bn;
