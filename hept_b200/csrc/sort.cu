@@ -30,7 +30,7 @@ constexpr int kSortWarps = kSortThreads / 32;
 #define HEPT_SORT_ITEMS 16
 #endif
 #ifndef HEPT_SORT_BLOCKS
-#define HEPT_SORT_BLOCKS 3
+#define HEPT_SORT_BLOCKS 5
 #endif
 constexpr int kItemsPerThread = HEPT_SORT_ITEMS;
 constexpr int kTile = kSortThreads * kItemsPerThread;  // 4096 keys per CTA
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(kSortThreads, HEPT_SORT_BLOCKS) radix_scatter_
   const size_t base = (size_t)seg * n;
 
   // (0) every global load of the CTA is issued before anything depends on one: keys, incoming indices, histograms
-  uint32_t key[kItemsPerThread], peers[kItemsPerThread];
+  uint32_t key[kItemsPerThread];
   const int wstart = tile * kTile + warp * (32 * kItemsPerThread);
 #pragma unroll
   for (int it = 0; it < kItemsPerThread; ++it) {
@@ -148,15 +148,13 @@ __global__ void __launch_bounds__(kSortThreads, HEPT_SORT_BLOCKS) radix_scatter_
   const uint32_t my_local = pre_m + inc_m - mine;
   local_start[tid] = my_local;
 
-  // (2) per-warp digit counts; each warp owns a contiguous run of 512 keys, kept in registers
+  // (2) per-warp digit counts; each warp owns a contiguous run of 512 keys, kept in registers.  Counts only: shared-memory
+  // atomics (their order does not matter), so that the ballot masks need not stay in registers until step (4) -- 16 fewer
+  // registers per thread are what lets FIVE CTAs share an SM, and the 720 CTAs of an attention call's 48 segments run as one wave
 #pragma unroll
   for (int it = 0; it < kItemsPerThread; ++it) {
     const int i = wstart + it * 32 + lane;
-    const bool ok = i < n;
-    const uint32_t dg = (key[it] >> shift) & (kRadix - 1);
-    peers[it] = same_digit_lanes(dg, ok);
-    if (ok && lane == __ffs(peers[it]) - 1) warp_off[warp][dg] += __popc(peers[it]);
-    __syncwarp();
+    if (i < n) atomicAdd(&warp_off[warp][(key[it] >> shift) & (kRadix - 1)], 1u);
   }
   __syncthreads();
   // (3) exclusive prefix over warps, seeded with the digit's tile-local start
@@ -170,17 +168,18 @@ __global__ void __launch_bounds__(kSortThreads, HEPT_SORT_BLOCKS) radix_scatter_
     }
   }
   __syncthreads();
-  // (4) rank in the same order and park every key at its tile-local slot
+  // (4) rank in index order (ballot masks of the lanes holding the same digit) and park every key at its tile-local slot
 #pragma unroll
   for (int it = 0; it < kItemsPerThread; ++it) {
-    int i = wstart + it * 32 + lane;
-    bool ok = i < n;
-    uint32_t dg = (key[it] >> shift) & (kRadix - 1);
-    uint32_t rank = __popc(peers[it] & ((1u << lane) - 1u));
+    const int i = wstart + it * 32 + lane;
+    const bool ok = i < n;
+    const uint32_t dg = (key[it] >> shift) & (kRadix - 1);
+    const uint32_t peers = same_digit_lanes(dg, ok);
+    const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
     uint32_t pos = 0;
     if (ok) pos = warp_off[warp][dg] + rank;
     __syncwarp();
-    if (ok && lane == __ffs(peers[it]) - 1) warp_off[warp][dg] += __popc(peers[it]);
+    if (ok && lane == __ffs(peers) - 1) warp_off[warp][dg] += __popc(peers);
     __syncwarp();
     if (ok) {
       s_key[pos] = key[it];
@@ -421,6 +420,12 @@ int hept::segmented_argsort_launch(const void* keys_v, int32_t num_segments, int
   uint32_t* kbuf[2] = {(uint32_t*)w, (uint32_t*)(w + p.keys_bytes)};  w += 2 * p.keys_bytes;
   int32_t* ibuf[2] = {(int32_t*)w, (int32_t*)(w + p.idx_bytes)};
   dim3 grid(p.tiles, num_segments);
+  static DeviceOnce configured;     // five CTAs of 43 KB per SM need the largest shared-memory carve-out
+  if (configured.needed()) {
+    cudaError_t e = cudaFuncSetAttribute(radix_scatter_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    HEPT_REQUIRE(e == cudaSuccess, HEPT_ECUDA, "segmented_argsort: %s", cudaGetErrorString(e));
+    configured.mark();
+  }
   const int passes = key_bits > 0 ? (key_bits + kRadixBits - 1) / kRadixBits : 32 / kRadixBits;
   const void* kin = keys;
   const int32_t* iin = nullptr;
