@@ -17,7 +17,8 @@
 //
 // The tensor-core accumulator truncates after every MMA and q'.k' is far larger than the score it cancels to, so the
 // small cross terms are accumulated first and the hi*hi steps are split over two accumulators that the epilogue adds
-// in fp32 (S0: cross terms + first half of the k-steps, S1: the rest).
+// in fp32 (S0: cross terms + first half of the k-steps, S1: the rest).  (One accumulator -- half the epilogue's TMEM loads --
+// passes the parity suite too but measured 1 % SLOWER: twelve score MMAs in one dependency chain.)
 //
 // Warp roles (896 threads = 7 warpgroups, register budgets 104 / 56 / 56 rebalanced with setmaxnreg):
 //   warps 0-7   epilogue: TMEM lane = (warp & 3) * 32 + lane, columns split in two parts (warp >> 2); software
