@@ -109,7 +109,9 @@ int hept_block_attention_fwd(const hept_shape* s, const float* q, const float* k
 int hept_or_combine(const hept_shape* s, const float* stage, float* out_pre, float* den_sum, void* stream);
 
 /* ---- a12, second half: out_linear (example/hept.py:80; nn.Linear(H*D, D)) ------------------------
- * out (N, D) = out_pre (N, H*D) weight^T (D, H*D) + bias (D), fp32 FMA, no library GEMM. */
+ * out (N, D) = out_pre (N, H*D) weight^T (D, H*D) + bias (D), no library GEMM.  Arithmetic: for (H, D) = (8, 24) the three
+ * products of this section run as 3xTF32 tensor-core products (every operand split into tf32 hi + lo, hi*hi + hi*lo + lo*hi
+ * accumulated in fp32: ~2^-22 relative per product, like the attention tiles); other shapes use fp32 FMAs. */
 int hept_out_linear_fwd(const hept_shape* s, const float* out_pre, const float* weight, const float* bias,
                         float* out, void* stream);
 /* its backward: d_out (N, D) -> d_out_pre (N, H*D) = d_out weight (skipped when d_out_pre is null),
@@ -182,6 +184,7 @@ int hept_attention_fwd_shifts32(const hept_shape* s, const float* q, const float
  *   forward outputs: wt (3, D, H*D) the transposed weights, x_normed (N, D) (both kept for the backward), q, k, v (N, H*D).
  *   backward: dq, dk, dv (N, H*D) -> dx (N, D) (the gradient through norm1 only: the block's residual path is the caller's),
  *   d_norm_weight, d_norm_bias (D), d_w_q, d_w_k, d_w_v (H*D, D); deterministic (fixed-order reductions).
+ * The products are 3xTF32 tensor-core products with fp32 accumulation (see out_linear above); LayerNorm and its backward are fp32.
  * Compiled for (H, D) = (8, 24): hept_attn_qkv_supported says so; other shapes return HEPT_EUNSUPPORTED. */
 int hept_attn_qkv_supported(int32_t H, int32_t D);
 int hept_attn_qkv_fwd(const float* x, const float* norm_weight, const float* norm_bias, const float* w_q, const float* w_k,
