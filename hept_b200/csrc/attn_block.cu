@@ -512,6 +512,7 @@ extern "C" int hept_attn_qkv_fwd(const float* x, const float* norm_weight, const
   HEPT_REQUIRE(x && norm_weight && norm_bias && w_q && w_k && w_v && wt && x_normed && q && k && v && N > 0, HEPT_EINVAL,
                "attn_qkv_fwd: bad argument");
   HEPT_REQUIRE(hept_attn_qkv_supported(H, D), HEPT_EUNSUPPORTED, "attn_qkv_fwd: (H=%d, D=%d) not compiled in", H, D);
+  HEPT_REQUIRE(aligned16({x, w_q, w_k, w_v, wt, x_normed, q, k, v}), HEPT_EINVAL, "attn_qkv_fwd: array pointers must be 16-byte aligned");
   return launch_qkv_fwd<24, 192>(x, norm_weight, norm_bias, w_q, w_k, w_v, N, eps, wt, x_normed, q, k, v, (cudaStream_t)stream);
 }
 
@@ -523,6 +524,8 @@ extern "C" int hept_attn_qkv_bwd(const float* x, const float* x_normed, const fl
                    d_w_v && workspace && N > 0,
                HEPT_EINVAL, "attn_qkv_bwd: bad argument");
   HEPT_REQUIRE(hept_attn_qkv_supported(H, D), HEPT_EUNSUPPORTED, "attn_qkv_bwd: (H=%d, D=%d) not compiled in", H, D);
+  HEPT_REQUIRE(aligned16({x, x_normed, wt, dq, dk, dv, dx, d_w_q, d_w_k, d_w_v, workspace}), HEPT_EINVAL,
+               "attn_qkv_bwd: array pointers must be 16-byte aligned");
   HEPT_REQUIRE(workspace_bytes >= hept_attn_qkv_bwd_workspace_bytes(N, H, D), HEPT_EWORKSPACE, "attn_qkv_bwd: workspace needs %zu bytes",
                hept_attn_qkv_bwd_workspace_bytes(N, H, D));
   return launch_qkv_bwd<24, 192>(x, x_normed, norm_weight, wt, dq, dk, dv, N, H, D, eps, dx, d_norm_weight, d_norm_bias, d_w_q,

@@ -1,5 +1,7 @@
 // Shared device/host helpers for the hept_b200 sm_100a library.
 #pragma once
+#include <initializer_list>
+#include <cstdint>
 
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -107,6 +109,11 @@ __device__ __forceinline__ void cp_async16_cg(void* smem_dst, const void* gsrc) 
 __device__ __forceinline__ void st_global_v8(float* dst, const float4 a, const float4 b) {
   asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
                :: "l"(dst), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
+}
+// the kernels read and write rows as 16-byte vectors: every array pointer of the ABI must be 16-byte aligned
+inline bool aligned16(std::initializer_list<const void*> ptrs) {
+  for (const void* p : ptrs) if (reinterpret_cast<uintptr_t>(p) & 15u) return false;
+  return true;
 }
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float2 ldg2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }

@@ -552,6 +552,8 @@ extern "C" int hept_out_linear_bwd(const hept_shape* s, const float* d_out, cons
                                    size_t workspace_bytes, void* stream) {
   if (int rc = validate_shape(s)) return rc;
   HEPT_REQUIRE(d_out && weight && out_pre && d_weight && d_bias && workspace, HEPT_EINVAL, "out_linear_bwd: null pointer");
+  HEPT_REQUIRE(aligned16({d_out, weight, out_pre, d_out_pre, d_weight, workspace}), HEPT_EINVAL,
+               "out_linear_bwd: array pointers must be 16-byte aligned");
   HEPT_REQUIRE(workspace_bytes >= hept_out_linear_bwd_workspace_bytes(s), HEPT_EWORKSPACE,
                "out_linear_bwd: workspace needs %zu bytes", hept_out_linear_bwd_workspace_bytes(s));
   cudaStream_t st = (cudaStream_t)stream;

@@ -8,7 +8,8 @@
  * this header through ctypes; INTEGRATION.md shows the stub a reference maintainer would add.
  *
  * Conventions
- *   - every pointer is a DEVICE pointer unless named `*_host`; tensors are dense row-major;
+ *   - every pointer is a DEVICE pointer unless named `*_host`; tensors are dense row-major and 16-byte aligned (rows are
+ *     read and written as 16-byte vectors; out_linear and the Attn front check it and return HEPT_EINVAL);
  *   - the library never allocates, frees or synchronises: the caller (torch) owns every buffer,
  *     including `workspace`, and passes the CUDA stream to enqueue on (`stream` is a cudaStream_t
  *     passed as void*);

@@ -119,3 +119,25 @@ def test_int32_codes_give_the_same_result_as_int64():
     b = ops.attention_fwd(d, q, k, v, kw["coords"], w, 10, al, combined_shifts=kw["combined_shifts32"])
     for x, y in zip(a, b):
         assert torch.equal(x, y)
+
+
+def test_misaligned_pointers_are_refused():
+    """Rows travel as 16-byte vectors: a view that starts 4 bytes into an allocation must be refused, not misread."""
+    import ctypes as C
+
+    from hept_b200 import _lib
+
+    lib = _lib.load()
+    n = 64
+    buf = torch.zeros(n * D + 1, device=DEV)
+    x = buf[1:].view(n, D)                              # 4 bytes past a 256-byte aligned allocation
+    assert x.data_ptr() % 16 != 0
+    gam, bet = torch.ones(D, device=DEV), torch.zeros(D, device=DEV)
+    w = [torch.zeros(H * D, D, device=DEV) for _ in range(3)]
+    wt = torch.empty(3, D, H * D, device=DEV)
+    xn = torch.empty(n, D, device=DEV)
+    q, k, v = (torch.empty(n, H * D, device=DEV) for _ in range(3))
+    p = lambda t: C.c_void_p(t.data_ptr())
+    rc = lib.hept_attn_qkv_fwd(p(x), p(gam), p(bet), p(w[0]), p(w[1]), p(w[2]), n, H, D, C.c_float(1e-5), p(wt), p(xn), p(q),
+                               p(k), p(v), None)
+    assert rc == -1 and b"aligned" in lib.hept_last_error()
