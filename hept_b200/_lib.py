@@ -58,6 +58,10 @@ SIGNATURES = {
     "hept_attn_qkv_fwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _i32, _i32, C.c_float, _p, _p, _p, _p, _p, _p]),
     "hept_attn_qkv_bwd_workspace_bytes": (_sz, [_i32, _i32, _i32]),
     "hept_attn_qkv_bwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _i32, _i32, _i32, C.c_float, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "hept_layer_norm_supported": (C.c_int, [_i32]),
+    "hept_layer_norm_fwd": (C.c_int, [_p, _p, _p, _i32, _i32, C.c_float, _p, _p, _p]),
+    "hept_layer_norm_bwd_workspace_bytes": (_sz, [_i32, _i32]),
+    "hept_layer_norm_bwd": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _p, _p, _p, _p, _sz, _p]),
     "hept_infonce_saved_bytes": (_sz, [_i32, C.c_int64]),
     "hept_infonce_workspace_bytes": (_sz, [_i32, C.c_int64, _i32]),
     "hept_infonce_fwd": (C.c_int, [_p, _i32, _i32, _p, C.c_int64, _p, _p, _p, C.c_float, _i32, C.c_float, _p, _p, _sz, _p, _sz, _p]),

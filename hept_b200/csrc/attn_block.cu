@@ -409,6 +409,11 @@ __global__ void __launch_bounds__(256) ln_params_reduce_kernel(const float* __re
   }
 }
 
+// (also used by layer_norm.cu)
+void ln_params_reduce_launch(const float* partial, int ctas, int DM, float* dgamma, float* dbeta, cudaStream_t st) {
+  ln_params_reduce_kernel<<<2 * DM, 256, 0, st>>>(partial, ctas, DM, dgamma, dbeta);
+}
+
 template <int DM, int OW>
 static int launch_qkv_fwd(const float* x, const float* gamma, const float* beta, const float* wq, const float* wk, const float* wv,
                           int N, float eps, float* wt, float* xn, float* q, float* k, float* v, cudaStream_t st) {

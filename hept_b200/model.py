@@ -7,7 +7,8 @@ Parameter names and shapes follow the reference so its checkpoints load with ``s
 (``example/ckpt/tracking-60k-model.pt``: ``regions``, ``feat_encoder.*``, ``attns.i.{w_q,w_k,w_v,norm1,norm2,ff,w_rpe}.*``,
 ``attns.i.attn.{out_linear.*, e2lsh.alpha}``, ``W.weight``, ``mlp_out.lins.j.*``, ``mlp_out.norms.j.*``).
 
-The dense layers are small library GEMMs (cuBLAS through ``nn.Linear``); only the attention is custom CUDA.
+The dense layers are small library GEMMs (cuBLAS through ``nn.Linear``); the attention, the front of the Attn block and the
+LayerNorms (``norm2``, the head's norms: ``hept_b200/layers.py``) are the library's CUDA kernels.
 ``mlp_out`` restates ``torch_geometric.nn.MLP(in, hidden 256, out, num_layers=5, norm="layer_norm", act="tanh")``:
 ``lin -> LayerNorm -> tanh`` four times, then a plain last ``lin`` (PyG is not a dependency here).
 """
@@ -21,6 +22,7 @@ import torch.nn as nn
 from . import prepare
 from . import ops
 from .attention import HEPTAttention, attn_front
+from .layers import LayerNorm, Linear
 
 
 def get_regions(num_regions: int, num_or_hashes: int, num_heads: int, num_and_hashes: int = 2) -> torch.Tensor:
@@ -42,8 +44,8 @@ class NodeMLP(nn.Module):
     def __init__(self, in_channels: int, hidden_channels: int, out_channels: int, num_layers: int):
         super().__init__()
         dims = [in_channels] + [hidden_channels] * (num_layers - 1) + [out_channels]
-        self.lins = nn.ModuleList(nn.Linear(a, b) for a, b in zip(dims[:-1], dims[1:]))
-        self.norms = nn.ModuleList(nn.LayerNorm(hidden_channels) for _ in range(num_layers - 1))
+        self.lins = nn.ModuleList(Linear(a, b) for a, b in zip(dims[:-1], dims[1:]))
+        self.norms = nn.ModuleList(LayerNorm(hidden_channels) for _ in range(num_layers - 1))
 
     def forward(self, x):
         for lin, norm in zip(self.lins[:-1], self.norms):
@@ -65,8 +67,8 @@ class Attn(nn.Module):
         self.attn = attn_cls(d + coords_dim, **kwargs)
         self.dropout = nn.Dropout(0.1)
         self.norm1 = nn.LayerNorm(d)
-        self.norm2 = nn.LayerNorm(d)
-        self.ff = nn.Sequential(nn.Linear(d, d), nn.ReLU(), nn.Linear(d, d))
+        self.norm2 = LayerNorm(d)                 # csrc/layer_norm.cu (norm1 is part of the fused front)
+        self.ff = nn.Sequential(Linear(d, d), nn.ReLU(), Linear(d, d))
         # eta / phi share the first weight group (example/transformer.py:153-154)
         self.w_rpe = nn.Linear(kwargs["num_w_per_dist"] * (coords_dim - 1), h * d)
 
@@ -97,11 +99,11 @@ class Transformer(nn.Module):
         if task == "pileup":                      # src/models/baselines/transformer.py:76-78
             self.pids_enc = nn.Embedding(7, 10)
             in_dim = in_dim - 1 + 10
-        self.feat_encoder = nn.Sequential(nn.Linear(in_dim, self.h_dim), nn.ReLU(), nn.Linear(self.h_dim, self.h_dim))
+        self.feat_encoder = nn.Sequential(Linear(in_dim, self.h_dim), nn.ReLU(), Linear(self.h_dim, self.h_dim))
         self.attns = nn.ModuleList(Attn(coords_dim, attn_cls=attn_cls, **kwargs) for _ in range(self.n_layers))
         self.dropout = nn.Dropout(dropout)
         half = int(self.h_dim // 2)
-        self.W = nn.Linear(self.h_dim * (self.n_layers + 1), half, bias=False)
+        self.W = Linear(self.h_dim * (self.n_layers + 1), half, bias=False)
         self.mlp_out = NodeMLP(half, 256, half, num_layers=5)
         self.regions = nn.Parameter(get_regions(kwargs["num_regions"], kwargs["n_hashes"], kwargs["num_heads"]),
                                     requires_grad=False)

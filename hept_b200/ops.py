@@ -265,6 +265,42 @@ def out_linear_bwd(d: Dims, d_out, weight, out_pre, need_input_grad: bool = True
     return dx, dw, db
 
 
+# ---------------------------------------------------------------- the caller's other LayerNorms (norm2, the model head)
+def layer_norm_supported(D: int) -> bool:
+    return bool(_lib.load().hept_layer_norm_supported(D))
+
+
+@_on_device
+def layer_norm_fwd(x, weight, bias, eps: float):
+    """x (N, D) -> y (N, D), mean_rstd (N, 2) (kept for the backward)."""
+    lib = _lib.load()
+    n, d = x.shape
+    x = _need(x, "x", torch.float32, (n, d))
+    g = _need(weight, "weight", torch.float32, (d,))
+    b = _need(bias, "bias", torch.float32, (d,))
+    y = torch.empty_like(x)
+    mr = torch.empty(n, 2, dtype=torch.float32, device=x.device)
+    _lib.check(lib.hept_layer_norm_fwd(_ptr(x), _ptr(g), _ptr(b), n, d, eps, _ptr(y), _ptr(mr), _stream(x)), "hept_layer_norm_fwd")
+    return y, mr
+
+
+@_on_device
+def layer_norm_bwd(x, mean_rstd, weight, dy):
+    """-> dx (N, D), d weight, d bias (D)."""
+    lib = _lib.load()
+    n, d = x.shape
+    x = _need(x, "x", torch.float32, (n, d))
+    mr = _need(mean_rstd, "mean_rstd", torch.float32, (n, 2))
+    g = _need(weight, "weight", torch.float32, (d,))
+    dy = _need(dy, "dy", torch.float32, (n, d))
+    dx = torch.empty_like(x)
+    dg, db = torch.empty(d, dtype=torch.float32, device=x.device), torch.empty(d, dtype=torch.float32, device=x.device)
+    ws = _workspace(lib.hept_layer_norm_bwd_workspace_bytes(n, d), x)
+    _lib.check(lib.hept_layer_norm_bwd(_ptr(x), _ptr(mr), _ptr(g), _ptr(dy), n, d, _ptr(dx), _ptr(dg), _ptr(db), _ptr(ws), ws.numel(),
+                                       _stream(x)), "hept_layer_norm_bwd")
+    return dx, dg, db
+
+
 # ---------------------------------------------------------------- SURVEY.md 8(f)-1: norm1 + w_q / w_k / w_v
 def attn_qkv_supported(H: int, D: int) -> bool:
     return bool(_lib.load().hept_attn_qkv_supported(H, D))

@@ -177,6 +177,18 @@ int hept_attention_fwd_shifts32(const hept_shape* s, const float* q, const float
                                 float* scale, int32_t* positions, float* out_pre, float* den_sum, void* workspace,
                                 size_t workspace_bytes, void* stream);
 
+/* ---- the caller's other LayerNorms: the Attn block's norm2 (example/transformer.py:163) and the model head's 256-wide norms
+ * (torch_geometric MLP, example/transformer.py:84).  torch.nn.functional.layer_norm over the last dimension: biased variance,
+ * eps inside the square root, y = (x - mean) rstd weight + bias; fp32.  4 <= D <= 256, D % 4 == 0.
+ *   forward:  x (N, D) -> y (N, D), mean_rstd (N, 2) kept for the backward
+ *   backward: dy (N, D) -> dx (N, D), d_weight, d_bias (D); deterministic (fixed-order reductions). */
+int hept_layer_norm_supported(int32_t D);
+int hept_layer_norm_fwd(const float* x, const float* weight, const float* bias, int32_t N, int32_t D, float eps, float* y,
+                        float* mean_rstd, void* stream);
+size_t hept_layer_norm_bwd_workspace_bytes(int32_t N, int32_t D);
+int hept_layer_norm_bwd(const float* x, const float* mean_rstd, const float* weight, const float* dy, int32_t N, int32_t D,
+                        float* dx, float* d_weight, float* d_bias, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- the front of the caller's Attn block ------------------------------------------------------
  * x_normed = norm1(x); q, k, v = w_q(x_normed), w_k(x_normed), w_v(x_normed)   (example/transformer.py:157-158,
  * src/models/baselines/transformer.py:209-212): LayerNorm over D (eps inside the square root) and three bias-free
