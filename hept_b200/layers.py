@@ -57,7 +57,15 @@ class _TallLinearFn(torch.autograd.Function):
         dw = torch.bmm(dy[:m].view(slabs, m // slabs, -1).transpose(1, 2), x[:m].view(slabs, m // slabs, -1)).sum(0)
         if m < n:
             dw = dw + dy[m:].t() @ x[m:]
-        db = dy.sum(0) if ctx.has_bias else None
+        db = None
+        if ctx.has_bias:
+            if dy.shape[1] >= 64:                     # wide rows: torch's column sum is 3x slower than two stages (72 vs 24 us at 60k x 256)
+                mb = n // 240 * 240
+                db = dy[:mb].view(240, mb // 240, -1).sum(1).sum(0)
+                if mb < n:
+                    db = db + dy[mb:].sum(0)
+            else:
+                db = dy.sum(0)
         return dx, dw, db
 
 
