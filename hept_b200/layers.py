@@ -25,12 +25,16 @@ class _LayerNormFn(torch.autograd.Function):
 
 class LayerNorm(nn.LayerNorm):
     """``nn.LayerNorm`` over the last dimension; CUDA fp32 inputs of a supported width (4 <= D <= 256, D % 4 == 0) run on the
-    library's kernels, anything else (the CPU twin of the tests, other dtypes) on torch's."""
+    library's kernels -- in every mode, so that eval, training and a captured CUDA graph see the same bits; anything else (the
+    CPU twin of the tests, other dtypes) runs on torch's."""
 
     def forward(self, x):
         if (x.is_cuda and x.dtype == torch.float32 and self.elementwise_affine and self.bias is not None
                 and len(self.normalized_shape) == 1 and x.numel() > 0 and ops.layer_norm_supported(self.normalized_shape[0])):
-            return _LayerNormFn.apply(x, self.weight, self.bias, self.eps)
+            if torch.is_grad_enabled() and (x.requires_grad or self.weight.requires_grad):
+                return _LayerNormFn.apply(x, self.weight, self.bias, self.eps)
+            y, _ = ops.layer_norm_fwd(x.reshape(-1, x.shape[-1]), self.weight, self.bias, self.eps)   # no autograd node to build
+            return y.view(x.shape)
         return super().forward(x)
 
 
