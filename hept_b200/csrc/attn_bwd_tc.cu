@@ -92,7 +92,8 @@ struct TcBwd {
 
 // timeline probe events (trace.cuh)
 enum BtEv { BE_QREADY, BE_DSRDY, BE_KREADY, BE_PTRDY, BE_DQDONE, BE_DQOUT, BE_DVDONE, BE_DSTRDY, BE_DVOUT, BE_DKDONE, BE_END,
-            BP_KFREE, BP_KFULL, BP_ISSUED, BP_MFREE, BP_MFULL, BM_DQ_GO, BM_DV_GO, BM_DK_GO, BM_SQ_GO, BM_SK_GO, BM_END };
+            BP_KFREE, BP_KFULL, BP_ISSUED, BP_MFREE, BP_MFULL, BM_DQ_GO, BM_DV_GO, BM_DK_GO, BM_SQ_GO, BM_SK_GO, BM_END,
+            BE_DSTISS, BE_DVWAIT, BE_DQACC, BE_DKACC };
 HEPT_TRACE_SETTER(hept_debug_trace_bwd)
 
 #ifndef HEPT_BWD_PROD_WAIT
@@ -466,6 +467,7 @@ __global__ void __launch_bounds__(kBtThreads, 1)
           __syncwarp();                                  // the other lanes' adds are ordered after lane 0's acquire
         }
       }
+      if (warp == 0) HEPT_TRACE_EVENT(BE_DVWAIT, it);
       {
         float acc[16];
         ld_acc(tO, acc, nullptr);
@@ -505,6 +507,7 @@ __global__ void __launch_bounds__(kBtThreads, 1)
         }
       }
       if (HEPT_BWD_SPLIT && !second_half) open_second_half();
+      if (warp == 0) HEPT_TRACE_EVENT(BE_DSTISS, it);
       arrive_tmem(DSTRDY);                               // also: this warp has read dV out of tO
       if (warp == 0) HEPT_TRACE_EVENT(BE_DSTRDY, it);
 
@@ -512,6 +515,7 @@ __global__ void __launch_bounds__(kBtThreads, 1)
       {
         float acc[16], xr[16], rs;
         ld_acc(tST, acc, &rs);                                     // rs = column E of dQ: sum_j dS_ij
+        if (warp == 0) HEPT_TRACE_EVENT(BE_DQACC, it);
         umma::fence_before_sync();
         __syncwarp();
         if (lane == 0) umma::mbar_arrive(&mbar[STFREE]);           // the next tile's key-side scores may overwrite tST
@@ -527,6 +531,7 @@ __global__ void __launch_bounds__(kBtThreads, 1)
       {
         float acc[16], xr[16], cs;
         ld_acc(tO, acc, &cs);                                      // cs = column E of dK: sum_i dS_ij
+        if (warp == 0) HEPT_TRACE_EVENT(BE_DKACC, it);
         centred_row(CF::MKH, CF::MKL, xr);
         umma::fence_before_sync();                       // the TMEM loads above precede the next tile's MMAs into tO
         __syncwarp();

@@ -3,7 +3,9 @@
     make -C hept_b200/csrc TRACE=1 && python tools/pipeline_trace.py
 
 Prints, per tile, each event's offset from the first stamp and the steady-state period / phases; writes
-gpurun_out/pipeline_trace.json."""
+gpurun_out/pipeline_trace.json.  The stamps cost the stamping warp ~100 cycles each: the traced CTA runs 10-15 % slower than
+the others (compare its period with the per-CTA durations), and phases that hold several stamps are stretched -- per-line
+stall samples (tools/ncu_lines.py) are the cross-check."""
 import ctypes
 import json
 import os
@@ -21,7 +23,7 @@ FWD = ["E_SREADY", "E_PREADY", "E_ODONE", "E_OUT", "P_QKFREE", "P_QKFULL", "P_VF
        "M_S_GO", "M_S_ISSUED", "M_PV_GO", "M_PV_ISSUED"]
 BWD = ["E_QREADY", "E_DSRDY", "E_KREADY", "E_PTRDY", "E_DQDONE", "E_DQOUT", "E_DVDONE", "E_DSTRDY", "E_DVOUT", "E_DKDONE",
        "E_END", "P_KFREE", "P_KFULL", "P_ISSUED", "P_MFREE", "P_MFULL", "M_DQ_GO", "M_DV_GO", "M_DK_GO", "M_SQ_GO",
-       "M_SK_GO", "M_END"]
+       "M_SK_GO", "M_END", "E_DSTISS", "E_DVWAIT", "E_DQACC", "E_DKACC"]
 TILES, EVENTS = 64, 32
 
 lib = _lib.load()
